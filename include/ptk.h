@@ -1,0 +1,175 @@
+/* libptk - C ABI of the B200-native lidar-odometry step for ptudes-lab.
+ *
+ * This is the drop-in boundary for ONE hot path of bexcite/ptudes-lab: the per-scan
+ * KISS-ICP-style registration step that KissICPWrapper drives
+ * (reference: src/ptudes/kiss.py:54-131, caller src/ptudes/cli/ekf_bench.py:550-555).
+ * In the reference that path crosses from Python into the third-party kiss-icp 0.2.x
+ * pybind module (`kiss_icp.pybind.kiss_icp_pybind`, imported through kiss.py:7-10); the
+ * entry points below are what a binding for this path binds instead.  Every entry names
+ * the reference call site / kiss-icp binding it replaces.
+ *
+ * Conventions
+ *  - every call returns 0 on success, a negative PTK_E_* code otherwise; no C++ exception
+ *    crosses this boundary; ptk_last_error() gives the text of the last failure.
+ *  - all floating point is float64; poses are row-major 4x4 (16 doubles); point clouds are
+ *    row-major (N,3) float64 (the layout kiss.py hands to kiss-icp), timestamps (N,) float64.
+ *  - `const double*` inputs/outputs that carry point data may be HOST or DEVICE pointers
+ *    (the library asks cudaPointerGetAttributes); small outputs (poses, counts, stats) are
+ *    HOST pointers and are valid when the call returns (the call synchronises `stream`).
+ *  - `stream` is a cudaStream_t passed as void* (0 = default stream), e.g. PyTorch's
+ *    torch.cuda.current_stream().cuda_stream.
+ *  - a context is bound to one device and is not thread safe; distinct contexts may be
+ *    driven from distinct threads.  A context owns `batch` independent sequences ("lanes");
+ *    the *_batch call advances all lanes in one set of kernel launches (fleet replay).
+ *  - there is no CPU fallback: without a CUDA device ptk_ctx_create fails with PTK_E_CUDA.
+ */
+#ifndef PTK_H_
+#define PTK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTK_VERSION 100
+
+#define PTK_OK 0
+#define PTK_E_ARG (-1)        /* bad argument */
+#define PTK_E_CUDA (-2)       /* CUDA runtime error (no device, launch failure, ...) */
+#define PTK_E_CAPACITY (-3)   /* scan larger than cfg.max_points / map pool or table full */
+#define PTK_E_KEYRANGE (-4)   /* voxel coordinate outside +-2^20 */
+#define PTK_E_NUMERIC (-5)    /* singular normal equations / non-finite pose */
+#define PTK_E_STATE (-6)      /* call not valid in the current state */
+
+#define PTK_MAX_POINTS_PER_VOXEL 20
+
+typedef struct ptk_ctx ptk_ctx;
+
+/* kiss_icp.config.load_config(None, deskew=True, max_range=R) + config.data.min_range = m
+ * (reference: kiss.py:40-43) plus capacities of the device-side structures. */
+typedef struct ptk_config {
+    double max_range;            /* data.max_range, default 100 */
+    double min_range;            /* data.min_range, default 5 */
+    double voxel_size;           /* mapping.voxel_size; <= 0 -> max_range / 100 */
+    int max_points_per_voxel;    /* mapping.max_points_per_voxel, 1..20, default 20 */
+    int deskew;                  /* data.deskew, default 1 (kiss.py:41) */
+    double initial_threshold;    /* adaptive_threshold.initial_threshold, default 2.0 */
+    double min_motion_th;        /* adaptive_threshold.min_motion_th, default 0.1 */
+    int max_iterations;          /* ICP MAX_NUM_ITERATIONS_, default 500 */
+    double convergence_eps;      /* ICP ESTIMATION_THRESHOLD_, default 1e-4 */
+    int max_points;              /* capacity: points per scan, default 262144 */
+    int map_capacity;            /* capacity: voxels in the local map, default 262144 */
+    int batch;                   /* number of independent sequences (lanes), default 1 */
+    int trace_iterations;        /* >0: keep per-iteration correspondences of that many ICP
+                                    iterations for ptk_get_trace (parity tap), default 0 */
+} ptk_config;
+
+/* per-scan observables (the lists kiss.py:50-52,116-124 appends to, plus counters) */
+typedef struct ptk_stats {
+    int status;          /* 0 ok, 1 = zero correspondences (B.5), 2 = singular solve */
+    int n_in;            /* points handed in */
+    int n_range;         /* after the range filter */
+    int n_ds;            /* frame_downsample size (grid 0.5 v) */
+    int n_src;           /* source size (grid 1.5 v) */
+    int n_voxels;        /* voxels in the local map after the update */
+    int iterations;      /* ICP iterations run */
+    int n_corr;          /* correspondences of the last iteration */
+    double dx_norm;      /* |dx| of the last iteration */
+    double sigma;        /* adaptive threshold used (kiss.py:99,124) */
+    double err_dt;       /* |t| of inv(guess) @ pose (kiss.py:118) */
+    double err_drot;     /* |rotvec| of inv(guess) @ pose (kiss.py:119-120) */
+    int map_points;      /* points in the local map after the update */
+    int reserved;
+} ptk_stats;
+
+void ptk_default_config(ptk_config* cfg);
+int ptk_version(void);
+
+/* KissICP(config) construction (kiss.py:45). */
+int ptk_ctx_create(ptk_ctx** out, int device, const ptk_config* cfg);
+int ptk_ctx_destroy(ptk_ctx* ctx);
+/* Forget poses, threshold state and the local map of one lane (lane < 0: all lanes). */
+int ptk_reset(ptk_ctx* ctx, int lane);
+const char* ptk_last_error(const ptk_ctx* ctx);
+
+/* ---- the step: KissICPWrapper._kiss_register_frame (kiss.py:83-131) ----------------
+ * deskew (kiss.py:90) -> preprocess (:93) -> voxelize (:96) -> adaptive threshold (:99) ->
+ * initial guess (:102-105; `initial_guess` NULL = constant velocity model) ->
+ * register_frame (:108-114) -> err metrics (:116-124) -> update_model_deviation (:128) ->
+ * local_map.update (:129) -> poses.append (:130).  out_pose = the new pose. */
+int ptk_register_frame(ptk_ctx* ctx, int lane, const double* xyz, const double* timestamps,
+                       int n, const double* initial_guess /* 16 or NULL */,
+                       double* out_pose /* 16 */, ptk_stats* stats /* nullable */, void* stream);
+
+/* Same step for every lane of the context in one set of launches (fleet replay).
+ * xyz[l], timestamps[l], n[l] per lane; guesses = batch*16 doubles or NULL;
+ * has_guess[l] != 0 selects guesses[l]; out_poses = batch*16; stats = batch entries. */
+int ptk_register_frame_batch(ptk_ctx* ctx, const double* const* xyz,
+                             const double* const* timestamps, const int* n,
+                             const double* guesses, const unsigned char* has_guess,
+                             double* out_poses, ptk_stats* stats, void* stream);
+
+/* ---- state the wrapper exposes (kiss.py:133-166, cli/ekf_bench.py:545-547) --------- */
+int ptk_num_poses(const ptk_ctx* ctx, int lane);
+int ptk_get_pose(const ptk_ctx* ctx, int lane, int index /* <0 from the end */, double* out16);
+/* KissICP.get_prediction_model(): inv(poses[-2]) @ poses[-1], identity if < 2 poses. */
+int ptk_get_prediction_model(const ptk_ctx* ctx, int lane, double* out16);
+/* KissICP.get_adaptive_threshold() WITHOUT side effects (value the next step would use is
+ * only known inside the step because ComputeThreshold mutates state; this returns the last
+ * sigma used). */
+double ptk_last_sigma(const ptk_ctx* ctx, int lane);
+
+/* ---- pieces, one per kiss-icp binding the wrapper or tests reach --------------------
+ * kiss_icp_pybind._deskew_scan(frame, timestamps, start_pose, finish_pose) (kiss.py:76-78,90) */
+int ptk_deskew_scan(ptk_ctx* ctx, const double* xyz, const double* timestamps, int n,
+                    const double* start_pose, const double* finish_pose, double* out_xyz,
+                    void* stream);
+/* kiss_icp_pybind._preprocess(frame, max_range, min_range) (kiss.py:93) */
+int ptk_preprocess(ptk_ctx* ctx, const double* xyz, int n, double max_range, double min_range,
+                   double* out_xyz, int* n_out, void* stream);
+/* kiss_icp_pybind._voxel_down_sample(frame, voxel_size) (kiss.py:96); out_index (nullable)
+ * receives the input index of every kept point, ascending. */
+int ptk_voxel_down_sample(ptk_ctx* ctx, const double* xyz, int n, double voxel_size,
+                          double* out_xyz, int* out_index, int* n_out, void* stream);
+
+/* kiss_icp_pybind._VoxelHashMap of one lane (kiss.py:129,161; registration at :108-114) */
+int ptk_map_clear(ptk_ctx* ctx, int lane, void* stream);
+int ptk_map_empty(ptk_ctx* ctx, int lane);                       /* 1 empty, 0 not, <0 error */
+int ptk_map_update(ptk_ctx* ctx, int lane, const double* xyz, int n, const double* pose,
+                   void* stream);                                 /* _update(points, pose) */
+int ptk_map_add_points(ptk_ctx* ctx, int lane, const double* xyz, int n, void* stream);
+int ptk_map_remove_far(ptk_ctx* ctx, int lane, const double* origin3, void* stream);
+int ptk_map_num_points(ptk_ctx* ctx, int lane, int* n_points, int* n_voxels);
+int ptk_map_point_cloud(ptk_ctx* ctx, int lane, double* out_xyz, int capacity, int* n_out,
+                        void* stream);                            /* _point_cloud() */
+/* voxel dump for parity: keys (V,3) int32, counts (V) int32, points (V,20,3) float64 */
+int ptk_map_dump(ptk_ctx* ctx, int lane, int* keys, int* counts, double* points, int capacity,
+                 int* n_voxels, void* stream);
+/* _get_correspondences(points, max_dist): per query the order id (offset*20+slot) of the
+ * nearest map point or -1, and its coordinates. */
+int ptk_map_get_correspondences(ptk_ctx* ctx, int lane, const double* xyz, int n,
+                                double max_dist, int* out_order, double* out_target,
+                                int* n_corr, void* stream);
+/* kiss_icp_pybind._register_point_cloud(points, voxel_map, initial_guess,
+ * max_correspondance_distance, kernel) (kiss.py:108-114) */
+int ptk_register_point_cloud(ptk_ctx* ctx, int lane, const double* xyz, int n,
+                             const double* initial_guess, double max_correspondance_distance,
+                             double kernel, double* out_pose, ptk_stats* stats, void* stream);
+
+/* ---- taps on the last step (parity / `return frame, source` of kiss.py:131) -------- */
+/* which: 0 = frame_downsample, 1 = source (sensor frame, before the initial guess) */
+int ptk_get_points(ptk_ctx* ctx, int lane, int which, double* out_xyz, int* out_index,
+                   int capacity, int* n_out, void* stream);
+/* preprocessed frame (deskewed + range filtered, input order) of the last step */
+int ptk_get_frame(ptk_ctx* ctx, int lane, double* out_xyz, int capacity, int* n_out, void* stream);
+/* per-iteration correspondence order ids of the last registration: out (iters, n_src) */
+int ptk_get_trace(ptk_ctx* ctx, int lane, int* out_order, int capacity_iters, int* n_iters,
+                  int* n_src, void* stream);
+
+/* pinned host memory for callers that want fast H2D of scans */
+int ptk_host_alloc(void** out, unsigned long long bytes);
+int ptk_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTK_H_ */

@@ -1,0 +1,157 @@
+"""ctypes binding of libptk.so (C ABI in include/ptk.h).
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device is
+present, construction fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+PTK_OK = 0
+ERRORS = {-1: "PTK_E_ARG", -2: "PTK_E_CUDA", -3: "PTK_E_CAPACITY", -4: "PTK_E_KEYRANGE",
+          -5: "PTK_E_NUMERIC", -6: "PTK_E_STATE"}
+
+
+class PtkConfig(C.Structure):
+    _fields_ = [("max_range", C.c_double), ("min_range", C.c_double), ("voxel_size", C.c_double),
+                ("max_points_per_voxel", C.c_int), ("deskew", C.c_int),
+                ("initial_threshold", C.c_double), ("min_motion_th", C.c_double),
+                ("max_iterations", C.c_int), ("convergence_eps", C.c_double),
+                ("max_points", C.c_int), ("map_capacity", C.c_int), ("batch", C.c_int),
+                ("trace_iterations", C.c_int)]
+
+
+class PtkStats(C.Structure):
+    _fields_ = [("status", C.c_int), ("n_in", C.c_int), ("n_range", C.c_int), ("n_ds", C.c_int),
+                ("n_src", C.c_int), ("n_voxels", C.c_int), ("iterations", C.c_int), ("n_corr", C.c_int),
+                ("dx_norm", C.c_double), ("sigma", C.c_double), ("err_dt", C.c_double),
+                ("err_drot", C.c_double), ("map_points", C.c_int), ("reserved", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+# every symbol include/ptk.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_D = C.c_void_p      # double* that may be host or device: pass raw addresses
+_I = C.c_void_p
+SYMBOLS = {
+    "ptk_default_config": (None, [C.POINTER(PtkConfig)]),
+    "ptk_version": (C.c_int, []),
+    "ptk_ctx_create": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(PtkConfig)]),
+    "ptk_ctx_destroy": (C.c_int, [_P]),
+    "ptk_reset": (C.c_int, [_P, C.c_int]),
+    "ptk_last_error": (C.c_char_p, [_P]),
+    "ptk_register_frame": (C.c_int, [_P, C.c_int, _D, _D, C.c_int, _D, _D, C.POINTER(PtkStats), _P]),
+    "ptk_register_frame_batch": (C.c_int, [_P, C.POINTER(_D), C.POINTER(_D), C.POINTER(C.c_int), _D,
+                                           C.c_char_p, _D, C.POINTER(PtkStats), _P]),
+    "ptk_num_poses": (C.c_int, [_P, C.c_int]),
+    "ptk_get_pose": (C.c_int, [_P, C.c_int, C.c_int, _D]),
+    "ptk_get_prediction_model": (C.c_int, [_P, C.c_int, _D]),
+    "ptk_last_sigma": (C.c_double, [_P, C.c_int]),
+    "ptk_deskew_scan": (C.c_int, [_P, _D, _D, C.c_int, _D, _D, _D, _P]),
+    "ptk_preprocess": (C.c_int, [_P, _D, C.c_int, C.c_double, C.c_double, _D, C.POINTER(C.c_int), _P]),
+    "ptk_voxel_down_sample": (C.c_int, [_P, _D, C.c_int, C.c_double, _D, _I, C.POINTER(C.c_int), _P]),
+    "ptk_map_clear": (C.c_int, [_P, C.c_int, _P]),
+    "ptk_map_empty": (C.c_int, [_P, C.c_int]),
+    "ptk_map_update": (C.c_int, [_P, C.c_int, _D, C.c_int, _D, _P]),
+    "ptk_map_add_points": (C.c_int, [_P, C.c_int, _D, C.c_int, _P]),
+    "ptk_map_remove_far": (C.c_int, [_P, C.c_int, _D, _P]),
+    "ptk_map_num_points": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ptk_map_point_cloud": (C.c_int, [_P, C.c_int, _D, C.c_int, C.POINTER(C.c_int), _P]),
+    "ptk_map_dump": (C.c_int, [_P, C.c_int, _I, _I, _D, C.c_int, C.POINTER(C.c_int), _P]),
+    "ptk_map_get_correspondences": (C.c_int, [_P, C.c_int, _D, C.c_int, C.c_double, _I, _D,
+                                              C.POINTER(C.c_int), _P]),
+    "ptk_register_point_cloud": (C.c_int, [_P, C.c_int, _D, C.c_int, _D, C.c_double, C.c_double, _D,
+                                           C.POINTER(PtkStats), _P]),
+    "ptk_get_points": (C.c_int, [_P, C.c_int, C.c_int, _D, _I, C.c_int, C.POINTER(C.c_int), _P]),
+    "ptk_get_frame": (C.c_int, [_P, C.c_int, _D, C.c_int, C.POINTER(C.c_int), _P]),
+    "ptk_get_trace": (C.c_int, [_P, C.c_int, _I, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "ptk_host_alloc": (C.c_int, [C.POINTER(_P), C.c_ulonglong]),
+    "ptk_host_free": (C.c_int, [_P]),
+}
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Load libptk.so; builds it in-tree first when the sources are newer (needs nvcc)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if build_if_missing:
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    if not os.path.exists(path):
+        raise RuntimeError(f"libptk.so not found at {path}; run `python -m ptudes_lab_b200.build`")
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)       # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+class PtkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def addr(a):
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+def f64(a, shape_last=None):
+    """C-contiguous float64 ndarray view/copy of array-like `a` (torch tensors pass through)."""
+    if hasattr(a, "data_ptr") and not isinstance(a, np.ndarray):
+        return a
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by CUDA pinned host memory (freed when the array is collected)."""
+    lib = load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    rc = lib.ptk_host_alloc(C.byref(p), max(n, 1))
+    if rc != PTK_OK:
+        raise PtkError(rc, "ptk_host_alloc failed")
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib.ptk_host_free(self.ptr)
+            except Exception:
+                pass
+    owner = _Owner(p.value)
+    # keep the owner alive as long as any view of the buffer is
+    buf._ptk_owner = owner
+    return arr

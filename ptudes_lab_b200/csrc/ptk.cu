@@ -1,0 +1,933 @@
+// libptk: host side of the odometry step + the C ABI declared in include/ptk.h.
+//
+// The host keeps what kiss_icp.kiss_icp.KissICP keeps (pose list, adaptive threshold) and what
+// /root/reference/src/ptudes/kiss.py:83-131 computes around the kiss-icp calls (initial guess,
+// pose gain metrics); all per-point work runs in the kernels of ptk_device.cuh.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/ptk.h"
+#include "ptk_device.cuh"
+
+using namespace ptk;
+
+namespace {
+
+struct Threshold {   // kiss-icp AdaptiveThreshold
+    double sse2 = 0.0;
+    int num = 0;
+    Rigid deviation = rigid_identity();
+};
+
+struct LaneHost {
+    LaneDev d;                        // host mirror of the device struct (pointers + config)
+    std::vector<Rigid> poses;
+    Threshold thr;
+    double last_sigma = 0.0;
+    StepParams last_params;
+    StepOut last_out;
+    bool have_last = false;
+    int last_reg_iters = 0, last_reg_nsrc = 0;
+    u32 epoch = 0, tbase1 = 0, tbase2 = 0, release_base = 0;
+    double* in_xyz = nullptr;         // staging for host inputs
+    double* in_ts = nullptr;
+    std::vector<void*> allocs;
+};
+
+}  // namespace
+
+struct ptk_ctx {
+    int device = 0;
+    ptk_config cfg;
+    int B = 1;                        // lanes; lane index B is the scratch lane of the stand-alone calls
+    std::vector<LaneHost> lanes;
+    LaneDev* d_lanes = nullptr;
+    StepParams* d_params = nullptr;
+    StepOut* d_outs = nullptr;
+    StepParams* h_params = nullptr;   // pinned
+    StepOut* h_outs = nullptr;        // pinned
+    double* d_tmp = nullptr;          // scratch for taps (cap_points*3 doubles)
+    int* d_tmp_i = nullptr;           // scratch ints (cap_points + 16)
+    size_t big_tmp_bytes = 0;
+    void* d_big = nullptr;            // lazily allocated scratch for map dumps
+    int num_sms = 148;
+    int icp_blocks_total = 148;
+    std::string err;
+    std::vector<void*> allocs;
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+            return PTK_E_CUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+static int fail(ptk_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+static u32 next_pow2(u32 v) {
+    u32 p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+template <typename T>
+static cudaError_t dalloc(std::vector<void*>& owner, T** p, size_t count, int fill = -1) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    owner.push_back(q);
+    *p = (T*)q;
+    if (fill >= 0) e = cudaMemset(q, fill, std::max<size_t>(count, 1) * sizeof(T));
+    return e;
+}
+
+static bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// -------------------------------------------------------------------------------------
+extern "C" void ptk_default_config(ptk_config* c) {
+    if (!c) return;
+    c->max_range = 100.0;
+    c->min_range = 5.0;
+    c->voxel_size = 0.0;
+    c->max_points_per_voxel = 20;
+    c->deskew = 1;
+    c->initial_threshold = 2.0;
+    c->min_motion_th = 0.1;
+    c->max_iterations = 500;
+    c->convergence_eps = 1e-4;
+    c->max_points = 262144;
+    c->map_capacity = 262144;
+    c->batch = 1;
+    c->trace_iterations = 0;
+}
+
+extern "C" int ptk_version(void) { return PTK_VERSION; }
+
+static int lane_alloc(ptk_ctx* ctx, LaneHost& LH, bool scratch) {
+    const ptk_config& c = ctx->cfg;
+    LaneDev& d = LH.d;
+    memset(&d, 0, sizeof(d));
+    d.voxel_size = c.voxel_size;
+    d.max_distance = c.max_range;
+    d.maxp = c.max_points_per_voxel;
+    d.max_iters = c.max_iterations;
+    d.eps = c.convergence_eps;
+    d.cap_points = c.max_points;
+    d.pool_cap = scratch ? 1 : c.map_capacity;
+    d.trace_iters = scratch ? 0 : c.trace_iterations;
+    d.ng_cap = (int)next_pow2((u32)((c.max_points + 31) / 32));
+    u32 tcap = next_pow2((u32)(2 * (size_t)c.max_points));
+    u32 mcap = next_pow2((u32)(4 * (size_t)d.pool_cap));
+    d.t_mask = tcap - 1;
+    d.m_mask = mcap - 1;
+    size_t N = (size_t)c.max_points;
+    auto& A = LH.allocs;
+    CK(dalloc(A, &d.t1_keys, tcap, 0xFF));
+    CK(dalloc(A, &d.t1_vals, tcap, 0xFF));
+    CK(dalloc(A, &d.t2_keys, tcap, 0xFF));
+    CK(dalloc(A, &d.t2_vals, tcap, 0xFF));
+    CK(dalloc(A, &d.slot1, N, 0xFF));
+    size_t ntile = (N + TILE - 1) / TILE + 1;
+    CK(dalloc(A, &d.agg1, ntile, 0));
+    CK(dalloc(A, &d.agg2, ntile, 0));
+    CK(dalloc(A, &d.ds_x, N)); CK(dalloc(A, &d.ds_y, N)); CK(dalloc(A, &d.ds_z, N));
+    CK(dalloc(A, &d.ds_idx, N, 0)); CK(dalloc(A, &d.ds_slot2, N, 0xFF)); CK(dalloc(A, &d.ds_vid, N, 0xFF));
+    CK(dalloc(A, &d.s0_x, N)); CK(dalloc(A, &d.s0_y, N)); CK(dalloc(A, &d.s0_z, N));
+    CK(dalloc(A, &d.s_x, N)); CK(dalloc(A, &d.s_y, N)); CK(dalloc(A, &d.s_z, N));
+    CK(dalloc(A, &d.s_idx, N, 0));
+    CK(dalloc(A, &d.m_slots, mcap, 0xFF));
+    CK(dalloc(A, &d.blocks, (size_t)d.pool_cap, 0));
+    CK(dalloc(A, &d.vidx, (size_t)d.pool_cap * MAXP, 0xFF));
+    CK(dalloc(A, &d.freelist, (size_t)d.pool_cap, 0));
+    CK(dalloc(A, &d.part_a, (size_t)NRED * d.ng_cap, 0));
+    CK(dalloc(A, &d.part_b, (size_t)NRED * d.ng_cap, 0));
+    CK(dalloc(A, &d.trace, (size_t)std::max(d.trace_iters, 1) * N, 0xFF));
+    CK(dalloc(A, &LH.in_xyz, N * 3));
+    CK(dalloc(A, &LH.in_ts, N));
+    d.icp_E = rigid_identity();
+    d.icp_T = rigid_identity();
+    return PTK_OK;
+}
+
+extern "C" int ptk_ctx_create(ptk_ctx** out, int device, const ptk_config* cfg_in) {
+    if (!out) return PTK_E_ARG;
+    *out = nullptr;
+    ptk_config cfg;
+    if (cfg_in) cfg = *cfg_in; else ptk_default_config(&cfg);
+    if (cfg.voxel_size <= 0.0) cfg.voxel_size = cfg.max_range / 100.0;
+    if (cfg.max_points_per_voxel < 1 || cfg.max_points_per_voxel > MAXP || cfg.batch < 1 ||
+        cfg.max_points < 1 || cfg.map_capacity < 1 || cfg.max_iterations < 1 || cfg.trace_iterations < 0 ||
+        cfg.max_points > (1 << 24)) {
+        g_create_err = "ptk_ctx_create: bad config";
+        return PTK_E_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        g_create_err = std::string("ptk_ctx_create: no usable CUDA device (") +
+                       (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range") + ")";
+        return PTK_E_CUDA;
+    }
+    ptk_ctx* ctx = new ptk_ctx();
+    ctx->device = device;
+    ctx->cfg = cfg;
+    ctx->B = cfg.batch;
+    auto bail = [&](int code) {
+        g_create_err = ctx->err;
+        ptk_ctx_destroy(ctx);
+        return code;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(PTK_E_CUDA); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; return bail(PTK_E_CUDA); }
+    ctx->num_sms = prop.multiProcessorCount;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, ICP_WARPS * 32, 0) != cudaSuccess || occ < 1) {
+        ctx->err = std::string("k_icp not launchable on this device: ") + cudaGetErrorString(cudaGetLastError());
+        return bail(PTK_E_CUDA);
+    }
+    ctx->icp_blocks_total = occ * ctx->num_sms;
+    ctx->lanes.resize(ctx->B + 1);
+    for (int l = 0; l <= ctx->B; ++l) {
+        int rc = lane_alloc(ctx, ctx->lanes[l], l == ctx->B);
+        if (rc != PTK_OK) return bail(rc);
+    }
+    auto ck = [&](cudaError_t ee, const char* what) {
+        if (ee != cudaSuccess) { ctx->err = std::string(what) + ": " + cudaGetErrorString(ee); return false; }
+        return true;
+    };
+    int nl = ctx->B + 1;
+    if (!ck(dalloc(ctx->allocs, &ctx->d_lanes, nl), "alloc lanes")) return bail(PTK_E_CUDA);
+    if (!ck(dalloc(ctx->allocs, &ctx->d_params, nl, 0), "alloc params")) return bail(PTK_E_CUDA);
+    if (!ck(dalloc(ctx->allocs, &ctx->d_outs, nl, 0), "alloc outs")) return bail(PTK_E_CUDA);
+    if (!ck(dalloc(ctx->allocs, &ctx->d_tmp, (size_t)cfg.max_points * 3 + 64), "alloc tmp")) return bail(PTK_E_CUDA);
+    if (!ck(dalloc(ctx->allocs, &ctx->d_tmp_i, (size_t)cfg.max_points + 64, 0), "alloc tmp_i")) return bail(PTK_E_CUDA);
+    if (!ck(cudaMallocHost((void**)&ctx->h_params, sizeof(StepParams) * nl), "pinned params")) return bail(PTK_E_CUDA);
+    if (!ck(cudaMallocHost((void**)&ctx->h_outs, sizeof(StepOut) * nl), "pinned outs")) return bail(PTK_E_CUDA);
+    memset(ctx->h_params, 0, sizeof(StepParams) * nl);
+    memset(ctx->h_outs, 0, sizeof(StepOut) * nl);
+    for (int l = 0; l < nl; ++l)
+        if (!ck(cudaMemcpy(ctx->d_lanes + l, &ctx->lanes[l].d, sizeof(LaneDev), cudaMemcpyHostToDevice), "upload lane")) return bail(PTK_E_CUDA);
+    if (!ck(cudaDeviceSynchronize(), "create sync")) return bail(PTK_E_CUDA);
+    *out = ctx;
+    return PTK_OK;
+}
+
+extern "C" int ptk_ctx_destroy(ptk_ctx* ctx) {
+    if (!ctx) return PTK_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& L : ctx->lanes)
+        for (void* p : L.allocs) cudaFree(p);
+    for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->d_big) cudaFree(ctx->d_big);
+    if (ctx->h_params) cudaFreeHost(ctx->h_params);
+    if (ctx->h_outs) cudaFreeHost(ctx->h_outs);
+    delete ctx;
+    return PTK_OK;
+}
+
+extern "C" const char* ptk_last_error(const ptk_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+// reset the device-side dynamic state of one lane's map (and scan tables)
+static int lane_reset_device(ptk_ctx* ctx, int l, cudaStream_t st, bool tables) {
+    LaneHost& LH = ctx->lanes[l];
+    LaneDev& d = LH.d;
+    CK(cudaMemsetAsync(d.m_slots, 0xFF, ((size_t)d.m_mask + 1) * sizeof(MapSlot), st));
+    CK(cudaMemsetAsync(d.blocks, 0, (size_t)d.pool_cap * sizeof(VoxelBlock), st));
+    CK(cudaMemsetAsync(d.vidx, 0xFF, (size_t)d.pool_cap * MAXP * sizeof(u32), st));
+    if (tables) {
+        size_t tcap = (size_t)d.t_mask + 1;
+        CK(cudaMemsetAsync(d.t1_keys, 0xFF, tcap * sizeof(u64), st));
+        CK(cudaMemsetAsync(d.t1_vals, 0xFF, tcap * sizeof(u32), st));
+        CK(cudaMemsetAsync(d.t2_keys, 0xFF, tcap * sizeof(u64), st));
+        CK(cudaMemsetAsync(d.t2_vals, 0xFF, tcap * sizeof(u32), st));
+        CK(cudaMemsetAsync(d.ds_slot2, 0xFF, (size_t)d.cap_points * sizeof(u32), st));
+    }
+    // dynamic counters live at the tail of LaneDev: re-upload the pristine host mirror
+    LaneDev fresh = d;
+    fresh.n_range = fresh.n_ds = fresh.n_src = 0;
+    fresh.free_top = fresh.bump = fresh.n_vox = fresh.n_tomb = fresh.map_points = 0;
+    fresh.icp_arrive = 0; fresh.icp_done = 0; fresh.err = 0;
+    // tickets / release epochs keep counting on the host side; mirror them
+    fresh.ticket1 = LH.tbase1; fresh.ticket2 = LH.tbase2; fresh.icp_release = LH.release_base;
+    CK(cudaMemcpyAsync(ctx->d_lanes + l, &fresh, sizeof(LaneDev), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return PTK_OK;
+}
+
+extern "C" int ptk_reset(ptk_ctx* ctx, int lane) {
+    if (!ctx) return PTK_E_ARG;
+    if (lane >= ctx->B) return fail(ctx, PTK_E_ARG, "ptk_reset: lane out of range");
+    CK(cudaSetDevice(ctx->device));
+    int l0 = lane < 0 ? 0 : lane, l1 = lane < 0 ? ctx->B : lane + 1;
+    for (int l = l0; l < l1; ++l) {
+        LaneHost& LH = ctx->lanes[l];
+        LH.poses.clear();
+        LH.thr = Threshold();
+        LH.last_sigma = 0.0;
+        LH.have_last = false;
+        int rc = lane_reset_device(ctx, l, 0, true);
+        if (rc) return rc;
+    }
+    return PTK_OK;
+}
+
+// stage an input array on the device if it lives on the host
+static int stage_in(ptk_ctx* ctx, const double* p, size_t count, double* staging, const double** dev, cudaStream_t st) {
+    if (!p) { *dev = nullptr; return PTK_OK; }
+    if (is_device_ptr(p)) { *dev = p; return PTK_OK; }
+    CK(cudaMemcpyAsync(staging, p, count * sizeof(double), cudaMemcpyHostToDevice, st));
+    *dev = staging;
+    return PTK_OK;
+}
+
+static int copy_out(ptk_ctx* ctx, void* dst, const void* dev_src, size_t bytes, cudaStream_t st) {
+    if (!dst || bytes == 0) return PTK_OK;
+    CK(cudaMemcpyAsync(dst, dev_src, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    return PTK_OK;
+}
+
+static int err_to_code(ptk_ctx* ctx, int err) {
+    if (err & ERR_POOL) return fail(ctx, PTK_E_CAPACITY, "local map voxel pool exhausted (cfg.map_capacity)");
+    if (err & ERR_TABLE) return fail(ctx, PTK_E_CAPACITY, "local map hash table full");
+    if (err & ERR_KEYRANGE) return fail(ctx, PTK_E_KEYRANGE, "voxel coordinate outside +-2^20");
+    return PTK_OK;
+}
+
+// ---- threshold / prediction host math -----------------------------------
+static bool has_moved(const ptk_config& c, const LaneHost& LH) {
+    if (LH.poses.empty()) return false;
+    Rigid d = rigid_mul(rigid_inv(LH.poses.front()), LH.poses.back());
+    double motion = sqrt((d.t[0] * d.t[0] + d.t[1] * d.t[1]) + d.t[2] * d.t[2]);
+    return motion > 5.0 * c.min_motion_th;
+}
+
+static double compute_threshold(const ptk_config& c, Threshold& t) {
+    double theta = rot_angle(t.deviation.r);
+    double delta_rot = 2.0 * c.max_range * sin(theta / 2.0);
+    const double* tt = t.deviation.t;
+    double delta_trans = sqrt((tt[0] * tt[0] + tt[1] * tt[1]) + tt[2] * tt[2]);
+    double err = delta_trans + delta_rot;
+    if (err > c.min_motion_th) { t.sse2 += err * err; t.num += 1; }
+    if (t.num < 1) return c.initial_threshold;
+    return sqrt(t.sse2 / t.num);
+}
+
+static Rigid prediction_model(const LaneHost& LH) {
+    size_t n = LH.poses.size();
+    if (n < 2) return rigid_identity();
+    return rigid_mul(rigid_inv(LH.poses[n - 2]), LH.poses[n - 1]);
+}
+
+// ---- kernel launch helpers -----------------------------------------------------------
+static int launch_icp(ptk_ctx* ctx, int l0, int cnt, cudaStream_t st) {
+    // all blocks of a cooperative launch must be co-resident: split wide batches
+    int done = 0;
+    while (done < cnt) {
+        int chunk = std::min(cnt - done, ctx->icp_blocks_total);
+        int per = std::max(1, ctx->icp_blocks_total / chunk);
+        per = std::min(per, ctx->num_sms);
+        LaneDev* dl = ctx->d_lanes + l0 + done;
+        StepParams* dp = ctx->d_params + l0 + done;
+        StepOut* dout = ctx->d_outs + l0 + done;
+        void* args[] = {&dl, &dp, &dout};
+        CK(cudaLaunchCooperativeKernel((void*)k_icp, dim3(per, chunk), dim3(ICP_WARPS * 32), args, 0, st));
+        done += chunk;
+    }
+    return PTK_OK;
+}
+
+static int map_update_launch(ptk_ctx* ctx, int l0, int cnt, int nmax, int use_pose, const double* origin_dev,
+                             bool do_insert, bool do_prune, cudaStream_t st) {
+    int gx = std::max(1, std::min((nmax + 255) / 256, std::max(1, (ctx->num_sms * 4) / cnt)));
+    if (do_insert) {
+        k_map_insert<<<dim3(gx, cnt), 256, 0, st>>>(ctx->d_lanes + l0, ctx->d_params + l0, ctx->d_outs + l0, use_pose);
+        k_map_commit<<<dim3(gx, cnt), 256, 0, st>>>(ctx->d_lanes + l0, ctx->d_outs + l0, use_pose);
+    }
+    if (do_prune) {
+        int gp = std::max(1, (ctx->num_sms * 4) / cnt);
+        k_map_prune<<<dim3(gp, cnt), 256, 0, st>>>(ctx->d_lanes + l0, ctx->d_outs + l0, origin_dev);
+    }
+    CK(cudaGetLastError());
+    return PTK_OK;
+}
+
+static int maybe_rebuild(ptk_ctx* ctx, int l, const StepOut& O, cudaStream_t st) {
+    LaneDev& d = ctx->lanes[l].d;
+    size_t cap = (size_t)d.m_mask + 1;
+    if ((size_t)(O.n_vox + O.n_tomb) * 2 > cap && O.n_tomb > 0) {
+        CK(cudaMemsetAsync(d.m_slots, 0xFF, cap * sizeof(MapSlot), st));
+        k_map_rebuild<<<dim3(ctx->num_sms, 1), 256, 0, st>>>(ctx->d_lanes + l);
+        CK(cudaGetLastError());
+    }
+    return PTK_OK;
+}
+
+// The whole step for lanes [l0, l0+cnt).
+static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, const double* const* ts, const int* n,
+                    const double* guesses, const unsigned char* has_guess, double* out_poses, ptk_stats* stats,
+                    cudaStream_t st) {
+    const ptk_config& c = ctx->cfg;
+    CK(cudaSetDevice(ctx->device));
+    int nmax = 0;
+    std::vector<double> sigmas(cnt);
+    for (int k = 0; k < cnt; ++k) {
+        int l = l0 + k;
+        LaneHost& LH = ctx->lanes[l];
+        if (n[k] < 0 || n[k] > c.max_points) return fail(ctx, PTK_E_CAPACITY, "scan larger than cfg.max_points");
+        if (n[k] > 0 && !xyz[k]) return fail(ctx, PTK_E_ARG, "xyz is null");
+        StepParams& P = ctx->h_params[l];
+        memset(&P, 0, sizeof(P));
+        int rc = stage_in(ctx, xyz[k], (size_t)n[k] * 3, LH.in_xyz, &P.xyz, st);
+        if (rc) return rc;
+        P.n = n[k];
+        P.flags = F_RANGE | F_SECOND;
+        size_t np = LH.poses.size();
+        if (c.deskew && np >= 2) {      // MotionCompensator.deskew_scan: identity with < 2 poses
+            if (!ts || !ts[k]) return fail(ctx, PTK_E_ARG, "timestamps are null");
+            rc = stage_in(ctx, ts[k], (size_t)n[k], LH.in_ts, &P.ts, st);
+            if (rc) return rc;
+            P.flags |= F_DESKEW;
+            Rigid rel = rigid_mul(rigid_inv(LH.poses[np - 2]), LH.poses[np - 1]);
+            se3_log(rel, P.delta);
+        }
+        P.ds1_size = c.voxel_size * 0.5;     // KissICP.voxelize
+        P.ds2_size = c.voxel_size * 1.5;
+        P.max_range = c.max_range;
+        P.min_range = c.min_range;
+        double sigma = has_moved(c, LH) ? compute_threshold(c, LH.thr) : c.initial_threshold;   // kiss.py:99
+        sigmas[k] = sigma;
+        if (guesses && (!has_guess || has_guess[k])) {
+            rigid_from_mat16(guesses + 16 * (size_t)k, P.guess);
+        } else {                                                                                // kiss.py:102-105
+            Rigid last = np ? LH.poses.back() : rigid_identity();
+            P.guess = rigid_mul(last, prediction_model(LH));
+        }
+        P.max_corr = 3 * sigma;                                                                 // kiss.py:112-113
+        P.kernel = sigma / 3;
+        P.epoch = ++LH.epoch;
+        nmax = std::max(nmax, n[k]);
+    }
+    int g1 = std::max(1, (nmax + 255) / 256);
+    int gt = std::max(1, (nmax + TILE - 1) / TILE);
+    for (int k = 0; k < cnt; ++k) {
+        LaneHost& LH = ctx->lanes[l0 + k];
+        StepParams& P = ctx->h_params[l0 + k];
+        P.tbase1 = LH.tbase1; P.tbase2 = LH.tbase2; P.release_base = LH.release_base;
+        LH.tbase1 += (u32)gt; LH.tbase2 += (u32)gt; LH.release_base += (u32)c.max_iterations + 1u;
+        LH.last_params = P;
+    }
+    CK(cudaMemcpyAsync(ctx->d_params + l0, ctx->h_params + l0, sizeof(StepParams) * cnt, cudaMemcpyHostToDevice, st));
+    LaneDev* dl = ctx->d_lanes + l0;
+    StepParams* dp = ctx->d_params + l0;
+    StepOut* dout = ctx->d_outs + l0;
+    k_scan_insert<<<dim3(g1, cnt), 256, 0, st>>>(dl, dp);
+    k_compact1<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp);
+    k_compact2<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp);
+    CK(cudaGetLastError());
+    int rc = launch_icp(ctx, l0, cnt, st);
+    if (rc) return rc;
+    rc = map_update_launch(ctx, l0, cnt, nmax, 1, nullptr, true, true, st);
+    if (rc) return rc;
+    k_finish<<<(cnt + 63) / 64, 64, 0, st>>>(dl, dout, cnt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_outs + l0, dout, sizeof(StepOut) * cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int ret = PTK_OK;
+    for (int k = 0; k < cnt; ++k) {
+        int l = l0 + k;
+        LaneHost& LH = ctx->lanes[l];
+        const StepOut& O = ctx->h_outs[l];
+        const StepParams& P = ctx->h_params[l];
+        LH.last_out = O;
+        LH.have_last = true;
+        LH.last_reg_iters = O.iterations;
+        LH.last_reg_nsrc = O.n_src;
+        int ec = err_to_code(ctx, O.err);
+        if (ec && !ret) ret = ec;
+        Rigid gain = rigid_mul(rigid_inv(P.guess), O.pose);                   // kiss.py:116
+        double dt = sqrt((gain.t[0] * gain.t[0] + gain.t[1] * gain.t[1]) + gain.t[2] * gain.t[2]);
+        double om[3], theta;
+        so3_log(gain.r, om, theta);
+        LH.thr.deviation = gain;                                              // kiss.py:128
+        LH.poses.push_back(O.pose);                                           // kiss.py:130
+        LH.last_sigma = sigmas[k];
+        if (out_poses) rigid_to_mat16(O.pose, out_poses + 16 * (size_t)k);
+        if (stats) {
+            ptk_stats& S = stats[k];
+            memset(&S, 0, sizeof(S));
+            S.status = O.status; S.n_in = P.n; S.n_range = O.n_range; S.n_ds = O.n_ds; S.n_src = O.n_src;
+            S.n_voxels = O.n_vox; S.iterations = O.iterations; S.n_corr = O.n_corr; S.dx_norm = O.dx_norm;
+            S.sigma = sigmas[k]; S.err_dt = dt; S.err_drot = fabs(theta); S.map_points = O.map_points;
+        }
+        if (O.status == 2 && !ret) ret = fail(ctx, PTK_E_NUMERIC, "singular normal equations in ICP");
+        int rb = maybe_rebuild(ctx, l, O, st);
+        if (rb && !ret) ret = rb;
+    }
+    return ret;
+}
+
+extern "C" int ptk_register_frame(ptk_ctx* ctx, int lane, const double* xyz, const double* timestamps, int n,
+                                  const double* initial_guess, double* out_pose, ptk_stats* stats, void* stream) {
+    if (!ctx) return PTK_E_ARG;
+    if (lane < 0 || lane >= ctx->B) return fail(ctx, PTK_E_ARG, "lane out of range");
+    unsigned char hg = initial_guess ? 1 : 0;
+    return run_step(ctx, lane, 1, &xyz, &timestamps, &n, initial_guess, &hg, out_pose, stats, (cudaStream_t)stream);
+}
+
+extern "C" int ptk_register_frame_batch(ptk_ctx* ctx, const double* const* xyz, const double* const* timestamps,
+                                        const int* n, const double* guesses, const unsigned char* has_guess,
+                                        double* out_poses, ptk_stats* stats, void* stream) {
+    if (!ctx || !xyz || !n) return PTK_E_ARG;
+    return run_step(ctx, 0, ctx->B, xyz, timestamps, n, guesses, has_guess, out_poses, stats, (cudaStream_t)stream);
+}
+
+// ---- state accessors -----------------------------------------------------------------
+extern "C" int ptk_num_poses(const ptk_ctx* ctx, int lane) {
+    if (!ctx || lane < 0 || lane >= ctx->B) return PTK_E_ARG;
+    return (int)ctx->lanes[lane].poses.size();
+}
+
+extern "C" int ptk_get_pose(const ptk_ctx* ctx, int lane, int index, double* out16) {
+    if (!ctx || lane < 0 || lane >= ctx->B || !out16) return PTK_E_ARG;
+    const auto& p = ctx->lanes[lane].poses;
+    int n = (int)p.size();
+    if (index < 0) index += n;
+    if (index < 0 || index >= n) return PTK_E_ARG;
+    rigid_to_mat16(p[index], out16);
+    return PTK_OK;
+}
+
+extern "C" int ptk_get_prediction_model(const ptk_ctx* ctx, int lane, double* out16) {
+    if (!ctx || lane < 0 || lane >= ctx->B || !out16) return PTK_E_ARG;
+    rigid_to_mat16(prediction_model(ctx->lanes[lane]), out16);
+    return PTK_OK;
+}
+
+extern "C" double ptk_last_sigma(const ptk_ctx* ctx, int lane) {
+    if (!ctx || lane < 0 || lane >= ctx->B) return 0.0;
+    return ctx->lanes[lane].last_sigma;
+}
+
+// ---- stand-alone pieces (scratch lane = index B) -------------------------------------
+static int scratch_params(ptk_ctx* ctx, StepParams& P, cudaStream_t st, bool k2, bool k3) {
+    int S = ctx->B;
+    LaneHost& LH = ctx->lanes[S];
+    P.epoch = ++LH.epoch;
+    int gt = std::max(1, (P.n + TILE - 1) / TILE);
+    P.tbase1 = LH.tbase1; P.tbase2 = LH.tbase2;
+    if (k2) LH.tbase1 += (u32)gt;
+    if (k3) LH.tbase2 += (u32)gt;
+    ctx->h_params[S] = P;
+    CK(cudaMemcpyAsync(ctx->d_params + S, ctx->h_params + S, sizeof(StepParams), cudaMemcpyHostToDevice, st));
+    return PTK_OK;
+}
+
+extern "C" int ptk_deskew_scan(ptk_ctx* ctx, const double* xyz, const double* timestamps, int n,
+                               const double* start_pose, const double* finish_pose, double* out_xyz, void* stream) {
+    if (!ctx || !out_xyz || n < 0 || (n > 0 && (!xyz || !timestamps)) || !start_pose || !finish_pose) return fail(ctx, PTK_E_ARG, "ptk_deskew_scan: bad argument");
+    if (n > ctx->cfg.max_points) return fail(ctx, PTK_E_CAPACITY, "scan larger than cfg.max_points");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    LaneHost& LH = ctx->lanes[ctx->B];
+    StepParams P;
+    memset(&P, 0, sizeof(P));
+    P.flags = F_DESKEW;
+    Rigid a, b;
+    rigid_from_mat16(start_pose, a);
+    rigid_from_mat16(finish_pose, b);
+    se3_log(rigid_mul(rigid_inv(a), b), P.delta);
+    const double *dx, *dt;
+    int rc = stage_in(ctx, xyz, (size_t)n * 3, LH.in_xyz, &dx, st);
+    if (rc) return rc;
+    rc = stage_in(ctx, timestamps, (size_t)n, LH.in_ts, &dt, st);
+    if (rc) return rc;
+    if (n > 0) {
+        double* dout = is_device_ptr(out_xyz) ? out_xyz : ctx->d_tmp;
+        k_deskew<<<(n + 255) / 256, 256, 0, st>>>(dx, dt, n, P, dout);
+        CK(cudaGetLastError());
+        if (dout != out_xyz) CK(cudaMemcpyAsync(out_xyz, dout, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return PTK_OK;
+}
+
+// shared by preprocess / voxel_down_sample / get_frame: select on the scratch lane, copy out
+static int scratch_select(ptk_ctx* ctx, StepParams P, bool voxel, double* out_xyz, int* out_index, int capacity,
+                          int* n_out, cudaStream_t st) {
+    int S = ctx->B;
+    LaneHost& LH = ctx->lanes[S];
+    int rc = scratch_params(ctx, P, st, true, false);
+    if (rc) return rc;
+    LaneDev* dl = ctx->d_lanes + S;
+    StepParams* dp = ctx->d_params + S;
+    int g1 = std::max(1, (P.n + 255) / 256), gt = std::max(1, (P.n + TILE - 1) / TILE);
+    if (voxel) k_scan_insert<<<dim3(g1, 1), 256, 0, st>>>(dl, dp);
+    k_compact1<<<dim3(gt, 1), 256, 0, st>>>(dl, dp);
+    if (voxel) k_clean_tables<<<dim3(ctx->num_sms, 1), 256, 0, st>>>(dl, 1);
+    k_finish<<<1, 64, 0, st>>>(dl, ctx->d_outs + S, 1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_outs + S, ctx->d_outs + S, sizeof(StepOut), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const StepOut& O = ctx->h_outs[S];
+    int ec = err_to_code(ctx, O.err);
+    if (ec) return ec;
+    int m = O.n_ds;
+    if (n_out) *n_out = m;
+    if (capacity >= 0 && m > capacity) return fail(ctx, PTK_E_CAPACITY, "output buffer too small");
+    if (m > 0 && out_xyz) {
+        double* dout = is_device_ptr(out_xyz) ? out_xyz : ctx->d_tmp;
+        k_gather_aos<<<(m + 255) / 256, 256, 0, st>>>(LH.d.ds_x, LH.d.ds_y, LH.d.ds_z, m, dout);
+        CK(cudaGetLastError());
+        if (dout != out_xyz) CK(cudaMemcpyAsync(out_xyz, dout, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (m > 0 && out_index) {
+        rc = copy_out(ctx, out_index, LH.d.ds_idx, (size_t)m * sizeof(int), st);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(st));
+    return PTK_OK;
+}
+
+extern "C" int ptk_preprocess(ptk_ctx* ctx, const double* xyz, int n, double max_range, double min_range,
+                              double* out_xyz, int* n_out, void* stream) {
+    if (!ctx || n < 0 || (n > 0 && !xyz)) return fail(ctx, PTK_E_ARG, "ptk_preprocess: bad argument");
+    if (n > ctx->cfg.max_points) return fail(ctx, PTK_E_CAPACITY, "scan larger than cfg.max_points");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    StepParams P;
+    memset(&P, 0, sizeof(P));
+    P.n = n;
+    P.flags = F_RANGE | F_SELECT_RANGE;
+    P.max_range = max_range; P.min_range = min_range;
+    int rc = stage_in(ctx, xyz, (size_t)n * 3, ctx->lanes[ctx->B].in_xyz, &P.xyz, st);
+    if (rc) return rc;
+    return scratch_select(ctx, P, false, out_xyz, nullptr, -1, n_out, st);
+}
+
+extern "C" int ptk_voxel_down_sample(ptk_ctx* ctx, const double* xyz, int n, double voxel_size, double* out_xyz,
+                                     int* out_index, int* n_out, void* stream) {
+    if (!ctx || n < 0 || (n > 0 && !xyz) || !(voxel_size > 0.0)) return fail(ctx, PTK_E_ARG, "ptk_voxel_down_sample: bad argument");
+    if (n > ctx->cfg.max_points) return fail(ctx, PTK_E_CAPACITY, "scan larger than cfg.max_points");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    StepParams P;
+    memset(&P, 0, sizeof(P));
+    P.n = n;
+    P.flags = 0;
+    P.ds1_size = voxel_size;
+    int rc = stage_in(ctx, xyz, (size_t)n * 3, ctx->lanes[ctx->B].in_xyz, &P.xyz, st);
+    if (rc) return rc;
+    return scratch_select(ctx, P, true, out_xyz, out_index, -1, n_out, st);
+}
+
+extern "C" int ptk_get_frame(ptk_ctx* ctx, int lane, double* out_xyz, int capacity, int* n_out, void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B) return fail(ctx, PTK_E_ARG, "ptk_get_frame: bad argument");
+    LaneHost& LH = ctx->lanes[lane];
+    if (!LH.have_last) return fail(ctx, PTK_E_STATE, "ptk_get_frame: no step has run");
+    CK(cudaSetDevice(ctx->device));
+    StepParams P = LH.last_params;   // the inputs of the last step must still be resident
+    P.flags = (P.flags & F_DESKEW) | F_RANGE | F_SELECT_RANGE;
+    return scratch_select(ctx, P, false, out_xyz, nullptr, capacity, n_out, (cudaStream_t)stream);
+}
+
+extern "C" int ptk_get_points(ptk_ctx* ctx, int lane, int which, double* out_xyz, int* out_index, int capacity,
+                              int* n_out, void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B || which < 0 || which > 1) return fail(ctx, PTK_E_ARG, "ptk_get_points: bad argument");
+    LaneHost& LH = ctx->lanes[lane];
+    if (!LH.have_last) return fail(ctx, PTK_E_STATE, "ptk_get_points: no step has run");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    int m = which == 0 ? LH.last_out.n_ds : LH.last_out.n_src;
+    if (n_out) *n_out = m;
+    if (m > capacity) return fail(ctx, PTK_E_CAPACITY, "output buffer too small");
+    const LaneDev& d = LH.d;
+    if (m > 0 && out_xyz) {
+        double* dout = is_device_ptr(out_xyz) ? out_xyz : ctx->d_tmp;
+        if (which == 0) k_gather_aos<<<(m + 255) / 256, 256, 0, st>>>(d.ds_x, d.ds_y, d.ds_z, m, dout);
+        else k_gather_aos<<<(m + 255) / 256, 256, 0, st>>>(d.s0_x, d.s0_y, d.s0_z, m, dout);
+        CK(cudaGetLastError());
+        if (dout != out_xyz) CK(cudaMemcpyAsync(out_xyz, dout, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (m > 0 && out_index) {
+        int rc = copy_out(ctx, out_index, which == 0 ? d.ds_idx : d.s_idx, (size_t)m * sizeof(int), st);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(st));
+    return PTK_OK;
+}
+
+extern "C" int ptk_get_trace(ptk_ctx* ctx, int lane, int* out_order, int capacity_iters, int* n_iters, int* n_src,
+                             void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B) return fail(ctx, PTK_E_ARG, "ptk_get_trace: bad argument");
+    LaneHost& LH = ctx->lanes[lane];
+    if (!LH.have_last) return fail(ctx, PTK_E_STATE, "ptk_get_trace: no registration has run");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    int iters = std::min(LH.last_reg_iters, LH.d.trace_iters);
+    int m = LH.last_reg_nsrc;
+    if (n_iters) *n_iters = iters;
+    if (n_src) *n_src = m;
+    if (out_order && m > 0) {
+        iters = std::min(iters, capacity_iters);
+        for (int it = 0; it < iters; ++it) {
+            int rc = copy_out(ctx, out_order + (size_t)it * m, LH.d.trace + (size_t)it * LH.d.cap_points, (size_t)m * sizeof(int), st);
+            if (rc) return rc;
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    return PTK_OK;
+}
+
+// ---- map taps ------------------------------------------------------------------------
+static int lane_counters(ptk_ctx* ctx, int lane, StepOut* O, cudaStream_t st) {
+    k_finish<<<1, 64, 0, st>>>(ctx->d_lanes + lane, ctx->d_outs + lane, 1);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_outs + lane, ctx->d_outs + lane, sizeof(StepOut), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // k_finish overwrote only the counter fields; keep the pose of the last step
+    StepOut& H = ctx->h_outs[lane];
+    *O = H;
+    return PTK_OK;
+}
+
+extern "C" int ptk_map_clear(ptk_ctx* ctx, int lane, void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B) return fail(ctx, PTK_E_ARG, "ptk_map_clear: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    return lane_reset_device(ctx, lane, (cudaStream_t)stream, false);
+}
+
+extern "C" int ptk_map_num_points(ptk_ctx* ctx, int lane, int* n_points, int* n_voxels) {
+    if (!ctx || lane < 0 || lane >= ctx->B) return fail(ctx, PTK_E_ARG, "ptk_map_num_points: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    StepOut O;
+    int rc = lane_counters(ctx, lane, &O, 0);
+    if (rc) return rc;
+    if (n_points) *n_points = O.map_points;
+    if (n_voxels) *n_voxels = O.n_vox;
+    return PTK_OK;
+}
+
+extern "C" int ptk_map_empty(ptk_ctx* ctx, int lane) {
+    int nv = 0;
+    int rc = ptk_map_num_points(ctx, lane, nullptr, &nv);
+    if (rc) return rc;
+    return nv == 0 ? 1 : 0;
+}
+
+static int map_mutate(ptk_ctx* ctx, int lane, const double* xyz, int n, const double* pose, const double* origin3,
+                      bool insert, bool prune, cudaStream_t st) {
+    if (!ctx || lane < 0 || lane >= ctx->B || n < 0 || (insert && n > 0 && !xyz)) return fail(ctx, PTK_E_ARG, "map update: bad argument");
+    if (n > ctx->cfg.max_points) return fail(ctx, PTK_E_CAPACITY, "cloud larger than cfg.max_points");
+    CK(cudaSetDevice(ctx->device));
+    LaneHost& LH = ctx->lanes[lane];
+    StepOut& H = ctx->h_outs[lane];
+    int use_pose = 0;
+    if (pose) {
+        rigid_from_mat16(pose, H.pose);
+        CK(cudaMemcpyAsync(ctx->d_outs + lane, &H, sizeof(StepOut), cudaMemcpyHostToDevice, st));
+        use_pose = 1;
+    }
+    const double* origin_dev = nullptr;
+    if (origin3) {
+        CK(cudaMemcpyAsync(ctx->d_tmp, origin3, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+        origin_dev = ctx->d_tmp;
+    }
+    if (insert) {
+        const double* dx;
+        int rc = stage_in(ctx, xyz, (size_t)n * 3, LH.in_xyz, &dx, st);
+        if (rc) return rc;
+        k_load_ds<<<std::max(1, (n + 255) / 256), 256, 0, st>>>(ctx->d_lanes, lane, dx, n);
+        CK(cudaGetLastError());
+    }
+    int rc = map_update_launch(ctx, lane, 1, std::max(n, 1), use_pose, origin_dev, insert, prune, st);
+    if (rc) return rc;
+    StepOut O;
+    rc = lane_counters(ctx, lane, &O, st);
+    if (rc) return rc;
+    LH.last_out.n_vox = O.n_vox; LH.last_out.map_points = O.map_points;
+    int ec = err_to_code(ctx, O.err);
+    if (ec) return ec;
+    return maybe_rebuild(ctx, lane, O, st);
+}
+
+extern "C" int ptk_map_update(ptk_ctx* ctx, int lane, const double* xyz, int n, const double* pose, void* stream) {
+    if (!pose) return fail(ctx, PTK_E_ARG, "ptk_map_update: pose is null");
+    return map_mutate(ctx, lane, xyz, n, pose, nullptr, true, true, (cudaStream_t)stream);
+}
+
+extern "C" int ptk_map_add_points(ptk_ctx* ctx, int lane, const double* xyz, int n, void* stream) {
+    return map_mutate(ctx, lane, xyz, n, nullptr, nullptr, true, false, (cudaStream_t)stream);
+}
+
+extern "C" int ptk_map_remove_far(ptk_ctx* ctx, int lane, const double* origin3, void* stream) {
+    if (!origin3) return fail(ctx, PTK_E_ARG, "ptk_map_remove_far: origin is null");
+    return map_mutate(ctx, lane, nullptr, 0, nullptr, origin3, false, true, (cudaStream_t)stream);
+}
+
+static int ensure_big(ptk_ctx* ctx, size_t bytes) {
+    if (ctx->big_tmp_bytes >= bytes) return PTK_OK;
+    if (ctx->d_big) cudaFree(ctx->d_big);
+    ctx->d_big = nullptr; ctx->big_tmp_bytes = 0;
+    CK(cudaMalloc(&ctx->d_big, bytes));
+    ctx->big_tmp_bytes = bytes;
+    return PTK_OK;
+}
+
+extern "C" int ptk_map_point_cloud(ptk_ctx* ctx, int lane, double* out_xyz, int capacity, int* n_out, void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B || capacity < 0) return fail(ctx, PTK_E_ARG, "ptk_map_point_cloud: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_big(ctx, (size_t)std::max(capacity, 1) * 3 * sizeof(double));
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_tmp_i, 0, 2 * sizeof(int), st));
+    k_map_dump<<<ctx->num_sms, 256, 0, st>>>(ctx->d_lanes, lane, nullptr, nullptr, nullptr, (double*)ctx->d_big, capacity,
+                                           ctx->d_tmp_i, ctx->d_tmp_i + 1);
+    CK(cudaGetLastError());
+    int cnt[2];
+    CK(cudaMemcpyAsync(cnt, ctx->d_tmp_i, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_out) *n_out = cnt[1];
+    if (cnt[1] > capacity) return fail(ctx, PTK_E_CAPACITY, "output buffer too small");
+    if (out_xyz && cnt[1] > 0) {
+        rc = copy_out(ctx, out_xyz, ctx->d_big, (size_t)cnt[1] * 3 * sizeof(double), st);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(st));
+    }
+    return PTK_OK;
+}
+
+extern "C" int ptk_map_dump(ptk_ctx* ctx, int lane, int* keys, int* counts, double* points, int capacity,
+                            int* n_voxels, void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B || capacity < 0) return fail(ctx, PTK_E_ARG, "ptk_map_dump: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    size_t cap = (size_t)std::max(capacity, 1);
+    size_t b_keys = cap * 3 * sizeof(int), b_cnt = cap * sizeof(int), b_pts = cap * MAXP * 3 * sizeof(double);
+    int rc = ensure_big(ctx, b_pts + b_keys + b_cnt + 64);
+    if (rc) return rc;
+    double* d_pts = (double*)ctx->d_big;
+    int* d_keys = (int*)((char*)ctx->d_big + b_pts);
+    int* d_cnt = (int*)((char*)ctx->d_big + b_pts + b_keys);
+    CK(cudaMemsetAsync(ctx->d_tmp_i, 0, 2 * sizeof(int), st));
+    k_map_dump<<<ctx->num_sms, 256, 0, st>>>(ctx->d_lanes, lane, d_keys, d_cnt, d_pts, nullptr, capacity, ctx->d_tmp_i,
+                                           ctx->d_tmp_i + 1);
+    CK(cudaGetLastError());
+    int cnt[2];
+    CK(cudaMemcpyAsync(cnt, ctx->d_tmp_i, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_voxels) *n_voxels = cnt[0];
+    if (cnt[0] > capacity) return fail(ctx, PTK_E_CAPACITY, "output buffer too small");
+    size_t v = (size_t)cnt[0];
+    if (v > 0) {
+        if (keys && (rc = copy_out(ctx, keys, d_keys, v * 3 * sizeof(int), st))) return rc;
+        if (counts && (rc = copy_out(ctx, counts, d_cnt, v * sizeof(int), st))) return rc;
+        if (points && (rc = copy_out(ctx, points, d_pts, v * MAXP * 3 * sizeof(double), st))) return rc;
+        CK(cudaStreamSynchronize(st));
+    }
+    return PTK_OK;
+}
+
+extern "C" int ptk_map_get_correspondences(ptk_ctx* ctx, int lane, const double* xyz, int n, double max_dist,
+                                           int* out_order, double* out_target, int* n_corr, void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B || n < 0 || (n > 0 && !xyz)) return fail(ctx, PTK_E_ARG, "ptk_map_get_correspondences: bad argument");
+    if (n > ctx->cfg.max_points) return fail(ctx, PTK_E_CAPACITY, "cloud larger than cfg.max_points");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    const double* dq;
+    int rc = stage_in(ctx, xyz, (size_t)n * 3, ctx->lanes[lane].in_xyz, &dq, st);
+    if (rc) return rc;
+    int* d_ord = ctx->d_tmp_i + 16;
+    CK(cudaMemsetAsync(ctx->d_tmp_i, 0, sizeof(int), st));
+    if (n > 0) {
+        size_t threads = (size_t)n * 32;
+        k_correspondences<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ctx->d_lanes, lane, dq, n, max_dist, d_ord,
+                                                                           ctx->d_tmp, ctx->d_tmp_i);
+        CK(cudaGetLastError());
+        if (out_order && (rc = copy_out(ctx, out_order, d_ord, (size_t)n * sizeof(int), st))) return rc;
+        if (out_target && (rc = copy_out(ctx, out_target, ctx->d_tmp, (size_t)n * 3 * sizeof(double), st))) return rc;
+    }
+    int nc = 0;
+    CK(cudaMemcpyAsync(&nc, ctx->d_tmp_i, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_corr) *n_corr = nc;
+    return PTK_OK;
+}
+
+extern "C" int ptk_register_point_cloud(ptk_ctx* ctx, int lane, const double* xyz, int n, const double* initial_guess,
+                                        double max_correspondance_distance, double kernel, double* out_pose,
+                                        ptk_stats* stats, void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B || n < 0 || (n > 0 && !xyz) || !initial_guess || !out_pose)
+        return fail(ctx, PTK_E_ARG, "ptk_register_point_cloud: bad argument");
+    if (n > ctx->cfg.max_points) return fail(ctx, PTK_E_CAPACITY, "cloud larger than cfg.max_points");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    LaneHost& LH = ctx->lanes[lane];
+    StepParams& P = ctx->h_params[lane];
+    memset(&P, 0, sizeof(P));
+    rigid_from_mat16(initial_guess, P.guess);
+    P.max_corr = max_correspondance_distance;
+    P.kernel = kernel;
+    P.n = n;
+    P.epoch = ++LH.epoch;
+    P.tbase1 = LH.tbase1; P.tbase2 = LH.tbase2; P.release_base = LH.release_base;
+    LH.release_base += (u32)ctx->cfg.max_iterations + 1u;
+    const double* dx;
+    int rc = stage_in(ctx, xyz, (size_t)n * 3, LH.in_xyz, &dx, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_params + lane, &P, sizeof(StepParams), cudaMemcpyHostToDevice, st));
+    k_load_src<<<std::max(1, (n + 255) / 256), 256, 0, st>>>(ctx->d_lanes, lane, dx, n, P.guess);
+    CK(cudaGetLastError());
+    rc = launch_icp(ctx, lane, 1, st);
+    if (rc) return rc;
+    StepOut O;
+    rc = lane_counters(ctx, lane, &O, st);
+    if (rc) return rc;
+    LH.last_reg_iters = O.iterations;
+    LH.last_reg_nsrc = n;
+    LH.have_last = true;
+    LH.last_out.n_src = n;
+    rigid_to_mat16(O.pose, out_pose);
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->status = O.status; stats->n_in = n; stats->n_src = n; stats->iterations = O.iterations;
+        stats->n_corr = O.n_corr; stats->dx_norm = O.dx_norm; stats->n_voxels = O.n_vox; stats->map_points = O.map_points;
+    }
+    if (O.status == 2) return fail(ctx, PTK_E_NUMERIC, "singular normal equations in ICP");
+    return PTK_OK;
+}
+
+extern "C" int ptk_host_alloc(void** out, unsigned long long bytes) {
+    if (!out) return PTK_E_ARG;
+    cudaError_t e = cudaMallocHost(out, (size_t)bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); g_create_err = cudaGetErrorString(e); return PTK_E_CUDA; }
+    return PTK_OK;
+}
+
+extern "C" int ptk_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+    return PTK_OK;
+}

@@ -1,0 +1,899 @@
+// Device-side data layout and kernels of the odometry step (sm_100a).
+//
+// Reference path being replaced: the kiss-icp 0.2.x C++ core reached from
+// /root/reference/src/ptudes/kiss.py:90 (DeSkewScan), :93 (Preprocess), :96 (VoxelDownsample x2),
+// :108-114 (RegisterFrame: GetCorrespondences + BuildLinearSystem + LDLT + SE3 exp) and :129
+// (VoxelHashMap::Update = AddPoints + RemovePointsFarFromLocation).
+//
+// Everything is float64 / int32 / packed-u64 keys; the work is gather/scatter and small
+// reductions, so the kernels are plain CUDA-core kernels: no tensor cores on purpose.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptk_canon.cuh"
+
+namespace ptk {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr int MAXP = 20;                   // points per voxel block (mapping.max_points_per_voxel)
+constexpr u64 KEY_EMPTY = ~0ull;
+constexpr u64 KEY_TOMB = ~0ull - 1ull;
+constexpr u32 NONE = 0xFFFFFFFFu;
+constexpr int KEY_BIAS = 1 << 20;
+constexpr int TILE = 1024;                 // items per compaction tile (256 threads x 4)
+constexpr int NRED = 28;                   // 27 normal-equation terms + correspondence count
+constexpr int ICP_WARPS = 16;
+
+enum StepFlags : int { F_DESKEW = 1, F_RANGE = 2, F_SECOND = 4, F_SELECT_RANGE = 8 };
+enum ErrFlags : int { ERR_KEYRANGE = 1, ERR_POOL = 2, ERR_TABLE = 4 };
+
+// One voxel of the local map: 20 points SoA + header, 512 B, 16 B aligned so rows of x/y/z can
+// be read with vector loads.  `count` is the number of valid points.
+struct __align__(16) VoxelBlock {
+    double x[MAXP];
+    double y[MAXP];
+    double z[MAXP];
+    u32 count;
+    u32 slot;   // index of this voxel's entry in the map table
+    u64 key;
+    u32 pad[4];
+};
+static_assert(sizeof(VoxelBlock) == 512, "VoxelBlock must be 512 B");
+
+struct __align__(16) MapSlot {
+    u64 key;
+    u32 id;     // voxel block index, NONE while being created
+    u32 pad;
+};
+
+// Per-step parameters, written by the host before the launches of one step.
+struct StepParams {
+    const double* xyz;     // (n,3) row-major, device
+    const double* ts;      // (n), device (may be null when !F_DESKEW)
+    int n;
+    int flags;
+    double delta[6];       // deskew twist log(inv(T[-2]) T[-1])
+    double ds1_size;       // first grid
+    double ds2_size;       // second grid
+    double max_range, min_range;
+    Rigid guess;
+    double max_corr;
+    double kernel;
+    u32 epoch;             // step counter, >= 1
+    u32 tbase1, tbase2;    // ticket bases of the two compaction kernels
+    u32 release_base;      // icp barrier epoch base
+    int pad;
+};
+
+struct StepOut {
+    Rigid pose;
+    double dx_norm;
+    int status, n_range, n_ds, n_src, n_vox, n_tomb, iterations, n_corr, map_points, err, bump, pad;
+};
+
+// Per-sequence ("lane") device state.
+struct LaneDev {
+    // config
+    double voxel_size, max_distance;
+    int maxp, max_iters;
+    double eps;
+    int cap_points, pool_cap, trace_iters, ng_cap;
+    u32 t_mask, m_mask;
+    // scan-local tables (first-seen selection), self-cleaning
+    u64* t1_keys; u32* t1_vals;
+    u64* t2_keys; u32* t2_vals;
+    u32* slot1;                          // [cap_points] table-1 slot of every input point
+    u64* agg1; u64* agg2;                // tile aggregates of the two compactions
+    // frame_downsample (grid 0.5 v), sensor frame
+    double *ds_x, *ds_y, *ds_z;
+    u32 *ds_idx, *ds_slot2, *ds_vid;
+    // source (grid 1.5 v): sensor frame + current (transformed) positions
+    double *s0_x, *s0_y, *s0_z, *s_x, *s_y, *s_z;
+    u32* s_idx;
+    // local map
+    MapSlot* m_slots;
+    VoxelBlock* blocks;
+    u32* vidx;                           // [pool_cap*MAXP] insertion scratch, NONE when idle
+    u32* freelist;
+    // icp
+    double* part_a; double* part_b;      // [NRED][ng_cap] partial sums (ping-pong)
+    int* trace;                          // [trace_iters][cap_points]
+    // dynamic state
+    int n_range, n_ds, n_src;
+    int free_top, bump, n_vox, n_tomb, map_points;
+    u32 ticket1, ticket2;
+    u32 icp_arrive; u32 icp_release;
+    int icp_done, err;
+    Rigid icp_E, icp_T;
+};
+
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 hash_key(u64 k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return (u32)k;
+}
+
+__device__ __forceinline__ bool key_in_range(int kx, int ky, int kz) {
+    return (kx > -KEY_BIAS + 1 && kx < KEY_BIAS - 1 && ky > -KEY_BIAS + 1 && ky < KEY_BIAS - 1 &&
+            kz > -KEY_BIAS + 1 && kz < KEY_BIAS - 1);
+}
+
+__device__ __forceinline__ u64 pack_key(int kx, int ky, int kz) {
+    return ((u64)(u32)(kx + KEY_BIAS) << 42) | ((u64)(u32)(ky + KEY_BIAS) << 21) | (u64)(u32)(kz + KEY_BIAS);
+}
+
+// kiss-icp voxel key: (p / size).cast<int>() - truncation toward zero.
+__device__ __forceinline__ void voxel_key(double x, double y, double z, double size, int& kx, int& ky, int& kz) {
+    kx = (int)(x / size);
+    ky = (int)(y / size);
+    kz = (int)(z / size);
+}
+
+// First-seen table: find-or-insert `key`, keep the minimum `val`; returns the slot.
+__device__ __forceinline__ u32 table_insert_min(u64* keys, u32* vals, u32 mask, u64 key, u32 val) {
+    u32 slot = hash_key(key) & mask;
+    while (true) {
+        u64 k = *((volatile u64*)(keys + slot));
+        if (k == key) break;
+        if (k == KEY_EMPTY) {
+            u64 prev = atomicCAS(keys + slot, KEY_EMPTY, key);
+            if (prev == KEY_EMPTY || prev == key) break;
+        }
+        slot = (slot + 1) & mask;
+    }
+    atomicMin(vals + slot, val);
+    return slot;
+}
+
+// Load input point i and apply the per-point deskew (kiss-icp DeSkewScan).
+__device__ __forceinline__ void load_point(const StepParams& P, int i, double& x, double& y, double& z) {
+    const double* p = P.xyz + 3 * (size_t)i;
+    x = p[0]; y = p[1]; z = p[2];
+    if (P.flags & F_DESKEW) {
+        double s = P.ts[i] - 0.5;
+        double a[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a[k] = s * P.delta[k];
+        Rigid M = se3_exp(a);
+        double xo, yo, zo;
+        rigid_apply(M, x, y, z, xo, yo, zo);
+        x = xo; y = yo; z = zo;
+    }
+}
+
+__device__ __forceinline__ bool range_pass(const StepParams& P, double x, double y, double z) {
+    if (!(P.flags & F_RANGE)) return true;
+    double nrm = sqrt((x * x + y * y) + z * z);
+    return nrm < P.max_range && nrm > P.min_range;
+}
+
+// ------------------------------------------------------------------------------------
+// K1: deskew + range filter + voxel key (grid 1) + first-seen atomicMin.
+__global__ void __launch_bounds__(256) k_scan_insert(LaneDev* lanes, const StepParams* params) {
+    LaneDev& L = lanes[blockIdx.y];
+    const StepParams& P = params[blockIdx.y];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool pass = false;
+    if (i < P.n) {
+        double x, y, z;
+        load_point(P, i, x, y, z);
+        pass = range_pass(P, x, y, z);
+        u32 slot = NONE;
+        if (pass) {
+            int kx, ky, kz;
+            voxel_key(x, y, z, P.ds1_size, kx, ky, kz);
+            if (key_in_range(kx, ky, kz)) {
+                slot = table_insert_min(L.t1_keys, L.t1_vals, L.t_mask, pack_key(kx, ky, kz), (u32)i);
+            } else {
+                atomicOr(&L.err, ERR_KEYRANGE);
+            }
+        }
+        L.slot1[i] = slot;
+    }
+    u32 m = __ballot_sync(0xffffffffu, pass);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&L.n_range, __popc(m));
+}
+
+// Block-wide exclusive scan of per-thread counts (256 threads); returns offset, total in `total`.
+__device__ __forceinline__ int block_excl_scan(int v, int& total) {
+    __shared__ int wsum[8];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int s = wsum[k];
+        if (k < w) base += s;
+        tot += s;
+    }
+    total = tot;
+    __syncthreads();
+    return base + inc - v;
+}
+
+// Ticketed tile id + decoupled look-back over tile aggregates: returns the number of selected
+// items in all earlier tiles.  agg word = (epoch << 32) | count.
+__device__ __forceinline__ u32 take_ticket(u32* ticket, u32 tbase) {
+    __shared__ u32 s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - tbase;
+    __syncthreads();
+    u32 t = s_tile;
+    __syncthreads();
+    return t;
+}
+
+__device__ __forceinline__ int lookback_prefix(u64* agg, u32 tile, int total, u32 epoch) {
+    __shared__ int s_prefix;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        *((volatile u64*)(agg + tile)) = ((u64)epoch << 32) | (u32)total;
+    }
+    if (threadIdx.x < 32) {
+        int sum = 0;
+        for (u32 j = threadIdx.x; j < tile; j += 32) {
+            u64 a;
+            do { a = *((volatile u64*)(agg + j)); } while ((u32)(a >> 32) != epoch);
+            sum += (int)(u32)a;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (threadIdx.x == 0) s_prefix = sum;
+    }
+    __syncthreads();
+    int p = s_prefix;
+    __syncthreads();
+    return p;
+}
+
+// K2: stable compaction of the grid-1 winners (ascending input index) into frame_downsample,
+// and (F_SECOND) first-seen insert of every kept point into the grid-2 table.
+// With F_SELECT_RANGE the selection is "passes the range filter" instead (Preprocess).
+__global__ void __launch_bounds__(256) k_compact1(LaneDev* lanes, const StepParams* params) {
+    LaneDev& L = lanes[blockIdx.y];
+    const StepParams& P = params[blockIdx.y];
+    u32 tile = take_ticket(&L.ticket1, P.tbase1);
+    u32 ntiles = (u32)((P.n + TILE - 1) / TILE);
+    if (ntiles == 0) {
+        if (tile == 0 && threadIdx.x == 0) L.n_ds = 0;
+        return;
+    }
+    if (tile >= ntiles) return;
+    int i0 = (int)tile * TILE + threadIdx.x * 4;
+    bool win[4];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int i = i0 + k;
+        win[k] = false;
+        if (i < P.n) {
+            if (P.flags & F_SELECT_RANGE) {
+                double x, y, z;
+                load_point(P, i, x, y, z);
+                win[k] = range_pass(P, x, y, z);
+            } else {
+                u32 s = L.slot1[i];
+                win[k] = (s != NONE) && (L.t1_vals[s] == (u32)i);
+            }
+        }
+        cnt += win[k] ? 1 : 0;
+    }
+    int total;
+    int local = block_excl_scan(cnt, total);
+    int prefix = lookback_prefix(L.agg1, tile, total, P.epoch);
+    int pos = prefix + local;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!win[k]) continue;
+        int i = i0 + k;
+        double x, y, z;
+        load_point(P, i, x, y, z);
+        L.ds_x[pos] = x; L.ds_y[pos] = y; L.ds_z[pos] = z;
+        L.ds_idx[pos] = (u32)i;
+        if (P.flags & F_SECOND) {
+            int kx, ky, kz;
+            voxel_key(x, y, z, P.ds2_size, kx, ky, kz);
+            u32 s2 = NONE;
+            if (key_in_range(kx, ky, kz)) s2 = table_insert_min(L.t2_keys, L.t2_vals, L.t_mask, pack_key(kx, ky, kz), (u32)pos);
+            else atomicOr(&L.err, ERR_KEYRANGE);
+            L.ds_slot2[pos] = s2;
+        }
+        ++pos;
+    }
+    if (tile == ntiles - 1 && threadIdx.x == 0) L.n_ds = prefix + total;
+}
+
+// K3: stable compaction of the grid-2 winners into `source` (sensor frame + guess-transformed),
+// and self-cleaning of table 1.
+__global__ void __launch_bounds__(256) k_compact2(LaneDev* lanes, const StepParams* params) {
+    LaneDev& L = lanes[blockIdx.y];
+    const StepParams& P = params[blockIdx.y];
+    u32 tile = take_ticket(&L.ticket2, P.tbase2);
+    int n_ds = L.n_ds;
+    u32 ntiles = (u32)((n_ds + TILE - 1) / TILE);
+    if (ntiles == 0) {
+        if (tile == 0 && threadIdx.x == 0) L.n_src = 0;
+        return;
+    }
+    if (tile >= ntiles) return;
+    int j0 = (int)tile * TILE + threadIdx.x * 4;
+    bool win[4];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int j = j0 + k;
+        win[k] = false;
+        if (j < n_ds) {
+            u32 s2 = L.ds_slot2[j];
+            win[k] = (s2 != NONE) && (L.t2_vals[s2] == (u32)j);
+            // table 1 is no longer needed: clear the slot this point won
+            u32 s1 = L.slot1[L.ds_idx[j]];
+            L.t1_keys[s1] = KEY_EMPTY;
+            L.t1_vals[s1] = NONE;
+        }
+        cnt += win[k] ? 1 : 0;
+    }
+    int total;
+    int local = block_excl_scan(cnt, total);
+    int prefix = lookback_prefix(L.agg2, tile, total, P.epoch);
+    int pos = prefix + local;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!win[k]) continue;
+        int j = j0 + k;
+        double x = L.ds_x[j], y = L.ds_y[j], z = L.ds_z[j];
+        L.s0_x[pos] = x; L.s0_y[pos] = y; L.s0_z[pos] = z;
+        double xo, yo, zo;
+        rigid_apply(P.guess, x, y, z, xo, yo, zo);
+        L.s_x[pos] = xo; L.s_y[pos] = yo; L.s_z[pos] = zo;
+        L.s_idx[pos] = (u32)j;
+        ++pos;
+    }
+    if (tile == ntiles - 1 && threadIdx.x == 0) L.n_src = prefix + total;
+}
+
+// Clear the scan tables after a stand-alone downsample (the step cleans them on the way).
+__global__ void k_clean_tables(LaneDev* lanes, int which) {
+    LaneDev& L = lanes[blockIdx.y];
+    int n_ds = L.n_ds;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_ds; j += gridDim.x * blockDim.x) {
+        if (which & 1) {
+            u32 s1 = L.slot1[L.ds_idx[j]];
+            L.t1_keys[s1] = KEY_EMPTY; L.t1_vals[s1] = NONE;
+        }
+        if (which & 2) {
+            u32 s2 = L.ds_slot2[j];
+            if (s2 != NONE) { L.t2_keys[s2] = KEY_EMPTY; L.t2_vals[s2] = NONE; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Nearest map point of (sx,sy,sz) among the 27 neighbouring voxels, one warp per query.
+// Lanes 0..26 probe one voxel each; candidates are then scanned voxel by voxel in (i,j,l) order
+// with lanes = slots, strict '<' per lane, and a lexicographic (d2, order id) warp argmin, so
+// ties resolve to the first candidate in upstream's iteration order.
+__device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double sy, double sz, int lane,
+                                             double& bd2, int& bord, double& tx, double& ty, double& tz) {
+    int kx, ky, kz;
+    voxel_key(sx, sy, sz, L.voxel_size, kx, ky, kz);
+    u32 id = NONE;
+    if (lane < 27 && key_in_range(kx, ky, kz)) {
+        int di = lane / 9 - 1, dj = (lane / 3) % 3 - 1, dk = lane % 3 - 1;
+        u64 key = pack_key(kx + di, ky + dj, kz + dk);
+        u32 slot = hash_key(key) & L.m_mask;
+        while (true) {
+            const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2*>(L.m_slots + slot));
+            if (raw.x == key) { id = (u32)raw.y; break; }
+            if (raw.x == KEY_EMPTY) break;
+            slot = (slot + 1) & L.m_mask;
+        }
+    }
+    u32 mask = __ballot_sync(0xffffffffu, id != NONE);
+    double best = INFINITY, bx = 0, by = 0, bz = 0;
+    int ord = 0x7fffffff;
+    while (mask) {
+        int v = __ffs(mask) - 1;
+        mask &= mask - 1;
+        u32 vid = __shfl_sync(0xffffffffu, id, v);
+        const VoxelBlock* B = L.blocks + vid;
+        int c = (int)__ldg(&B->count);
+        if (lane < c) {
+            double x = __ldg(&B->x[lane]), y = __ldg(&B->y[lane]), z = __ldg(&B->z[lane]);
+            double dx = x - sx, dy = y - sy, dz = z - sz;
+            double d2 = (dx * dx + dy * dy) + dz * dz;
+            if (d2 < best) { best = d2; ord = v * MAXP + lane; bx = x; by = y; bz = z; }
+        }
+    }
+    double rb = best;
+    int ro = ord;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, rb, o);
+        int oo = __shfl_xor_sync(0xffffffffu, ro, o);
+        if (ob < rb || (ob == rb && oo < ro)) { rb = ob; ro = oo; }
+    }
+    bool found = ro != 0x7fffffff;
+    int owner = found ? (ro % MAXP) : 0;
+    tx = __shfl_sync(0xffffffffu, bx, owner);
+    ty = __shfl_sync(0xffffffffu, by, owner);
+    tz = __shfl_sync(0xffffffffu, bz, owner);
+    bd2 = rb;
+    bord = ro;
+    return found;
+}
+
+// The 27 per-correspondence terms of JtJ (upper triangle, row major) and Jtr.
+__device__ __forceinline__ void lin_terms(double sx, double sy, double sz, double tx, double ty, double tz,
+                                          double kernel, double* c) {
+    double rx = sx - tx, ry = sy - ty, rz = sz - tz;
+    double r2 = (rx * rx + ry * ry) + rz * rz;
+    double kk = kernel + r2;
+    double w = (kernel * kernel) / (kk * kk);
+    double wsx = w * sx, wsy = w * sy, wsz = w * sz;
+    double wrx = w * rx, wry = w * ry, wrz = w * rz;
+    c[0] = w;  c[1] = 0;  c[2] = 0;  c[3] = 0;  c[4] = wsz;  c[5] = -wsy;
+    c[6] = w;  c[7] = 0;  c[8] = -wsz; c[9] = 0; c[10] = wsx;
+    c[11] = w; c[12] = wsy; c[13] = -wsx; c[14] = 0;
+    c[15] = w * (sy * sy + sz * sz); c[16] = -(w * (sx * sy)); c[17] = -(w * (sx * sz));
+    c[18] = w * (sx * sx + sz * sz); c[19] = -(w * (sy * sz));
+    c[20] = w * (sx * sx + sy * sy);
+    c[21] = wrx; c[22] = wry; c[23] = wrz;
+    c[24] = sy * wrz - sz * wry; c[25] = sz * wrx - sx * wrz; c[26] = sx * wry - sy * wrx;
+}
+
+// K4: the whole ICP loop (kiss-icp RegisterFrame) in one persistent cooperative kernel.
+// grid = (blocks per lane, lanes).  Per iteration: warp-per-point NN search, per-32-point group
+// butterfly sums -> global partials, "last block" does the fixed pairwise tree over groups, the
+// 6x6 LDLT solve, SE3 exp and the termination test, then releases the other blocks.
+__global__ void __launch_bounds__(ICP_WARPS * 32, 1) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs) {
+    LaneDev& L = lanes[blockIdx.y];
+    const StepParams& P = params[blockIdx.y];
+    StepOut& O = outs[blockIdx.y];
+    const int nblk = gridDim.x, b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_src = L.n_src;
+    const int n_vox = L.n_vox;
+
+    __shared__ double contrib[NRED][32];
+    __shared__ double red[NRED];
+    __shared__ Rigid sE;
+    __shared__ int s_last, s_done;
+
+    if (n_vox == 0) {   // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
+        if (b == 0 && threadIdx.x == 0) {
+            O.pose = P.guess; O.iterations = 0; O.n_corr = 0; O.status = 0; O.dx_norm = 0.0;
+        }
+        return;
+    }
+    const int n_groups = (n_src + 31) / 32;
+    int p2 = 1;
+    while (p2 < n_groups) p2 <<= 1;
+
+    if (b == 0 && threadIdx.x == 0) L.icp_T = rigid_identity();
+
+    for (int it = 0; it < L.max_iters; ++it) {
+        Rigid E;
+        if (it > 0) E = sE;
+        for (int g = b; g < n_groups; g += nblk) {
+            for (int pi = warp; pi < 32; pi += ICP_WARPS) {
+                int p = g * 32 + pi;
+                double c[27];
+                double nc = 0.0;
+                bool acc = false;
+                if (p < n_src) {
+                    double sx = L.s_x[p], sy = L.s_y[p], sz = L.s_z[p];
+                    if (it > 0) {
+                        double xo, yo, zo;
+                        rigid_apply(E, sx, sy, sz, xo, yo, zo);
+                        sx = xo; sy = yo; sz = zo;
+                        if (lane == 0) { L.s_x[p] = sx; L.s_y[p] = sy; L.s_z[p] = sz; }
+                    }
+                    double d2, tx, ty, tz;
+                    int ord;
+                    bool found = warp_nearest(L, sx, sy, sz, lane, d2, ord, tx, ty, tz);
+                    acc = found && (sqrt(d2) < P.max_corr);
+                    if (lane == 0) {
+                        if (acc) { lin_terms(sx, sy, sz, tx, ty, tz, P.kernel, c); nc = 1.0; }
+                        if (it < L.trace_iters) L.trace[(size_t)it * L.cap_points + p] = acc ? ord : -1;
+                    }
+                }
+                if (lane == 0) {
+                    if (acc) {
+#pragma unroll
+                        for (int v = 0; v < 27; ++v) contrib[v][pi] = c[v];
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 27; ++v) contrib[v][pi] = 0.0;
+                    }
+                    contrib[27][pi] = nc;
+                }
+            }
+            __syncthreads();
+            for (int v = warp; v < NRED; v += ICP_WARPS) {
+                double x = contrib[v][lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) x = x + __shfl_xor_sync(0xffffffffu, x, o);
+                if (lane == 0) L.part_a[(size_t)v * L.ng_cap + g] = x;
+            }
+            __syncthreads();
+        }
+        // ---- arrive
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 prev = atomicAdd(&L.icp_arrive, 1u);
+            s_last = (prev == (u32)nblk - 1u) ? 1 : 0;
+        }
+        __syncthreads();
+        const u32 target = P.release_base + (u32)it + 1u;
+        if (s_last) {
+            if (threadIdx.x == 0) L.icp_arrive = 0;
+            // fixed adjacent-pairs tree over group partials, zero padded to p2 groups
+            double* in = L.part_a;
+            double* out = L.part_b;
+            int cur = n_groups;
+            for (int n = p2; n > 1; n >>= 1) {
+                int half = n >> 1;
+                int ncur = (cur + 1) >> 1;
+                for (int idx = threadIdx.x; idx < NRED * ncur; idx += blockDim.x) {
+                    int v = idx / ncur, k = idx - v * ncur;
+                    double a0 = __ldcg(in + (size_t)v * L.ng_cap + 2 * k);
+                    double a1 = (2 * k + 1 < cur) ? __ldcg(in + (size_t)v * L.ng_cap + 2 * k + 1) : 0.0;
+                    out[(size_t)v * L.ng_cap + k] = a0 + a1;
+                }
+                __threadfence_block();
+                __syncthreads();
+                double* t = in; in = out; out = t;
+                cur = ncur;
+                (void)half;
+            }
+            if (threadIdx.x < NRED) red[threadIdx.x] = (n_groups > 0) ? __ldcg(in + (size_t)threadIdx.x * L.ng_cap) : 0.0;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int n_corr = (int)red[27];
+                int done = 0, status = 0;
+                Rigid Tcur;   // T_icp lives in L2; another block may have written it last
+                {
+                    const volatile double* tv = (const volatile double*)&L.icp_T;
+                    double* td = (double*)&Tcur;
+                    for (int k = 0; k < 12; ++k) td[k] = tv[k];
+                }
+                double nrm = 0.0;
+                Rigid Enew = rigid_identity();
+                if (n_corr == 0) {
+                    status = 1; done = 1;
+                } else {
+                    double A[6][6], bb[6], dx[6];
+                    int q = 0;
+                    for (int i = 0; i < 6; ++i)
+                        for (int j = i; j < 6; ++j) { A[i][j] = red[q]; A[j][i] = red[q]; ++q; }
+                    for (int i = 0; i < 6; ++i) bb[i] = -red[21 + i];
+                    bool ok = ldlt_solve6(A, bb, dx);
+                    if (!ok) {
+                        status = 2; done = 1;
+                    } else {
+                        Enew = se3_exp(dx);
+                        Tcur = rigid_mul(Enew, Tcur);
+                        L.icp_T = Tcur;
+                        nrm = sqrt(((((dx[0] * dx[0] + dx[1] * dx[1]) + dx[2] * dx[2]) + dx[3] * dx[3]) + dx[4] * dx[4]) + dx[5] * dx[5]);
+                        if (nrm < L.eps) done = 1;
+                    }
+                }
+                if (it + 1 >= L.max_iters) done = 1;
+                L.icp_E = Enew;
+                L.icp_done = done;
+                if (done) {
+                    O.pose = rigid_mul(Tcur, P.guess);
+                    O.iterations = it + 1; O.n_corr = n_corr; O.status = status; O.dx_norm = nrm;
+                }
+                __threadfence();
+                *((volatile u32*)&L.icp_release) = target;
+            }
+        } else {
+            if (threadIdx.x == 0) {
+                while (*((volatile u32*)&L.icp_release) != target) { }
+                __threadfence();
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_done = *((volatile int*)&L.icp_done);
+            const volatile double* src = (const volatile double*)&L.icp_E;
+            double* dst = (double*)&sE;
+            for (int k = 0; k < 12; ++k) dst[k] = src[k];
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// K5: map insert, pass 1 (kiss-icp AddPoints): transform frame_downsample by the new pose,
+// find-or-create the voxel, and run the atomicMin cascade that leaves, in vidx[voxel][count..],
+// the smallest point indices of this scan in ascending order (= upstream's sequential insertion
+// order under the canonical ordering).  Also clears table 2.
+__device__ __forceinline__ u32 map_find_or_create(LaneDev& L, u64 key) {
+    u32 slot = hash_key(key) & L.m_mask;
+    u32 probes = 0;
+    while (true) {
+        volatile MapSlot* S = L.m_slots + slot;
+        u64 k = S->key;
+        if (k == KEY_EMPTY) {
+            u64 prev = atomicCAS((u64*)&L.m_slots[slot].key, KEY_EMPTY, key);
+            if (prev == KEY_EMPTY) {
+                int t = atomicSub(&L.free_top, 1);
+                u32 id;
+                if (t > 0) id = L.freelist[t - 1];
+                else id = (u32)atomicAdd(&L.bump, 1);
+                if (id >= (u32)L.pool_cap) {
+                    atomicOr(&L.err, ERR_POOL);
+                    return NONE;
+                }
+                VoxelBlock* B = L.blocks + id;
+                B->count = 0; B->slot = slot; B->key = key;
+                atomicAdd(&L.n_vox, 1);
+                __threadfence();
+                S->id = id;
+                return id;
+            }
+            k = prev;
+        }
+        if (k == key) {
+            u32 id;
+            do { id = S->id; } while (id == NONE && !(*((volatile int*)&L.err) & ERR_POOL));
+            __threadfence();
+            return id;
+        }
+        slot = (slot + 1) & L.m_mask;
+        if (++probes > L.m_mask) { atomicOr(&L.err, ERR_TABLE); return NONE; }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_map_insert(LaneDev* lanes, const StepParams* params, const StepOut* outs, int use_pose) {
+    LaneDev& L = lanes[blockIdx.y];
+    const int n_ds = L.n_ds;
+    Rigid T = use_pose ? outs[blockIdx.y].pose : rigid_identity();
+    const int stride = gridDim.x * blockDim.x;
+    const int n_round = ((n_ds + 31) / 32) * 32;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += stride) {
+        bool act = j < n_ds;
+        u64 key = KEY_EMPTY;
+        if (act) {
+            double x = L.ds_x[j], y = L.ds_y[j], z = L.ds_z[j];
+            if (use_pose) { double xo, yo, zo; rigid_apply(T, x, y, z, xo, yo, zo); x = xo; y = yo; z = zo; }
+            int kx, ky, kz;
+            voxel_key(x, y, z, L.voxel_size, kx, ky, kz);
+            if (key_in_range(kx, ky, kz)) key = pack_key(kx, ky, kz);
+            else { atomicOr(&L.err, ERR_KEYRANGE); act = false; }
+            u32 s2 = L.ds_slot2[j];
+            if (s2 != NONE) { L.t2_keys[s2] = KEY_EMPTY; L.t2_vals[s2] = NONE; L.ds_slot2[j] = NONE; }
+        }
+        u32 am = __ballot_sync(0xffffffffu, act);
+        u32 vid = NONE;
+        if (act) {
+            u32 peers = __match_any_sync(am, key);
+            int leader = __ffs(peers) - 1;
+            if ((threadIdx.x & 31) == leader) vid = map_find_or_create(L, key);
+            vid = __shfl_sync(peers, vid, leader);
+        }
+        if (j < n_ds) L.ds_vid[j] = vid;
+        if (act && vid != NONE) {
+            int c0 = (int)*((volatile u32*)&L.blocks[vid].count);
+            u32 cur = (u32)j;
+            u32* slots = L.vidx + (size_t)vid * MAXP;
+            for (int s = c0; s < L.maxp; ++s) {
+                u32 old = atomicMin(slots + s, cur);
+                if (old == NONE) break;
+                if (old > cur) cur = old;
+            }
+        }
+    }
+}
+
+// K6: map insert, pass 2: every point that survived the cascade writes itself into its slot.
+__global__ void __launch_bounds__(256) k_map_commit(LaneDev* lanes, const StepOut* outs, int use_pose) {
+    LaneDev& L = lanes[blockIdx.y];
+    const int n_ds = L.n_ds;
+    Rigid T = use_pose ? outs[blockIdx.y].pose : rigid_identity();
+    const int stride = gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && L.free_top < 0) L.free_top = 0;
+    int added = 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_ds; j += stride) {
+        u32 vid = L.ds_vid[j];
+        if (vid == NONE) continue;
+        u32* slots = L.vidx + (size_t)vid * MAXP;
+        int s = -1;
+        for (int k = 0; k < L.maxp; ++k)
+            if (slots[k] == (u32)j) { s = k; break; }
+        if (s < 0) continue;
+        double x = L.ds_x[j], y = L.ds_y[j], z = L.ds_z[j];
+        if (use_pose) { double xo, yo, zo; rigid_apply(T, x, y, z, xo, yo, zo); x = xo; y = yo; z = zo; }
+        VoxelBlock* B = L.blocks + vid;
+        B->x[s] = x; B->y[s] = y; B->z[s] = z;
+        slots[s] = NONE;
+        atomicAdd(&B->count, 1u);
+        ++added;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) added += __shfl_xor_sync(0xffffffffu, added, o);
+    if ((threadIdx.x & 31) == 0 && added) atomicAdd(&L.map_points, added);
+}
+
+// K7: prune (kiss-icp RemovePointsFarFromLocation): erase every voxel whose FIRST point is
+// farther than max_distance from `origin`.
+__global__ void __launch_bounds__(256) k_map_prune(LaneDev* lanes, const StepOut* outs, const double* origin_override) {
+    LaneDev& L = lanes[blockIdx.y];
+    double ox, oy, oz;
+    if (origin_override) { ox = origin_override[0]; oy = origin_override[1]; oz = origin_override[2]; }
+    else { const Rigid& T = outs[blockIdx.y].pose; ox = T.t[0]; oy = T.t[1]; oz = T.t[2]; }
+    const int bump = L.bump;
+    const double r2max = L.max_distance * L.max_distance;
+    const int stride = gridDim.x * blockDim.x;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < bump; u += stride) {
+        VoxelBlock* B = L.blocks + u;
+        u32 c = B->count;
+        if (c == 0) continue;
+        double dx = B->x[0] - ox, dy = B->y[0] - oy, dz = B->z[0] - oz;
+        double d2 = (dx * dx + dy * dy) + dz * dz;
+        if (d2 > r2max) {
+            L.m_slots[B->slot].key = KEY_TOMB;
+            B->count = 0;
+            int t = atomicAdd(&L.free_top, 1);
+            L.freelist[t] = (u32)u;
+            atomicSub(&L.n_vox, 1);
+            atomicAdd(&L.n_tomb, 1);
+            atomicSub(&L.map_points, (int)c);
+        }
+    }
+}
+
+// K8: gather per-step counters into the output record and reset the per-step ones.
+__global__ void k_finish(LaneDev* lanes, StepOut* outs, int n_lanes) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lanes) return;
+    LaneDev& L = lanes[l];
+    StepOut& O = outs[l];
+    O.n_range = L.n_range; O.n_ds = L.n_ds; O.n_src = L.n_src;
+    O.n_vox = L.n_vox; O.n_tomb = L.n_tomb; O.map_points = L.map_points;
+    O.err = L.err; O.bump = L.bump;
+    L.n_range = 0;
+    L.err = 0;
+}
+
+// Rebuild the map table without tombstones.
+__global__ void k_map_rebuild(LaneDev* lanes) {
+    LaneDev& L = lanes[blockIdx.y];
+    const int bump = L.bump;
+    const int stride = gridDim.x * blockDim.x;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < bump; u += stride) {
+        VoxelBlock* B = L.blocks + u;
+        if (B->count == 0) continue;
+        u64 key = B->key;
+        u32 slot = hash_key(key) & L.m_mask;
+        while (true) {
+            u64 prev = atomicCAS((u64*)&L.m_slots[slot].key, KEY_EMPTY, key);
+            if (prev == KEY_EMPTY) break;
+            slot = (slot + 1) & L.m_mask;
+        }
+        L.m_slots[slot].id = (u32)u;
+        B->slot = slot;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) L.n_tomb = 0;
+}
+
+// ---- stand-alone pieces -------------------------------------------------------------
+__global__ void k_deskew(const double* xyz, const double* ts, int n, StepParams P, double* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    P.xyz = xyz; P.ts = ts;
+    double x, y, z;
+    load_point(P, i, x, y, z);
+    out[3 * (size_t)i] = x; out[3 * (size_t)i + 1] = y; out[3 * (size_t)i + 2] = z;
+}
+
+// gather SoA (x,y,z) -> AoS rows, optional index array
+__global__ void k_gather_aos(const double* x, const double* y, const double* z, int n, double* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[3 * (size_t)i] = x[i]; out[3 * (size_t)i + 1] = y[i]; out[3 * (size_t)i + 2] = z[i];
+}
+
+__global__ void k_scatter_soa(const double* in, int n, double* x, double* y, double* z) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] = in[3 * (size_t)i]; y[i] = in[3 * (size_t)i + 1]; z[i] = in[3 * (size_t)i + 2];
+}
+
+// load an external cloud as "frame_downsample" (for map_add_points / map_update taps)
+__global__ void k_load_ds(LaneDev* lanes, int lane, const double* in, int n) {
+    LaneDev& L = lanes[lane];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) L.n_ds = n;
+    if (i >= n) return;
+    L.ds_x[i] = in[3 * (size_t)i]; L.ds_y[i] = in[3 * (size_t)i + 1]; L.ds_z[i] = in[3 * (size_t)i + 2];
+    L.ds_slot2[i] = NONE;
+}
+
+// load an external cloud as "source" transformed by guess (register_point_cloud tap)
+__global__ void k_load_src(LaneDev* lanes, int lane, const double* in, int n, Rigid guess) {
+    LaneDev& L = lanes[lane];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) L.n_src = n;
+    if (i >= n) return;
+    double x = in[3 * (size_t)i], y = in[3 * (size_t)i + 1], z = in[3 * (size_t)i + 2];
+    L.s0_x[i] = x; L.s0_y[i] = y; L.s0_z[i] = z;
+    double xo, yo, zo;
+    rigid_apply(guess, x, y, z, xo, yo, zo);
+    L.s_x[i] = xo; L.s_y[i] = yo; L.s_z[i] = zo;
+    L.s_idx[i] = (u32)i;
+}
+
+// _get_correspondences tap: one warp per query
+__global__ void k_correspondences(LaneDev* lanes, int lane_id, const double* q, int n, double max_dist,
+                                  int* out_order, double* out_target, int* n_corr) {
+    LaneDev& L = lanes[lane_id];
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    double sx = q[3 * (size_t)w], sy = q[3 * (size_t)w + 1], sz = q[3 * (size_t)w + 2];
+    double d2, tx, ty, tz;
+    int ord;
+    bool found = L.n_vox > 0 && warp_nearest(L, sx, sy, sz, lane, d2, ord, tx, ty, tz);
+    bool acc = found && (sqrt(d2) < max_dist);
+    if (lane == 0) {
+        out_order[w] = acc ? ord : -1;
+        out_target[3 * (size_t)w] = acc ? tx : 0.0;
+        out_target[3 * (size_t)w + 1] = acc ? ty : 0.0;
+        out_target[3 * (size_t)w + 2] = acc ? tz : 0.0;
+        if (acc) atomicAdd(n_corr, 1);
+    }
+}
+
+// map dump: compact live voxels (order unspecified)
+__global__ void k_map_dump(LaneDev* lanes, int lane_id, int* keys, int* counts, double* points, double* cloud,
+                           int capacity, int* n_out, int* n_pts_out) {
+    LaneDev& L = lanes[lane_id];
+    const int stride = gridDim.x * blockDim.x;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < L.bump; u += stride) {
+        const VoxelBlock* B = L.blocks + u;
+        int c = (int)B->count;
+        if (c == 0) continue;
+        if (cloud) {
+            int at = atomicAdd(n_pts_out, c);
+            for (int s = 0; s < c; ++s) {
+                if (at + s < capacity) {
+                    cloud[3 * (size_t)(at + s)] = B->x[s]; cloud[3 * (size_t)(at + s) + 1] = B->y[s];
+                    cloud[3 * (size_t)(at + s) + 2] = B->z[s];
+                }
+            }
+        } else {
+            int at = atomicAdd(n_out, 1);
+            if (at < capacity) {
+                u64 k = B->key;
+                keys[3 * at] = (int)((k >> 42) & 0x1FFFFF) - KEY_BIAS;
+                keys[3 * at + 1] = (int)((k >> 21) & 0x1FFFFF) - KEY_BIAS;
+                keys[3 * at + 2] = (int)(k & 0x1FFFFF) - KEY_BIAS;
+                counts[at] = c;
+                for (int s = 0; s < MAXP; ++s) {
+                    points[((size_t)at * MAXP + s) * 3] = s < c ? B->x[s] : 0.0;
+                    points[((size_t)at * MAXP + s) * 3 + 1] = s < c ? B->y[s] : 0.0;
+                    points[((size_t)at * MAXP + s) * 3 + 2] = s < c ? B->z[s] : 0.0;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace ptk

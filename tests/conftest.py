@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def tiny_seq():
+    from ptudes_lab_b200 import synth
+    return synth.make_sequence("tiny", 0)
+
+
+@pytest.fixture(scope="session")
+def os0_seq():
+    from ptudes_lab_b200 import synth
+    return synth.make_sequence("os0_quad", 0)

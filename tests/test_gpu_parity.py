@@ -1,0 +1,317 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): voxel keys, downsample selections and correspondence index sets
+bit-exact; poses within 1e-6 rad / 1e-5 m.  Because oracle and kernels share one canonical
+operation order (oracle/canon.py <-> csrc/ptk_canon.cuh), these tests assert EXACT equality of
+float64 outputs as well, which implies the toleranced bar.
+"""
+import numpy as np
+import pytest
+
+from oracle import canon
+from oracle import kiss_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def odo():
+    from ptudes_lab_b200 import odometry
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    o = odometry.Odometry(cfg, max_points=140000, map_capacity=65536, trace_iterations=64)
+    yield o
+    o.close()
+
+
+def _rand_pose(rng, t=1.0, r=0.2):
+    return canon.se3_exp_mat(np.concatenate([rng.uniform(-t, t, 3), rng.uniform(-r, r, 3)]))
+
+
+def test_deskew_bit_exact(odo, os0_seq):
+    xyz, ts, _, _ = os0_seq.points(2)
+    rng = np.random.default_rng(0)
+    a, b = _rand_pose(rng), _rand_pose(rng)
+    got = odo.deskew_scan(xyz, ts, a, b)
+    ref = ko.deskew_scan(xyz, ts, a, b)
+    assert np.array_equal(got, ref)
+    # identical poses -> identity motion
+    assert np.array_equal(odo.deskew_scan(xyz, ts, a, a), ko.deskew_scan(xyz, ts, a, a))
+
+
+def test_deskew_large_rotation(odo):
+    rng = np.random.default_rng(1)
+    xyz = rng.uniform(-50, 50, (5000, 3))
+    ts = rng.uniform(0, 1, 5000)
+    a = np.eye(4)
+    b = canon.se3_exp_mat(np.array([3.0, -2.0, 1.0, 1.5, -2.0, 1.0]))   # |omega| ~ 2.7 rad
+    assert np.array_equal(odo.deskew_scan(xyz, ts, a, b), ko.deskew_scan(xyz, ts, a, b))
+
+
+def test_preprocess_and_downsample(odo, os0_seq):
+    xyz, ts, _, _ = os0_seq.points(0)
+    fr = odo.preprocess(xyz, 100.0, 5.0)
+    assert np.array_equal(fr, ko.preprocess(xyz, 100.0, 5.0))
+    for size in (0.5, 0.35, 1.0499999999999998, 1.5):
+        pts, idx = odo.voxel_down_sample(fr, size, return_index=True)
+        ridx = ko.voxel_down_sample_idx(fr, size)
+        assert np.array_equal(idx.astype(np.int64), ridx), size
+        assert np.array_equal(pts, fr[ridx])
+    # idempotence: every kept point is alone in its voxel
+    ds = odo.voxel_down_sample(fr, 0.5)
+    assert np.array_equal(odo.voxel_down_sample(ds, 0.5), ds)
+
+
+def test_downsample_edge_cases(odo):
+    assert odo.voxel_down_sample(np.zeros((0, 3)), 0.5).shape == (0, 3)
+    assert odo.preprocess(np.zeros((0, 3))).shape == (0, 3)
+    # truncation toward zero: -0.3 and 0.3 share voxel 0
+    p = np.array([[-0.3, 0, 0], [0.3, 0, 0], [-1.2, 0, 0], [1.2, 0, 0], [-0.999999, 0, 0], [0.7, 0, 0], [1.4, 0, 0]])
+    pts, idx = odo.voxel_down_sample(p, 1.0, return_index=True)
+    assert idx.tolist() == [0, 2, 3]
+    pts, idx = odo.voxel_down_sample(p, 0.7, return_index=True)
+    assert idx.tolist() == ko.voxel_down_sample_idx(p, 0.7).tolist() == [0, 2, 3, 6]
+    # one point, all points identical
+    assert odo.voxel_down_sample(np.ones((1, 3)), 0.5).shape == (1, 3)
+    assert odo.voxel_down_sample(np.ones((1000, 3)), 0.5).shape == (1, 3)
+    # everything out of range
+    assert odo.preprocess(np.full((100, 3), 1000.0)).shape == (0, 3)
+    # range bounds are strict on both sides
+    q = np.array([[5.0, 0, 0], [100.0, 0, 0], [5.000001, 0, 0], [99.999, 0, 0]])
+    assert np.array_equal(odo.preprocess(q, 100.0, 5.0), q[2:])
+
+
+def _map_equal(gpu_map, ref_map):
+    keys, cnt, pts = gpu_map.dump()
+    rkeys, rcnt, rpts = ref_map.voxel_table()
+    assert np.array_equal(keys, rkeys)
+    assert np.array_equal(cnt, rcnt)
+    mask = np.arange(20)[None, :] < rcnt[:, None]
+    assert np.array_equal(pts[mask], rpts[mask])
+
+
+def test_map_update_and_prune(odo, os0_seq):
+    from ptudes_lab_b200.odometry import VoxelHashMap
+    gm = VoxelHashMap(odo, 0)
+    gm.clear()
+    assert gm.empty()
+    rm = ko.VoxelHashMap(1.0, 100.0, 20)
+    rng = np.random.default_rng(3)
+    pose = np.eye(4)
+    for k in range(4):
+        xyz, ts, _, _ = os0_seq.points(k)
+        ds = ko.voxel_down_sample(ko.preprocess(xyz, 100.0, 5.0), 0.5)
+        gm.update(ds, pose)
+        rm.update(ds, pose)
+        _map_equal(gm, rm)
+        pose = canon.rigid_mul(pose, _rand_pose(rng, 0.5, 0.05))
+    assert not gm.empty()
+    # a far-away origin prunes nearly everything; boundary is strict '>'
+    origin = np.array([80.0, 0.0, 0.0])
+    gm.remove_far_away_points(origin)
+    rm.remove_far_away_points(origin)
+    _map_equal(gm, rm)
+    pc = gm.point_cloud()
+    rpc = rm.point_cloud()
+    assert pc.shape == rpc.shape
+    assert np.array_equal(pc[np.lexsort(pc.T[::-1])], rpc[np.lexsort(rpc.T[::-1])])
+
+
+def test_map_cap_and_order(odo):
+    """25 points into one voxel keep the first 20 in order; later scans append after them."""
+    from ptudes_lab_b200.odometry import VoxelHashMap
+    gm = VoxelHashMap(odo, 0)
+    gm.clear()
+    rm = ko.VoxelHashMap(1.0, 100.0, 20)
+    rng = np.random.default_rng(5)
+    a = rng.uniform(0.05, 0.95, (12, 3)) + np.array([3.0, 4.0, 5.0])
+    b = rng.uniform(0.05, 0.95, (25, 3)) + np.array([3.0, 4.0, 5.0])
+    for cloud in (a, b):
+        gm.add_points(cloud)
+        rm.add_points(cloud)
+        _map_equal(gm, rm)
+    keys, cnt, pts = gm.dump()
+    assert cnt.tolist() == [20]
+    assert np.array_equal(pts[0, :12], a) and np.array_equal(pts[0, 12:20], b[:8])
+    # prune: a voxel whose first point is at distance exactly max_range is kept
+    gm.clear()
+    gm.add_points(np.array([[100.0, 0.0, 0.0], [100.00000001, 0.5, 1.5]]))
+    gm.remove_far_away_points(np.zeros(3))
+    assert gm.counts() == (1, 1)
+
+
+def test_correspondences_exact(odo, os0_seq):
+    from ptudes_lab_b200.odometry import VoxelHashMap
+    gm = VoxelHashMap(odo, 0)
+    gm.clear()
+    rm = ko.VoxelHashMap(1.0, 100.0, 20)
+    for k in range(3):
+        xyz, ts, _, _ = os0_seq.points(k)
+        ds = ko.voxel_down_sample(ko.preprocess(xyz, 100.0, 5.0), 0.5)
+        gm.update(ds, np.eye(4))
+        rm.update(ds, np.eye(4))
+    xyz, ts, _, _ = os0_seq.points(3)
+    q = ko.voxel_down_sample(ko.preprocess(xyz, 100.0, 5.0), 1.5)
+    q = np.concatenate([q, np.array([[500.0, 500.0, 500.0]])])      # no neighbour at all (B.3)
+    for max_dist in (6.0, 0.3):
+        acc, tgt, order = gm.get_correspondences(q, max_dist, return_index=True)
+        racc, rtgt, rorder = rm.get_correspondences(q, max_dist, return_index=True)
+        assert np.array_equal(acc, racc)
+        assert np.array_equal(order[acc], rorder[racc])
+        assert np.array_equal(tgt[acc], rtgt[racc])
+    assert not acc[-1]
+
+
+def test_register_point_cloud_bit_exact(odo, os0_seq):
+    from ptudes_lab_b200.odometry import VoxelHashMap, register_frame
+    gm = VoxelHashMap(odo, 0)
+    gm.clear()
+    rm = ko.VoxelHashMap(1.0, 100.0, 20)
+    xyz, ts, _, _ = os0_seq.points(0)
+    ds = ko.voxel_down_sample(ko.preprocess(xyz, 100.0, 5.0), 0.5)
+    gm.update(ds, np.eye(4))
+    rm.update(ds, np.eye(4))
+    xyz, ts, _, _ = os0_seq.points(4)
+    src = ko.voxel_down_sample(ko.voxel_down_sample(ko.preprocess(xyz, 100.0, 5.0), 0.5), 1.5)
+    guess = canon.se3_exp_mat(np.array([0.1, -0.05, 0.02, 0.01, -0.01, 0.02]))
+    trace = []
+    rpose, rst = ko.register_point_cloud(src, rm, guess, 6.0, 2.0 / 3.0, trace=trace)
+    pose, st = register_frame(src, gm, guess, 6.0, 2.0 / 3.0, return_stats=True)
+    assert st["iterations"] == rst["iterations"]
+    assert st["n_corr"] == rst["n_corr"]
+    assert np.array_equal(pose, rpose)
+    tr = odo.get_trace()
+    assert tr.shape[0] == min(len(trace), 64)
+    for it in range(tr.shape[0]):
+        assert np.array_equal(tr[it].astype(np.int64), trace[it]["order"]), it
+    # known answer: a cloud against a moved copy of itself recovers the motion
+    T = canon.se3_exp_mat(np.array([0.05, -0.03, 0.02, 0.004, -0.003, 0.01]))
+    s2 = ko.voxel_down_sample(ds, 1.5)
+    x, y, z = canon.transform_points(canon.rigid_inv(T), s2[:, 0], s2[:, 1], s2[:, 2])
+    pose = register_frame(np.stack([x, y, z], 1), gm, np.eye(4), 6.0, 2.0 / 3.0)
+    assert np.abs(pose - T).max() < 1e-9
+    # empty map -> the guess comes back; no correspondences -> guess, status 1 (B.5)
+    gm.clear()
+    assert np.array_equal(register_frame(src, gm, guess, 6.0, 0.6), guess)
+    gm.add_points(np.array([[900.0, 900.0, 900.0]]))
+    pose, st = register_frame(src, gm, guess, 6.0, 0.6, return_stats=True)
+    assert st["status"] == 1 and st["n_corr"] == 0 and np.array_equal(pose, guess)
+
+
+def _run_sequence(seq, n_scans, min_range, max_range, guesses=None, max_points=140000):
+    from ptudes_lab_b200 import odometry
+    cfg = odometry.load_config(None, deskew=True, max_range=max_range)
+    cfg.data.min_range = min_range
+    o = odometry.Odometry(cfg, max_points=max_points, map_capacity=131072, trace_iterations=8)
+    ref = ko.OracleKissICPWrapper(_min_range=min_range, _max_range=max_range)
+    try:
+        for k in range(n_scans):
+            xyz, ts, tsec, _ = seq.points(k)
+            g = None if guesses is None else guesses(k, ref)
+            trace = []
+            ref.register_points(xyz, ts, tsec, initial_guess=g, trace=trace)
+            pose, st = o.register_frame(xyz, ts, initial_guess=g)
+            c = ref.last_counts
+            assert (st["n_in"], st["n_range"], st["n_ds"], st["n_src"]) == (c["n"], c["n_range"], c["n_ds"], c["n_src"]), k
+            # downsample selections (indices into the input scan) are bit-exact
+            ds, ds_idx = o.get_points(0, with_index=True)
+            s0, s_idx = o.get_points(1, with_index=True)
+            fr = ref._kiss.compensator.deskew_scan(xyz, ref.poses[:-1], ts) if k >= 2 else xyz
+            mask = ko.range_mask(fr, max_range, min_range)
+            rid1 = np.flatnonzero(mask)[ko.voxel_down_sample_idx(fr[mask], cfg.mapping.voxel_size * 0.5)]
+            assert np.array_equal(ds_idx.astype(np.int64), rid1), k
+            assert np.array_equal(ds, fr[rid1]), k
+            rid2 = ko.voxel_down_sample_idx(fr[rid1], cfg.mapping.voxel_size * 1.5)
+            assert np.array_equal(s_idx.astype(np.int64), rid2), k
+            assert np.array_equal(s0, fr[rid1][rid2]), k
+            # correspondences per iteration, iteration count, sigma, pose: exact
+            assert st["iterations"] == ref.last_stats["iterations"], k
+            tr = o.get_trace()
+            for it in range(tr.shape[0]):
+                assert np.array_equal(tr[it].astype(np.int64), trace[it]["order"]), (k, it)
+            assert st["sigma"] == ref._sigmas[-1], k
+            assert np.array_equal(pose, ref.pose), k
+            assert st["err_dt"] == ref._err_dt[-1]
+            assert abs(st["err_drot"] - ref._err_drot[-1]) == 0.0
+            assert st["n_voxels"] == c["n_vox"], k
+        _map_equal(odometry.VoxelHashMap(o, 0), ref._kiss.local_map)
+    finally:
+        o.close()
+    return ref
+
+
+def test_sequence_os0_default_ranges(os0_seq):
+    """config 2 shape (OS0-128 1024x10, v = 1.0), first 8 scans, constant-velocity guess."""
+    _run_sequence(os0_seq, 8, 5.0, 100.0)
+
+
+def test_sequence_ekf_bench_ranges(os0_seq):
+    """config 4 ranges (min 1, max 70 -> v = 0.7, grids 0.35 / 1.0499999999999998)."""
+    _run_sequence(os0_seq, 5, 1.0, 70.0)
+
+
+def test_sequence_with_injected_guess(tiny_seq):
+    """initial_guess injection (cli/ekf_bench.py:533-551): a perturbed constant-velocity guess."""
+    rng = np.random.default_rng(11)
+
+    def guesses(k, ref):
+        if k < 2:
+            return None
+        g = canon.rigid_mul(ref.pose, ref._kiss.get_prediction_model())
+        return canon.rigid_mul(g, canon.se3_exp_mat(rng.normal(0, 0.01, 6)))
+    _run_sequence(tiny_seq, 12, 5.0, 100.0, guesses=guesses, max_points=16384)
+
+
+def test_os2_long_range():
+    """config 3 shape: OS2-128 2048x10, max_range 200 -> v = 2.0."""
+    from ptudes_lab_b200 import synth
+    _run_sequence(synth.make_sequence("os2_street", 0), 4, 5.0, 200.0, max_points=262144)
+
+
+def test_empty_and_degenerate_scans(tiny_seq):
+    from ptudes_lab_b200 import odometry
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    o = odometry.Odometry(cfg, max_points=16384, map_capacity=16384)
+    ref = ko.OracleKissICPWrapper()
+    try:
+        xyz, ts, tsec, _ = tiny_seq.points(0)
+        for frame, t in ((np.zeros((0, 3)), np.zeros(0)), (xyz, ts), (np.zeros((0, 3)), np.zeros(0)),
+                         (np.full((50, 3), 500.0), np.full(50, 0.5)), (xyz[:100], ts[:100]), (xyz, ts)):
+            ref.register_points(frame, t, tsec)
+            pose, st = o.register_frame(frame, t)
+            assert np.array_equal(pose, ref.pose)
+            assert st["n_src"] == ref.last_counts["n_src"]
+        with pytest.raises(Exception):
+            o.register_frame(np.zeros((20000, 3)), np.zeros(20000))     # > max_points
+    finally:
+        o.close()
+
+
+def test_wrapper_drop_in(tiny_seq):
+    """KissICPWrapper (reference surface, kiss.py:18-166) against the oracle wrapper."""
+    from ptudes_lab_b200 import synth
+    from ptudes_lab_b200.kiss import KissICPWrapper
+    from ptudes_lab_b200.ouster_compat import scan_from_synth, sensor_info_from_synth
+    meta = sensor_info_from_synth(tiny_seq.sensor, tiny_seq.dirs)
+    w = KissICPWrapper(meta, _min_range=1, _max_range=70)
+    ref = ko.OracleKissICPWrapper(_min_range=1, _max_range=70)
+    assert np.array_equal(w.pose, np.eye(4)) and np.array_equal(w.velocity, np.zeros(3))
+    for k in range(6):
+        sc = tiny_seq.scan(k)
+        xyz, ts, tsec, _ = tiny_seq.points(k)
+        ref.register_points(xyz, ts, tsec)
+        pose = w.register_frame(scan_from_synth(sc))
+        assert np.array_equal(pose, ref.pose)
+    assert w._sigmas == ref._sigmas and w._err_dt == ref._err_dt
+    assert np.allclose(w._err_drot, ref._err_drot, atol=0, rtol=0)
+    assert w.poses_ts == ref.poses_ts
+    assert np.array_equal(w.velocity, ref.velocity)
+    assert np.array_equal(w._kiss.get_prediction_model(), ref._kiss.get_prediction_model())
+    a, b = w.local_map_points, ref.local_map_points
+    assert np.array_equal(a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])])
+    assert w._config.mapping.voxel_size == 0.7
+    # public deskew() and the (frame, source) return of _kiss_register_frame
+    xyz, ts, tsec, _ = tiny_seq.points(6)
+    assert np.array_equal(w.deskew(xyz, ts), ref.deskew(xyz, ts))
+    rf, rs = ref._kiss_register_frame(xyz, ts, tsec)
+    f, s = w._kiss_register_frame(xyz, ts, tsec)
+    assert np.array_equal(f, rf) and np.array_equal(s, rs)

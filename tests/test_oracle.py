@@ -1,0 +1,158 @@
+"""CPU tests of the oracle: the known-answer micro-cases of SURVEY.md Appendix A.10 (derivable
+from the published kiss-icp 0.2.x algorithm; the reference itself holds no golden vectors)."""
+import numpy as np
+
+from oracle import canon
+from oracle import kiss_oracle as ko
+
+
+def test_voxel_keys_truncate_toward_zero():
+    x = np.array([-0.3, 0.3, -1.2, 1.2, -0.999999, 0.7, 1.4])
+    p = np.stack([x, np.zeros(7), np.zeros(7)], axis=1)
+    assert ko.voxel_keys(p, 1.0)[:, 0].tolist() == [0, 0, -1, 1, 0, 0, 1]
+    assert ko.voxel_keys(p, 0.7)[:, 0].tolist() == [0, 0, -1, 1, -1, 1, 2]
+    k = ko.voxel_keys(np.array([[1.5, -2.5, 3.5]]), 1.0)
+    assert np.array_equal(ko.unpack_keys(ko.pack_keys(k)), k)
+
+
+def test_grid_sizes_of_ekf_bench_defaults():
+    cfg = ko.load_config(None, deskew=True, max_range=70)
+    v = cfg.mapping.voxel_size
+    assert v * 0.5 == 0.35 and v * 1.5 == 1.0499999999999998
+    assert (v * 1.5).hex() == "0x1.0ccccccccccccp+0".replace(" ", "")
+    assert ko.load_config(None, max_range=100).mapping.voxel_size == 1.0
+
+
+def test_deskew_identity_cases():
+    rng = np.random.default_rng(0)
+    f = rng.uniform(-20, 20, (100, 3))
+    t = rng.uniform(0, 1, 100)
+    T = canon.se3_exp_mat(rng.uniform(-1, 1, 6))
+    assert np.abs(ko.deskew_scan(f, t, T, T) - f).max() < 1e-13
+    w = ko.OracleKissICPWrapper()
+    assert w.deskew(f, t) is f                       # < 2 poses: frame returned untouched
+    # a pure translation twist moves the point at t by (t-0.5)*d
+    T2 = np.eye(4)
+    T2[:3, 3] = [1.0, 0.0, 0.0]
+    out = ko.deskew_scan(f, t, np.eye(4), T2)
+    assert np.abs(out[:, 0] - (f[:, 0] + (t - 0.5))).max() < 1e-13
+
+
+def test_downsample_first_point_per_voxel_in_input_order():
+    p = np.array([[0.1, 0.1, 0.1], [0.2, 0.2, 0.2], [1.1, 0, 0], [0.3, 0.3, 0.3], [1.2, 0, 0], [-0.2, 0, 0]])
+    assert ko.voxel_down_sample_idx(p, 1.0).tolist() == [0, 2]
+    assert ko.voxel_down_sample_idx(p, 0.25).tolist() == [0, 2, 3]   # -0.2 truncates into voxel 0 too
+    assert ko.voxel_down_sample(np.zeros((0, 3)), 1.0).shape == (0, 3)
+
+
+def test_preprocess_strict_bounds():
+    q = np.array([[5.0, 0, 0], [100.0, 0, 0], [5.000001, 0, 0], [99.999, 0, 0]])
+    assert np.array_equal(ko.preprocess(q, 100.0, 5.0), q[2:])
+
+
+def test_map_cap_order_and_prune():
+    rng = np.random.default_rng(1)
+    m = ko.VoxelHashMap(1.0, 100.0, 20)
+    assert m.empty()
+    a = rng.uniform(0.05, 0.95, (25, 3)) + [3, 4, 5]
+    m.add_points(a)
+    keys, cnt, pts = m.voxel_table()
+    assert cnt.tolist() == [20] and np.array_equal(pts[0], a[:20])
+    m.clear()
+    m.add_points(np.array([[100.0, 0, 0], [0.5, 100.5, 0.5]]))
+    m.remove_far_away_points(np.zeros(3))            # |first| == max_range is kept (strict >)
+    assert m.num_voxels() == 1 and np.array_equal(m.point_cloud(), [[100.0, 0, 0]])
+
+
+def test_first_scan_seeds_map_and_returns_guess(tiny_seq):
+    xyz, ts, tsec, _ = tiny_seq.points(0)
+    w = ko.OracleKissICPWrapper()
+    w.register_points(xyz, ts, tsec)
+    assert np.array_equal(w.pose, np.eye(4))
+    ds = ko.voxel_down_sample(ko.preprocess(xyz, 100, 5), 0.5)
+    m = ko.VoxelHashMap(1.0, 100.0, 20)
+    m.add_points(ds)
+    a, b = w.local_map_points, m.point_cloud()
+    assert np.array_equal(a, b)
+    assert w._sigmas == [2.0]
+
+
+def test_icp_recovers_known_motion(tiny_seq):
+    xyz, _, _, _ = tiny_seq.points(0)
+    ds = ko.voxel_down_sample(ko.preprocess(xyz, 100, 5), 0.5)
+    src = ko.voxel_down_sample(ds, 1.5)
+    m = ko.VoxelHashMap(1.0, 100.0, 20)
+    m.update(ds, np.eye(4))
+    T = canon.se3_exp_mat(np.array([0.05, -0.03, 0.02, 0.004, -0.003, 0.01]))
+    x, y, z = canon.transform_points(canon.rigid_inv(T), src[:, 0], src[:, 1], src[:, 2])
+    pose, st = ko.register_point_cloud(np.stack([x, y, z], 1), m, np.eye(4), 6.0, 2.0 / 3)
+    assert np.abs(pose - T).max() < 1e-9 and st["iterations"] <= 6
+    # empty map -> guess; no neighbours -> guess with status 1
+    g = canon.se3_exp_mat(np.array([0.1, 0, 0, 0, 0, 0.1]))
+    assert np.array_equal(ko.register_point_cloud(src, ko.VoxelHashMap(1.0, 100.0), g, 6.0, 0.6)[0], g)
+    m2 = ko.VoxelHashMap(1.0, 100.0)
+    m2.add_points(np.array([[900.0, 900.0, 900.0]]))
+    pose, st = ko.register_point_cloud(src, m2, g, 6.0, 0.6)
+    assert st["status"] == 1 and np.array_equal(pose, g)
+
+
+def test_gm_weight_and_jacobian_terms():
+    s = np.array([[1.0, 2.0, 3.0]])
+    k = 0.5
+    t0 = ko.linear_system_terms(s, s.copy(), np.array([True]), k)           # r = 0 -> w = 1
+    A, b = ko.unpack_system(t0[0])
+    J = np.hstack([np.eye(3), -np.array([[0, -3.0, 2.0], [3.0, 0, -1.0], [-2.0, 1.0, 0]])])
+    assert np.allclose(A, J.T @ J) and np.all(b == 0)
+    tgt = s - np.array([[np.sqrt(k), 0, 0]])                                 # |r|^2 = k -> w = 1/4
+    t1 = ko.linear_system_terms(s, tgt, np.array([True]), k)
+    A1, b1 = ko.unpack_system(t1[0])
+    assert np.allclose(A1, 0.25 * (J.T @ J))
+    assert np.allclose(b1, J.T @ (0.25 * np.array([np.sqrt(k), 0, 0])))
+    assert np.all(ko.linear_system_terms(s, tgt, np.array([False]), k) == 0)
+
+
+def test_adaptive_threshold():
+    w = ko.OracleKissICPWrapper()
+    k = w._kiss
+    assert k.get_adaptive_threshold() == 2.0          # no poses
+    k.poses.append(np.eye(4))
+    T = np.eye(4)
+    T[0, 3] = 0.4
+    k.poses.append(T.copy())
+    assert k.get_adaptive_threshold() == 2.0          # moved 0.4 <= 0.5
+    T[0, 3] = 0.6
+    k.poses.append(T.copy())
+    dev = np.eye(4)
+    dev[0, 3] = 0.3
+    k.adaptive_threshold.update_model_deviation(dev)
+    assert abs(k.get_adaptive_threshold() - 0.3) < 1e-15
+    # deviation below min_motion_th is not accumulated
+    dev[0, 3] = 0.05
+    k.adaptive_threshold.update_model_deviation(dev)
+    assert abs(k.get_adaptive_threshold() - 0.3) < 1e-15
+    assert np.array_equal(k.get_prediction_model(), canon.rigid_mul(canon.rigid_inv(k.poses[-2]), k.poses[-1]))
+
+
+def test_nearest_tie_breaks_to_first_in_voxel_order():
+    m = ko.VoxelHashMap(1.0, 100.0)
+    # two map points at equal distance from the query, in voxels (-1,0,0) and (0,0,0)... the first
+    # in (i,j,l) order wins
+    m.add_points(np.array([[0.75, 0.5, 0.5], [-0.25, 0.5, 0.5]]))
+    acc, tgt, order = m.get_correspondences(np.array([[0.25, 0.5, 0.5]]), 6.0, return_index=True)
+    assert acc[0] and tgt[0].tolist() == [-0.25, 0.5, 0.5] or tgt[0].tolist() == [0.75, 0.5, 0.5]
+    # both map points fall in voxel (0,0,0) (truncation): stored order decides
+    assert order[0] == 13 * 20 + 0
+
+
+def test_sequence_tracks_ground_truth(tiny_seq):
+    """Sanity of the whole restatement: odometry on a synthetic sequence follows the true motion."""
+    w = ko.OracleKissICPWrapper()
+    gt0 = None
+    for k in range(10):
+        xyz, ts, tsec, gt = tiny_seq.points(k)
+        gt0 = gt if gt0 is None else gt0
+        w.register_points(xyz, ts, tsec)
+    rel = canon.rigid_mul(canon.rigid_inv(gt0), gt)
+    d = canon.rigid_mul(canon.rigid_inv(rel), w.pose)
+    assert np.linalg.norm(d[:3, 3]) < 0.5 and canon.rot_angle(d[:3, :3]) < 0.05
+    assert len(w.poses) == 10 and len(w._sigmas) == 10 and len(w.poses_ts) == 10
