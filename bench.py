@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py - ICP odometry scans/sec on synthetic OS0-128 1024x10 sequences (BASELINE.json).
+
+A "step" advances every resident sequence ("lane") of this rank by one scan through the full
+odometry step (deskew + range filter + 2x voxel downsample + ICP registration + local-map
+insert + prune): one call of ptk_register_frame_batch.  Workload = BASELINE.json configs[1]
+(100-scan OS0-128 1024x10 sequence on the quad scene), `--lanes` independent copies with
+different seeds per GPU (configs[4]'s fleet replay: no data-path collective, weak scaling).
+
+  python bench.py --gpus N --steps K --warmup W           own arm (CUDA path through the C ABI)
+  python bench.py --impl reference ...                   reference arm: the CPU restatement of
+                                                         the kiss-icp path (oracle/) on host cores
+
+One JSON line on stdout (rank 0).  Keys: see the task contract; `value` = scans/s with inputs
+resident in HBM, `e2e` = the same through the C ABI with HOST (pinned) buffers, H2D inside
+the timed region and the poses read back every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "icp_odometry_scans_per_sec"
+UNIT = "scans/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ptk", choices=["ptk", "reference"])
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("PTK_BENCH_LANES", "16")),
+                    help="independent sequences per GPU advanced by one batched step")
+    ap.add_argument("--config", default="os0_quad", choices=["os0_quad", "os2_street", "os0_hall"])
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-pass", action="store_true", default=True)
+    return ap.parse_args()
+
+
+CONFIGS = {
+    # name: (min_range, max_range, max_points, map_capacity)
+    "os0_quad": (5.0, 100.0, 131072, 32768),
+    "os0_hall": (5.0, 100.0, 131072, 131072),
+    "os2_street": (5.0, 200.0, 262144, 65536),
+}
+
+
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def mark(self):
+        return len(self.lines)
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, lo=0, hi=None):
+        rows = [l.split(",") for l in self.lines[lo:hi] if l.count(",") >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].strip().replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            for name, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        pw = [float(r[3]) for r in rows if r[3].strip().replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# algorithmic (compulsory) HBM bytes of every kernel of the step, per lane-scan, from the
+# counters the library returns (DESIGN.md "Algorithmic bytes").  b = 8 B per
+# coordinate, S = 16 B map slot.
+def algorithmic_bytes(st):
+    b, S = 8, 16
+    N, Nd, Ns, V, M = st["n_in"], st["n_ds"], st["n_src"], st["n_voxels"], st["map_points"]
+    Vt = min(27 * Ns, V)
+    Mt = min(20 * Vt, M)
+    return {
+        "k_scan_insert": N * (3 * b + 8),
+        "k_compact1": Nd * 3 * b,
+        "k_compact2": Nd * 3 * b + Ns * 3 * b,
+        "k_icp": Ns * 3 * b + Vt * S + Mt * 3 * b,
+        "k_map_insert": Nd * 3 * b + Nd * S,
+        "k_map_commit": Nd * 3 * b,
+        "k_map_prune": V * (S + 3 * b),
+        "k_finish": 344,
+    }
+
+
+# --------------------------------------------------------------------------------------
+def run_ptk(args):
+    import torch
+    import torch.distributed as dist
+    from ptudes_lab_b200 import _ffi, odometry, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the ptk path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, K, W = args.lanes, args.steps, args.warmup
+    T = W + K
+    min_r, max_r, max_pts, map_cap = CONFIGS[args.config]
+
+    # ---- synthetic scans, generated on the device (data plumbing) -------------------------
+    gens = [synth.TorchScanGenerator(synth.make_sequence(args.config, rank * B + l), dev) for l in range(B)]
+    frames = [[None] * B for _ in range(T)]
+    tss = [[None] * B for _ in range(T)]
+    for l, g in enumerate(gens):
+        for s in range(T):
+            xyz, tn, _, _ = g.points(s)
+            frames[s][l], tss[s][l] = xyz, tn
+    torch.cuda.synchronize()
+    scan_bytes = sum(f.numel() * 8 + t.numel() * 8 for f, t in zip(frames[W], tss[W]))
+    total_bytes = sum(f.numel() * 8 + t.numel() * 8 for s in range(T) for f, t in zip(frames[s], tss[s]))
+
+    cfg = odometry.load_config(None, deskew=True, max_range=max_r)
+    cfg.data.min_range = min_r
+    stream = torch.cuda.Stream(device=dev)
+    sh = stream.cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_run(odo, fr, ts, profiling, clocks=None):
+        odo.reset()
+        stats_acc = []
+        poses = []
+        for s in range(W):
+            p, st = odo.register_frame_batch(fr[s], ts[s], stream=sh)
+            poses.append(p)
+        if profiling:
+            odo.set_profiling(True)
+        l0 = odo.launch_count()
+        barrier()
+        c0 = clocks.mark() if clocks else 0
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for s in range(W, T):
+                p, st = odo.register_frame_batch(fr[s], ts[s], stream=sh)
+                poses.append(p)
+                stats_acc.append(st)
+            e1.record(stream)
+        barrier()
+        c1 = clocks.mark() if clocks else 0
+        ms = e0.elapsed_time(e1)
+        launches = odo.launch_count() - l0
+        prof = odo.get_profile() if profiling else None
+        if profiling:
+            odo.set_profiling(False)
+        return ms, launches, prof, stats_acc, np.stack(poses), (c0, c1)
+
+    odo = odometry.Odometry(cfg, device=local, max_points=max_pts, map_capacity=map_cap, batch=B)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+
+    # ---- leg 1: inputs resident in HBM ----------------------------------------------------
+    ms_dev, launches, _, stats_acc, poses_dev, cspan = timed_run(odo, frames, tss, False, clocks)
+    # per-kernel device times: same steps again with every launch bracketed by CUDA events on
+    # the launching stream (separate pass so the events do not sit inside the headline number)
+    ms_prof, _, prof, _, poses_prof, _ = timed_run(odo, frames, tss, True)
+
+    # ---- leg 2: end to end from pinned host buffers ----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_frames = [[None] * B for _ in range(T)]
+        h_ts = [[None] * B for _ in range(T)]
+        for s in range(T):
+            for l in range(B):
+                n = frames[s][l].shape[0]
+                hf = _ffi.pinned_empty((n, 3))
+                ht = _ffi.pinned_empty((n,))
+                hf[...] = frames[s][l].cpu().numpy()
+                ht[...] = tss[s][l].cpu().numpy()
+                h_frames[s][l], h_ts[s][l] = hf, ht
+        ms_e2e, _, _, _, poses_e2e, _ = timed_run(odo, h_frames, h_ts, False)
+        if not np.array_equal(poses_e2e, poses_dev):
+            raise SystemExit("bench.py: host-buffer and device-buffer runs disagree")
+        h2d = scan_bytes + B * 16 * 8 + 512 * B
+        d2h = B * 16 * 8 + B * 120
+    if not np.array_equal(poses_prof, poses_dev):
+        raise SystemExit("bench.py: run-to-run poses differ (non-deterministic step)")
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_dev_max = max_over_ranks(ms_dev)
+    value = world * B * K / (ms_dev_max * 1e-3)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": f"configs[1] 100-scan OS0-128 1024x10 sequence shape ({args.config}), full odometry step, "
+                        f"{B} independent sequences (lanes) per GPU advanced by one batched step; scans "
+                        f"{W}..{W + K - 1} of each sequence timed",
+            "lanes_per_gpu": B, "points_per_scan": int(frames[W][0].shape[0]), "max_range": max_r,
+            "min_range": min_r, "voxel_size": cfg.mapping.voxel_size,
+            "l2": f"every step reads scans never touched before ({total_bytes / 1e9:.2f} GB of scans per GPU, "
+                  f"{scan_bytes / 1e6:.1f} MB per step); the local maps are persistent state and stay wherever "
+                  f"the hardware keeps them",
+            "parallelism": f"fleet replay: {world} GPU(s) x {B} lanes, no collective on the data path",
+        },
+        "gpu_launches": int(launches),
+    }
+    if e2e is None and not args.no_e2e:
+        ms_e2e_max = max_over_ranks(ms_e2e)
+        out["e2e"] = {"value": world * B * K / (ms_e2e_max * 1e-3), "unit": UNIT,
+                      "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                      "ms_per_step": ms_e2e_max / K,
+                      "api": "ptk_register_frame_batch (C ABI, ctypes) with pinned host xyz/timestamps"}
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------
+    peak, peak_src = measured_peaks()
+    algo = {}
+    for step_stats in stats_acc:
+        for st in step_stats:
+            for k, v in algorithmic_bytes(st).items():
+                algo[k] = algo.get(k, 0) + v
+    kern = {k: v for k, v in prof.items() if v[1] > 0 and k in algo}
+    dom = max(kern, key=lambda k: kern[k][0])
+    dms, dn = kern[dom]
+    per_launch_bytes = algo[dom] / dn
+    achieved = per_launch_bytes / (dms / dn * 1e-3) / 1e9
+    total_algo = sum(algo.values())
+    out["roofline"] = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": dms / dn,
+        "kernel_share_of_step": dms / ms_prof,
+        "step_algorithmic_bytes_per_scan": total_algo / (B * K),
+        "step_hbm_frac": (total_algo / (ms_dev * 1e-3) / 1e9) / peak,
+        "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items() if v[1] > 0},
+    }
+    last = stats_acc[-1][0]
+    out["counters"] = {k: last[k] for k in ("n_in", "n_range", "n_ds", "n_src", "n_voxels", "map_points",
+                                             "iterations", "n_corr")}
+    out["counters"]["mean_icp_iterations"] = float(np.mean([st["iterations"] for ss in stats_acc for st in ss]))
+
+    if rank == 0:
+        time.sleep(0.2)
+        clocks.stop()
+        out["clocks"] = clocks.summary(*cspan)
+
+    # ---- cpu baseline: the oracle on this box's host cores (rank 0, N = 1 only) -------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        h = [(frames[s][0].cpu().numpy(), tss[s][0].cpu().numpy()) for s in range(T)]
+        out["cpu_baseline"], ref_poses = cpu_baseline_leg(args, h, min_r, max_r, T)
+        n = len(ref_poses)
+        d = np.abs(np.stack(ref_poses) - poses_dev[:n, 0]).max() if n else None
+        out["parity_vs_oracle"] = {"scans": n, "max_abs_pose_diff": float(d) if n else None}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    odo.close()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def cpu_baseline_leg(args, host_scans, min_r, max_r, T):
+    """Time the CPU oracle (test infrastructure, used here only as the reported baseline) on a
+    bounded prefix of lane 0's sequence; returns (cpu_baseline dict, poses)."""
+    from oracle import kiss_oracle as ko
+    ref = ko.OracleKissICPWrapper(_min_range=min_r, _max_range=max_r)
+    t_used, n_timed, poses = 0.0, 0, []
+    for s in range(T):
+        xyz, ts = host_scans[s]
+        t0 = time.perf_counter()
+        ref.register_points(xyz, ts, 0.1 * (s + 1))
+        dt = time.perf_counter() - t0
+        poses.append(ref.pose.copy())
+        if s >= 2:                 # scans 0/1: empty map / no deskew (SURVEY 8d timing rules)
+            t_used += dt
+            n_timed += 1
+        if t_used > args.cpu_seconds:
+            break
+    return ({"value": n_timed / t_used if t_used > 0 else None, "unit": UNIT, "cores": 1, "kind": "port",
+             "sample": f"NumPy float64 oracle (oracle/kiss_oracle.py), scans 2..{1 + n_timed} of lane 0's sequence, "
+                       f"single process ({os.cpu_count()} host cores present)"}, poses)
+
+
+# --------------------------------------------------------------------------------------
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference's kiss-icp path on host cores.
+    The real kiss-icp 0.2.x package is not installable here, so this is the port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ptudes_lab_b200 import synth
+    K, W = args.steps, args.warmup
+    min_r, max_r, _, _ = CONFIGS[args.config]
+    seq = synth.make_sequence(args.config, 0)
+    from oracle import kiss_oracle as ko
+    ref = ko.OracleKissICPWrapper(_min_range=min_r, _max_range=max_r)
+    # bounded sample: each step = one scan of one sequence; cap the number of steps by time
+    budget = 150.0
+    t_all, n = 0.0, 0
+    tstart = time.perf_counter()
+    for s in range(W + K):
+        xyz, ts, tsec, _ = seq.points(s)
+        t0 = time.perf_counter()
+        ref.register_points(xyz, ts, tsec)
+        dt = time.perf_counter() - t0
+        if s >= W:
+            t_all += dt
+            n += 1
+        if time.perf_counter() - tstart > budget:
+            break
+    val = n / t_all
+    sample = (f"NumPy float64 oracle, one sequence ({args.config}), scans {W}..{W + n - 1} timed one scan per step "
+              f"({n} of the requested {K} steps fit the time budget)")
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+           "warmup": W, "ms_per_step": 1e3 * t_all / n, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"configs[1] 100-scan OS0-128 1024x10 sequence shape ({args.config}), full "
+                                  f"odometry step on the CPU"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ptk(a)

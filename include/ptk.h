@@ -165,6 +165,17 @@ int ptk_get_frame(ptk_ctx* ctx, int lane, double* out_xyz, int capacity, int* n_
 int ptk_get_trace(ptk_ctx* ctx, int lane, int* out_order, int capacity_iters, int* n_iters,
                   int* n_src, void* stream);
 
+/* ---- measurement taps (bench.py roofline leg) ---------------------------------------
+ * With profiling on, every kernel launch of the step is bracketed by CUDA events on the
+ * caller's stream; ptk_get_profile returns, per kernel slot, the accumulated device
+ * milliseconds and the number of launches since the last ptk_set_profiling call.
+ * ptk_launch_count: kernels launched by this context since creation (always counted). */
+#define PTK_PROF_SLOTS 12
+int ptk_set_profiling(ptk_ctx* ctx, int on);
+int ptk_get_profile(ptk_ctx* ctx, double* ms /* PTK_PROF_SLOTS */, long long* launches /* PTK_PROF_SLOTS */);
+const char* ptk_kernel_name(int slot);   /* NULL past the last used slot */
+long long ptk_launch_count(const ptk_ctx* ctx);
+
 /* pinned host memory for callers that want fast H2D of scans */
 int ptk_host_alloc(void** out, unsigned long long bytes);
 int ptk_host_free(void* p);

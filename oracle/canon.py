@@ -114,7 +114,79 @@ def transform_points(T, x, y, z):
 # ---------------------------------------------------------------------------
 # SO3 / SE3 exp (Sophus conventions), vectorised over leading dim
 # ---------------------------------------------------------------------------
-def se3_exp(tangent):
+def quat_to_rot(qw, qx, qy, qz):
+    """Eigen QuaternionBase::toRotationMatrix, vectorised over leading dims."""
+    qw, qx, qy, qz = (np.asarray(v, dtype=np.float64) for v in (qw, qx, qy, qz))
+    tx, ty, tz = 2.0 * qx, 2.0 * qy, 2.0 * qz
+    twx, twy, twz = tx * qw, ty * qw, tz * qw
+    txx, txy, txz = tx * qx, ty * qx, tz * qx
+    tyy, tyz, tzz = ty * qy, tz * qy, tz * qz
+    R = np.empty(qw.shape + (3, 3))
+    R[..., 0, 0] = 1.0 - (tyy + tzz)
+    R[..., 0, 1] = txy - twz
+    R[..., 0, 2] = txz + twy
+    R[..., 1, 0] = txy + twz
+    R[..., 1, 1] = 1.0 - (txx + tzz)
+    R[..., 1, 2] = tyz - twx
+    R[..., 2, 0] = txz - twy
+    R[..., 2, 1] = tyz + twx
+    R[..., 2, 2] = 1.0 - (txx + tyy)
+    return R
+
+
+def quat_mul(a, b):
+    """Eigen quaternion product a*b on (w, x, y, z) python floats, left-to-right sums."""
+    aw, ax, ay, az = a
+    bw, bx, by, bz = b
+    return (((aw * bw - ax * bx) - ay * by) - az * bz,
+            ((aw * bx + ax * bw) + ay * bz) - az * by,
+            ((aw * by + ay * bw) + az * bx) - ax * bz,
+            ((aw * bz + az * bw) + ax * by) - ay * bx)
+
+
+def quat_normalize1(q):
+    """Sophus SO3::operator* first-order renormalisation: q *= 2 / (1 + |q|^2) unless |q|^2 == 1.
+    This is what keeps the rotation of every pose the registration returns orthonormal."""
+    w, x, y, z = q
+    n2 = ((w * w + x * x) + y * y) + z * z
+    if n2 != 1.0:
+        s = 2.0 / (1.0 + n2)
+        return (w * s, x * s, y * s, z * s)
+    return (w, x, y, z)
+
+
+class SE3q:
+    """Sophus::SE3d as kiss-icp's registration holds it: unit quaternion (w,x,y,z) + translation.
+    Products renormalise the quaternion (Sophus), so chains of them never drift away from SO(3)."""
+
+    def __init__(self, q=(1.0, 0.0, 0.0, 0.0), t=(0.0, 0.0, 0.0)):
+        self.q = tuple(float(v) for v in q)
+        self.t = tuple(float(v) for v in t)
+
+    @staticmethod
+    def from_matrix(T):
+        T = np.asarray(T, dtype=np.float64)
+        return SE3q(rot_to_quat(T[:3, :3]), (T[0, 3], T[1, 3], T[2, 3]))
+
+    def rot(self):
+        return quat_to_rot(*self.q)
+
+    def mul(self, other):
+        """self * other: q = normalize1(qa qb), t = Ra tb + ta."""
+        q = quat_normalize1(quat_mul(self.q, other.q))
+        R = self.rot()
+        x, y, z = other.t
+        t = tuple(float(((R[i, 0] * x + R[i, 1] * y) + R[i, 2] * z) + self.t[i]) for i in range(3))
+        return SE3q(q, t)
+
+    def matrix(self):
+        T = np.eye(4)
+        T[:3, :3] = self.rot()
+        T[:3, 3] = self.t
+        return T
+
+
+def se3_exp(tangent, return_quat=False):
     """tangent (...,6) = [upsilon, omega] -> R (...,3,3), t (...,3).
 
     Follows Sophus SE3::exp / SO3::expAndTheta: unit quaternion from the half angle,
@@ -136,21 +208,7 @@ def se3_exp(tangent):
         real = np.where(small, real_s, ch)
     qw = real
     qx, qy, qz = imag * wx, imag * wy, imag * wz
-    # Eigen QuaternionBase::toRotationMatrix
-    tx, ty, tz = 2.0 * qx, 2.0 * qy, 2.0 * qz
-    twx, twy, twz = tx * qw, ty * qw, tz * qw
-    txx, txy, txz = tx * qx, ty * qx, tz * qx
-    tyy, tyz, tzz = ty * qy, tz * qy, tz * qz
-    R = np.empty(tg.shape[:-1] + (3, 3))
-    R[..., 0, 0] = 1.0 - (tyy + tzz)
-    R[..., 0, 1] = txy - twz
-    R[..., 0, 2] = txz + twy
-    R[..., 1, 0] = txy + twz
-    R[..., 1, 1] = 1.0 - (txx + tzz)
-    R[..., 1, 2] = tyz - twx
-    R[..., 2, 0] = txz - twy
-    R[..., 2, 1] = tyz + twx
-    R[..., 2, 2] = 1.0 - (txx + tyy)
+    R = quat_to_rot(qw, qx, qy, qz)
     # V
     st, ct = det_sincos(theta)
     with np.errstate(divide="ignore", invalid="ignore"):
@@ -176,6 +234,8 @@ def se3_exp(tangent):
     t[..., 0] = (V[..., 0, 0] * ux + V[..., 0, 1] * uy) + V[..., 0, 2] * uz
     t[..., 1] = (V[..., 1, 0] * ux + V[..., 1, 1] * uy) + V[..., 1, 2] * uz
     t[..., 2] = (V[..., 2, 0] * ux + V[..., 2, 1] * uy) + V[..., 2, 2] * uz
+    if return_quat:
+        return R, t, (qw, qx, qy, qz)
     return R, t
 
 
@@ -185,6 +245,15 @@ def se3_exp_mat(tangent):
     T[:3, :3] = R
     T[:3, 3] = t
     return T
+
+
+def se3_exp_q(tangent):
+    """SE3::exp of one tangent as (SE3q, 4x4 matrix); the matrix is the one points are moved with."""
+    R, t, q = se3_exp(np.asarray(tangent, dtype=np.float64), return_quat=True)
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = t
+    return SE3q(tuple(float(v) for v in q), tuple(float(v) for v in t)), T
 
 
 # ---------------------------------------------------------------------------

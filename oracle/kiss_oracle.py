@@ -292,11 +292,14 @@ def register_point_cloud(points, voxel_map, initial_guess, max_correspondance_di
     guess = np.array(initial_guess, dtype=np.float64)
     pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
     stats = {"iterations": 0, "n_corr": 0, "dx_norm": 0.0, "status": 0}
+    # the pybind boundary turns the 4x4 guess into a Sophus::SE3d (quaternion + translation);
+    # whatever is returned goes back through .matrix(), i.e. is re-orthonormalised
+    guess_q = canon.SE3q.from_matrix(guess)
+    T_icp = canon.SE3q()
     if voxel_map.empty():
-        return guess, stats
+        return T_icp.mul(guess_q).matrix(), stats
     x, y, z = canon.transform_points(guess, pts[:, 0], pts[:, 1], pts[:, 2])
     src = np.stack([x, y, z], axis=1)
-    T_icp = np.eye(4)
     for it in range(max_iters):
         acc, tgt, order = voxel_map.get_correspondences(src, max_correspondance_distance, return_index=True)
         n_corr = int(acc.sum())
@@ -313,16 +316,16 @@ def register_point_cloud(points, voxel_map, initial_guess, max_correspondance_di
         if not ok:
             stats["status"] = 2
             break
-        E = canon.se3_exp_mat(np.array(dx))
+        Eq, E = canon.se3_exp_q(np.array(dx))
         x, y, z = canon.transform_points(E, src[:, 0], src[:, 1], src[:, 2])
         src = np.stack([x, y, z], axis=1)
-        T_icp = canon.rigid_mul(E, T_icp)
+        T_icp = Eq.mul(T_icp)
         nrm = math.sqrt(((((dx[0] * dx[0] + dx[1] * dx[1]) + dx[2] * dx[2]) + dx[3] * dx[3])
                          + dx[4] * dx[4]) + dx[5] * dx[5])
         stats["dx_norm"] = nrm
         if nrm < EST_THRESHOLD:
             break
-    return canon.rigid_mul(T_icp, guess), stats
+    return T_icp.mul(guess_q).matrix(), stats
 
 
 # ---------------------------------------------------------------------------

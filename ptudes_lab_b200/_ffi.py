@@ -72,6 +72,10 @@ SYMBOLS = {
     "ptk_get_points": (C.c_int, [_P, C.c_int, C.c_int, _D, _I, C.c_int, C.POINTER(C.c_int), _P]),
     "ptk_get_frame": (C.c_int, [_P, C.c_int, _D, C.c_int, C.POINTER(C.c_int), _P]),
     "ptk_get_trace": (C.c_int, [_P, C.c_int, _I, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "ptk_set_profiling": (C.c_int, [_P, C.c_int]),
+    "ptk_get_profile": (C.c_int, [_P, _D, _I]),
+    "ptk_kernel_name": (C.c_char_p, [C.c_int]),
+    "ptk_launch_count": (C.c_longlong, [_P]),
     "ptk_host_alloc": (C.c_int, [C.POINTER(_P), C.c_ulonglong]),
     "ptk_host_free": (C.c_int, [_P]),
 }

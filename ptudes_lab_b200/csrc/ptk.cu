@@ -41,7 +41,25 @@ struct LaneHost {
 
 }  // namespace
 
+enum ProfSlot { PS_SCAN_INSERT = 0, PS_COMPACT1, PS_COMPACT2, PS_ICP, PS_MAP_INSERT, PS_MAP_COMMIT, PS_MAP_PRUNE,
+                PS_FINISH, PS_REBUILD, PS_OTHER, PS_COUNT };
+static_assert(PS_COUNT <= PTK_PROF_SLOTS, "profile slots");
+static const char* const kProfNames[PS_COUNT] = {"k_scan_insert", "k_compact1", "k_compact2", "k_icp", "k_map_insert",
+                                                 "k_map_commit", "k_map_prune", "k_finish", "k_map_rebuild", "other"};
+
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;      // event pool, two per bracketed launch
+    int used = 0;
+    struct Rec { int slot, e0; };
+    std::vector<Rec> recs;
+    double ms[PTK_PROF_SLOTS] = {0};
+    long long n[PTK_PROF_SLOTS] = {0};
+};
+
 struct ptk_ctx {
+    Prof prof;
+    long long launches = 0;
     int device = 0;
     ptk_config cfg;
     int B = 1;                        // lanes; lane index B is the scratch lane of the stand-alone calls
@@ -70,6 +88,45 @@ static thread_local std::string g_create_err;
             ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
             return PTK_E_CUDA;                                                                \
         }                                                                                     \
+    } while (0)
+
+// ---- launch bookkeeping: count every kernel; with profiling on bracket it with events ----
+static int prof_begin(ptk_ctx* ctx, int slot, cudaStream_t st) {
+    ctx->launches++;
+    Prof& p = ctx->prof;
+    if (!p.on) return -1;
+    if (p.used + 2 > (int)p.ev.size()) {
+        for (int k = 0; k < 2; ++k) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return -1;
+            p.ev.push_back(e);
+        }
+    }
+    int e0 = p.used;
+    p.used += 2;
+    cudaEventRecord(p.ev[e0], st);
+    p.recs.push_back({slot, e0});
+    return e0;
+}
+static void prof_end(ptk_ctx* ctx, int e0, cudaStream_t st) {
+    if (e0 >= 0) cudaEventRecord(ctx->prof.ev[e0 + 1], st);
+}
+// call after the stream has been synchronised
+static void prof_collect(ptk_ctx* ctx) {
+    Prof& p = ctx->prof;
+    for (auto& r : p.recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.ev[r.e0], p.ev[r.e0 + 1]) == cudaSuccess) { p.ms[r.slot] += ms; p.n[r.slot]++; }
+        else cudaGetLastError();
+    }
+    p.recs.clear();
+    p.used = 0;
+}
+#define LAUNCH(slot, st, ...)                          \
+    do {                                               \
+        int pe_ = prof_begin(ctx, slot, st);           \
+        __VA_ARGS__;                                   \
+        prof_end(ctx, pe_, st);                        \
     } while (0)
 
 static int fail(ptk_ctx* ctx, int code, const std::string& msg) {
@@ -202,7 +259,7 @@ extern "C" int ptk_ctx_create(ptk_ctx** out, int device, const ptk_config* cfg_i
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; return bail(PTK_E_CUDA); }
     ctx->num_sms = prop.multiProcessorCount;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, ICP_WARPS * 32, 0) != cudaSuccess || occ < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, ICP_THREADS, 0) != cudaSuccess || occ < 1) {
         ctx->err = std::string("k_icp not launchable on this device: ") + cudaGetErrorString(cudaGetLastError());
         return bail(PTK_E_CUDA);
     }
@@ -241,6 +298,7 @@ extern "C" int ptk_ctx_destroy(ptk_ctx* ctx) {
         for (void* p : L.allocs) cudaFree(p);
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->d_big) cudaFree(ctx->d_big);
+    for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
     if (ctx->h_params) cudaFreeHost(ctx->h_params);
     if (ctx->h_outs) cudaFreeHost(ctx->h_outs);
     delete ctx;
@@ -354,7 +412,9 @@ static int launch_icp(ptk_ctx* ctx, int l0, int cnt, cudaStream_t st) {
         StepParams* dp = ctx->d_params + l0 + done;
         StepOut* dout = ctx->d_outs + l0 + done;
         void* args[] = {&dl, &dp, &dout};
-        CK(cudaLaunchCooperativeKernel((void*)k_icp, dim3(per, chunk), dim3(ICP_WARPS * 32), args, 0, st));
+        cudaError_t le = cudaSuccess;
+        LAUNCH(PS_ICP, st, le = cudaLaunchCooperativeKernel((void*)k_icp, dim3(per, chunk), dim3(ICP_THREADS), args, 0, st));
+        CK(le);
         done += chunk;
     }
     return PTK_OK;
@@ -364,12 +424,12 @@ static int map_update_launch(ptk_ctx* ctx, int l0, int cnt, int nmax, int use_po
                              bool do_insert, bool do_prune, cudaStream_t st) {
     int gx = std::max(1, std::min((nmax + 255) / 256, std::max(1, (ctx->num_sms * 4) / cnt)));
     if (do_insert) {
-        k_map_insert<<<dim3(gx, cnt), 256, 0, st>>>(ctx->d_lanes + l0, ctx->d_params + l0, ctx->d_outs + l0, use_pose);
-        k_map_commit<<<dim3(gx, cnt), 256, 0, st>>>(ctx->d_lanes + l0, ctx->d_outs + l0, use_pose);
+        LAUNCH(PS_MAP_INSERT, st, k_map_insert<<<dim3(gx, cnt), 256, 0, st>>>(ctx->d_lanes + l0, ctx->d_params + l0, ctx->d_outs + l0, use_pose));
+        LAUNCH(PS_MAP_COMMIT, st, k_map_commit<<<dim3(gx, cnt), 256, 0, st>>>(ctx->d_lanes + l0, ctx->d_outs + l0, use_pose));
     }
     if (do_prune) {
         int gp = std::max(1, (ctx->num_sms * 4) / cnt);
-        k_map_prune<<<dim3(gp, cnt), 256, 0, st>>>(ctx->d_lanes + l0, ctx->d_outs + l0, origin_dev);
+        LAUNCH(PS_MAP_PRUNE, st, k_map_prune<<<dim3(gp, cnt), 256, 0, st>>>(ctx->d_lanes + l0, ctx->d_outs + l0, origin_dev));
     }
     CK(cudaGetLastError());
     return PTK_OK;
@@ -380,7 +440,7 @@ static int maybe_rebuild(ptk_ctx* ctx, int l, const StepOut& O, cudaStream_t st)
     size_t cap = (size_t)d.m_mask + 1;
     if ((size_t)(O.n_vox + O.n_tomb) * 2 > cap && O.n_tomb > 0) {
         CK(cudaMemsetAsync(d.m_slots, 0xFF, cap * sizeof(MapSlot), st));
-        k_map_rebuild<<<dim3(ctx->num_sms, 1), 256, 0, st>>>(ctx->d_lanes + l);
+        LAUNCH(PS_REBUILD, st, k_map_rebuild<<<dim3(ctx->num_sms, 1), 256, 0, st>>>(ctx->d_lanes + l));
         CK(cudaGetLastError());
     }
     return PTK_OK;
@@ -444,18 +504,19 @@ static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, con
     LaneDev* dl = ctx->d_lanes + l0;
     StepParams* dp = ctx->d_params + l0;
     StepOut* dout = ctx->d_outs + l0;
-    k_scan_insert<<<dim3(g1, cnt), 256, 0, st>>>(dl, dp);
-    k_compact1<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp);
-    k_compact2<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp);
+    LAUNCH(PS_SCAN_INSERT, st, k_scan_insert<<<dim3(g1, cnt), 256, 0, st>>>(dl, dp));
+    LAUNCH(PS_COMPACT1, st, k_compact1<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
+    LAUNCH(PS_COMPACT2, st, k_compact2<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
     CK(cudaGetLastError());
     int rc = launch_icp(ctx, l0, cnt, st);
     if (rc) return rc;
     rc = map_update_launch(ctx, l0, cnt, nmax, 1, nullptr, true, true, st);
     if (rc) return rc;
-    k_finish<<<(cnt + 63) / 64, 64, 0, st>>>(dl, dout, cnt);
+    LAUNCH(PS_FINISH, st, k_finish<<<(cnt + 63) / 64, 64, 0, st>>>(dl, dout, cnt));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_outs + l0, dout, sizeof(StepOut) * cnt, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    prof_collect(ctx);
     int ret = PTK_OK;
     for (int k = 0; k < cnt; ++k) {
         int l = l0 + k;
@@ -567,7 +628,7 @@ extern "C" int ptk_deskew_scan(ptk_ctx* ctx, const double* xyz, const double* ti
     if (rc) return rc;
     if (n > 0) {
         double* dout = is_device_ptr(out_xyz) ? out_xyz : ctx->d_tmp;
-        k_deskew<<<(n + 255) / 256, 256, 0, st>>>(dx, dt, n, P, dout);
+        LAUNCH(PS_OTHER, st, k_deskew<<<(n + 255) / 256, 256, 0, st>>>(dx, dt, n, P, dout));
         CK(cudaGetLastError());
         if (dout != out_xyz) CK(cudaMemcpyAsync(out_xyz, dout, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
@@ -585,10 +646,10 @@ static int scratch_select(ptk_ctx* ctx, StepParams P, bool voxel, double* out_xy
     LaneDev* dl = ctx->d_lanes + S;
     StepParams* dp = ctx->d_params + S;
     int g1 = std::max(1, (P.n + 255) / 256), gt = std::max(1, (P.n + TILE - 1) / TILE);
-    if (voxel) k_scan_insert<<<dim3(g1, 1), 256, 0, st>>>(dl, dp);
-    k_compact1<<<dim3(gt, 1), 256, 0, st>>>(dl, dp);
-    if (voxel) k_clean_tables<<<dim3(ctx->num_sms, 1), 256, 0, st>>>(dl, 1);
-    k_finish<<<1, 64, 0, st>>>(dl, ctx->d_outs + S, 1);
+    if (voxel) LAUNCH(PS_OTHER, st, k_scan_insert<<<dim3(g1, 1), 256, 0, st>>>(dl, dp));
+    LAUNCH(PS_OTHER, st, k_compact1<<<dim3(gt, 1), 256, 0, st>>>(dl, dp));
+    if (voxel) LAUNCH(PS_OTHER, st, k_clean_tables<<<dim3(ctx->num_sms, 1), 256, 0, st>>>(dl, 1));
+    LAUNCH(PS_OTHER, st, k_finish<<<1, 64, 0, st>>>(dl, ctx->d_outs + S, 1));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_outs + S, ctx->d_outs + S, sizeof(StepOut), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -600,7 +661,7 @@ static int scratch_select(ptk_ctx* ctx, StepParams P, bool voxel, double* out_xy
     if (capacity >= 0 && m > capacity) return fail(ctx, PTK_E_CAPACITY, "output buffer too small");
     if (m > 0 && out_xyz) {
         double* dout = is_device_ptr(out_xyz) ? out_xyz : ctx->d_tmp;
-        k_gather_aos<<<(m + 255) / 256, 256, 0, st>>>(LH.d.ds_x, LH.d.ds_y, LH.d.ds_z, m, dout);
+        LAUNCH(PS_OTHER, st, k_gather_aos<<<(m + 255) / 256, 256, 0, st>>>(LH.d.ds_x, LH.d.ds_y, LH.d.ds_z, m, dout));
         CK(cudaGetLastError());
         if (dout != out_xyz) CK(cudaMemcpyAsync(out_xyz, dout, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
@@ -667,8 +728,8 @@ extern "C" int ptk_get_points(ptk_ctx* ctx, int lane, int which, double* out_xyz
     const LaneDev& d = LH.d;
     if (m > 0 && out_xyz) {
         double* dout = is_device_ptr(out_xyz) ? out_xyz : ctx->d_tmp;
-        if (which == 0) k_gather_aos<<<(m + 255) / 256, 256, 0, st>>>(d.ds_x, d.ds_y, d.ds_z, m, dout);
-        else k_gather_aos<<<(m + 255) / 256, 256, 0, st>>>(d.s0_x, d.s0_y, d.s0_z, m, dout);
+        if (which == 0) LAUNCH(PS_OTHER, st, k_gather_aos<<<(m + 255) / 256, 256, 0, st>>>(d.ds_x, d.ds_y, d.ds_z, m, dout));
+        else LAUNCH(PS_OTHER, st, k_gather_aos<<<(m + 255) / 256, 256, 0, st>>>(d.s0_x, d.s0_y, d.s0_z, m, dout));
         CK(cudaGetLastError());
         if (dout != out_xyz) CK(cudaMemcpyAsync(out_xyz, dout, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
@@ -704,7 +765,7 @@ extern "C" int ptk_get_trace(ptk_ctx* ctx, int lane, int* out_order, int capacit
 
 // ---- map taps ------------------------------------------------------------------------
 static int lane_counters(ptk_ctx* ctx, int lane, StepOut* O, cudaStream_t st) {
-    k_finish<<<1, 64, 0, st>>>(ctx->d_lanes + lane, ctx->d_outs + lane, 1);
+    LAUNCH(PS_OTHER, st, k_finish<<<1, 64, 0, st>>>(ctx->d_lanes + lane, ctx->d_outs + lane, 1));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_outs + lane, ctx->d_outs + lane, sizeof(StepOut), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -760,7 +821,7 @@ static int map_mutate(ptk_ctx* ctx, int lane, const double* xyz, int n, const do
         const double* dx;
         int rc = stage_in(ctx, xyz, (size_t)n * 3, LH.in_xyz, &dx, st);
         if (rc) return rc;
-        k_load_ds<<<std::max(1, (n + 255) / 256), 256, 0, st>>>(ctx->d_lanes, lane, dx, n);
+        LAUNCH(PS_OTHER, st, k_load_ds<<<std::max(1, (n + 255) / 256), 256, 0, st>>>(ctx->d_lanes, lane, dx, n));
         CK(cudaGetLastError());
     }
     int rc = map_update_launch(ctx, lane, 1, std::max(n, 1), use_pose, origin_dev, insert, prune, st);
@@ -804,6 +865,7 @@ extern "C" int ptk_map_point_cloud(ptk_ctx* ctx, int lane, double* out_xyz, int 
     int rc = ensure_big(ctx, (size_t)std::max(capacity, 1) * 3 * sizeof(double));
     if (rc) return rc;
     CK(cudaMemsetAsync(ctx->d_tmp_i, 0, 2 * sizeof(int), st));
+    ctx->launches++;
     k_map_dump<<<ctx->num_sms, 256, 0, st>>>(ctx->d_lanes, lane, nullptr, nullptr, nullptr, (double*)ctx->d_big, capacity,
                                            ctx->d_tmp_i, ctx->d_tmp_i + 1);
     CK(cudaGetLastError());
@@ -833,6 +895,7 @@ extern "C" int ptk_map_dump(ptk_ctx* ctx, int lane, int* keys, int* counts, doub
     int* d_keys = (int*)((char*)ctx->d_big + b_pts);
     int* d_cnt = (int*)((char*)ctx->d_big + b_pts + b_keys);
     CK(cudaMemsetAsync(ctx->d_tmp_i, 0, 2 * sizeof(int), st));
+    ctx->launches++;
     k_map_dump<<<ctx->num_sms, 256, 0, st>>>(ctx->d_lanes, lane, d_keys, d_cnt, d_pts, nullptr, capacity, ctx->d_tmp_i,
                                            ctx->d_tmp_i + 1);
     CK(cudaGetLastError());
@@ -864,6 +927,7 @@ extern "C" int ptk_map_get_correspondences(ptk_ctx* ctx, int lane, const double*
     CK(cudaMemsetAsync(ctx->d_tmp_i, 0, sizeof(int), st));
     if (n > 0) {
         size_t threads = (size_t)n * 32;
+        ctx->launches++;
         k_correspondences<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ctx->d_lanes, lane, dq, n, max_dist, d_ord,
                                                                            ctx->d_tmp, ctx->d_tmp_i);
         CK(cudaGetLastError());
@@ -899,7 +963,7 @@ extern "C" int ptk_register_point_cloud(ptk_ctx* ctx, int lane, const double* xy
     int rc = stage_in(ctx, xyz, (size_t)n * 3, LH.in_xyz, &dx, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->d_params + lane, &P, sizeof(StepParams), cudaMemcpyHostToDevice, st));
-    k_load_src<<<std::max(1, (n + 255) / 256), 256, 0, st>>>(ctx->d_lanes, lane, dx, n, P.guess);
+    LAUNCH(PS_OTHER, st, k_load_src<<<std::max(1, (n + 255) / 256), 256, 0, st>>>(ctx->d_lanes, lane, dx, n, P.guess));
     CK(cudaGetLastError());
     rc = launch_icp(ctx, lane, 1, st);
     if (rc) return rc;
@@ -919,6 +983,29 @@ extern "C" int ptk_register_point_cloud(ptk_ctx* ctx, int lane, const double* xy
     if (O.status == 2) return fail(ctx, PTK_E_NUMERIC, "singular normal equations in ICP");
     return PTK_OK;
 }
+
+extern "C" int ptk_set_profiling(ptk_ctx* ctx, int on) {
+    if (!ctx) return PTK_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    prof_collect(ctx);
+    ctx->prof.on = on != 0;
+    for (int k = 0; k < PTK_PROF_SLOTS; ++k) { ctx->prof.ms[k] = 0.0; ctx->prof.n[k] = 0; }
+    return PTK_OK;
+}
+
+extern "C" int ptk_get_profile(ptk_ctx* ctx, double* ms, long long* launches) {
+    if (!ctx) return PTK_E_ARG;
+    for (int k = 0; k < PTK_PROF_SLOTS; ++k) {
+        if (ms) ms[k] = ctx->prof.ms[k];
+        if (launches) launches[k] = ctx->prof.n[k];
+    }
+    return PTK_OK;
+}
+
+extern "C" const char* ptk_kernel_name(int slot) { return (slot >= 0 && slot < PS_COUNT) ? kProfNames[slot] : nullptr; }
+
+extern "C" long long ptk_launch_count(const ptk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int ptk_host_alloc(void** out, unsigned long long bytes) {
     if (!out) return PTK_E_ARG;

@@ -107,7 +107,40 @@ PTK_HD void rigid_to_mat16(const Rigid& T, double* m) {
 }
 
 // ---- SE3 exp (Sophus SE3::exp / SO3::expAndTheta, Eigen quaternion->matrix) ----------
-PTK_HD Rigid se3_exp(const double* a) {
+struct Quat { double w, x, y, z; };
+
+// Eigen quaternion product a*b, sums left to right.
+PTK_HD Quat quat_mul(const Quat& a, const Quat& b) {
+    Quat c;
+    c.w = ((a.w * b.w - a.x * b.x) - a.y * b.y) - a.z * b.z;
+    c.x = ((a.w * b.x + a.x * b.w) + a.y * b.z) - a.z * b.y;
+    c.y = ((a.w * b.y + a.y * b.w) + a.z * b.x) - a.x * b.z;
+    c.z = ((a.w * b.z + a.z * b.w) + a.x * b.y) - a.y * b.x;
+    return c;
+}
+
+// Sophus SO3::operator* first-order renormalisation.
+PTK_HD Quat quat_normalize1(Quat q) {
+    const double n2 = ((q.w * q.w + q.x * q.x) + q.y * q.y) + q.z * q.z;
+    if (n2 != 1.0) {
+        const double s = 2.0 / (1.0 + n2);
+        q.w = q.w * s; q.x = q.x * s; q.y = q.y * s; q.z = q.z * s;
+    }
+    return q;
+}
+
+// Eigen QuaternionBase::toRotationMatrix
+PTK_HD void quat_to_rot(const Quat& q, double* r) {
+    const double tx = 2.0 * q.x, ty = 2.0 * q.y, tz = 2.0 * q.z;
+    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+    const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    r[0] = 1.0 - (tyy + tzz); r[1] = txy - twz;         r[2] = txz + twy;
+    r[3] = txy + twz;         r[4] = 1.0 - (txx + tzz); r[5] = tyz - twx;
+    r[6] = txz - twy;         r[7] = tyz + twx;         r[8] = 1.0 - (txx + tyy);
+}
+
+PTK_HD Rigid se3_exp_q(const double* a, Quat* qout) {
     const double ux = a[0], uy = a[1], uz = a[2], wx = a[3], wy = a[4], wz = a[5];
     const double theta_sq = (wx * wx + wy * wy) + wz * wz;
     const bool small_ = theta_sq < kSophusEps * kSophusEps;
@@ -123,15 +156,11 @@ PTK_HD Rigid se3_exp(const double* a) {
         imag = sh / theta;
         real = ch;
     }
-    const double qw = real, qx = imag * wx, qy = imag * wy, qz = imag * wz;
-    const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
-    const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
-    const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
-    const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    Quat q;
+    q.w = real; q.x = imag * wx; q.y = imag * wy; q.z = imag * wz;
+    if (qout) *qout = q;
     Rigid T;
-    T.r[0] = 1.0 - (tyy + tzz); T.r[1] = txy - twz;         T.r[2] = txz + twy;
-    T.r[3] = txy + twz;         T.r[4] = 1.0 - (txx + tzz); T.r[5] = tyz - twx;
-    T.r[6] = txz - twy;         T.r[7] = tyz + twx;         T.r[8] = 1.0 - (txx + tyy);
+    quat_to_rot(q, T.r);
     double v[9];
     if (theta >= kSophusEps) {
         double st, ct;
@@ -151,6 +180,40 @@ PTK_HD Rigid se3_exp(const double* a) {
     T.t[0] = (v[0] * ux + v[1] * uy) + v[2] * uz;
     T.t[1] = (v[3] * ux + v[4] * uy) + v[5] * uz;
     T.t[2] = (v[6] * ux + v[7] * uy) + v[8] * uz;
+    return T;
+}
+
+PTK_HD Rigid se3_exp(const double* a) { return se3_exp_q(a, nullptr); }
+
+// Sophus::SE3d as kiss-icp's registration holds poses: unit quaternion + translation.  Products
+// renormalise the quaternion, so the rotation of every returned pose stays orthonormal.
+struct SE3q {
+    Quat q;
+    double t[3];
+};
+
+PTK_HD SE3q se3q_identity() {
+    SE3q T;
+    T.q.w = 1.0; T.q.x = 0.0; T.q.y = 0.0; T.q.z = 0.0;
+    T.t[0] = 0.0; T.t[1] = 0.0; T.t[2] = 0.0;
+    return T;
+}
+
+// a * b: q = normalize1(qa qb), t = R(qa) tb + ta
+PTK_HD SE3q se3q_mul(const SE3q& a, const SE3q& b) {
+    SE3q c;
+    c.q = quat_normalize1(quat_mul(a.q, b.q));
+    double r[9];
+    quat_to_rot(a.q, r);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) c.t[i] = ((r[3 * i] * b.t[0] + r[3 * i + 1] * b.t[1]) + r[3 * i + 2] * b.t[2]) + a.t[i];
+    return c;
+}
+
+PTK_HD Rigid se3q_matrix(const SE3q& a) {
+    Rigid T;
+    quat_to_rot(a.q, T.r);
+    T.t[0] = a.t[0]; T.t[1] = a.t[1]; T.t[2] = a.t[2];
     return T;
 }
 
@@ -202,8 +265,8 @@ PTK_HD bool ldlt_solve6(double (*a)[6], const double* b, double* x) {
     return ok;
 }
 
-// ---- host-only scalars (once per scan): libm atan2/sin/cos like the oracle -----------
-inline void rot_to_quat(const double* r, double& w, double& x, double& y, double& z) {
+// Eigen rotation matrix -> quaternion (sqrt and divisions only: bit-exact on host and device)
+PTK_HD void rot_to_quat(const double* r, double& w, double& x, double& y, double& z) {
     double m[3][3] = {{r[0], r[1], r[2]}, {r[3], r[4], r[5]}, {r[6], r[7], r[8]}};
     double t = (m[0][0] + m[1][1]) + m[2][2];
     double q[3] = {0, 0, 0};
@@ -228,6 +291,15 @@ inline void rot_to_quat(const double* r, double& w, double& x, double& y, double
     }
     x = q[0]; y = q[1]; z = q[2];
 }
+
+PTK_HD SE3q se3q_from_rigid(const Rigid& T) {
+    SE3q a;
+    rot_to_quat(T.r, a.q.w, a.q.x, a.q.y, a.q.z);
+    a.t[0] = T.t[0]; a.t[1] = T.t[1]; a.t[2] = T.t[2];
+    return a;
+}
+
+// ---- host-only scalars (once per scan): libm atan2/sin/cos like the oracle -----------
 
 inline void so3_log(const double* r, double* om, double& theta) {
     double w, x, y, z;

@@ -25,8 +25,10 @@ constexpr u64 KEY_TOMB = ~0ull - 1ull;
 constexpr u32 NONE = 0xFFFFFFFFu;
 constexpr int KEY_BIAS = 1 << 20;
 constexpr int TILE = 1024;                 // items per compaction tile (256 threads x 4)
-constexpr int NRED = 28;                   // 27 normal-equation terms + correspondence count
-constexpr int ICP_WARPS = 16;
+constexpr int NSUM = 17;                   // distinct normal-equation sums (16) + correspondence count
+constexpr int NRED = NSUM;
+constexpr int ICP_THREADS = 1024;
+constexpr int ICP_WARPS = ICP_THREADS / 32;
 
 enum StepFlags : int { F_DESKEW = 1, F_RANGE = 2, F_SECOND = 4, F_SELECT_RANGE = 8 };
 enum ErrFlags : int { ERR_KEYRANGE = 1, ERR_POOL = 2, ERR_TABLE = 4 };
@@ -321,6 +323,7 @@ __global__ void __launch_bounds__(256) k_compact2(LaneDev* lanes, const StepPara
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
     u32 tile = take_ticket(&L.ticket2, P.tbase2);
+    if (tile == 0 && threadIdx.x == 0) L.icp_arrive = 0;    // barrier counter of the k_icp that follows
     int n_ds = L.n_ds;
     u32 ntiles = (u32)((n_ds + TILE - 1) / TILE);
     if (ntiles == 0) {
@@ -381,12 +384,17 @@ __global__ void k_clean_tables(LaneDev* lanes, int which) {
 }
 
 // ------------------------------------------------------------------------------------
-// Nearest map point of (sx,sy,sz) among the 27 neighbouring voxels, one warp per query.
-// Lanes 0..26 probe one voxel each; candidates are then scanned voxel by voxel in (i,j,l) order
-// with lanes = slots, strict '<' per lane, and a lexicographic (d2, order id) warp argmin, so
-// ties resolve to the first candidate in upstream's iteration order.
+// Nearest map point of (sx,sy,sz) among the 27 neighbouring voxels, one warp per query
+// (kiss-icp VoxelHashMap::GetCorrespondences).
+// Lanes 0..26 probe one voxel each (one 16 B slot load, usually a first-probe hit); the hits are
+// then scanned four voxels per round in (i,j,l) order with lanes = slots: the 12 row loads of a
+// round are independent, so a query costs ~1 + ceil(hits/4) L2 latencies.  Unused slots of a
+// block hold +inf (set when the voxel is created), so no per-voxel count is needed.  Strict '<'
+// per lane plus a lexicographic (d2, order id) warp argmin reproduce upstream's "first
+// candidate in iteration order wins ties".
 __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double sy, double sz, int lane,
                                              double& bd2, int& bord, double& tx, double& ty, double& tz) {
+    const u32 FULL = 0xffffffffu;
     int kx, ky, kz;
     voxel_key(sx, sy, sz, L.voxel_size, kx, ky, kz);
     u32 id = NONE;
@@ -401,220 +409,244 @@ __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double
             slot = (slot + 1) & L.m_mask;
         }
     }
-    u32 mask = __ballot_sync(0xffffffffu, id != NONE);
+    u32 mask = __ballot_sync(FULL, id != NONE);
     double best = INFINITY, bx = 0, by = 0, bz = 0;
     int ord = 0x7fffffff;
+    const int sl = lane < MAXP ? lane : 0;
     while (mask) {
-        int v = __ffs(mask) - 1;
-        mask &= mask - 1;
-        u32 vid = __shfl_sync(0xffffffffu, id, v);
-        const VoxelBlock* B = L.blocks + vid;
-        int c = (int)__ldg(&B->count);
-        if (lane < c) {
-            double x = __ldg(&B->x[lane]), y = __ldg(&B->y[lane]), z = __ldg(&B->z[lane]);
-            double dx = x - sx, dy = y - sy, dz = z - sz;
-            double d2 = (dx * dx + dy * dy) + dz * dz;
-            if (d2 < best) { best = d2; ord = v * MAXP + lane; bx = x; by = y; bz = z; }
+        // up to four voxels per round; absent ones repeat the first (a repeat never wins: strict '<')
+        int v0 = __ffs(mask) - 1; mask &= mask - 1;
+        int v1 = v0, v2 = v0, v3 = v0;
+        if (mask) { v1 = __ffs(mask) - 1; mask &= mask - 1; }
+        if (mask) { v2 = __ffs(mask) - 1; mask &= mask - 1; }
+        if (mask) { v3 = __ffs(mask) - 1; mask &= mask - 1; }
+        const VoxelBlock* B0 = L.blocks + __shfl_sync(FULL, id, v0);
+        const VoxelBlock* B1 = L.blocks + __shfl_sync(FULL, id, v1);
+        const VoxelBlock* B2 = L.blocks + __shfl_sync(FULL, id, v2);
+        const VoxelBlock* B3 = L.blocks + __shfl_sync(FULL, id, v3);
+        if (lane < MAXP) {
+            double x0 = __ldg(&B0->x[sl]), y0 = __ldg(&B0->y[sl]), z0 = __ldg(&B0->z[sl]);
+            double x1 = __ldg(&B1->x[sl]), y1 = __ldg(&B1->y[sl]), z1 = __ldg(&B1->z[sl]);
+            double x2 = __ldg(&B2->x[sl]), y2 = __ldg(&B2->y[sl]), z2 = __ldg(&B2->z[sl]);
+            double x3 = __ldg(&B3->x[sl]), y3 = __ldg(&B3->y[sl]), z3 = __ldg(&B3->z[sl]);
+            double dx, dy, dz, d2;
+            dx = x0 - sx; dy = y0 - sy; dz = z0 - sz; d2 = (dx * dx + dy * dy) + dz * dz;
+            if (d2 < best) { best = d2; ord = v0 * MAXP + lane; bx = x0; by = y0; bz = z0; }
+            dx = x1 - sx; dy = y1 - sy; dz = z1 - sz; d2 = (dx * dx + dy * dy) + dz * dz;
+            if (d2 < best) { best = d2; ord = v1 * MAXP + lane; bx = x1; by = y1; bz = z1; }
+            dx = x2 - sx; dy = y2 - sy; dz = z2 - sz; d2 = (dx * dx + dy * dy) + dz * dz;
+            if (d2 < best) { best = d2; ord = v2 * MAXP + lane; bx = x2; by = y2; bz = z2; }
+            dx = x3 - sx; dy = y3 - sy; dz = z3 - sz; d2 = (dx * dx + dy * dy) + dz * dz;
+            if (d2 < best) { best = d2; ord = v3 * MAXP + lane; bx = x3; by = y3; bz = z3; }
         }
     }
-    double rb = best;
-    int ro = ord;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_xor_sync(0xffffffffu, rb, o);
-        int oo = __shfl_xor_sync(0xffffffffu, ro, o);
-        if (ob < rb || (ob == rb && oo < ro)) { rb = ob; ro = oo; }
-    }
-    bool found = ro != 0x7fffffff;
-    int owner = found ? (ro % MAXP) : 0;
-    tx = __shfl_sync(0xffffffffu, bx, owner);
-    ty = __shfl_sync(0xffffffffu, by, owner);
-    tz = __shfl_sync(0xffffffffu, bz, owner);
-    bd2 = rb;
-    bord = ro;
+    // lexicographic (d2, ord) argmin: d2 >= 0, so its bit pattern orders like the value
+    const u64 bits = (u64)__double_as_longlong(best);
+    const u32 hi = (u32)(bits >> 32), lo = (u32)bits;
+    const u32 mhi = __reduce_min_sync(FULL, hi);
+    const u32 mlo = __reduce_min_sync(FULL, hi == mhi ? lo : 0xffffffffu);
+    const bool cand = (hi == mhi) && (lo == mlo);
+    const u32 mord = __reduce_min_sync(FULL, cand ? (u32)ord : 0x7fffffffu);
+    const bool found = mord != 0x7fffffffu;
+    const int owner = found ? (int)(mord % MAXP) : 0;
+    tx = __shfl_sync(FULL, bx, owner);
+    ty = __shfl_sync(FULL, by, owner);
+    tz = __shfl_sync(FULL, bz, owner);
+    bd2 = __longlong_as_double((long long)(((u64)mhi << 32) | (u64)mlo));
+    bord = (int)mord;
     return found;
 }
 
-// The 27 per-correspondence terms of JtJ (upper triangle, row major) and Jtr.
+// The distinct sums behind the 27 normal-equation terms: the 27 columns the oracle
+// reduces contain 6 structural zeros, three copies of w and three +-pairs, so 16 sums (+ the
+// correspondence count) determine all of them bit for bit (a sum of negated terms is the negated
+// sum).  Order: w, w*sx, w*sy, w*sz, the 6 entries of the lower-right block, the 6 of Jtr, count.
 __device__ __forceinline__ void lin_terms(double sx, double sy, double sz, double tx, double ty, double tz,
                                           double kernel, double* c) {
     double rx = sx - tx, ry = sy - ty, rz = sz - tz;
     double r2 = (rx * rx + ry * ry) + rz * rz;
     double kk = kernel + r2;
     double w = (kernel * kernel) / (kk * kk);
-    double wsx = w * sx, wsy = w * sy, wsz = w * sz;
     double wrx = w * rx, wry = w * ry, wrz = w * rz;
-    c[0] = w;  c[1] = 0;  c[2] = 0;  c[3] = 0;  c[4] = wsz;  c[5] = -wsy;
-    c[6] = w;  c[7] = 0;  c[8] = -wsz; c[9] = 0; c[10] = wsx;
-    c[11] = w; c[12] = wsy; c[13] = -wsx; c[14] = 0;
-    c[15] = w * (sy * sy + sz * sz); c[16] = -(w * (sx * sy)); c[17] = -(w * (sx * sz));
-    c[18] = w * (sx * sx + sz * sz); c[19] = -(w * (sy * sz));
-    c[20] = w * (sx * sx + sy * sy);
-    c[21] = wrx; c[22] = wry; c[23] = wrz;
-    c[24] = sy * wrz - sz * wry; c[25] = sz * wrx - sx * wrz; c[26] = sx * wry - sy * wrx;
+    c[0] = w; c[1] = w * sx; c[2] = w * sy; c[3] = w * sz;
+    c[4] = w * (sy * sy + sz * sz); c[5] = -(w * (sx * sy)); c[6] = -(w * (sx * sz));
+    c[7] = w * (sx * sx + sz * sz); c[8] = -(w * (sy * sz));
+    c[9] = w * (sx * sx + sy * sy);
+    c[10] = wrx; c[11] = wry; c[12] = wrz;
+    c[13] = sy * wrz - sz * wry; c[14] = sz * wrx - sx * wrz; c[15] = sx * wry - sy * wrx;
+}
+
+__device__ __forceinline__ double warp_butterfly(double x) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) x = x + __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// Adjacent-pairs binary tree over p[0..n), zero padded to a power of two: the canonical reduction
+// over 32-point group partials (oracle/canon.py pairwise_tree_sum), computed by one warp with
+// butterflies only.  Element idx sits in lane idx & 31 of butterfly idx >> 5.
+__device__ __forceinline__ double warp_tree_sum(const double* p, int n, int lane) {
+    int m = 1;
+    while (m * 32 < n) m <<= 1;
+    if (m == 1) return warp_butterfly(lane < n ? __ldcg(p + lane) : 0.0);
+    if (m <= 32) {
+        double reg = 0.0;
+        for (int j = 0; j < m; ++j) {
+            int idx = j * 32 + lane;
+            double x = warp_butterfly(idx < n ? __ldcg(p + idx) : 0.0);
+            if (lane == j) reg = x;
+        }
+        return warp_butterfly(reg);
+    }
+    double U[8];                        // m in {64, 128, 256}: n_src up to 262144
+    const int mc = m >> 5;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        U[c] = 0.0;
+        if (c < mc) {
+            double reg = 0.0;
+            for (int j = 0; j < 32; ++j) {
+                int idx = (c * 32 + j) * 32 + lane;
+                double x = warp_butterfly(idx < n ? __ldcg(p + idx) : 0.0);
+                if (lane == j) reg = x;
+            }
+            U[c] = warp_butterfly(reg);
+        }
+    }
+    return ((U[0] + U[1]) + (U[2] + U[3])) + ((U[4] + U[5]) + (U[6] + U[7]));
+}
+
+// One thread per block: expand the 17 sums into the 6x6 system, solve, update T_icp, decide
+// termination (kiss-icp RegisterFrame loop body after BuildLinearSystem).  Kept out of line so
+// its registers and stack do not weigh on the search loop.
+__device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, StepOut& O, const double* red,
+                                            Rigid* sE, SE3q* sT, int* s_done, int it, bool writer) {
+    const int n_corr = (int)red[16];
+    int done = 0, status = 0;
+    double nrm = 0.0;
+    Rigid Enew = rigid_identity();
+    if (n_corr == 0) {
+        status = 1; done = 1;            // B.5
+    } else {
+        const double w = red[0], wsx = red[1], wsy = red[2], wsz = red[3];
+        double A[6][6], bb[6], dx[6];
+        A[0][0] = w;   A[0][1] = 0.0; A[0][2] = 0.0; A[0][3] = 0.0;  A[0][4] = wsz;  A[0][5] = -wsy;
+        A[1][1] = w;   A[1][2] = 0.0; A[1][3] = -wsz; A[1][4] = 0.0; A[1][5] = wsx;
+        A[2][2] = w;   A[2][3] = wsy; A[2][4] = -wsx; A[2][5] = 0.0;
+        A[3][3] = red[4]; A[3][4] = red[5]; A[3][5] = red[6];
+        A[4][4] = red[7]; A[4][5] = red[8];
+        A[5][5] = red[9];
+        for (int i = 1; i < 6; ++i)
+            for (int j = 0; j < i; ++j) A[i][j] = A[j][i];
+        for (int i = 0; i < 6; ++i) bb[i] = -red[10 + i];
+        if (!ldlt_solve6(A, bb, dx)) {
+            status = 2; done = 1;
+        } else {
+            SE3q Eq;
+            Enew = se3_exp_q(dx, &Eq.q);
+            Eq.t[0] = Enew.t[0]; Eq.t[1] = Enew.t[1]; Eq.t[2] = Enew.t[2];
+            *sT = se3q_mul(Eq, *sT);
+            nrm = sqrt(((((dx[0] * dx[0] + dx[1] * dx[1]) + dx[2] * dx[2]) + dx[3] * dx[3]) + dx[4] * dx[4]) + dx[5] * dx[5]);
+            if (nrm < L.eps) done = 1;
+        }
+    }
+    if (it + 1 >= L.max_iters) done = 1;
+    *sE = Enew;
+    *s_done = done;
+    if (done && writer) {
+        O.pose = se3q_matrix(se3q_mul(*sT, se3q_from_rigid(P.guess)));
+        O.iterations = it + 1; O.n_corr = n_corr; O.status = status; O.dx_norm = nrm;
+    }
 }
 
 // K4: the whole ICP loop (kiss-icp RegisterFrame) in one persistent cooperative kernel.
-// grid = (blocks per lane, lanes).  Per iteration: warp-per-point NN search, per-32-point group
-// butterfly sums -> global partials, "last block" does the fixed pairwise tree over groups, the
-// 6x6 LDLT solve, SE3 exp and the termination test, then releases the other blocks.
-__global__ void __launch_bounds__(ICP_WARPS * 32, 1) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs) {
+// grid = (blocks per lane, lanes), 1024 threads.  Per iteration a block takes 32-point groups:
+// one warp per point (transform by the last increment, NN search), lane 0 leaves the point's 17
+// terms in shared memory, 17 warps butterfly them into the group's partial sums.  A counter
+// barrier over the lane's blocks follows; after it EVERY block reduces the group partials with
+// the same fixed tree, solves the 6x6 system and updates its copy of T_icp (identical code,
+// identical bits), so one grid-wide hop per iteration is all the synchronisation there is.
+__global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs) {
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
     StepOut& O = outs[blockIdx.y];
     const int nblk = gridDim.x, b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_src = L.n_src;
-    const int n_vox = L.n_vox;
 
-    __shared__ double contrib[NRED][32];
-    __shared__ double red[NRED];
+    __shared__ double contrib[NSUM][33];
+    __shared__ double red[NSUM];
     __shared__ Rigid sE;
-    __shared__ int s_last, s_done;
+    __shared__ SE3q sT;
+    __shared__ int s_done;
 
-    if (n_vox == 0) {   // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
+    if (L.n_vox == 0) {   // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
         if (b == 0 && threadIdx.x == 0) {
-            O.pose = P.guess; O.iterations = 0; O.n_corr = 0; O.status = 0; O.dx_norm = 0.0;
+            O.pose = se3q_matrix(se3q_mul(se3q_identity(), se3q_from_rigid(P.guess)));
+            O.iterations = 0; O.n_corr = 0; O.status = 0; O.dx_norm = 0.0;
         }
         return;
     }
-    const int n_groups = (n_src + 31) / 32;
-    int p2 = 1;
-    while (p2 < n_groups) p2 <<= 1;
+    const int n_groups = (n_src + 31) >> 5;
+    const double max_corr = P.max_corr, kern = P.kernel;
+    if (threadIdx.x == 0) sT = se3q_identity();
 
-    if (b == 0 && threadIdx.x == 0) L.icp_T = rigid_identity();
-
-    for (int it = 0; it < L.max_iters; ++it) {
-        Rigid E;
-        if (it > 0) E = sE;
+    for (int it = 0;; ++it) {
+        double* part = (it & 1) ? L.part_b : L.part_a;
         for (int g = b; g < n_groups; g += nblk) {
             for (int pi = warp; pi < 32; pi += ICP_WARPS) {
-                int p = g * 32 + pi;
-                double c[27];
-                double nc = 0.0;
+                const int p = g * 32 + pi;
                 bool acc = false;
+                double sx = 0, sy = 0, sz = 0, tx = 0, ty = 0, tz = 0;
+                int ord = -1;
                 if (p < n_src) {
-                    double sx = L.s_x[p], sy = L.s_y[p], sz = L.s_z[p];
+                    sx = __ldcg(L.s_x + p); sy = __ldcg(L.s_y + p); sz = __ldcg(L.s_z + p);
                     if (it > 0) {
                         double xo, yo, zo;
-                        rigid_apply(E, sx, sy, sz, xo, yo, zo);
+                        rigid_apply(sE, sx, sy, sz, xo, yo, zo);
                         sx = xo; sy = yo; sz = zo;
                         if (lane == 0) { L.s_x[p] = sx; L.s_y[p] = sy; L.s_z[p] = sz; }
                     }
-                    double d2, tx, ty, tz;
-                    int ord;
+                    double d2;
                     bool found = warp_nearest(L, sx, sy, sz, lane, d2, ord, tx, ty, tz);
-                    acc = found && (sqrt(d2) < P.max_corr);
-                    if (lane == 0) {
-                        if (acc) { lin_terms(sx, sy, sz, tx, ty, tz, P.kernel, c); nc = 1.0; }
-                        if (it < L.trace_iters) L.trace[(size_t)it * L.cap_points + p] = acc ? ord : -1;
-                    }
+                    acc = found && (sqrt(d2) < max_corr);
+                    if (lane == 0 && it < L.trace_iters) L.trace[(size_t)it * L.cap_points + p] = acc ? ord : -1;
                 }
                 if (lane == 0) {
                     if (acc) {
+                        double c[16];
+                        lin_terms(sx, sy, sz, tx, ty, tz, kern, c);
 #pragma unroll
-                        for (int v = 0; v < 27; ++v) contrib[v][pi] = c[v];
+                        for (int v = 0; v < 16; ++v) contrib[v][pi] = c[v];
+                        contrib[16][pi] = 1.0;
                     } else {
 #pragma unroll
-                        for (int v = 0; v < 27; ++v) contrib[v][pi] = 0.0;
-                    }
-                    contrib[27][pi] = nc;
-                }
-            }
-            __syncthreads();
-            for (int v = warp; v < NRED; v += ICP_WARPS) {
-                double x = contrib[v][lane];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) x = x + __shfl_xor_sync(0xffffffffu, x, o);
-                if (lane == 0) L.part_a[(size_t)v * L.ng_cap + g] = x;
-            }
-            __syncthreads();
-        }
-        // ---- arrive
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            u32 prev = atomicAdd(&L.icp_arrive, 1u);
-            s_last = (prev == (u32)nblk - 1u) ? 1 : 0;
-        }
-        __syncthreads();
-        const u32 target = P.release_base + (u32)it + 1u;
-        if (s_last) {
-            if (threadIdx.x == 0) L.icp_arrive = 0;
-            // fixed adjacent-pairs tree over group partials, zero padded to p2 groups
-            double* in = L.part_a;
-            double* out = L.part_b;
-            int cur = n_groups;
-            for (int n = p2; n > 1; n >>= 1) {
-                int half = n >> 1;
-                int ncur = (cur + 1) >> 1;
-                for (int idx = threadIdx.x; idx < NRED * ncur; idx += blockDim.x) {
-                    int v = idx / ncur, k = idx - v * ncur;
-                    double a0 = __ldcg(in + (size_t)v * L.ng_cap + 2 * k);
-                    double a1 = (2 * k + 1 < cur) ? __ldcg(in + (size_t)v * L.ng_cap + 2 * k + 1) : 0.0;
-                    out[(size_t)v * L.ng_cap + k] = a0 + a1;
-                }
-                __threadfence_block();
-                __syncthreads();
-                double* t = in; in = out; out = t;
-                cur = ncur;
-                (void)half;
-            }
-            if (threadIdx.x < NRED) red[threadIdx.x] = (n_groups > 0) ? __ldcg(in + (size_t)threadIdx.x * L.ng_cap) : 0.0;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int n_corr = (int)red[27];
-                int done = 0, status = 0;
-                Rigid Tcur;   // T_icp lives in L2; another block may have written it last
-                {
-                    const volatile double* tv = (const volatile double*)&L.icp_T;
-                    double* td = (double*)&Tcur;
-                    for (int k = 0; k < 12; ++k) td[k] = tv[k];
-                }
-                double nrm = 0.0;
-                Rigid Enew = rigid_identity();
-                if (n_corr == 0) {
-                    status = 1; done = 1;
-                } else {
-                    double A[6][6], bb[6], dx[6];
-                    int q = 0;
-                    for (int i = 0; i < 6; ++i)
-                        for (int j = i; j < 6; ++j) { A[i][j] = red[q]; A[j][i] = red[q]; ++q; }
-                    for (int i = 0; i < 6; ++i) bb[i] = -red[21 + i];
-                    bool ok = ldlt_solve6(A, bb, dx);
-                    if (!ok) {
-                        status = 2; done = 1;
-                    } else {
-                        Enew = se3_exp(dx);
-                        Tcur = rigid_mul(Enew, Tcur);
-                        L.icp_T = Tcur;
-                        nrm = sqrt(((((dx[0] * dx[0] + dx[1] * dx[1]) + dx[2] * dx[2]) + dx[3] * dx[3]) + dx[4] * dx[4]) + dx[5] * dx[5]);
-                        if (nrm < L.eps) done = 1;
+                        for (int v = 0; v < NSUM; ++v) contrib[v][pi] = 0.0;
                     }
                 }
-                if (it + 1 >= L.max_iters) done = 1;
-                L.icp_E = Enew;
-                L.icp_done = done;
-                if (done) {
-                    O.pose = rigid_mul(Tcur, P.guess);
-                    O.iterations = it + 1; O.n_corr = n_corr; O.status = status; O.dx_norm = nrm;
-                }
-                __threadfence();
-                *((volatile u32*)&L.icp_release) = target;
             }
-        } else {
-            if (threadIdx.x == 0) {
-                while (*((volatile u32*)&L.icp_release) != target) { }
-                __threadfence();
+            __syncthreads();
+            if (warp < NSUM) {
+                double x = warp_butterfly(contrib[warp][lane]);
+                if (lane == 0) part[(size_t)warp * L.ng_cap + g] = x;
             }
+            __syncthreads();
+        }
+        // ---- one barrier over the lane's blocks (icp_arrive was zeroed by the previous kernel)
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&L.icp_arrive, 1u);
+            const u32 target = (u32)nblk * (u32)(it + 1);
+            while (*((volatile u32*)&L.icp_arrive) < target) { }
+            __threadfence();
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            s_done = *((volatile int*)&L.icp_done);
-            const volatile double* src = (const volatile double*)&L.icp_E;
-            double* dst = (double*)&sE;
-            for (int k = 0; k < 12; ++k) dst[k] = src[k];
+        if (warp < NSUM) {
+            double x = warp_tree_sum(part + (size_t)warp * L.ng_cap, n_groups, lane);
+            if (lane == 0) red[warp] = x;
         }
+        __syncthreads();
+        if (threadIdx.x == 0) icp_solve_step(L, P, O, red, &sE, &sT, &s_done, it, b == 0);
         __syncthreads();
         if (s_done) break;
     }
@@ -643,6 +675,9 @@ __device__ __forceinline__ u32 map_find_or_create(LaneDev& L, u64 key) {
                     return NONE;
                 }
                 VoxelBlock* B = L.blocks + id;
+                double2* rows = reinterpret_cast<double2*>(B);   // unused slots read as +inf in the NN search
+#pragma unroll
+                for (int k = 0; k < (3 * MAXP) / 2; ++k) rows[k] = make_double2(INFINITY, INFINITY);
                 B->count = 0; B->slot = slot; B->key = key;
                 atomicAdd(&L.n_vox, 1);
                 __threadfence();
@@ -831,7 +866,7 @@ __global__ void k_load_ds(LaneDev* lanes, int lane, const double* in, int n) {
 __global__ void k_load_src(LaneDev* lanes, int lane, const double* in, int n, Rigid guess) {
     LaneDev& L = lanes[lane];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) L.n_src = n;
+    if (i == 0) { L.n_src = n; L.icp_arrive = 0; }
     if (i >= n) return;
     double x = in[3 * (size_t)i], y = in[3 * (size_t)i + 1], z = in[3 * (size_t)i + 2];
     L.s0_x[i] = x; L.s0_y[i] = y; L.s0_z[i] = z;

@@ -92,6 +92,26 @@ class Odometry:
     def reset(self, lane=-1):
         self._check(self._lib.ptk_reset(self._h, lane))
 
+    # -- measurement taps ----------------------------------------------------------
+    def set_profiling(self, on=True):
+        self._check(self._lib.ptk_set_profiling(self._h, 1 if on else 0))
+
+    def get_profile(self):
+        """{kernel name: (device ms, launches)} accumulated since set_profiling()."""
+        ms = np.zeros(12)
+        n = np.zeros(12, dtype=np.int64)
+        self._check(self._lib.ptk_get_profile(self._h, addr(ms), addr(n)))
+        out = {}
+        for k in range(12):
+            name = self._lib.ptk_kernel_name(k)
+            if name is None:
+                break
+            out[name.decode()] = (float(ms[k]), int(n[k]))
+        return out
+
+    def launch_count(self):
+        return int(self._lib.ptk_launch_count(self._h))
+
     # -- the step ------------------------------------------------------------------
     def register_frame(self, frame, timestamps, initial_guess=None, lane=0, stream=0):
         """One odometry step (kiss.py:83-131).  Returns (pose 4x4, stats dict)."""

@@ -28,17 +28,28 @@ OS0_128_1024 = SensorModel("OS0-128 1024x10", 128, 1024, 45.0, -45.0)
 OS2_128_2048 = SensorModel("OS2-128 2048x10", 128, 2048, 11.25, -11.25)
 
 
+MOUNT_YPR = (0.4, 0.07, -0.05)   # fixed mounting attitude of the sensor on the platform (rad)
+
+
 def beam_directions(sensor: SensorModel) -> np.ndarray:
-    """(H, W, 3) float64 unit directions in the sensor frame; column c looks at azimuth
-    2*pi*(1 - c/W) (Ouster encoder convention), row 0 is the top beam."""
-    alt = np.deg2rad(np.linspace(sensor.fov_up_deg, sensor.fov_down_deg, sensor.H))
-    az = 2.0 * np.pi * (1.0 - np.arange(sensor.W) / sensor.W)
+    """(H, W, 3) float64 unit directions in the platform frame; column c looks at azimuth
+    2*pi*(1 - c/W) (Ouster encoder convention) plus the per-beam azimuth offset of the four
+    staggered emitter columns (Ouster beam_azimuth_angles), row 0 is the top beam; beam
+    altitudes carry a small fixed calibration irregularity; the sensor is mounted with a
+    slight tilt so that its axes are not aligned with the walls of the synthetic scenes."""
+    H, W = sensor.H, sensor.W
+    rng = np.random.default_rng(4242)
+    alt = np.deg2rad(np.linspace(sensor.fov_up_deg, sensor.fov_down_deg, H) + rng.uniform(-0.1, 0.1, H))
+    stag = np.deg2rad(np.tile([4.2, 1.4, -1.4, -4.2], H // 4 + 1)[:H] + rng.uniform(-0.05, 0.05, H))
+    az = 2.0 * np.pi * (1.0 - np.arange(W) / W)
+    A = az[None, :] + stag[:, None]
     ca, sa = np.cos(alt)[:, None], np.sin(alt)[:, None]
-    d = np.empty((sensor.H, sensor.W, 3))
-    d[..., 0] = ca * np.cos(az)[None, :]
-    d[..., 1] = ca * np.sin(az)[None, :]
-    d[..., 2] = sa * np.ones((1, sensor.W))
-    return d
+    d = np.empty((H, W, 3))
+    d[..., 0] = ca * np.cos(A)
+    d[..., 1] = ca * np.sin(A)
+    d[..., 2] = sa * np.ones((1, W))
+    R = _rot_zyx(np.float64(MOUNT_YPR[0]), np.float64(MOUNT_YPR[1]), np.float64(MOUNT_YPR[2]))
+    return d @ R.T
 
 
 @dataclass
@@ -50,13 +61,40 @@ class Scene:
     closed_top: bool = False
 
 
+def _clutter(rng, n, xlim, ylim, z0, a, b, lo=0.72, hi=1.32):
+    """n seeded boxes inside xlim x ylim that stay clear of the corridor around the ellipse
+    x = a cos, y = b sin (the LoopTrajectory path)."""
+    boxes = []
+    while len(boxes) < n:
+        cx, cy = rng.uniform(*xlim), rng.uniform(*ylim)
+        sx, sy, h = rng.uniform(0.3, 3.0), rng.uniform(0.3, 3.0), rng.uniform(0.5, 9.0)
+        pts = [(cx + dx * sx / 2, cy + dy * sy / 2) for dx in (-1, 0, 1) for dy in (-1, 0, 1)]
+        if any(lo < np.hypot(px / a, py / b) < hi for px, py in pts):
+            continue
+        boxes.append(((cx - sx / 2, cy - sy / 2, z0), (cx + sx / 2, cy + sy / 2, z0 + h)))
+    return boxes
+
+
 def quad_scene() -> Scene:
-    """'quad' 50 x 35 m courtyard with a few buildings/pillars (config 1, 2, 4)."""
-    boxes = [((8, 6, -1.5), (12, 9, 4.0)), ((-14, -9, -1.5), (-10, -5, 6.0)),
-             ((-6, 10, -1.5), (-4, 12, 3.0)), ((15, -12, -1.5), (19, -10, 5.0)),
-             ((-20, 8, -1.5), (-18, 9, 2.5)), ((2, -14, -1.5), (3, -13, 8.0)),
-             ((20, 4, -1.5), (21, 5, 8.0)), ((-2, -3, -1.5), (-1, -2, 1.0))]
+    """'quad' 50 x 35 m courtyard with buildings, pillars and clutter; the 30 x 20 m loop the
+    platform drives stays clear of every obstacle (config 1, 2, 4)."""
+    boxes = [((-3, -2, -1.5), (3, 2, 6.0)), ((-6, 3, -1.5), (-4, 5, 3.0)),
+             ((21, -14, -1.5), (24, -11, 5.0)), ((-24, 13, -1.5), (-22, 16, 2.5)),
+             ((21.5, 12, -1.5), (22.5, 13, 8.0)), ((-23, -15, -1.5), (-22, -14, 8.0))]
+    boxes += _clutter(np.random.default_rng(7), 54, (-24.0, 24.0), (-16.5, 16.5), -1.5, 15.0, 10.0)
     return Scene((-25.0, -17.5, -1.5), (25.0, 17.5, 18.0), boxes, closed_top=True)
+
+
+RELIEF_AMP = 0.04   # metres; world-fixed surface texture added along the ray
+
+
+def surface_relief(x, y, z, amp=RELIEF_AMP, xp=np):
+    """Smooth pseudo-random displacement as a function of the WORLD hit position: it gives the
+    flat synthetic surfaces the sub-voxel structure real surfaces have (without it a
+    point-to-point ICP on a sensor-fixed sampling lattice drags the estimate towards zero
+    motion).  `xp` is numpy or torch."""
+    return amp * (xp.sin(7.1 * x + 1.3 * xp.sin(3.3 * y)) * xp.sin(6.3 * y + 0.7 * z)
+                  + 0.6 * xp.sin(13.7 * z + 2.1 * x) * xp.cos(11.9 * y - 3.0 * x))
 
 
 def street_scene() -> Scene:
@@ -78,9 +116,10 @@ def street_scene() -> Scene:
 
 
 def hall_scene() -> Scene:
-    return Scene((-60.0, -40.0, -1.5), (60.0, 40.0, 20.0),
-                 [((10, 10, -1.5), (14, 14, 10.0)), ((-30, -20, -1.5), (-25, -10, 12.0)),
-                  ((-10, 25, -1.5), (0, 28, 6.0)), ((35, -30, -1.5), (40, -22, 15.0))])
+    boxes = [((-4, -4, -1.5), (4, 4, 10.0)), ((-52, -30, -1.5), (-47, -20, 12.0)),
+             ((-10, 34, -1.5), (0, 37, 6.0)), ((48, -36, -1.5), (53, -28, 15.0))]
+    boxes += _clutter(np.random.default_rng(11), 80, (-58.0, 58.0), (-38.0, 38.0), -1.5, 30.0, 20.0)
+    return Scene((-60.0, -40.0, -1.5), (60.0, 40.0, 20.0), boxes)
 
 
 # --------------------------------------------------------------------------- trajectories
@@ -203,9 +242,11 @@ class SynthSequence:
         d_world = np.einsum("wij,hwj->hwi", R, self.dirs)
         o_world = np.broadcast_to(p[None, :, :], d_world.shape)
         r = _raycast(self.scene, o_world, d_world)
+        hit = o_world + r[..., None] * d_world
         rng = np.random.default_rng([self.seed, k])
         noise = rng.normal(0.0, self.range_sigma, size=r.shape)
-        r = np.where(r > 0, np.maximum(r + noise, 0.0), 0.0)
+        rel = surface_relief(hit[..., 0], hit[..., 1], hit[..., 2])
+        r = np.where(r > 0, np.maximum(r + noise + rel, 0.0), 0.0)
         range_mm = np.rint(r * 1000.0).astype(np.uint32)
         Rm, pm = self.traj.pose(self.t0 + (k + 0.5) * s.scan_period)
         ts = np.rint(tcol * 1e9).astype(np.int64)
@@ -242,3 +283,84 @@ def make_sequence(config: str, seed=0) -> SynthSequence:
         return SynthSequence(SensorModel("tiny 32x256", 32, 256, 30.0, -30.0), quad_scene(),
                              LoopTrajectory(seed), seed)
     raise ValueError(config)
+
+
+# --------------------------------------------------------------------------- torch generator
+# Same scene/trajectory/sensor model evaluated with torch tensors so that a bench can build
+# hundreds of scans per second on the GPU it is about to measure (data plumbing only; the
+# numpy generator above stays the one the parity tests and golden fixtures use - the two agree
+# except for the noise stream, which comes from torch's generator here).
+def _raycast_torch(scene: Scene, o, d):
+    import torch
+    inf = float("inf")
+    inv = 1.0 / d
+    rmin = torch.as_tensor(scene.room_min, dtype=d.dtype, device=d.device)
+    rmax = torch.as_tensor(scene.room_max, dtype=d.dtype, device=d.device)
+    lo = (rmin - o) * inv
+    hi = (rmax - o) * inv
+    t_exit_axes = torch.maximum(lo, hi)
+    t_exit, axis = torch.min(t_exit_axes, dim=-1)
+    rng = t_exit
+    if not scene.closed_top:
+        open_top = (axis == 2) & (d[..., 2] > 0)
+        rng = torch.where(open_top, torch.full_like(rng, inf), rng)
+    for bmin, bmax in scene.boxes:
+        l2 = (torch.as_tensor(bmin, dtype=d.dtype, device=d.device) - o) * inv
+        h2 = (torch.as_tensor(bmax, dtype=d.dtype, device=d.device) - o) * inv
+        tn = torch.max(torch.minimum(l2, h2), dim=-1).values
+        tf = torch.min(torch.maximum(l2, h2), dim=-1).values
+        hit = (tn < tf) & (tn > 0) & (tn < rng)
+        rng = torch.where(hit, tn, rng)
+    return torch.where(torch.isfinite(rng), rng, torch.zeros_like(rng))
+
+
+class TorchScanGenerator:
+    """SynthSequence evaluated on a torch device.  `points(k)` returns what
+    KissICPWrapper.register_frame hands to the step (kiss.py:59-65) as device tensors."""
+
+    def __init__(self, seq: SynthSequence, device):
+        import torch
+        self.seq = seq
+        self.device = torch.device(device)
+        self.dirs = torch.as_tensor(seq.dirs, dtype=torch.float64, device=self.device)
+        W, H = seq.sensor.W, seq.sensor.H
+        self.tnorm = torch.as_tensor(np.tile(np.linspace(0, 1.0, W, endpoint=False), (H, 1)),
+                                     dtype=torch.float64, device=self.device)
+
+    def range_image(self, k: int):
+        """(range_mm (H,W) int32 tensor, ts of the last column in seconds, gt pose 4x4 ndarray)."""
+        import torch
+        seq, s = self.seq, self.seq.sensor
+        tcol = seq.t0 + (k + np.arange(s.W) / s.W) * s.scan_period
+        R, p = seq.traj.pose(tcol)
+        Rt = torch.as_tensor(R, dtype=torch.float64, device=self.device)
+        pt = torch.as_tensor(p, dtype=torch.float64, device=self.device)
+        d_world = torch.einsum("wij,hwj->hwi", Rt, self.dirs)
+        o_world = pt[None, :, :].expand_as(d_world)
+        r = _raycast_torch(seq.scene, o_world, d_world)
+        hit = o_world + r[..., None] * d_world
+        g = torch.Generator(device=self.device)
+        g.manual_seed(int(seq.seed) * 1000003 + int(k))
+        noise = torch.randn(r.shape, generator=g, dtype=torch.float64, device=self.device) * seq.range_sigma
+        rel = surface_relief(hit[..., 0], hit[..., 1], hit[..., 2], xp=torch)
+        r = torch.where(r > 0, torch.clamp(r + noise + rel, min=0.0), torch.zeros_like(r))
+        range_mm = torch.round(r * 1000.0).to(torch.int32)
+        Rm, pm = seq.traj.pose(seq.t0 + (k + 0.5) * s.scan_period)
+        ts_last = float(np.rint(tcol[-1] * 1e9)) * 1e-9
+        return range_mm, ts_last, pose_mat(Rm, pm)
+
+    def project(self, range_mm):
+        sel = range_mm != 0
+        r = range_mm.to(torch_float64()) * 0.001
+        xyz = (self.dirs * r[..., None])[sel]
+        return xyz.contiguous(), self.tnorm[sel].contiguous()
+
+    def points(self, k: int):
+        range_mm, ts_last, gt = self.range_image(k)
+        xyz, tn = self.project(range_mm)
+        return xyz, tn, ts_last, gt
+
+
+def torch_float64():
+    import torch
+    return torch.float64

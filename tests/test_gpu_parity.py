@@ -190,11 +190,18 @@ def test_register_point_cloud_bit_exact(odo, os0_seq):
     pose = register_frame(np.stack([x, y, z], 1), gm, np.eye(4), 6.0, 2.0 / 3.0)
     assert np.abs(pose - T).max() < 1e-9
     # empty map -> the guess comes back; no correspondences -> guess, status 1 (B.5)
+    # (the guess crosses the boundary as a Sophus::SE3d upstream, so it comes back re-orthonormalised)
     gm.clear()
-    assert np.array_equal(register_frame(src, gm, guess, 6.0, 0.6), guess)
-    gm.add_points(np.array([[900.0, 900.0, 900.0]]))
+    rempty = ko.VoxelHashMap(1.0, 100.0, 20)
+    pose = register_frame(src, gm, guess, 6.0, 0.6)
+    assert np.array_equal(pose, ko.register_point_cloud(src, rempty, guess, 6.0, 0.6)[0])
+    assert np.abs(pose - guess).max() < 1e-15
+    far = np.array([[900.0, 900.0, 900.0]])
+    gm.add_points(far)
+    rempty.add_points(far)
     pose, st = register_frame(src, gm, guess, 6.0, 0.6, return_stats=True)
-    assert st["status"] == 1 and st["n_corr"] == 0 and np.array_equal(pose, guess)
+    assert st["status"] == 1 and st["n_corr"] == 0
+    assert np.array_equal(pose, ko.register_point_cloud(src, rempty, guess, 6.0, 0.6)[0])
 
 
 def _run_sequence(seq, n_scans, min_range, max_range, guesses=None, max_points=140000):

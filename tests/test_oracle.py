@@ -89,11 +89,12 @@ def test_icp_recovers_known_motion(tiny_seq):
     assert np.abs(pose - T).max() < 1e-9 and st["iterations"] <= 6
     # empty map -> guess; no neighbours -> guess with status 1
     g = canon.se3_exp_mat(np.array([0.1, 0, 0, 0, 0, 0.1]))
-    assert np.array_equal(ko.register_point_cloud(src, ko.VoxelHashMap(1.0, 100.0), g, 6.0, 0.6)[0], g)
+    # (the guess enters as a Sophus::SE3d upstream: it comes back re-orthonormalised, not bit-identical)
+    assert np.abs(ko.register_point_cloud(src, ko.VoxelHashMap(1.0, 100.0), g, 6.0, 0.6)[0] - g).max() < 1e-15
     m2 = ko.VoxelHashMap(1.0, 100.0)
     m2.add_points(np.array([[900.0, 900.0, 900.0]]))
     pose, st = ko.register_point_cloud(src, m2, g, 6.0, 0.6)
-    assert st["status"] == 1 and np.array_equal(pose, g)
+    assert st["status"] == 1 and np.abs(pose - g).max() < 1e-15
 
 
 def test_gm_weight_and_jacobian_terms():
@@ -156,3 +157,16 @@ def test_sequence_tracks_ground_truth(tiny_seq):
     d = canon.rigid_mul(canon.rigid_inv(rel), w.pose)
     assert np.linalg.norm(d[:3, 3]) < 0.5 and canon.rot_angle(d[:3, :3]) < 0.05
     assert len(w.poses) == 10 and len(w._sigmas) == 10 and len(w.poses_ts) == 10
+
+
+def test_poses_stay_orthonormal_over_a_long_run(tiny_seq):
+    """Regression: registration composes poses as Sophus does (unit quaternion, renormalised on
+    every product).  With plain 3x3 products and transpose-inverses the orthonormality error of
+    the constant-velocity guess triples every scan and the odometry diverges near scan 40."""
+    w = ko.OracleKissICPWrapper()
+    for k in range(60):
+        xyz, ts, tsec, _ = tiny_seq.points(k)
+        w.register_points(xyz, ts, tsec)
+        R = w.pose[:3, :3]
+        assert np.abs(R @ R.T - np.eye(3)).max() < 1e-14, k
+    assert w.last_counts["n_vox"] < 20000 and w.last_stats["iterations"] < 200
