@@ -259,7 +259,8 @@ extern "C" int ptk_ctx_create(ptk_ctx** out, int device, const ptk_config* cfg_i
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; return bail(PTK_E_CUDA); }
     ctx->num_sms = prop.multiProcessorCount;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, ICP_THREADS, 0) != cudaSuccess || occ < 1) {
+    if (cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, ICP_THREADS, ICP_SMEM) != cudaSuccess || occ < 1) {
         ctx->err = std::string("k_icp not launchable on this device: ") + cudaGetErrorString(cudaGetLastError());
         return bail(PTK_E_CUDA);
     }
@@ -401,19 +402,21 @@ static Rigid prediction_model(const LaneHost& LH) {
 }
 
 // ---- kernel launch helpers -----------------------------------------------------------
-static int launch_icp(ptk_ctx* ctx, int l0, int cnt, cudaStream_t st) {
+// `groups_hint`: upper estimate of the 32-point source groups per lane (0 = unknown); blocks beyond
+// one per group would only add arrivals to the per-iteration barrier.
+static int launch_icp(ptk_ctx* ctx, int l0, int cnt, int groups_hint, cudaStream_t st) {
     // all blocks of a cooperative launch must be co-resident: split wide batches
     int done = 0;
     while (done < cnt) {
         int chunk = std::min(cnt - done, ctx->icp_blocks_total);
         int per = std::max(1, ctx->icp_blocks_total / chunk);
-        per = std::min(per, ctx->num_sms);
+        if (groups_hint > 0) per = std::max(1, std::min(per, groups_hint));
         LaneDev* dl = ctx->d_lanes + l0 + done;
         StepParams* dp = ctx->d_params + l0 + done;
         StepOut* dout = ctx->d_outs + l0 + done;
         void* args[] = {&dl, &dp, &dout};
         cudaError_t le = cudaSuccess;
-        LAUNCH(PS_ICP, st, le = cudaLaunchCooperativeKernel((void*)k_icp, dim3(per, chunk), dim3(ICP_THREADS), args, 0, st));
+        LAUNCH(PS_ICP, st, le = cudaLaunchCooperativeKernel((void*)k_icp, dim3(per, chunk), dim3(ICP_THREADS), args, ICP_SMEM, st));
         CK(le);
         done += chunk;
     }
@@ -508,7 +511,14 @@ static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, con
     LAUNCH(PS_COMPACT1, st, k_compact1<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
     LAUNCH(PS_COMPACT2, st, k_compact2<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
     CK(cudaGetLastError());
-    int rc = launch_icp(ctx, l0, cnt, st);
+    // source size changes slowly from scan to scan: size the ICP grid from the last one
+    int groups_hint = 0;
+    for (int k = 0; k < cnt; ++k) {
+        const LaneHost& LH = ctx->lanes[l0 + k];
+        if (!LH.have_last || LH.last_out.n_src <= 0) { groups_hint = 0; break; }
+        groups_hint = std::max(groups_hint, (int)(((long long)LH.last_out.n_src * 5 / 4 + 31) / 32) + 1);
+    }
+    int rc = launch_icp(ctx, l0, cnt, groups_hint, st);
     if (rc) return rc;
     rc = map_update_launch(ctx, l0, cnt, nmax, 1, nullptr, true, true, st);
     if (rc) return rc;
@@ -965,7 +975,7 @@ extern "C" int ptk_register_point_cloud(ptk_ctx* ctx, int lane, const double* xy
     CK(cudaMemcpyAsync(ctx->d_params + lane, &P, sizeof(StepParams), cudaMemcpyHostToDevice, st));
     LAUNCH(PS_OTHER, st, k_load_src<<<std::max(1, (n + 255) / 256), 256, 0, st>>>(ctx->d_lanes, lane, dx, n, P.guess));
     CK(cudaGetLastError());
-    rc = launch_icp(ctx, lane, 1, st);
+    rc = launch_icp(ctx, lane, 1, std::max(1, (n + 31) / 32), st);
     if (rc) return rc;
     StepOut O;
     rc = lane_counters(ctx, lane, &O, st);

@@ -27,8 +27,11 @@ constexpr int KEY_BIAS = 1 << 20;
 constexpr int TILE = 1024;                 // items per compaction tile (256 threads x 4)
 constexpr int NSUM = 17;                   // distinct normal-equation sums (16) + correspondence count
 constexpr int NRED = NSUM;
-constexpr int ICP_THREADS = 1024;
+constexpr int ICP_THREADS = 512;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
+constexpr int ICP_CHUNK = 16;              // 32-point groups whose terms one block stages in shared memory at a time
+constexpr int ICP_SRC_CAP = 1024;           // source points a block keeps in shared memory across iterations
+constexpr int ICP_SMEM = ICP_CHUNK * 32 * NSUM * 8 + 3 * ICP_SRC_CAP * 8;
 
 enum StepFlags : int { F_DESKEW = 1, F_RANGE = 2, F_SECOND = 4, F_SELECT_RANGE = 8 };
 enum ErrFlags : int { ERR_KEYRANGE = 1, ERR_POOL = 2, ERR_TABLE = 4 };
@@ -386,21 +389,44 @@ __global__ void k_clean_tables(LaneDev* lanes, int which) {
 // ------------------------------------------------------------------------------------
 // Nearest map point of (sx,sy,sz) among the 27 neighbouring voxels, one warp per query
 // (kiss-icp VoxelHashMap::GetCorrespondences).
-// Lanes 0..26 probe one voxel each (one 16 B slot load, usually a first-probe hit); the hits are
-// then scanned four voxels per round in (i,j,l) order with lanes = slots: the 12 row loads of a
-// round are independent, so a query costs ~1 + ceil(hits/4) L2 latencies.  Unused slots of a
-// block hold +inf (set when the voxel is created), so no per-voxel count is needed.  Strict '<'
-// per lane plus a lexicographic (d2, order id) warp argmin reproduce upstream's "first
-// candidate in iteration order wins ties".
-__device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double sy, double sz, int lane,
+//
+// Lanes 0..26 probe one voxel each (one 16 B slot load, usually a first-probe hit) and compute a
+// conservative lower bound of the distance from the query to that voxel's box.  The query's own
+// voxel is scanned first, then the remaining hits four per round (lanes = slots, the 12 row
+// loads of a round are independent), skipping every voxel whose box is farther than the best
+// distance so far (or than `max_d2`, beyond which a match would be rejected anyway).  A skipped
+// voxel holds only points STRICTLY farther than the current best, so the result - including
+// ties, which go to the first candidate in upstream's (i,j,l)-then-stored order through the
+// lexicographic (d2, order id) compare - is the same as scanning all 27.  Unused slots of a
+// block hold +inf (set when the voxel is created), so no per-voxel count is needed.
+__device__ __forceinline__ void nn_visit(const VoxelBlock* B, int v, int lane, int sl, double sx, double sy, double sz,
+                                         double& best, int& ord, double& bx, double& by, double& bz) {
+    double x = __ldg(&B->x[sl]), y = __ldg(&B->y[sl]), z = __ldg(&B->z[sl]);
+    double dx = x - sx, dy = y - sy, dz = z - sz;
+    double d2 = (dx * dx + dy * dy) + dz * dz;
+    int o = v * MAXP + lane;
+    if (d2 < best || (d2 == best && o < ord)) { best = d2; ord = o; bx = x; by = y; bz = z; }
+}
+
+__device__ __forceinline__ double warp_min_upper(double best) {
+    // an upper bound of the warp-wide minimum of non-negative doubles with one redux
+    u32 hi = (u32)((u64)__double_as_longlong(best) >> 32);
+    u32 mhi = __reduce_min_sync(0xffffffffu, hi);
+    return __longlong_as_double((long long)(((u64)mhi << 32) | 0xffffffffull));
+}
+
+__device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double sy, double sz, int lane, double max_d2,
                                              double& bd2, int& bord, double& tx, double& ty, double& tz) {
     const u32 FULL = 0xffffffffu;
+    const double v = L.voxel_size;
     int kx, ky, kz;
-    voxel_key(sx, sy, sz, L.voxel_size, kx, ky, kz);
+    voxel_key(sx, sy, sz, v, kx, ky, kz);
     u32 id = NONE;
+    double lb2 = INFINITY;
     if (lane < 27 && key_in_range(kx, ky, kz)) {
         int di = lane / 9 - 1, dj = (lane / 3) % 3 - 1, dk = lane % 3 - 1;
-        u64 key = pack_key(kx + di, ky + dj, kz + dk);
+        int nx = kx + di, ny = ky + dj, nz = kz + dk;
+        u64 key = pack_key(nx, ny, nz);
         u32 slot = hash_key(key) & L.m_mask;
         while (true) {
             const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2*>(L.m_slots + slot));
@@ -408,37 +434,48 @@ __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double
             if (raw.x == KEY_EMPTY) break;
             slot = (slot + 1) & L.m_mask;
         }
+        // voxel n covers [n v, (n+1) v) for n > 0, (-v, v) for n == 0 and ((n-1) v, n v] for n < 0
+        // (keys truncate toward zero); 1e-7 m of slack per axis covers every rounding involved
+        double lo, hi, ax, ay, az;
+        lo = (double)(nx > 0 ? nx : nx - 1) * v; hi = (double)(nx < 0 ? nx : nx + 1) * v;
+        ax = fmax(fmax(lo - sx, sx - hi) - 1e-7, 0.0);
+        lo = (double)(ny > 0 ? ny : ny - 1) * v; hi = (double)(ny < 0 ? ny : ny + 1) * v;
+        ay = fmax(fmax(lo - sy, sy - hi) - 1e-7, 0.0);
+        lo = (double)(nz > 0 ? nz : nz - 1) * v; hi = (double)(nz < 0 ? nz : nz + 1) * v;
+        az = fmax(fmax(lo - sz, sz - hi) - 1e-7, 0.0);
+        lb2 = ((ax * ax + ay * ay) + az * az) * (1.0 - 1e-9);
     }
-    u32 mask = __ballot_sync(FULL, id != NONE);
     double best = INFINITY, bx = 0, by = 0, bz = 0;
     int ord = 0x7fffffff;
     const int sl = lane < MAXP ? lane : 0;
-    while (mask) {
-        // up to four voxels per round; absent ones repeat the first (a repeat never wins: strict '<')
+    double bound = max_d2;
+    u32 remaining = __ballot_sync(FULL, id != NONE);
+    if (remaining & (1u << 13)) {        // the query's own voxel first: it usually holds the answer
+        const VoxelBlock* B = L.blocks + __shfl_sync(FULL, id, 13);
+        if (lane < MAXP) nn_visit(B, 13, lane, sl, sx, sy, sz, best, ord, bx, by, bz);
+        remaining &= ~(1u << 13);
+        bound = fmin(bound, warp_min_upper(best));
+    }
+    while (true) {
+        u32 mask = __ballot_sync(FULL, lb2 <= bound) & remaining;
+        if (!mask) break;
         int v0 = __ffs(mask) - 1; mask &= mask - 1;
         int v1 = v0, v2 = v0, v3 = v0;
         if (mask) { v1 = __ffs(mask) - 1; mask &= mask - 1; }
         if (mask) { v2 = __ffs(mask) - 1; mask &= mask - 1; }
-        if (mask) { v3 = __ffs(mask) - 1; mask &= mask - 1; }
+        if (mask) { v3 = __ffs(mask) - 1; }
+        remaining &= ~((1u << v0) | (1u << v1) | (1u << v2) | (1u << v3));
         const VoxelBlock* B0 = L.blocks + __shfl_sync(FULL, id, v0);
         const VoxelBlock* B1 = L.blocks + __shfl_sync(FULL, id, v1);
         const VoxelBlock* B2 = L.blocks + __shfl_sync(FULL, id, v2);
         const VoxelBlock* B3 = L.blocks + __shfl_sync(FULL, id, v3);
         if (lane < MAXP) {
-            double x0 = __ldg(&B0->x[sl]), y0 = __ldg(&B0->y[sl]), z0 = __ldg(&B0->z[sl]);
-            double x1 = __ldg(&B1->x[sl]), y1 = __ldg(&B1->y[sl]), z1 = __ldg(&B1->z[sl]);
-            double x2 = __ldg(&B2->x[sl]), y2 = __ldg(&B2->y[sl]), z2 = __ldg(&B2->z[sl]);
-            double x3 = __ldg(&B3->x[sl]), y3 = __ldg(&B3->y[sl]), z3 = __ldg(&B3->z[sl]);
-            double dx, dy, dz, d2;
-            dx = x0 - sx; dy = y0 - sy; dz = z0 - sz; d2 = (dx * dx + dy * dy) + dz * dz;
-            if (d2 < best) { best = d2; ord = v0 * MAXP + lane; bx = x0; by = y0; bz = z0; }
-            dx = x1 - sx; dy = y1 - sy; dz = z1 - sz; d2 = (dx * dx + dy * dy) + dz * dz;
-            if (d2 < best) { best = d2; ord = v1 * MAXP + lane; bx = x1; by = y1; bz = z1; }
-            dx = x2 - sx; dy = y2 - sy; dz = z2 - sz; d2 = (dx * dx + dy * dy) + dz * dz;
-            if (d2 < best) { best = d2; ord = v2 * MAXP + lane; bx = x2; by = y2; bz = z2; }
-            dx = x3 - sx; dy = y3 - sy; dz = z3 - sz; d2 = (dx * dx + dy * dy) + dz * dz;
-            if (d2 < best) { best = d2; ord = v3 * MAXP + lane; bx = x3; by = y3; bz = z3; }
+            nn_visit(B0, v0, lane, sl, sx, sy, sz, best, ord, bx, by, bz);
+            if (v1 != v0) nn_visit(B1, v1, lane, sl, sx, sy, sz, best, ord, bx, by, bz);
+            if (v2 != v0) nn_visit(B2, v2, lane, sl, sx, sy, sz, best, ord, bx, by, bz);
+            if (v3 != v0) nn_visit(B3, v3, lane, sl, sx, sy, sz, best, ord, bx, by, bz);
         }
+        bound = fmin(bound, warp_min_upper(best));
     }
     // lexicographic (d2, ord) argmin: d2 >= 0, so its bit pattern orders like the value
     const u64 bits = (u64)__double_as_longlong(best);
@@ -491,10 +528,20 @@ __device__ __forceinline__ double warp_tree_sum(const double* p, int n, int lane
     if (m == 1) return warp_butterfly(lane < n ? __ldcg(p + lane) : 0.0);
     if (m <= 32) {
         double reg = 0.0;
-        for (int j = 0; j < m; ++j) {
-            int idx = j * 32 + lane;
-            double x = warp_butterfly(idx < n ? __ldcg(p + idx) : 0.0);
-            if (lane == j) reg = x;
+        for (int j = 0; j < m; j += 4) {      // m is 2 or a multiple of 4; loads of a quad go out together
+            int i0 = j * 32 + lane;
+            double x0 = i0 < n ? __ldcg(p + i0) : 0.0;
+            double x1 = i0 + 32 < n ? __ldcg(p + i0 + 32) : 0.0;
+            double x2 = (m > 2 && i0 + 64 < n) ? __ldcg(p + i0 + 64) : 0.0;
+            double x3 = (m > 2 && i0 + 96 < n) ? __ldcg(p + i0 + 96) : 0.0;
+            x0 = warp_butterfly(x0); x1 = warp_butterfly(x1);
+            if (lane == j) reg = x0;
+            if (lane == j + 1) reg = x1;
+            if (m > 2) {
+                x2 = warp_butterfly(x2); x3 = warp_butterfly(x3);
+                if (lane == j + 2) reg = x2;
+                if (lane == j + 3) reg = x3;
+            }
         }
         return warp_butterfly(reg);
     }
@@ -516,32 +563,117 @@ __device__ __forceinline__ double warp_tree_sum(const double* p, int n, int lane
     return ((U[0] + U[1]) + (U[2] + U[3])) + ((U[4] + U[5]) + (U[6] + U[7]));
 }
 
-// One thread per block: expand the 17 sums into the 6x6 system, solve, update T_icp, decide
-// termination (kiss-icp RegisterFrame loop body after BuildLinearSystem).  Kept out of line so
-// its registers and stack do not weigh on the search loop.
-__device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, StepOut& O, const double* red,
-                                            Rigid* sE, SE3q* sT, int* s_done, int it, bool writer) {
+// Where the 17 sums go in the symmetric 6x6 matrix (row-major, both triangles): +k+1 = +red[k],
+// -(k+1) = -red[k], 0 = structural zero.  J = [I | -hat(s)].
+__constant__ signed char kJtJMap[36] = {
+    1, 0, 0, 0, 4, -3,
+    0, 1, 0, -4, 0, 2,
+    0, 0, 1, 3, -2, 0,
+    0, -4, 3, 5, 6, 7,
+    4, 0, -2, 6, 8, 9,
+    -3, 2, 0, 7, 9, 10};
+// lower-triangle pairs (a >= b) in row-major order: the trailing-block update of step k uses the
+// first m(m+1)/2 of them, m = 5 - k
+__constant__ unsigned char kPairA[15] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4};
+__constant__ unsigned char kPairB[15] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4};
+
+struct SolveSmem {
+    double A[36];
+    double y[6];
+    double dx[6];
+};
+
+// Warp 0 of every block: expand the 17 sums into the 6x6 system, solve it, update T_icp, decide
+// termination (kiss-icp RegisterFrame loop body after BuildLinearSystem).  The LDL^T with
+// diagonal pivoting is ptk_canon.cuh's ldlt_solve6 operation for operation, but the matrix sits
+// in shared memory, rows/columns are permuted virtually (a packed permutation instead of data
+// movement) and the independent divisions / trailing updates of a step run on separate lanes.
+__device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, StepOut& O, const double* red, SolveSmem* S,
+                                            Rigid* sE, SE3q* sT, int* s_done, int it, bool writer, int lane) {
+    const u32 FULL = 0xffffffffu;
     const int n_corr = (int)red[16];
     int done = 0, status = 0;
     double nrm = 0.0;
-    Rigid Enew = rigid_identity();
+    bool ok = false;
     if (n_corr == 0) {
         status = 1; done = 1;            // B.5
     } else {
-        const double w = red[0], wsx = red[1], wsy = red[2], wsz = red[3];
-        double A[6][6], bb[6], dx[6];
-        A[0][0] = w;   A[0][1] = 0.0; A[0][2] = 0.0; A[0][3] = 0.0;  A[0][4] = wsz;  A[0][5] = -wsy;
-        A[1][1] = w;   A[1][2] = 0.0; A[1][3] = -wsz; A[1][4] = 0.0; A[1][5] = wsx;
-        A[2][2] = w;   A[2][3] = wsy; A[2][4] = -wsx; A[2][5] = 0.0;
-        A[3][3] = red[4]; A[3][4] = red[5]; A[3][5] = red[6];
-        A[4][4] = red[7]; A[4][5] = red[8];
-        A[5][5] = red[9];
-        for (int i = 1; i < 6; ++i)
-            for (int j = 0; j < i; ++j) A[i][j] = A[j][i];
-        for (int i = 0; i < 6; ++i) bb[i] = -red[10 + i];
-        if (!ldlt_solve6(A, bb, dx)) {
-            status = 2; done = 1;
-        } else {
+        for (int e = lane; e < 36; e += 32) {
+            int m = kJtJMap[e];
+            S->A[e] = m > 0 ? red[m - 1] : (m < 0 ? -red[-m - 1] : 0.0);
+        }
+        if (lane < 6) S->y[lane] = -red[10 + lane];
+        __syncwarp();
+        u32 perm = 0;                    // virtual index i -> physical index, 3 bits each
+#pragma unroll
+        for (int i = 0; i < 6; ++i) perm |= (u32)i << (3 * i);
+#define PERM(i) ((int)((perm >> (3 * (i))) & 7u))
+        ok = true;
+        for (int k = 0; k < 6; ++k) {
+            int p = k;
+            double best = fabs(S->A[PERM(k) * 7]);
+            for (int i = k + 1; i < 6; ++i) {
+                double v = fabs(S->A[PERM(i) * 7]);
+                if (v > best) { best = v; p = i; }
+            }
+            if (p != k) {
+                u32 a = (perm >> (3 * k)) & 7u, c = (perm >> (3 * p)) & 7u;
+                perm = (perm & ~((7u << (3 * k)) | (7u << (3 * p)))) | (c << (3 * k)) | (a << (3 * p));
+            }
+            const int pk = PERM(k);
+            const double d = S->A[pk * 7];
+            if (d == 0.0 || d != d) { ok = false; break; }
+            if (lane < 5 - k) {
+                int pi = PERM(k + 1 + lane);
+                S->A[pi * 6 + pk] = S->A[pi * 6 + pk] / d;
+            }
+            __syncwarp();
+            const int m = 5 - k;
+            if (lane < (m * (m + 1)) / 2) {
+                int pi = PERM(k + 1 + kPairA[lane]), pj = PERM(k + 1 + kPairB[lane]);
+                double ljd = S->A[pj * 6 + pk] * d;
+                double v = S->A[pi * 6 + pj] - S->A[pi * 6 + pk] * ljd;
+                S->A[pi * 6 + pj] = v;
+                S->A[pj * 6 + pi] = v;
+            }
+            __syncwarp();
+        }
+        if (ok && lane == 0) {
+            double y[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) y[i] = S->y[PERM(i)];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double acc = y[i];
+#pragma unroll
+                for (int j = 0; j < i; ++j) acc = acc - S->A[PERM(i) * 6 + PERM(j)] * y[j];
+                y[i] = acc;
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) y[i] = y[i] / S->A[PERM(i) * 7];
+#pragma unroll
+            for (int i = 5; i >= 0; --i) {
+                double acc = y[i];
+#pragma unroll
+                for (int j = i + 1; j < 6; ++j) acc = acc - S->A[PERM(j) * 6 + PERM(i)] * y[j];
+                y[i] = acc;
+            }
+            bool fin = true;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                S->dx[PERM(i)] = y[i];
+                if (!(fabs(y[i]) <= 1.7976931348623157e308)) fin = false;
+            }
+            ok = fin;
+        }
+#undef PERM
+        ok = __shfl_sync(FULL, ok ? 1 : 0, 0) != 0;
+        if (!ok) { status = 2; done = 1; }
+    }
+    if (lane == 0) {
+        Rigid Enew = rigid_identity();
+        if (ok) {
+            const double* dx = S->dx;
             SE3q Eq;
             Enew = se3_exp_q(dx, &Eq.q);
             Eq.t[0] = Enew.t[0]; Eq.t[1] = Enew.t[1]; Eq.t[2] = Enew.t[2];
@@ -549,24 +681,26 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
             nrm = sqrt(((((dx[0] * dx[0] + dx[1] * dx[1]) + dx[2] * dx[2]) + dx[3] * dx[3]) + dx[4] * dx[4]) + dx[5] * dx[5]);
             if (nrm < L.eps) done = 1;
         }
-    }
-    if (it + 1 >= L.max_iters) done = 1;
-    *sE = Enew;
-    *s_done = done;
-    if (done && writer) {
-        O.pose = se3q_matrix(se3q_mul(*sT, se3q_from_rigid(P.guess)));
-        O.iterations = it + 1; O.n_corr = n_corr; O.status = status; O.dx_norm = nrm;
+        if (it + 1 >= L.max_iters) done = 1;
+        *sE = Enew;
+        *s_done = done;
+        if (done && writer) {
+            O.pose = se3q_matrix(se3q_mul(*sT, se3q_from_rigid(P.guess)));
+            O.iterations = it + 1; O.n_corr = n_corr; O.status = status; O.dx_norm = nrm;
+        }
     }
 }
 
 // K4: the whole ICP loop (kiss-icp RegisterFrame) in one persistent cooperative kernel.
-// grid = (blocks per lane, lanes), 1024 threads.  Per iteration a block takes 32-point groups:
-// one warp per point (transform by the last increment, NN search), lane 0 leaves the point's 17
-// terms in shared memory, 17 warps butterfly them into the group's partial sums.  A counter
+// grid = (blocks per lane, lanes), ICP_THREADS threads, two blocks per SM (normally of different
+// lanes, so one lane's barrier wait overlaps another lane's search).  Per iteration a block takes
+// its 32-point groups in chunks of ICP_CHUNK: one warp per point (transform by the last
+// increment, NN search), lane 0 leaves the point's 17 terms in shared memory; after one
+// __syncthreads the warps butterfly (group, term) pairs into the groups' partial sums.  A counter
 // barrier over the lane's blocks follows; after it EVERY block reduces the group partials with
 // the same fixed tree, solves the 6x6 system and updates its copy of T_icp (identical code,
 // identical bits), so one grid-wide hop per iteration is all the synchronisation there is.
-__global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs) {
+__global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs) {
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
     StepOut& O = outs[blockIdx.y];
@@ -574,10 +708,14 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(LaneDev* lanes, const St
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_src = L.n_src;
 
-    __shared__ double contrib[NSUM][33];
+    extern __shared__ double contrib[];          // [ICP_CHUNK * 32 points][NSUM], then the block's source points
+    double* const ssx = contrib + ICP_CHUNK * 32 * NSUM;
+    double* const ssy = ssx + ICP_SRC_CAP;
+    double* const ssz = ssy + ICP_SRC_CAP;
     __shared__ double red[NSUM];
     __shared__ Rigid sE;
     __shared__ SE3q sT;
+    __shared__ SolveSmem sS;
     __shared__ int s_done;
 
     if (L.n_vox == 0) {   // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
@@ -588,51 +726,66 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(LaneDev* lanes, const St
         return;
     }
     const int n_groups = (n_src + 31) >> 5;
+    // contiguous range of groups of this block
+    const int gper = (n_groups + nblk - 1) / nblk;
+    const int g_begin = min(b * gper, n_groups), g_end = min(g_begin + gper, n_groups);
     const double max_corr = P.max_corr, kern = P.kernel;
+    const double max_d2 = (max_corr * max_corr) * (1.0 + 1e-9);   // farther candidates are rejected anyway
+    // the moving copy of this block's source points lives in shared memory when it fits
+    const bool src_in_smem = (g_end - g_begin) * 32 <= ICP_SRC_CAP;
     if (threadIdx.x == 0) sT = se3q_identity();
 
     for (int it = 0;; ++it) {
         double* part = (it & 1) ? L.part_b : L.part_a;
-        for (int g = b; g < n_groups; g += nblk) {
-            for (int pi = warp; pi < 32; pi += ICP_WARPS) {
-                const int p = g * 32 + pi;
+        for (int g0 = g_begin; g0 < g_end; g0 += ICP_CHUNK) {
+            const int gc = min(ICP_CHUNK, g_end - g0);
+            if (g0 != g_begin) __syncthreads();           // previous chunk's butterflies are done
+            for (int q = warp; q < gc * 32; q += ICP_WARPS) {
+                const int p = g0 * 32 + q;
                 bool acc = false;
                 double sx = 0, sy = 0, sz = 0, tx = 0, ty = 0, tz = 0;
                 int ord = -1;
                 if (p < n_src) {
-                    sx = __ldcg(L.s_x + p); sy = __ldcg(L.s_y + p); sz = __ldcg(L.s_z + p);
+                    const int sp = (g0 - g_begin) * 32 + q;
+                    if (it == 0 || !src_in_smem) {
+                        sx = __ldcg(L.s_x + p); sy = __ldcg(L.s_y + p); sz = __ldcg(L.s_z + p);
+                    } else {
+                        sx = ssx[sp]; sy = ssy[sp]; sz = ssz[sp];
+                    }
                     if (it > 0) {
                         double xo, yo, zo;
                         rigid_apply(sE, sx, sy, sz, xo, yo, zo);
                         sx = xo; sy = yo; sz = zo;
-                        if (lane == 0) { L.s_x[p] = sx; L.s_y[p] = sy; L.s_z[p] = sz; }
+                    }
+                    if (lane == 0) {
+                        if (src_in_smem) { ssx[sp] = sx; ssy[sp] = sy; ssz[sp] = sz; }
+                        else if (it > 0) { L.s_x[p] = sx; L.s_y[p] = sy; L.s_z[p] = sz; }
                     }
                     double d2;
-                    bool found = warp_nearest(L, sx, sy, sz, lane, d2, ord, tx, ty, tz);
+                    bool found = warp_nearest(L, sx, sy, sz, lane, max_d2, d2, ord, tx, ty, tz);
                     acc = found && (sqrt(d2) < max_corr);
                     if (lane == 0 && it < L.trace_iters) L.trace[(size_t)it * L.cap_points + p] = acc ? ord : -1;
                 }
                 if (lane == 0) {
+                    double* c = contrib + (size_t)q * NSUM;
                     if (acc) {
-                        double c[16];
                         lin_terms(sx, sy, sz, tx, ty, tz, kern, c);
-#pragma unroll
-                        for (int v = 0; v < 16; ++v) contrib[v][pi] = c[v];
-                        contrib[16][pi] = 1.0;
+                        c[16] = 1.0;
                     } else {
 #pragma unroll
-                        for (int v = 0; v < NSUM; ++v) contrib[v][pi] = 0.0;
+                        for (int v = 0; v < NSUM; ++v) c[v] = 0.0;
                     }
                 }
             }
             __syncthreads();
-            if (warp < NSUM) {
-                double x = warp_butterfly(contrib[warp][lane]);
-                if (lane == 0) part[(size_t)warp * L.ng_cap + g] = x;
+            for (int task = warp; task < gc * NSUM; task += ICP_WARPS) {
+                const int c = task / NSUM, v = task - c * NSUM;
+                double x = warp_butterfly(contrib[(size_t)(c * 32 + lane) * NSUM + v]);
+                if (lane == 0) part[(size_t)v * L.ng_cap + g0 + c] = x;
             }
-            __syncthreads();
         }
         // ---- one barrier over the lane's blocks (icp_arrive was zeroed by the previous kernel)
+        __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(&L.icp_arrive, 1u);
@@ -641,12 +794,12 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(LaneDev* lanes, const St
             __threadfence();
         }
         __syncthreads();
-        if (warp < NSUM) {
-            double x = warp_tree_sum(part + (size_t)warp * L.ng_cap, n_groups, lane);
-            if (lane == 0) red[warp] = x;
+        for (int v = warp; v < NSUM; v += ICP_WARPS) {
+            double x = warp_tree_sum(part + (size_t)v * L.ng_cap, n_groups, lane);
+            if (lane == 0) red[v] = x;
         }
         __syncthreads();
-        if (threadIdx.x == 0) icp_solve_step(L, P, O, red, &sE, &sT, &s_done, it, b == 0);
+        if (warp == 0) icp_solve_step(L, P, O, red, &sS, &sE, &sT, &s_done, it, b == 0, lane);
         __syncthreads();
         if (s_done) break;
     }
@@ -885,7 +1038,7 @@ __global__ void k_correspondences(LaneDev* lanes, int lane_id, const double* q, 
     double sx = q[3 * (size_t)w], sy = q[3 * (size_t)w + 1], sz = q[3 * (size_t)w + 2];
     double d2, tx, ty, tz;
     int ord;
-    bool found = L.n_vox > 0 && warp_nearest(L, sx, sy, sz, lane, d2, ord, tx, ty, tz);
+    bool found = L.n_vox > 0 && warp_nearest(L, sx, sy, sz, lane, (max_dist * max_dist) * (1.0 + 1e-9), d2, ord, tx, ty, tz);
     bool acc = found && (sqrt(d2) < max_dist);
     if (lane == 0) {
         out_order[w] = acc ? ord : -1;
