@@ -305,6 +305,11 @@ def run_ptk(args):
     out["counters"] = {k: last[k] for k in ("n_in", "n_range", "n_ds", "n_src", "n_voxels", "map_points",
                                              "iterations", "n_corr")}
     out["counters"]["mean_icp_iterations"] = float(np.mean([st["iterations"] for ss in stats_acc for st in ss]))
+    queries = sum(st["iterations"] * st["n_src"] for ss in stats_acc for st in ss)
+    searches = sum(st["icp_searches"] for ss in stats_acc for st in ss)
+    out["icp"] = {"nn_queries": int(queries), "full_searches": int(searches),
+                  "cache_hit_rate": 1.0 - searches / max(queries, 1),
+                  "block0_phase_cycles_last_scan": odo.icp_phases(0)}
 
     if rank == 0:
         time.sleep(0.2)

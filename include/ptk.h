@@ -78,7 +78,8 @@ typedef struct ptk_stats {
     double err_dt;       /* |t| of inv(guess) @ pose (kiss.py:118) */
     double err_drot;     /* |rotvec| of inv(guess) @ pose (kiss.py:119-120) */
     int map_points;      /* points in the local map after the update */
-    int reserved;
+    int icp_searches;    /* full 27-voxel searches run (the rest of n_src * iterations hit the
+                            correspondence cache) */
 } ptk_stats;
 
 void ptk_default_config(ptk_config* cfg);
@@ -174,6 +175,9 @@ int ptk_get_trace(ptk_ctx* ctx, int lane, int* out_order, int capacity_iters, in
 int ptk_set_profiling(ptk_ctx* ctx, int on);
 int ptk_get_profile(ptk_ctx* ctx, double* ms /* PTK_PROF_SLOTS */, long long* launches /* PTK_PROF_SLOTS */);
 const char* ptk_kernel_name(int slot);   /* NULL past the last used slot */
+/* clock64 cycles block 0 of the last step's ICP kernel spent per phase: cache pass, searches,
+ * sums, barrier wait, tree reduction, solve */
+int ptk_get_icp_phases(const ptk_ctx* ctx, int lane, long long* cycles6);
 long long ptk_launch_count(const ptk_ctx* ctx);
 
 /* pinned host memory for callers that want fast H2D of scans */

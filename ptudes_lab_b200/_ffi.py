@@ -30,10 +30,10 @@ class PtkStats(C.Structure):
     _fields_ = [("status", C.c_int), ("n_in", C.c_int), ("n_range", C.c_int), ("n_ds", C.c_int),
                 ("n_src", C.c_int), ("n_voxels", C.c_int), ("iterations", C.c_int), ("n_corr", C.c_int),
                 ("dx_norm", C.c_double), ("sigma", C.c_double), ("err_dt", C.c_double),
-                ("err_drot", C.c_double), ("map_points", C.c_int), ("reserved", C.c_int)]
+                ("err_drot", C.c_double), ("map_points", C.c_int), ("icp_searches", C.c_int)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 # every symbol include/ptk.h declares: name -> (restype, argtypes)
@@ -76,6 +76,7 @@ SYMBOLS = {
     "ptk_get_profile": (C.c_int, [_P, _D, _I]),
     "ptk_kernel_name": (C.c_char_p, [C.c_int]),
     "ptk_launch_count": (C.c_longlong, [_P]),
+    "ptk_get_icp_phases": (C.c_int, [_P, C.c_int, _I]),
     "ptk_host_alloc": (C.c_int, [C.POINTER(_P), C.c_ulonglong]),
     "ptk_host_free": (C.c_int, [_P]),
 }

@@ -5,7 +5,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(CSRC, "libptk.so")
+# PTK_LIB_SUFFIX / PTK_NVCC_EXTRA: build and load a tuning variant next to the default library
+# (e.g. PTK_LIB_SUFFIX=_t256 PTK_NVCC_EXTRA="-DPTK_ICP_THREADS=256 -DPTK_ICP_MINBLOCKS=3")
+LIB = os.path.join(CSRC, "libptk%s.so" % os.environ.get("PTK_LIB_SUFFIX", ""))
 SOURCES = [os.path.join(CSRC, "ptk.cu")]
 HEADERS = [os.path.join(CSRC, "ptk_device.cuh"), os.path.join(CSRC, "ptk_canon.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "ptk.h")]
@@ -29,7 +31,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra = os.environ.get("PTK_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -217,6 +217,8 @@ static int lane_alloc(ptk_ctx* ctx, LaneHost& LH, bool scratch) {
     CK(dalloc(A, &d.freelist, (size_t)d.pool_cap, 0));
     CK(dalloc(A, &d.part_a, (size_t)NRED * d.ng_cap, 0));
     CK(dalloc(A, &d.part_b, (size_t)NRED * d.ng_cap, 0));
+    CK(dalloc(A, &d.c_tx, N)); CK(dalloc(A, &d.c_ty, N)); CK(dalloc(A, &d.c_tz, N)); CK(dalloc(A, &d.c_slack, N));
+    CK(dalloc(A, &d.c_key, N)); CK(dalloc(A, &d.c_ord, N));
     CK(dalloc(A, &d.trace, (size_t)std::max(d.trace_iters, 1) * N, 0xFF));
     CK(dalloc(A, &LH.in_xyz, N * 3));
     CK(dalloc(A, &LH.in_ts, N));
@@ -329,7 +331,7 @@ static int lane_reset_device(ptk_ctx* ctx, int l, cudaStream_t st, bool tables) 
     LaneDev fresh = d;
     fresh.n_range = fresh.n_ds = fresh.n_src = 0;
     fresh.free_top = fresh.bump = fresh.n_vox = fresh.n_tomb = fresh.map_points = 0;
-    fresh.icp_arrive = 0; fresh.icp_done = 0; fresh.err = 0;
+    fresh.icp_arrive = 0; fresh.icp_done = 0; fresh.err = 0; fresh.icp_searches = 0;
     // tickets / release epochs keep counting on the host side; mirror them
     fresh.ticket1 = LH.tbase1; fresh.ticket2 = LH.tbase2; fresh.icp_release = LH.release_base;
     CK(cudaMemcpyAsync(ctx->d_lanes + l, &fresh, sizeof(LaneDev), cudaMemcpyHostToDevice, st));
@@ -553,6 +555,7 @@ static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, con
             S.status = O.status; S.n_in = P.n; S.n_range = O.n_range; S.n_ds = O.n_ds; S.n_src = O.n_src;
             S.n_voxels = O.n_vox; S.iterations = O.iterations; S.n_corr = O.n_corr; S.dx_norm = O.dx_norm;
             S.sigma = sigmas[k]; S.err_dt = dt; S.err_drot = fabs(theta); S.map_points = O.map_points;
+            S.icp_searches = O.icp_searches;
         }
         if (O.status == 2 && !ret) ret = fail(ctx, PTK_E_NUMERIC, "singular normal equations in ICP");
         int rb = maybe_rebuild(ctx, l, O, st);
@@ -989,8 +992,17 @@ extern "C" int ptk_register_point_cloud(ptk_ctx* ctx, int lane, const double* xy
         memset(stats, 0, sizeof(*stats));
         stats->status = O.status; stats->n_in = n; stats->n_src = n; stats->iterations = O.iterations;
         stats->n_corr = O.n_corr; stats->dx_norm = O.dx_norm; stats->n_voxels = O.n_vox; stats->map_points = O.map_points;
+        stats->icp_searches = O.icp_searches;
     }
     if (O.status == 2) return fail(ctx, PTK_E_NUMERIC, "singular normal equations in ICP");
+    return PTK_OK;
+}
+
+extern "C" int ptk_get_icp_phases(const ptk_ctx* ctx, int lane, long long* cycles6) {
+    if (!ctx || lane < 0 || lane >= ctx->B || !cycles6) return PTK_E_ARG;
+    const LaneHost& LH = ctx->lanes[lane];
+    if (!LH.have_last) return PTK_E_STATE;
+    for (int k = 0; k < 6; ++k) cycles6[k] = LH.last_out.icp_cyc[k];
     return PTK_OK;
 }
 

@@ -27,11 +27,17 @@ constexpr int KEY_BIAS = 1 << 20;
 constexpr int TILE = 1024;                 // items per compaction tile (256 threads x 4)
 constexpr int NSUM = 17;                   // distinct normal-equation sums (16) + correspondence count
 constexpr int NRED = NSUM;
-constexpr int ICP_THREADS = 512;
+#ifndef PTK_ICP_THREADS
+#define PTK_ICP_THREADS 512
+#endif
+#ifndef PTK_ICP_MINBLOCKS
+#define PTK_ICP_MINBLOCKS 2
+#endif
+constexpr int ICP_THREADS = PTK_ICP_THREADS;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
-constexpr int ICP_CHUNK = 16;              // 32-point groups whose terms one block stages in shared memory at a time
-constexpr int ICP_SRC_CAP = 1024;           // source points a block keeps in shared memory across iterations
-constexpr int ICP_SMEM = ICP_CHUNK * 32 * NSUM * 8 + 3 * ICP_SRC_CAP * 8;
+constexpr int ICP_CHUNK = ICP_WARPS;        // 32-point groups a block handles at a time: one point per thread
+constexpr int ICP_SRC_CAP = 1024;           // source points (+ their cache entries) a block keeps in shared memory
+constexpr int ICP_SMEM = ICP_SRC_CAP * (3 * 8 + 4 * 8 + 8 + 4);
 
 enum StepFlags : int { F_DESKEW = 1, F_RANGE = 2, F_SECOND = 4, F_SELECT_RANGE = 8 };
 enum ErrFlags : int { ERR_KEYRANGE = 1, ERR_POOL = 2, ERR_TABLE = 4 };
@@ -77,7 +83,8 @@ struct StepParams {
 struct StepOut {
     Rigid pose;
     double dx_norm;
-    int status, n_range, n_ds, n_src, n_vox, n_tomb, iterations, n_corr, map_points, err, bump, pad;
+    int status, n_range, n_ds, n_src, n_vox, n_tomb, iterations, n_corr, map_points, err, bump, icp_searches;
+    long long icp_cyc[6];      // block 0's clock64 spent in: cache pass, searches, sums, barrier, tree, solve
 };
 
 // Per-sequence ("lane") device state.
@@ -106,6 +113,8 @@ struct LaneDev {
     u32* freelist;
     // icp
     double* part_a; double* part_b;      // [NRED][ng_cap] partial sums (ping-pong)
+    double *c_tx, *c_ty, *c_tz, *c_slack; // correspondence cache of blocks too wide for shared memory
+    u64* c_key; int* c_ord;
     int* trace;                          // [trace_iters][cap_points]
     // dynamic state
     int n_range, n_ds, n_src;
@@ -113,6 +122,7 @@ struct LaneDev {
     u32 ticket1, ticket2;
     u32 icp_arrive; u32 icp_release;
     int icp_done, err;
+    int icp_searches;
     Rigid icp_E, icp_T;
 };
 
@@ -400,12 +410,13 @@ __global__ void k_clean_tables(LaneDev* lanes, int which) {
 // lexicographic (d2, order id) compare - is the same as scanning all 27.  Unused slots of a
 // block hold +inf (set when the voxel is created), so no per-voxel count is needed.
 __device__ __forceinline__ void nn_visit(const VoxelBlock* B, int v, int lane, int sl, double sx, double sy, double sz,
-                                         double& best, int& ord, double& bx, double& by, double& bz) {
+                                         double& best, double& sec, int& ord, double& bx, double& by, double& bz) {
     double x = __ldg(&B->x[sl]), y = __ldg(&B->y[sl]), z = __ldg(&B->z[sl]);
     double dx = x - sx, dy = y - sy, dz = z - sz;
     double d2 = (dx * dx + dy * dy) + dz * dz;
     int o = v * MAXP + lane;
-    if (d2 < best || (d2 == best && o < ord)) { best = d2; ord = o; bx = x; by = y; bz = z; }
+    if (d2 < best || (d2 == best && o < ord)) { sec = best; best = d2; ord = o; bx = x; by = y; bz = z; }
+    else sec = fmin(sec, d2);
 }
 
 __device__ __forceinline__ double warp_min_upper(double best) {
@@ -415,8 +426,14 @@ __device__ __forceinline__ double warp_min_upper(double best) {
     return __longlong_as_double((long long)(((u64)mhi << 32) | 0xffffffffull));
 }
 
+// `slack` (out): how far the query may move, staying in its voxel, before the answer can change:
+// half the gap between the nearest candidate and a lower bound of the distance to every other
+// candidate of the 27 voxels (the runner-up among the visited points, the box distance of every
+// voxel the search skipped), minus a margin far above any rounding involved.  While the accumulated
+// motion stays below it, a full search would return the same map point (strictly nearest, so no
+// tie rule involved) - k_icp uses that to skip the search (see there).  Negative = never skip.
 __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double sy, double sz, int lane, double max_d2,
-                                             double& bd2, int& bord, double& tx, double& ty, double& tz) {
+                                             double& bd2, int& bord, double& tx, double& ty, double& tz, double& slack) {
     const u32 FULL = 0xffffffffu;
     const double v = L.voxel_size;
     int kx, ky, kz;
@@ -445,14 +462,14 @@ __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double
         az = fmax(fmax(lo - sz, sz - hi) - 1e-7, 0.0);
         lb2 = ((ax * ax + ay * ay) + az * az) * (1.0 - 1e-9);
     }
-    double best = INFINITY, bx = 0, by = 0, bz = 0;
+    double best = INFINITY, sec = INFINITY, bx = 0, by = 0, bz = 0;
     int ord = 0x7fffffff;
     const int sl = lane < MAXP ? lane : 0;
     double bound = max_d2;
     u32 remaining = __ballot_sync(FULL, id != NONE);
     if (remaining & (1u << 13)) {        // the query's own voxel first: it usually holds the answer
         const VoxelBlock* B = L.blocks + __shfl_sync(FULL, id, 13);
-        if (lane < MAXP) nn_visit(B, 13, lane, sl, sx, sy, sz, best, ord, bx, by, bz);
+        if (lane < MAXP) nn_visit(B, 13, lane, sl, sx, sy, sz, best, sec, ord, bx, by, bz);
         remaining &= ~(1u << 13);
         bound = fmin(bound, warp_min_upper(best));
     }
@@ -470,10 +487,10 @@ __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double
         const VoxelBlock* B2 = L.blocks + __shfl_sync(FULL, id, v2);
         const VoxelBlock* B3 = L.blocks + __shfl_sync(FULL, id, v3);
         if (lane < MAXP) {
-            nn_visit(B0, v0, lane, sl, sx, sy, sz, best, ord, bx, by, bz);
-            if (v1 != v0) nn_visit(B1, v1, lane, sl, sx, sy, sz, best, ord, bx, by, bz);
-            if (v2 != v0) nn_visit(B2, v2, lane, sl, sx, sy, sz, best, ord, bx, by, bz);
-            if (v3 != v0) nn_visit(B3, v3, lane, sl, sx, sy, sz, best, ord, bx, by, bz);
+            nn_visit(B0, v0, lane, sl, sx, sy, sz, best, sec, ord, bx, by, bz);
+            if (v1 != v0) nn_visit(B1, v1, lane, sl, sx, sy, sz, best, sec, ord, bx, by, bz);
+            if (v2 != v0) nn_visit(B2, v2, lane, sl, sx, sy, sz, best, sec, ord, bx, by, bz);
+            if (v3 != v0) nn_visit(B3, v3, lane, sl, sx, sy, sz, best, sec, ord, bx, by, bz);
         }
         bound = fmin(bound, warp_min_upper(best));
     }
@@ -491,6 +508,12 @@ __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double
     tz = __shfl_sync(FULL, bz, owner);
     bd2 = __longlong_as_double((long long)(((u64)mhi << 32) | (u64)mlo));
     bord = (int)mord;
+    // lower bound of the squared distance to every candidate but the winner
+    double other = (found && lane == owner) ? sec : best;
+    if ((remaining >> lane) & 1u) other = fmin(other, lb2);
+    const u32 ohi = __reduce_min_sync(FULL, (u32)((u64)__double_as_longlong(other) >> 32));
+    const double d2_other = __longlong_as_double((long long)((u64)ohi << 32));     // low word zero: rounds down
+    slack = found ? (sqrt(d2_other) - sqrt(bd2)) * 0.5 - 1e-9 : -1.0;
     return found;
 }
 
@@ -517,6 +540,37 @@ __device__ __forceinline__ double warp_butterfly(double x) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) x = x + __shfl_xor_sync(0xffffffffu, x, o);
     return x;
+}
+
+// 16 values per lane -> 16 warp-wide sums with 16 shuffles instead of 80: at the stage with xor
+// mask m a lane keeps one half of its values and adds the partner's copies of that half, so the
+// working set halves every stage.  Every sum is still x[l] + x[l ^ m] over the same partial sums
+// as warp_butterfly (addition commutes bit for bit), i.e. the canonical adjacent-pairs tree.
+// Returns the total of value bitrev4(lane & 15).
+__device__ __forceinline__ double warp_reduce16(const double* c, int lane) {
+    const u32 FULL = 0xffffffffu;
+    double a[8], b4[4], b2[2], b1;
+    const bool u0 = lane & 1, u1 = lane & 2, u2 = lane & 4, u3 = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double keep = u0 ? c[i + 8] : c[i], send = u0 ? c[i] : c[i + 8];
+        a[i] = keep + __shfl_xor_sync(FULL, send, 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double keep = u1 ? a[i + 4] : a[i], send = u1 ? a[i] : a[i + 4];
+        b4[i] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double keep = u2 ? b4[i + 2] : b4[i], send = u2 ? b4[i] : b4[i + 2];
+        b2[i] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+    {
+        const double keep = u3 ? b2[1] : b2[0], send = u3 ? b2[0] : b2[1];
+        b1 = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+    return b1 + __shfl_xor_sync(FULL, b1, 16);
 }
 
 // Adjacent-pairs binary tree over p[0..n), zero padded to a power of two: the canonical reduction
@@ -692,15 +746,22 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
 }
 
 // K4: the whole ICP loop (kiss-icp RegisterFrame) in one persistent cooperative kernel.
-// grid = (blocks per lane, lanes), ICP_THREADS threads, two blocks per SM (normally of different
-// lanes, so one lane's barrier wait overlaps another lane's search).  Per iteration a block takes
-// its 32-point groups in chunks of ICP_CHUNK: one warp per point (transform by the last
-// increment, NN search), lane 0 leaves the point's 17 terms in shared memory; after one
-// __syncthreads the warps butterfly (group, term) pairs into the groups' partial sums.  A counter
-// barrier over the lane's blocks follows; after it EVERY block reduces the group partials with
-// the same fixed tree, solves the 6x6 system and updates its copy of T_icp (identical code,
+// grid = (blocks per lane, lanes), ICP_THREADS threads.  A block owns a contiguous range of
+// 32-point groups and walks it in chunks of ICP_CHUNK groups (= one point per thread).  Per
+// iteration and chunk:
+//   1. thread per point: move the point by the last increment, then try the correspondence cache:
+//      if the point is still in the voxel it was searched from and has moved less than the slack
+//      that search left (see warp_nearest), the nearest map point is provably the cached one and no
+//      search is needed; otherwise the point goes on the block's work list;
+//   2. warp per listed point: the pruned 27-voxel search, refreshing the cache entry;
+//   3. thread per point: residual, Geman-McClure weight and the 16 distinct sums (+ count) in
+//      registers; a warp IS a 32-point group, so xor-butterflies give the group partials directly.
+// A counter barrier over the lane's blocks follows; after it EVERY block reduces the group partials
+// with the same fixed tree, solves the 6x6 system and updates its copy of T_icp (identical code,
 // identical bits), so one grid-wide hop per iteration is all the synchronisation there is.
-__global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs) {
+// The cache changes which points are searched, never what a search would have returned, so the
+// per-iteration correspondence sets stay bit-exact (tests compare them with the oracle's).
+__global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs) {
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
     StepOut& O = outs[blockIdx.y];
@@ -708,8 +769,8 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(LaneDev* lanes, const St
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_src = L.n_src;
 
-    extern __shared__ double contrib[];          // [ICP_CHUNK * 32 points][NSUM], then the block's source points
-    double* const ssx = contrib + ICP_CHUNK * 32 * NSUM;
+    extern __shared__ double dyn_smem[];         // source points + cache entries of this block
+    double* const ssx = dyn_smem;
     double* const ssy = ssx + ICP_SRC_CAP;
     double* const ssz = ssy + ICP_SRC_CAP;
     __shared__ double red[NSUM];
@@ -717,6 +778,8 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(LaneDev* lanes, const St
     __shared__ SE3q sT;
     __shared__ SolveSmem sS;
     __shared__ int s_done;
+    __shared__ int s_nmiss;
+    __shared__ unsigned short s_miss[ICP_CHUNK * 32];
 
     if (L.n_vox == 0) {   // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
         if (b == 0 && threadIdx.x == 0) {
@@ -731,61 +794,121 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(LaneDev* lanes, const St
     const int g_begin = min(b * gper, n_groups), g_end = min(g_begin + gper, n_groups);
     const double max_corr = P.max_corr, kern = P.kernel;
     const double max_d2 = (max_corr * max_corr) * (1.0 + 1e-9);   // farther candidates are rejected anyway
-    // the moving copy of this block's source points lives in shared memory when it fits
-    const bool src_in_smem = (g_end - g_begin) * 32 <= ICP_SRC_CAP;
+    // the moving copy of this block's source points and their cache entries live in shared memory when they fit
+    const bool in_smem = (g_end - g_begin) * 32 <= ICP_SRC_CAP;
+    // cache entry arrays: computed where used (one base + constants) instead of six live pointers
+    const int goff = g_begin * 32;
+#define C_TX(i) (*(in_smem ? dyn_smem + 3 * ICP_SRC_CAP + (i) : L.c_tx + goff + (i)))
+#define C_TY(i) (*(in_smem ? dyn_smem + 4 * ICP_SRC_CAP + (i) : L.c_ty + goff + (i)))
+#define C_TZ(i) (*(in_smem ? dyn_smem + 5 * ICP_SRC_CAP + (i) : L.c_tz + goff + (i)))
+#define C_SLACK(i) (*(in_smem ? dyn_smem + 6 * ICP_SRC_CAP + (i) : L.c_slack + goff + (i)))
+#define C_KEY(i) (*(in_smem ? reinterpret_cast<u64*>(dyn_smem + 7 * ICP_SRC_CAP) + (i) : L.c_key + goff + (i)))
+#define C_ORD(i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + 8 * ICP_SRC_CAP) + (i) : L.c_ord + goff + (i)))
     if (threadIdx.x == 0) sT = se3q_identity();
+    const double voxel = L.voxel_size;
+    // phase clocks of block 0 (thread 0 only; six clock reads per iteration)
+    const bool clk = b == 0 && threadIdx.x == 0;
+    __shared__ long long s_cyc[6];
+    __shared__ int s_searches;
+    if (threadIdx.x < 6) s_cyc[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_searches = 0;
+    long long tlast = clk ? clock64() : 0;
+#define ICP_TICK(slot) do { if (clk) { const long long t_ = clock64(); s_cyc[slot] += t_ - tlast; tlast = t_; } } while (0)
 
     for (int it = 0;; ++it) {
         double* part = (it & 1) ? L.part_b : L.part_a;
         for (int g0 = g_begin; g0 < g_end; g0 += ICP_CHUNK) {
             const int gc = min(ICP_CHUNK, g_end - g0);
-            if (g0 != g_begin) __syncthreads();           // previous chunk's butterflies are done
-            for (int q = warp; q < gc * 32; q += ICP_WARPS) {
-                const int p = g0 * 32 + q;
-                bool acc = false;
-                double sx = 0, sy = 0, sz = 0, tx = 0, ty = 0, tz = 0;
-                int ord = -1;
-                if (p < n_src) {
-                    const int sp = (g0 - g_begin) * 32 + q;
-                    if (it == 0 || !src_in_smem) {
-                        sx = __ldcg(L.s_x + p); sy = __ldcg(L.s_y + p); sz = __ldcg(L.s_z + p);
-                    } else {
-                        sx = ssx[sp]; sy = ssy[sp]; sz = ssz[sp];
-                    }
-                    if (it > 0) {
-                        double xo, yo, zo;
-                        rigid_apply(sE, sx, sy, sz, xo, yo, zo);
-                        sx = xo; sy = yo; sz = zo;
-                    }
-                    if (lane == 0) {
-                        if (src_in_smem) { ssx[sp] = sx; ssy[sp] = sy; ssz[sp] = sz; }
-                        else if (it > 0) { L.s_x[p] = sx; L.s_y[p] = sy; L.s_z[p] = sz; }
-                    }
-                    double d2;
-                    bool found = warp_nearest(L, sx, sy, sz, lane, max_d2, d2, ord, tx, ty, tz);
-                    acc = found && (sqrt(d2) < max_corr);
-                    if (lane == 0 && it < L.trace_iters) L.trace[(size_t)it * L.cap_points + p] = acc ? ord : -1;
+            const int q = threadIdx.x;                     // point of this thread within the chunk
+            const int p = g0 * 32 + q;                     // ... within the lane's source
+            const int sp = (g0 - g_begin) * 32 + q;        // ... within the block
+            const bool live = q < gc * 32 && p < n_src;
+            if (threadIdx.x == 0) s_nmiss = 0;
+            __syncthreads();                               // also: previous chunk / iteration fully consumed
+            // ---- 1. move the point, consult the cache
+            double sx = 0, sy = 0, sz = 0;
+            bool miss = false;
+            if (live) {
+                if (it == 0 || !in_smem) { sx = __ldcg(L.s_x + p); sy = __ldcg(L.s_y + p); sz = __ldcg(L.s_z + p); }
+                else { sx = ssx[sp]; sy = ssy[sp]; sz = ssz[sp]; }
+                miss = true;
+                if (it > 0) {
+                    double xo, yo, zo;
+                    rigid_apply(sE, sx, sy, sz, xo, yo, zo);
+                    const double mx = xo - sx, my = yo - sy, mz = zo - sz;
+                    sx = xo; sy = yo; sz = zo;
+                    const double slack = C_SLACK(sp) - (sqrt((mx * mx + my * my) + mz * mz) + 1e-10);
+                    C_SLACK(sp) = slack;
+                    int kx, ky, kz;
+                    voxel_key(sx, sy, sz, voxel, kx, ky, kz);
+                    miss = !(slack > 0.0 && key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == C_KEY(sp));
                 }
-                if (lane == 0) {
-                    double* c = contrib + (size_t)q * NSUM;
-                    if (acc) {
-                        lin_terms(sx, sy, sz, tx, ty, tz, kern, c);
-                        c[16] = 1.0;
-                    } else {
-#pragma unroll
-                        for (int v = 0; v < NSUM; ++v) c[v] = 0.0;
-                    }
+                if (in_smem) { ssx[sp] = sx; ssy[sp] = sy; ssz[sp] = sz; }
+                else if (it > 0) { L.s_x[p] = sx; L.s_y[p] = sy; L.s_z[p] = sz; }
+            }
+            {
+                const u32 mm = __ballot_sync(0xffffffffu, miss);
+                if (mm) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_nmiss, __popc(mm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (miss) s_miss[base + __popc(mm & ((1u << lane) - 1u))] = (unsigned short)q;
                 }
             }
             __syncthreads();
-            for (int task = warp; task < gc * NSUM; task += ICP_WARPS) {
-                const int c = task / NSUM, v = task - c * NSUM;
-                double x = warp_butterfly(contrib[(size_t)(c * 32 + lane) * NSUM + v]);
-                if (lane == 0) part[(size_t)v * L.ng_cap + g0 + c] = x;
+            ICP_TICK(0);
+            // ---- 2. full search of the listed points, one warp each
+            const int nmiss = s_nmiss;
+            if (threadIdx.x == 0) s_searches += nmiss;
+            for (int i = warp; i < nmiss; i += ICP_WARPS) {
+                const int mq = s_miss[i];
+                const int msp = (g0 - g_begin) * 32 + mq;
+                double qx, qy, qz;
+                if (in_smem) { qx = ssx[msp]; qy = ssy[msp]; qz = ssz[msp]; }
+                else { const int mp = g0 * 32 + mq; qx = __ldcg(L.s_x + mp); qy = __ldcg(L.s_y + mp); qz = __ldcg(L.s_z + mp); }
+                double d2, tx, ty, tz, slack;
+                int ord;
+                const bool found = warp_nearest(L, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, slack);
+                if (lane == 0) {
+                    int kx, ky, kz;
+                    voxel_key(qx, qy, qz, voxel, kx, ky, kz);
+                    C_TX(msp) = tx; C_TY(msp) = ty; C_TZ(msp) = tz;
+                    C_SLACK(msp) = slack;
+                    C_KEY(msp) = key_in_range(kx, ky, kz) ? pack_key(kx, ky, kz) : KEY_EMPTY;
+                    C_ORD(msp) = found ? ord : -1;
+                }
+            }
+            __syncthreads();
+            ICP_TICK(1);
+            // ---- 3. residual + weights, group partials by warp butterflies
+            if (warp < gc) {
+                double c[16];
+                bool acc = false;
+                int ord = -1;
+                if (live) {
+                    ord = C_ORD(sp);
+                    if (ord >= 0) {
+                        const double tx = C_TX(sp), ty = C_TY(sp), tz = C_TZ(sp);
+                        const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
+                        const double d2 = (dx * dx + dy * dy) + dz * dz;
+                        acc = sqrt(d2) < max_corr;
+                        if (acc) lin_terms(sx, sy, sz, tx, ty, tz, kern, c);
+                    }
+                    if (it < L.trace_iters) L.trace[(size_t)it * L.cap_points + p] = acc ? ord : -1;
+                }
+                if (!acc) {
+#pragma unroll
+                    for (int v = 0; v < 16; ++v) c[v] = 0.0;
+                }
+                const double mine = warp_reduce16(c, lane);
+                const u32 nacc = __popc(__ballot_sync(0xffffffffu, acc));   // a sum of 1.0s is exact in any order
+                if (lane < 16) part[(size_t)(__brev((u32)lane) >> 28) * L.ng_cap + g0 + warp] = mine;
+                else if (lane == 16) part[(size_t)16 * L.ng_cap + g0 + warp] = (double)nacc;
             }
         }
         // ---- one barrier over the lane's blocks (icp_arrive was zeroed by the previous kernel)
         __syncthreads();
+        ICP_TICK(2);
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(&L.icp_arrive, 1u);
@@ -794,15 +917,30 @@ __global__ void __launch_bounds__(ICP_THREADS, 2) k_icp(LaneDev* lanes, const St
             __threadfence();
         }
         __syncthreads();
+        ICP_TICK(3);
         for (int v = warp; v < NSUM; v += ICP_WARPS) {
             double x = warp_tree_sum(part + (size_t)v * L.ng_cap, n_groups, lane);
             if (lane == 0) red[v] = x;
         }
         __syncthreads();
+        ICP_TICK(4);
         if (warp == 0) icp_solve_step(L, P, O, red, &sS, &sE, &sT, &s_done, it, b == 0, lane);
         __syncthreads();
+        ICP_TICK(5);
         if (s_done) break;
     }
+#undef ICP_TICK
+    if (threadIdx.x == 0 && s_searches) atomicAdd(&L.icp_searches, s_searches);
+    if (clk) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) O.icp_cyc[k] = s_cyc[k];
+    }
+#undef C_TX
+#undef C_TY
+#undef C_TZ
+#undef C_SLACK
+#undef C_KEY
+#undef C_ORD
 }
 
 // ------------------------------------------------------------------------------------
@@ -956,9 +1094,10 @@ __global__ void k_finish(LaneDev* lanes, StepOut* outs, int n_lanes) {
     StepOut& O = outs[l];
     O.n_range = L.n_range; O.n_ds = L.n_ds; O.n_src = L.n_src;
     O.n_vox = L.n_vox; O.n_tomb = L.n_tomb; O.map_points = L.map_points;
-    O.err = L.err; O.bump = L.bump;
+    O.err = L.err; O.bump = L.bump; O.icp_searches = L.icp_searches;
     L.n_range = 0;
     L.err = 0;
+    L.icp_searches = 0;
 }
 
 // Rebuild the map table without tombstones.
@@ -1036,9 +1175,9 @@ __global__ void k_correspondences(LaneDev* lanes, int lane_id, const double* q, 
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n) return;
     double sx = q[3 * (size_t)w], sy = q[3 * (size_t)w + 1], sz = q[3 * (size_t)w + 2];
-    double d2, tx, ty, tz;
+    double d2, tx, ty, tz, slack;
     int ord;
-    bool found = L.n_vox > 0 && warp_nearest(L, sx, sy, sz, lane, (max_dist * max_dist) * (1.0 + 1e-9), d2, ord, tx, ty, tz);
+    bool found = L.n_vox > 0 && warp_nearest(L, sx, sy, sz, lane, (max_dist * max_dist) * (1.0 + 1e-9), d2, ord, tx, ty, tz, slack);
     bool acc = found && (sqrt(d2) < max_dist);
     if (lane == 0) {
         out_order[w] = acc ? ord : -1;

@@ -109,6 +109,12 @@ class Odometry:
             out[name.decode()] = (float(ms[k]), int(n[k]))
         return out
 
+    def icp_phases(self, lane=0):
+        """clock64 cycles block 0 of the last ICP launch spent per phase (measurement tap)."""
+        out = np.zeros(6, dtype=np.int64)
+        self._check(self._lib.ptk_get_icp_phases(self._h, lane, addr(out)))
+        return dict(zip(("cache_pass", "searches", "sums", "barrier", "tree", "solve"), out.tolist()))
+
     def launch_count(self):
         return int(self._lib.ptk_launch_count(self._h))
 
