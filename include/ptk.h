@@ -109,6 +109,23 @@ int ptk_register_frame_batch(ptk_ctx* ctx, const double* const* xyz,
                              const double* guesses, const unsigned char* has_guess,
                              double* out_poses, ptk_stats* stats, void* stream);
 
+/* ---- the same step fed with the sensor's RANGE image: KissICPWrapper.register_frame (kiss.py:54-74)
+ * including its host-side prologue - `sel = scan.field(RANGE) != 0` (:59), `xyz = xyz_lut(scan)[sel]`
+ * (:60), `timestamps = self._timestamps[sel]` (:61) - on the device: 4 bytes per pixel cross the bus
+ * instead of 32.  ptk_set_sensor replaces `client.XYZLut(metadata, use_extrinsics)` (kiss.py:28-29)
+ * and the per-column timestamp table (kiss.py:34-35): xyz = direction * (range * range_unit)
+ * [+ offset]; `offset` and `col_timestamps` may be NULL (no offset; w / W).  Pass the SDK's
+ * pre-scaled direction with range_unit = 1.  `out_index` of ptk_get_points then refers to pixel
+ * indices h * W + w (ascending, i.e. the same order as the masked cloud). */
+int ptk_set_sensor(ptk_ctx* ctx, int H, int W, const double* direction /* H*W*3 */,
+                   const double* offset /* H*W*3 or NULL */, const double* col_timestamps /* W or NULL */,
+                   double range_unit);
+int ptk_register_scan(ptk_ctx* ctx, int lane, const unsigned int* range_mm /* H*W, host or device */,
+                      const double* initial_guess /* 16 or NULL */, double* out_pose /* 16 */,
+                      ptk_stats* stats /* nullable */, void* stream);
+int ptk_register_scan_batch(ptk_ctx* ctx, const unsigned int* const* range_mm, const double* guesses,
+                            const unsigned char* has_guess, double* out_poses, ptk_stats* stats, void* stream);
+
 /* ---- state the wrapper exposes (kiss.py:133-166, cli/ekf_bench.py:545-547) --------- */
 int ptk_num_poses(const ptk_ctx* ctx, int lane);
 int ptk_get_pose(const ptk_ctx* ctx, int lane, int index /* <0 from the end */, double* out16);

@@ -50,6 +50,9 @@ SYMBOLS = {
     "ptk_register_frame": (C.c_int, [_P, C.c_int, _D, _D, C.c_int, _D, _D, C.POINTER(PtkStats), _P]),
     "ptk_register_frame_batch": (C.c_int, [_P, C.POINTER(_D), C.POINTER(_D), C.POINTER(C.c_int), _D,
                                            C.c_char_p, _D, C.POINTER(PtkStats), _P]),
+    "ptk_set_sensor": (C.c_int, [_P, C.c_int, C.c_int, _D, _D, _D, C.c_double]),
+    "ptk_register_scan": (C.c_int, [_P, C.c_int, _I, _D, _D, C.POINTER(PtkStats), _P]),
+    "ptk_register_scan_batch": (C.c_int, [_P, C.POINTER(_I), _D, C.c_char_p, _D, C.POINTER(PtkStats), _P]),
     "ptk_num_poses": (C.c_int, [_P, C.c_int]),
     "ptk_get_pose": (C.c_int, [_P, C.c_int, C.c_int, _D]),
     "ptk_get_prediction_model": (C.c_int, [_P, C.c_int, _D]),

@@ -36,16 +36,18 @@ struct LaneHost {
     u32 epoch = 0, tbase1 = 0, tbase2 = 0, release_base = 0;
     double* in_xyz = nullptr;         // staging for host inputs
     double* in_ts = nullptr;
+    u32* in_range = nullptr;          // staging for host range images
+    double* col_motion = nullptr;     // [12][W] per-column deskew motion (range-image mode)
     std::vector<void*> allocs;
 };
 
 }  // namespace
 
 enum ProfSlot { PS_SCAN_INSERT = 0, PS_COMPACT1, PS_COMPACT2, PS_ICP, PS_MAP_INSERT, PS_MAP_COMMIT, PS_MAP_PRUNE,
-                PS_FINISH, PS_REBUILD, PS_OTHER, PS_COUNT };
+                PS_FINISH, PS_REBUILD, PS_OTHER, PS_COL_MOTION, PS_COUNT };
 static_assert(PS_COUNT <= PTK_PROF_SLOTS, "profile slots");
 static const char* const kProfNames[PS_COUNT] = {"k_scan_insert", "k_compact1", "k_compact2", "k_icp", "k_map_insert",
-                                                 "k_map_commit", "k_map_prune", "k_finish", "k_map_rebuild", "other"};
+                                                 "k_map_commit", "k_map_prune", "k_finish", "k_map_rebuild", "other", "k_col_motion"};
 
 struct Prof {
     bool on = false;
@@ -73,6 +75,13 @@ struct ptk_ctx {
     int* d_tmp_i = nullptr;           // scratch ints (cap_points + 16)
     size_t big_tmp_bytes = 0;
     void* d_big = nullptr;            // lazily allocated scratch for map dumps
+    // sensor model of the range-image entry points (ptk_set_sensor)
+    int sen_H = 0, sen_W = 0;
+    double sen_unit = 0.001;
+    double* d_lut_dir = nullptr;
+    double* d_lut_off = nullptr;
+    double* d_col_ts = nullptr;
+    std::vector<void*> sensor_allocs;
     int num_sms = 148;
     int icp_blocks_total = 148;
     std::string err;
@@ -222,6 +231,7 @@ static int lane_alloc(ptk_ctx* ctx, LaneHost& LH, bool scratch) {
     CK(dalloc(A, &d.trace, (size_t)std::max(d.trace_iters, 1) * N, 0xFF));
     CK(dalloc(A, &LH.in_xyz, N * 3));
     CK(dalloc(A, &LH.in_ts, N));
+    CK(dalloc(A, &LH.in_range, N));
     d.icp_E = rigid_identity();
     d.icp_T = rigid_identity();
     return PTK_OK;
@@ -300,6 +310,7 @@ extern "C" int ptk_ctx_destroy(ptk_ctx* ctx) {
     for (auto& L : ctx->lanes)
         for (void* p : L.allocs) cudaFree(p);
     for (void* p : ctx->allocs) cudaFree(p);
+    for (void* p : ctx->sensor_allocs) cudaFree(p);
     if (ctx->d_big) cudaFree(ctx->d_big);
     for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
     if (ctx->h_params) cudaFreeHost(ctx->h_params);
@@ -329,7 +340,7 @@ static int lane_reset_device(ptk_ctx* ctx, int l, cudaStream_t st, bool tables) 
     }
     // dynamic counters live at the tail of LaneDev: re-upload the pristine host mirror
     LaneDev fresh = d;
-    fresh.n_range = fresh.n_ds = fresh.n_src = 0;
+    fresh.n_range = fresh.n_ds = fresh.n_src = fresh.n_valid = 0;
     fresh.free_top = fresh.bump = fresh.n_vox = fresh.n_tomb = fresh.map_points = 0;
     fresh.icp_arrive = 0; fresh.icp_done = 0; fresh.err = 0; fresh.icp_searches = 0;
     // tickets / release epochs keep counting on the host side; mirror them
@@ -452,29 +463,49 @@ static int maybe_rebuild(ptk_ctx* ctx, int l, const StepOut& O, cudaStream_t st)
 }
 
 // The whole step for lanes [l0, l0+cnt).
-static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, const double* const* ts, const int* n,
-                    const double* guesses, const unsigned char* has_guess, double* out_poses, ptk_stats* stats,
-                    cudaStream_t st) {
+// `range` non-null selects the range-image input (one H*W uint32 image per lane; xyz/ts/n unused).
+static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, const double* const* ts, const int* n_in,
+                    const unsigned int* const* range, const double* guesses, const unsigned char* has_guess,
+                    double* out_poses, ptk_stats* stats, cudaStream_t st) {
     const ptk_config& c = ctx->cfg;
     CK(cudaSetDevice(ctx->device));
     int nmax = 0;
     std::vector<double> sigmas(cnt);
+    std::vector<int> nv(cnt);
+    const int* n = nv.data();
+    const int npix = ctx->sen_H * ctx->sen_W;
+    if (range && npix <= 0) return fail(ctx, PTK_E_STATE, "ptk_set_sensor has not been called");
     for (int k = 0; k < cnt; ++k) {
         int l = l0 + k;
         LaneHost& LH = ctx->lanes[l];
+        nv[k] = range ? npix : n_in[k];
         if (n[k] < 0 || n[k] > c.max_points) return fail(ctx, PTK_E_CAPACITY, "scan larger than cfg.max_points");
-        if (n[k] > 0 && !xyz[k]) return fail(ctx, PTK_E_ARG, "xyz is null");
+        if (!range && n[k] > 0 && !xyz[k]) return fail(ctx, PTK_E_ARG, "xyz is null");
+        if (range && !range[k]) return fail(ctx, PTK_E_ARG, "range image is null");
         StepParams& P = ctx->h_params[l];
         memset(&P, 0, sizeof(P));
-        int rc = stage_in(ctx, xyz[k], (size_t)n[k] * 3, LH.in_xyz, &P.xyz, st);
-        if (rc) return rc;
+        int rc = PTK_OK;
+        if (range) {
+            if (is_device_ptr(range[k])) P.range = range[k];
+            else {
+                CK(cudaMemcpyAsync(LH.in_range, range[k], (size_t)npix * sizeof(u32), cudaMemcpyHostToDevice, st));
+                P.range = LH.in_range;
+            }
+            P.lut_dir = ctx->d_lut_dir; P.lut_off = ctx->d_lut_off; P.col_ts = ctx->d_col_ts;
+            P.col_motion = LH.col_motion; P.W = ctx->sen_W; P.range_unit = ctx->sen_unit;
+        } else {
+            rc = stage_in(ctx, xyz[k], (size_t)n[k] * 3, LH.in_xyz, &P.xyz, st);
+            if (rc) return rc;
+        }
         P.n = n[k];
         P.flags = F_RANGE | F_SECOND;
         size_t np = LH.poses.size();
         if (c.deskew && np >= 2) {      // MotionCompensator.deskew_scan: identity with < 2 poses
-            if (!ts || !ts[k]) return fail(ctx, PTK_E_ARG, "timestamps are null");
-            rc = stage_in(ctx, ts[k], (size_t)n[k], LH.in_ts, &P.ts, st);
-            if (rc) return rc;
+            if (!range) {
+                if (!ts || !ts[k]) return fail(ctx, PTK_E_ARG, "timestamps are null");
+                rc = stage_in(ctx, ts[k], (size_t)n[k], LH.in_ts, &P.ts, st);
+                if (rc) return rc;
+            }
             P.flags |= F_DESKEW;
             Rigid rel = rigid_mul(rigid_inv(LH.poses[np - 2]), LH.poses[np - 1]);
             se3_log(rel, P.delta);
@@ -509,6 +540,11 @@ static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, con
     LaneDev* dl = ctx->d_lanes + l0;
     StepParams* dp = ctx->d_params + l0;
     StepOut* dout = ctx->d_outs + l0;
+    if (range) {
+        bool any = false;
+        for (int k = 0; k < cnt; ++k) any = any || (ctx->h_params[l0 + k].flags & F_DESKEW);
+        if (any) LAUNCH(PS_COL_MOTION, st, k_col_motion<<<dim3((ctx->sen_W + 127) / 128, cnt), 128, 0, st>>>(dp));
+    }
     LAUNCH(PS_SCAN_INSERT, st, k_scan_insert<<<dim3(g1, cnt), 256, 0, st>>>(dl, dp));
     LAUNCH(PS_COMPACT1, st, k_compact1<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
     LAUNCH(PS_COMPACT2, st, k_compact2<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
@@ -552,7 +588,7 @@ static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, con
         if (stats) {
             ptk_stats& S = stats[k];
             memset(&S, 0, sizeof(S));
-            S.status = O.status; S.n_in = P.n; S.n_range = O.n_range; S.n_ds = O.n_ds; S.n_src = O.n_src;
+            S.status = O.status; S.n_in = P.range ? O.n_valid : P.n; S.n_range = O.n_range; S.n_ds = O.n_ds; S.n_src = O.n_src;
             S.n_voxels = O.n_vox; S.iterations = O.iterations; S.n_corr = O.n_corr; S.dx_norm = O.dx_norm;
             S.sigma = sigmas[k]; S.err_dt = dt; S.err_drot = fabs(theta); S.map_points = O.map_points;
             S.icp_searches = O.icp_searches;
@@ -569,14 +605,61 @@ extern "C" int ptk_register_frame(ptk_ctx* ctx, int lane, const double* xyz, con
     if (!ctx) return PTK_E_ARG;
     if (lane < 0 || lane >= ctx->B) return fail(ctx, PTK_E_ARG, "lane out of range");
     unsigned char hg = initial_guess ? 1 : 0;
-    return run_step(ctx, lane, 1, &xyz, &timestamps, &n, initial_guess, &hg, out_pose, stats, (cudaStream_t)stream);
+    return run_step(ctx, lane, 1, &xyz, &timestamps, &n, nullptr, initial_guess, &hg, out_pose, stats, (cudaStream_t)stream);
 }
 
 extern "C" int ptk_register_frame_batch(ptk_ctx* ctx, const double* const* xyz, const double* const* timestamps,
                                         const int* n, const double* guesses, const unsigned char* has_guess,
                                         double* out_poses, ptk_stats* stats, void* stream) {
     if (!ctx || !xyz || !n) return PTK_E_ARG;
-    return run_step(ctx, 0, ctx->B, xyz, timestamps, n, guesses, has_guess, out_poses, stats, (cudaStream_t)stream);
+    return run_step(ctx, 0, ctx->B, xyz, timestamps, n, nullptr, guesses, has_guess, out_poses, stats, (cudaStream_t)stream);
+}
+
+// ---- range-image entry points (kiss.py:54-74 with the projection on the device) ---------
+extern "C" int ptk_set_sensor(ptk_ctx* ctx, int H, int W, const double* direction, const double* offset,
+                              const double* col_timestamps, double range_unit) {
+    if (!ctx || H < 1 || W < 1 || !direction || !(range_unit > 0.0)) return fail(ctx, PTK_E_ARG, "ptk_set_sensor: bad argument");
+    if ((long long)H * W > ctx->cfg.max_points) return fail(ctx, PTK_E_CAPACITY, "ptk_set_sensor: H*W exceeds cfg.max_points");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    for (void* p : ctx->sensor_allocs) cudaFree(p);
+    ctx->sensor_allocs.clear();
+    ctx->d_lut_dir = ctx->d_lut_off = ctx->d_col_ts = nullptr;
+    ctx->sen_H = ctx->sen_W = 0;
+    size_t np = (size_t)H * W;
+    auto up = [&](double** dst, const double* src, size_t count) -> int {
+        CK(dalloc(ctx->sensor_allocs, dst, count));
+        CK(cudaMemcpy(*dst, src, count * sizeof(double), is_device_ptr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+        return PTK_OK;
+    };
+    int rc = up(&ctx->d_lut_dir, direction, np * 3);
+    if (rc) return rc;
+    if (offset && (rc = up(&ctx->d_lut_off, offset, np * 3))) return rc;
+    std::vector<double> cts;
+    if (!col_timestamps) {      // np.linspace(0, 1.0, w, endpoint=False) (kiss.py:34)
+        cts.resize(W);
+        const double step = 1.0 / (double)W;
+        for (int w = 0; w < W; ++w) cts[w] = (double)w * step;
+        col_timestamps = cts.data();
+    }
+    if ((rc = up(&ctx->d_col_ts, col_timestamps, (size_t)W))) return rc;
+    for (auto& LH : ctx->lanes) CK(dalloc(ctx->sensor_allocs, &LH.col_motion, (size_t)12 * W));
+    ctx->sen_H = H; ctx->sen_W = W; ctx->sen_unit = range_unit;
+    return PTK_OK;
+}
+
+extern "C" int ptk_register_scan(ptk_ctx* ctx, int lane, const unsigned int* range_mm, const double* initial_guess,
+                                 double* out_pose, ptk_stats* stats, void* stream) {
+    if (!ctx) return PTK_E_ARG;
+    if (lane < 0 || lane >= ctx->B) return fail(ctx, PTK_E_ARG, "lane out of range");
+    unsigned char hg = initial_guess ? 1 : 0;
+    return run_step(ctx, lane, 1, nullptr, nullptr, nullptr, &range_mm, initial_guess, &hg, out_pose, stats, (cudaStream_t)stream);
+}
+
+extern "C" int ptk_register_scan_batch(ptk_ctx* ctx, const unsigned int* const* range_mm, const double* guesses,
+                                       const unsigned char* has_guess, double* out_poses, ptk_stats* stats, void* stream) {
+    if (!ctx || !range_mm) return PTK_E_ARG;
+    return run_step(ctx, 0, ctx->B, nullptr, nullptr, nullptr, range_mm, guesses, has_guess, out_poses, stats, (cudaStream_t)stream);
 }
 
 // ---- state accessors -----------------------------------------------------------------

@@ -77,13 +77,21 @@ struct StepParams {
     u32 epoch;             // step counter, >= 1
     u32 tbase1, tbase2;    // ticket bases of the two compaction kernels
     u32 release_base;      // icp barrier epoch base
-    int pad;
+    int W;                 // range-image mode: columns per frame (n = H * W pixels)
+    // range-image input (kiss.py:59-61 on the device): non-null `range` selects it
+    const u32* range;      // (H*W) RANGE field in millimetres, 0 = no return
+    double range_unit;     // metres per RANGE count the direction LUT expects (0.001, or 1 if pre-scaled)
+    const double* lut_dir; // (H*W,3) XYZLut direction
+    const double* lut_off; // (H*W,3) XYZLut offset or null
+    const double* col_ts;  // (W) normalised column timestamps (kiss.py:34-35)
+    double* col_motion;    // [12][W] deskew motion of every column, written by k_col_motion
 };
 
 struct StepOut {
     Rigid pose;
     double dx_norm;
     int status, n_range, n_ds, n_src, n_vox, n_tomb, iterations, n_corr, map_points, err, bump, icp_searches;
+    int n_valid, pad;
     long long icp_cyc[6];      // block 0's clock64 spent in: cache pass, searches, sums, barrier, tree, solve
 };
 
@@ -117,7 +125,7 @@ struct LaneDev {
     u64* c_key; int* c_ord;
     int* trace;                          // [trace_iters][cap_points]
     // dynamic state
-    int n_range, n_ds, n_src;
+    int n_range, n_ds, n_src, n_valid;
     int free_top, bump, n_vox, n_tomb, map_points;
     u32 ticket1, ticket2;
     u32 icp_arrive; u32 icp_release;
@@ -166,8 +174,32 @@ __device__ __forceinline__ u32 table_insert_min(u64* keys, u32* vals, u32 mask, 
     return slot;
 }
 
-// Load input point i and apply the per-point deskew (kiss-icp DeSkewScan).
-__device__ __forceinline__ void load_point(const StepParams& P, int i, double& x, double& y, double& z) {
+// Load input point i and apply the per-point deskew (kiss-icp DeSkewScan).  Returns false for a
+// pixel without return (range-image mode only; kiss.py:59 `scan.field(RANGE) != 0`).
+// Range-image mode restates kiss.py:60 (XYZLut: range * direction [+ offset]) and looks the deskew
+// motion of the pixel's column up in the table k_col_motion built with the very same se3_exp call,
+// so the result is bit-identical to the per-point path on the projected cloud.
+__device__ __forceinline__ bool load_point(const StepParams& P, int i, double& x, double& y, double& z) {
+    if (P.range) {
+        const u32 r = __ldg(P.range + i);
+        if (r == 0) return false;
+        const double rr = (double)r * P.range_unit;
+        const double* d = P.lut_dir + 3 * (size_t)i;
+        x = __ldg(d) * rr; y = __ldg(d + 1) * rr; z = __ldg(d + 2) * rr;
+        if (P.lut_off) {
+            const double* o = P.lut_off + 3 * (size_t)i;
+            x = x + __ldg(o); y = y + __ldg(o + 1); z = z + __ldg(o + 2);
+        }
+        if (P.flags & F_DESKEW) {
+            const double* m = P.col_motion + (i % P.W);
+            const int W = P.W;
+            const double xo = ((m[0] * x + m[W] * y) + m[2 * W] * z) + m[9 * W];
+            const double yo = ((m[3 * W] * x + m[4 * W] * y) + m[5 * W] * z) + m[10 * W];
+            const double zo = ((m[6 * W] * x + m[7 * W] * y) + m[8 * W] * z) + m[11 * W];
+            x = xo; y = yo; z = zo;
+        }
+        return true;
+    }
     const double* p = P.xyz + 3 * (size_t)i;
     x = p[0]; y = p[1]; z = p[2];
     if (P.flags & F_DESKEW) {
@@ -180,6 +212,25 @@ __device__ __forceinline__ void load_point(const StepParams& P, int i, double& x
         rigid_apply(M, x, y, z, xo, yo, zo);
         x = xo; y = yo; z = zo;
     }
+    return true;
+}
+
+// Deskew motion exp((t_w - 0.5) * delta) of every column of the range image, [12][W] (9 rotation
+// entries row-major, then the translation), so that threads of consecutive columns read
+// consecutive words.
+__global__ void k_col_motion(const StepParams* params) {
+    const StepParams& P = params[blockIdx.y];
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!P.range || !(P.flags & F_DESKEW) || w >= P.W) return;
+    const double s = P.col_ts[w] - 0.5;
+    double a[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = s * P.delta[k];
+    const Rigid M = se3_exp(a);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) P.col_motion[k * P.W + w] = M.r[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) P.col_motion[(9 + k) * P.W + w] = M.t[k];
 }
 
 __device__ __forceinline__ bool range_pass(const StepParams& P, double x, double y, double z) {
@@ -194,11 +245,11 @@ __global__ void __launch_bounds__(256) k_scan_insert(LaneDev* lanes, const StepP
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool pass = false;
+    bool pass = false, valid = false;
     if (i < P.n) {
         double x, y, z;
-        load_point(P, i, x, y, z);
-        pass = range_pass(P, x, y, z);
+        valid = load_point(P, i, x, y, z);
+        pass = valid && range_pass(P, x, y, z);
         u32 slot = NONE;
         if (pass) {
             int kx, ky, kz;
@@ -213,6 +264,10 @@ __global__ void __launch_bounds__(256) k_scan_insert(LaneDev* lanes, const StepP
     }
     u32 m = __ballot_sync(0xffffffffu, pass);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&L.n_range, __popc(m));
+    if (P.range) {          // len(frame) of kiss.py:60: pixels with a return
+        m = __ballot_sync(0xffffffffu, valid);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&L.n_valid, __popc(m));
+    }
 }
 
 // Block-wide exclusive scan of per-thread counts (256 threads); returns offset, total in `total`.
@@ -296,8 +351,7 @@ __global__ void __launch_bounds__(256) k_compact1(LaneDev* lanes, const StepPara
         if (i < P.n) {
             if (P.flags & F_SELECT_RANGE) {
                 double x, y, z;
-                load_point(P, i, x, y, z);
-                win[k] = range_pass(P, x, y, z);
+                win[k] = load_point(P, i, x, y, z) && range_pass(P, x, y, z);
             } else {
                 u32 s = L.slot1[i];
                 win[k] = (s != NONE) && (L.t1_vals[s] == (u32)i);
@@ -1094,8 +1148,9 @@ __global__ void k_finish(LaneDev* lanes, StepOut* outs, int n_lanes) {
     StepOut& O = outs[l];
     O.n_range = L.n_range; O.n_ds = L.n_ds; O.n_src = L.n_src;
     O.n_vox = L.n_vox; O.n_tomb = L.n_tomb; O.map_points = L.map_points;
-    O.err = L.err; O.bump = L.bump; O.icp_searches = L.icp_searches;
+    O.err = L.err; O.bump = L.bump; O.icp_searches = L.icp_searches; O.n_valid = L.n_valid;
     L.n_range = 0;
+    L.n_valid = 0;
     L.err = 0;
     L.icp_searches = 0;
 }

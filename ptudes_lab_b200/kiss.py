@@ -90,6 +90,13 @@ class KissICPWrapper:
                            max_points=_max_points if _max_points else max(w * h, 1024),
                            map_capacity=_map_capacity, trace_iterations=_trace_iterations)
 
+        # With a LUT that exposes its direction/offset tables the projection, the RANGE != 0 mask
+        # and the timestamp gather of register_frame run on the device (ptk_register_scan).
+        self._device_projection = hasattr(self._xyz_lut, "direction") and hasattr(self._xyz_lut, "range_unit")
+        if self._device_projection:
+            self._kiss._odo.set_sensor(self._xyz_lut.direction, getattr(self._xyz_lut, "offset", None),
+                                       self._timestamps[0], self._xyz_lut.range_unit)
+
         # using last valid column timestamp as a pose ts
         self._poses_ts = []
 
@@ -100,13 +107,16 @@ class KissICPWrapper:
 
     def register_frame(self, scan, initial_guess: Optional[PoseH] = None) -> PoseH:
         """Register scan with kiss icp"""
-        sel_flag = scan.field(ChanField.RANGE) != 0
-        xyz = self._xyz_lut(scan)[sel_flag]
-        timestamps = self._timestamps[sel_flag]
-
         ts = last_valid_column_ts(scan) * 1e-09
 
-        self._kiss_register_frame(xyz, timestamps, ts, initial_guess=initial_guess, _want_frames=False)
+        if self._device_projection:
+            new_pose, st = self._kiss._odo.register_scan(scan.field(ChanField.RANGE), initial_guess=initial_guess)
+            self._record(new_pose, st)
+        else:
+            sel_flag = scan.field(ChanField.RANGE) != 0
+            xyz = self._xyz_lut(scan)[sel_flag]
+            timestamps = self._timestamps[sel_flag]
+            self._kiss_register_frame(xyz, timestamps, ts, initial_guess=initial_guess, _want_frames=False)
 
         self._poses_ts.append(ts)
 
@@ -122,14 +132,17 @@ class KissICPWrapper:
         ignore them)."""
         odo = self._kiss._odo
         new_pose, st = odo.register_frame(frame, timestamps, initial_guess=initial_guess)
-        self._err_dt.append(st["err_dt"])
-        self._err_drot.append(st["err_drot"])
-        self._sigmas.append(st["sigma"])
-        self._kiss.poses.append(new_pose)
-        self._last_stats = st
+        self._record(new_pose, st)
         if not _want_frames:
             return None, None
         return odo.get_frame(), odo.get_points(1)
+
+    def _record(self, new_pose, st):
+        self._err_dt.append(st["err_dt"])           # kiss.py:122-124
+        self._err_drot.append(st["err_drot"])
+        self._sigmas.append(st["sigma"])
+        self._kiss.poses.append(new_pose)           # kiss.py:130
+        self._last_stats = st
 
     @property
     def velocity(self) -> Vec3:

@@ -156,6 +156,51 @@ class Odometry:
         self._check(rc)
         return poses, [s.as_dict() for s in stats]
 
+    # -- the step fed with range images (kiss.py:54-74 incl. the XYZLut projection) ---------
+    def set_sensor(self, direction, offset=None, col_timestamps=None, range_unit=0.001):
+        """client.XYZLut + the timestamp table of KissICPWrapper.__init__ (kiss.py:28-35).
+        direction (H, W, 3); xyz = direction * (range * range_unit) [+ offset]."""
+        d = np.ascontiguousarray(direction, dtype=np.float64)
+        H, W = int(d.shape[0]), int(d.shape[1])
+        o = None if offset is None else np.ascontiguousarray(offset, dtype=np.float64).reshape(H, W, 3)
+        t = None if col_timestamps is None else np.ascontiguousarray(col_timestamps, dtype=np.float64).reshape(W)
+        self._check(self._lib.ptk_set_sensor(self._h, H, W, addr(d), addr(o), addr(t), float(range_unit)))
+        self.sensor_shape = (H, W)
+
+    @staticmethod
+    def _u32(a):
+        if hasattr(a, "data_ptr") and not isinstance(a, np.ndarray):
+            return a                      # torch tensor (int32/uint32 storage), already on the device
+        return np.ascontiguousarray(a, dtype=np.uint32)
+
+    def register_scan(self, range_mm, initial_guess=None, lane=0, stream=0):
+        """One odometry step from the RANGE field (H, W) uint32 mm.  Returns (pose 4x4, stats)."""
+        r = self._u32(range_mm)
+        g = _mat16(initial_guess) if initial_guess is not None else None
+        pose = np.empty((4, 4))
+        st = PtkStats()
+        self._check(self._lib.ptk_register_scan(self._h, lane, addr(r), addr(g), addr(pose), C.byref(st), stream))
+        return pose, st.as_dict()
+
+    def register_scan_batch(self, ranges, guesses=None, stream=0):
+        B = self.batch
+        assert len(ranges) == B
+        rs = [self._u32(r) for r in ranges]
+        ptrs = (C.c_void_p * B)(*[addr(r) for r in rs])
+        gbuf, hg = None, None
+        if guesses is not None:
+            gbuf = np.zeros((B, 4, 4))
+            flags = bytearray(B)
+            for i, g in enumerate(guesses):
+                if g is not None:
+                    gbuf[i] = _mat16(g)
+                    flags[i] = 1
+            hg = bytes(flags)
+        poses = np.empty((B, 4, 4))
+        stats = (PtkStats * B)()
+        self._check(self._lib.ptk_register_scan_batch(self._h, ptrs, addr(gbuf), hg, addr(poses), stats, stream))
+        return poses, [s.as_dict() for s in stats]
+
     # -- KissICP state -------------------------------------------------------------
     def num_poses(self, lane=0):
         return self._lib.ptk_num_poses(self._h, lane)

@@ -47,18 +47,26 @@ except Exception:  # ModuleNotFoundError here
             return self._range
 
     class XYZLut:
-        """range image (mm) -> (H, W, 3) float64 metres, optionally through `extrinsic`."""
+        """range image (mm) -> (H, W, 3) float64 metres.  Like the SDK's LUT it is a per-pixel
+        `direction` and `offset` table with the extrinsic folded in at construction:
+        xyz = direction * (range * range_unit) + offset, zero where range == 0."""
+        range_unit = 0.001
 
         def __init__(self, metadata, use_extrinsics=False):
-            self.direction = metadata.directions
-            self.extrinsic = metadata.extrinsic if use_extrinsics else None
+            d = np.ascontiguousarray(metadata.directions, dtype=np.float64)
+            self.offset = None
+            if use_extrinsics and not np.array_equal(metadata.extrinsic, np.eye(4)):
+                E = metadata.extrinsic
+                d = np.ascontiguousarray(d @ E[:3, :3].T)
+                self.offset = np.ascontiguousarray(np.broadcast_to(E[:3, 3], d.shape))
+            self.direction = d
 
         def __call__(self, scan):
-            r = (scan.field(ChanField.RANGE) if hasattr(scan, "field") else scan).astype(np.float64) * 0.001
+            rng = scan.field(ChanField.RANGE) if hasattr(scan, "field") else scan
+            r = rng.astype(np.float64) * self.range_unit
             xyz = self.direction * r[..., None]
-            if self.extrinsic is not None:
-                E = self.extrinsic
-                xyz = xyz @ E[:3, :3].T + np.where(r[..., None] > 0, E[:3, 3], 0.0)
+            if self.offset is not None:
+                xyz = np.where(rng[..., None] != 0, xyz + self.offset, 0.0)
             return xyz
 
     def last_valid_column_ts(scan):

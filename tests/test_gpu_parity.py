@@ -322,3 +322,87 @@ def test_wrapper_drop_in(tiny_seq):
     rf, rs = ref._kiss_register_frame(xyz, ts, tsec)
     f, s = w._kiss_register_frame(xyz, ts, tsec)
     assert np.array_equal(f, rf) and np.array_equal(s, rs)
+
+
+def test_register_scan_range_image_path(tiny_seq):
+    """ptk_register_scan (projection + mask + column timestamps on the device, kiss.py:59-61)
+    against the oracle fed with the host-projected cloud, and against the xyz entry point."""
+    from ptudes_lab_b200 import odometry
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    a = odometry.Odometry(cfg, max_points=16384, map_capacity=32768, trace_iterations=4)
+    b = odometry.Odometry(cfg, max_points=16384, map_capacity=32768, trace_iterations=4)
+    ref = ko.OracleKissICPWrapper()
+    try:
+        a.set_sensor(tiny_seq.dirs)
+        with pytest.raises(Exception):
+            b.register_scan(tiny_seq.scan(0).range_mm)          # no sensor set on b
+        for k in range(7):
+            sc = tiny_seq.scan(k)
+            rng = sc.range_mm.copy()
+            if k == 4:
+                rng[:] = 0                                       # a scan without a single return
+            if k == 5:
+                rng[::2, ::3] = 0                                # ragged: many dropped returns
+            from ptudes_lab_b200.synth import project_scan
+            xyz, ts = project_scan(rng, tiny_seq.dirs)
+            ref.register_points(xyz, ts, 0.1 * (k + 1))
+            pa, sa = a.register_scan(rng)
+            pb, sb = b.register_frame(xyz, ts)
+            assert np.array_equal(pa, ref.pose) and np.array_equal(pb, ref.pose), k
+            for key in ("n_in", "n_range", "n_ds", "n_src", "n_voxels", "iterations", "n_corr", "sigma", "err_dt"):
+                assert sa[key] == sb[key], (k, key)
+            assert sa["n_in"] == xyz.shape[0]
+            pix = np.flatnonzero(rng.reshape(-1) != 0)
+            da, ia = a.get_points(0, with_index=True)
+            db, ib = b.get_points(0, with_index=True)
+            assert np.array_equal(da, db) and np.array_equal(ia, pix[ib]), k
+            assert np.array_equal(a.get_points(1), b.get_points(1))
+            assert np.array_equal(a.get_trace(), b.get_trace())
+            assert np.array_equal(a.get_frame(), b.get_frame())
+        _map_equal(odometry.VoxelHashMap(a, 0), ref._kiss.local_map)
+    finally:
+        a.close()
+        b.close()
+
+
+def test_wrapper_with_extrinsics_and_offsets(tiny_seq):
+    """_use_extrinsics=True (cli/ekf_bench.py:451-454): the LUT carries direction AND offset."""
+    from ptudes_lab_b200.kiss import KissICPWrapper
+    from ptudes_lab_b200.ouster_compat import ChanField, scan_from_synth, sensor_info_from_synth
+    meta = sensor_info_from_synth(tiny_seq.sensor, tiny_seq.dirs)
+    meta.extrinsic = canon.se3_exp_mat(np.array([0.05, -0.02, 0.1, 0.02, -0.03, 0.4]))
+    w = KissICPWrapper(meta, _min_range=1, _max_range=70, _use_extrinsics=True)
+    assert w._device_projection and w._xyz_lut.offset is not None
+    ref = ko.OracleKissICPWrapper(_min_range=1, _max_range=70)
+    for k in range(5):
+        scan = scan_from_synth(tiny_seq.scan(k))
+        sel = scan.field(ChanField.RANGE) != 0                   # kiss.py:59-61 on the host for the oracle
+        ref.register_points(w._xyz_lut(scan)[sel], w._timestamps[sel], 0.1 * (k + 1))
+        assert np.array_equal(w.register_frame(scan), ref.pose), k
+    assert w._sigmas == ref._sigmas and w._err_dt == ref._err_dt
+    a, b = w.local_map_points, ref.local_map_points
+    assert np.array_equal(a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])])
+
+
+def test_register_scan_batch_matches_single(tiny_seq):
+    from ptudes_lab_b200 import odometry, synth
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    B = 3
+    seqs = [synth.make_sequence("tiny", s) for s in range(B)]
+    ob = odometry.Odometry(cfg, max_points=16384, map_capacity=32768, batch=B)
+    singles = [odometry.Odometry(cfg, max_points=16384, map_capacity=32768) for _ in range(B)]
+    try:
+        ob.set_sensor(seqs[0].dirs)
+        for o in singles:
+            o.set_sensor(seqs[0].dirs)
+        for k in range(5):
+            rngs = [s.scan(k).range_mm for s in seqs]
+            poses, stats = ob.register_scan_batch(rngs)
+            for l in range(B):
+                p1, s1 = singles[l].register_scan(rngs[l])
+                assert np.array_equal(poses[l], p1), (k, l)
+                assert stats[l]["iterations"] == s1["iterations"] and stats[l]["n_src"] == s1["n_src"]
+    finally:
+        ob.close()
+        for o in singles:
+            o.close()
