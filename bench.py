@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("PTK_BENCH_LANES", "16")),
                     help="independent sequences per GPU advanced by one batched step")
     ap.add_argument("--config", default="os0_quad", choices=["os0_quad", "os2_street", "os0_hall"])
+    ap.add_argument("--input", default="range", choices=["range", "xyz"],
+                    help="range: RANGE image as KissICPWrapper.register_frame gets it; xyz: projected cloud")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -123,13 +125,15 @@ def measured_peaks():
 # algorithmic (compulsory) HBM bytes of every kernel of the step, per lane-scan, from the
 # counters the library returns (DESIGN.md "Algorithmic bytes").  b = 8 B per
 # coordinate, S = 16 B map slot.
-def algorithmic_bytes(st):
+def algorithmic_bytes(st, n_pixels=0):
     b, S = 8, 16
     N, Nd, Ns, V, M = st["n_in"], st["n_ds"], st["n_src"], st["n_voxels"], st["map_points"]
     Vt = min(27 * Ns, V)
     Mt = min(20 * Vt, M)
     return {
-        "k_scan_insert": N * (3 * b + 8),
+        # range-image input: 4 B per pixel; the direction LUT is a per-sensor constant (3 MB) shared by
+        # every lane and scan, not per-scan traffic
+        "k_scan_insert": n_pixels * 4 if n_pixels else N * (3 * b + 8),
         "k_compact1": Nd * 3 * b,
         "k_compact2": Nd * 3 * b + Ns * 3 * b,
         "k_icp": Ns * 3 * b + Vt * S + Mt * 3 * b,
@@ -162,16 +166,28 @@ def run_ptk(args):
     min_r, max_r, max_pts, map_cap = CONFIGS[args.config]
 
     # ---- synthetic scans, generated on the device (data plumbing) -------------------------
+    # input = "range": the scan as KissICPWrapper.register_frame receives it (kiss.py:54-61): the RANGE
+    # image (H, W) uint32 mm; projection + mask + column timestamps run inside the step.
+    # input = "xyz": the already projected (N,3)+(N,) float64 cloud of _kiss_register_frame (kiss.py:83).
+    use_range = args.input == "range"
     gens = [synth.TorchScanGenerator(synth.make_sequence(args.config, rank * B + l), dev) for l in range(B)]
     frames = [[None] * B for _ in range(T)]
     tss = [[None] * B for _ in range(T)]
+    ranges = [[None] * B for _ in range(T)]
     for l, g in enumerate(gens):
         for s in range(T):
-            xyz, tn, _, _ = g.points(s)
-            frames[s][l], tss[s][l] = xyz, tn
+            rng, _, _ = g.range_image(s)
+            ranges[s][l] = rng.contiguous()
+            if not use_range or l < (os.cpu_count() or 1):      # the CPU baseline needs projected clouds
+                frames[s][l], tss[s][l] = g.project(rng)
     torch.cuda.synchronize()
-    scan_bytes = sum(f.numel() * 8 + t.numel() * 8 for f, t in zip(frames[W], tss[W]))
-    total_bytes = sum(f.numel() * 8 + t.numel() * 8 for s in range(T) for f, t in zip(frames[s], tss[s]))
+    if use_range:
+        scan_bytes = sum(r.numel() * 4 for r in ranges[W])
+        total_bytes = sum(r.numel() * 4 for s in range(T) for r in ranges[s])
+    else:
+        scan_bytes = sum(f.numel() * 8 + t.numel() * 8 for f, t in zip(frames[W], tss[W]))
+        total_bytes = sum(f.numel() * 8 + t.numel() * 8 for s in range(T) for f, t in zip(frames[s], tss[s]))
+    n_points = int((ranges[W][0] != 0).sum().item())
 
     cfg = odometry.load_config(None, deskew=True, max_range=max_r)
     cfg.data.min_range = min_r
@@ -183,12 +199,17 @@ def run_ptk(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def step(odo, fr, ts, s):
+        if use_range:
+            return odo.register_scan_batch(fr[s], stream=sh)
+        return odo.register_frame_batch(fr[s], ts[s], stream=sh)
+
     def timed_run(odo, fr, ts, profiling, clocks=None):
         odo.reset()
         stats_acc = []
         poses = []
         for s in range(W):
-            p, st = odo.register_frame_batch(fr[s], ts[s], stream=sh)
+            p, st = step(odo, fr, ts, s)
             poses.append(p)
         if profiling:
             odo.set_profiling(True)
@@ -200,7 +221,7 @@ def run_ptk(args):
         with torch.cuda.stream(stream):
             e0.record(stream)
             for s in range(W, T):
-                p, st = odo.register_frame_batch(fr[s], ts[s], stream=sh)
+                p, st = step(odo, fr, ts, s)
                 poses.append(p)
                 stats_acc.append(st)
             e1.record(stream)
@@ -214,16 +235,19 @@ def run_ptk(args):
         return ms, launches, prof, stats_acc, np.stack(poses), (c0, c1)
 
     odo = odometry.Odometry(cfg, device=local, max_points=max_pts, map_capacity=map_cap, batch=B)
+    if use_range:
+        odo.set_sensor(gens[0].seq.dirs)
+    dev_in = ranges if use_range else frames
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
 
     # ---- leg 1: inputs resident in HBM ----------------------------------------------------
-    ms_dev, launches, _, stats_acc, poses_dev, cspan = timed_run(odo, frames, tss, False, clocks)
+    ms_dev, launches, _, stats_acc, poses_dev, cspan = timed_run(odo, dev_in, tss, False, clocks)
     # per-kernel device times: same steps again with every launch bracketed by CUDA events on
     # the launching stream (separate pass so the events do not sit inside the headline number)
-    ms_prof, _, prof, _, poses_prof, _ = timed_run(odo, frames, tss, True)
+    ms_prof, _, prof, _, poses_prof, _ = timed_run(odo, dev_in, tss, True)
 
     # ---- leg 2: end to end from pinned host buffers ----------------------------------------
     e2e = None
@@ -232,17 +256,25 @@ def run_ptk(args):
         h_ts = [[None] * B for _ in range(T)]
         for s in range(T):
             for l in range(B):
-                n = frames[s][l].shape[0]
-                hf = _ffi.pinned_empty((n, 3))
-                ht = _ffi.pinned_empty((n,))
-                hf[...] = frames[s][l].cpu().numpy()
-                ht[...] = tss[s][l].cpu().numpy()
-                h_frames[s][l], h_ts[s][l] = hf, ht
+                if use_range:
+                    hr = _ffi.pinned_empty(tuple(ranges[s][l].shape), dtype=np.uint32)
+                    hr[...] = ranges[s][l].cpu().numpy().astype(np.uint32)
+                    h_frames[s][l] = hr
+                else:
+                    n = frames[s][l].shape[0]
+                    hf = _ffi.pinned_empty((n, 3))
+                    ht = _ffi.pinned_empty((n,))
+                    hf[...] = frames[s][l].cpu().numpy()
+                    ht[...] = tss[s][l].cpu().numpy()
+                    h_frames[s][l], h_ts[s][l] = hf, ht
         ms_e2e, _, _, _, poses_e2e, _ = timed_run(odo, h_frames, h_ts, False)
         if not np.array_equal(poses_e2e, poses_dev):
             raise SystemExit("bench.py: host-buffer and device-buffer runs disagree")
-        h2d = scan_bytes + B * 16 * 8 + 512 * B
-        d2h = B * 16 * 8 + B * 120
+        import ctypes
+        cb_in, cb_out = ctypes.c_int(0), ctypes.c_int(0)
+        _ffi.load().ptk_control_bytes(ctypes.byref(cb_in), ctypes.byref(cb_out))
+        h2d = scan_bytes + B * cb_in.value          # scans + the per-lane parameter records
+        d2h = B * cb_out.value                      # per-lane result records (pose + counters)
     if not np.array_equal(poses_prof, poses_dev):
         raise SystemExit("bench.py: run-to-run poses differ (non-deterministic step)")
 
@@ -263,7 +295,7 @@ def run_ptk(args):
             "workload": f"configs[1] 100-scan OS0-128 1024x10 sequence shape ({args.config}), full odometry step, "
                         f"{B} independent sequences (lanes) per GPU advanced by one batched step; scans "
                         f"{W}..{W + K - 1} of each sequence timed",
-            "lanes_per_gpu": B, "points_per_scan": int(frames[W][0].shape[0]), "max_range": max_r,
+            "lanes_per_gpu": B, "points_per_scan": n_points, "input": args.input, "max_range": max_r,
             "min_range": min_r, "voxel_size": cfg.mapping.voxel_size,
             "l2": f"every step reads scans never touched before ({total_bytes / 1e9:.2f} GB of scans per GPU, "
                   f"{scan_bytes / 1e6:.1f} MB per step); the local maps are persistent state and stay wherever "
@@ -277,14 +309,16 @@ def run_ptk(args):
         out["e2e"] = {"value": world * B * K / (ms_e2e_max * 1e-3), "unit": UNIT,
                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                       "ms_per_step": ms_e2e_max / K,
-                      "api": "ptk_register_frame_batch (C ABI, ctypes) with pinned host xyz/timestamps"}
+                      "api": ("ptk_register_scan_batch (C ABI, ctypes) with pinned host RANGE images (uint32 mm)"
+                              if use_range else
+                              "ptk_register_frame_batch (C ABI, ctypes) with pinned host xyz/timestamps")}
 
     # ---- roofline of the dominant kernel ---------------------------------------------------
     peak, peak_src = measured_peaks()
     algo = {}
     for step_stats in stats_acc:
         for st in step_stats:
-            for k, v in algorithmic_bytes(st).items():
+            for k, v in algorithmic_bytes(st, int(ranges[W][0].numel()) if use_range else 0).items():
                 algo[k] = algo.get(k, 0) + v
     kern = {k: v for k, v in prof.items() if v[1] > 0 and k in algo}
     dom = max(kern, key=lambda k: kern[k][0])
@@ -320,6 +354,8 @@ def run_ptk(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         C = max(1, min(B, os.cpu_count() or 1))
         h = [[(frames[s][l].cpu().numpy(), tss[s][l].cpu().numpy()) for s in range(T)] for l in range(C)]
+        # (the reference's CPU path also projects the scan in NumPy inside register_frame, kiss.py:59-61;
+        #  that part is NOT timed here - the baseline is handed ready-made clouds)
         out["cpu_baseline"], ref_poses = cpu_baseline_leg(args, h, min_r, max_r, T)
         n = min(len(p) for p in ref_poses)
         ref = np.stack([np.stack(p[:n]) for p in ref_poses], axis=1) if n else None       # (n, C, 4, 4)

@@ -196,6 +196,9 @@ const char* ptk_kernel_name(int slot);   /* NULL past the last used slot */
  * sums, barrier wait, tree reduction, solve */
 int ptk_get_icp_phases(const ptk_ctx* ctx, int lane, long long* cycles6);
 long long ptk_launch_count(const ptk_ctx* ctx);
+/* bytes of control data one step moves per lane besides the scan itself: the parameter record
+ * uploaded before the launches and the result record (pose, counters) read back after them */
+void ptk_control_bytes(int* h2d_per_lane, int* d2h_per_lane);
 
 /* pinned host memory for callers that want fast H2D of scans */
 int ptk_host_alloc(void** out, unsigned long long bytes);

@@ -80,6 +80,7 @@ SYMBOLS = {
     "ptk_kernel_name": (C.c_char_p, [C.c_int]),
     "ptk_launch_count": (C.c_longlong, [_P]),
     "ptk_get_icp_phases": (C.c_int, [_P, C.c_int, _I]),
+    "ptk_control_bytes": (None, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ptk_host_alloc": (C.c_int, [C.POINTER(_P), C.c_ulonglong]),
     "ptk_host_free": (C.c_int, [_P]),
 }

@@ -193,6 +193,7 @@ static int lane_alloc(ptk_ctx* ctx, LaneHost& LH, bool scratch) {
     LaneDev& d = LH.d;
     memset(&d, 0, sizeof(d));
     d.voxel_size = c.voxel_size;
+    d.voxel_inv = 1.0 / c.voxel_size;
     d.max_distance = c.max_range;
     d.maxp = c.max_points_per_voxel;
     d.max_iters = c.max_iterations;
@@ -228,6 +229,7 @@ static int lane_alloc(ptk_ctx* ctx, LaneHost& LH, bool scratch) {
     CK(dalloc(A, &d.part_b, (size_t)NRED * d.ng_cap, 0));
     CK(dalloc(A, &d.c_tx, N)); CK(dalloc(A, &d.c_ty, N)); CK(dalloc(A, &d.c_tz, N)); CK(dalloc(A, &d.c_slack, N));
     CK(dalloc(A, &d.c_key, N)); CK(dalloc(A, &d.c_ord, N));
+    CK(dalloc(A, &d.c_px, N)); CK(dalloc(A, &d.c_py, N)); CK(dalloc(A, &d.c_pz, N));
     CK(dalloc(A, &d.trace, (size_t)std::max(d.trace_iters, 1) * N, 0xFF));
     CK(dalloc(A, &LH.in_xyz, N * 3));
     CK(dalloc(A, &LH.in_ts, N));
@@ -512,6 +514,7 @@ static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, con
         }
         P.ds1_size = c.voxel_size * 0.5;     // KissICP.voxelize
         P.ds2_size = c.voxel_size * 1.5;
+        P.ds1_inv = 1.0 / P.ds1_size; P.ds2_inv = 1.0 / P.ds2_size;
         P.max_range = c.max_range;
         P.min_range = c.min_range;
         double sigma = has_moved(c, LH) ? compute_threshold(c, LH.thr) : c.initial_threshold;   // kiss.py:99
@@ -796,6 +799,7 @@ extern "C" int ptk_voxel_down_sample(ptk_ctx* ctx, const double* xyz, int n, dou
     P.n = n;
     P.flags = 0;
     P.ds1_size = voxel_size;
+    P.ds1_inv = 1.0 / voxel_size;
     int rc = stage_in(ctx, xyz, (size_t)n * 3, ctx->lanes[ctx->B].in_xyz, &P.xyz, st);
     if (rc) return rc;
     return scratch_select(ctx, P, true, out_xyz, out_index, -1, n_out, st);
@@ -1111,6 +1115,11 @@ extern "C" int ptk_get_profile(ptk_ctx* ctx, double* ms, long long* launches) {
 extern "C" const char* ptk_kernel_name(int slot) { return (slot >= 0 && slot < PS_COUNT) ? kProfNames[slot] : nullptr; }
 
 extern "C" long long ptk_launch_count(const ptk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void ptk_control_bytes(int* h2d_per_lane, int* d2h_per_lane) {
+    if (h2d_per_lane) *h2d_per_lane = (int)sizeof(StepParams);
+    if (d2h_per_lane) *d2h_per_lane = (int)sizeof(StepOut);
+}
 
 extern "C" int ptk_host_alloc(void** out, unsigned long long bytes) {
     if (!out) return PTK_E_ARG;

@@ -37,7 +37,7 @@ constexpr int ICP_THREADS = PTK_ICP_THREADS;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 constexpr int ICP_CHUNK = ICP_WARPS;        // 32-point groups a block handles at a time: one point per thread
 constexpr int ICP_SRC_CAP = 1024;           // source points (+ their cache entries) a block keeps in shared memory
-constexpr int ICP_SMEM = ICP_SRC_CAP * (3 * 8 + 4 * 8 + 8 + 4);
+constexpr int ICP_SMEM = ICP_SRC_CAP * (3 * 8 + 4 * 8 + 8 + 4 + 3 * 8);
 
 enum StepFlags : int { F_DESKEW = 1, F_RANGE = 2, F_SECOND = 4, F_SELECT_RANGE = 8 };
 enum ErrFlags : int { ERR_KEYRANGE = 1, ERR_POOL = 2, ERR_TABLE = 4 };
@@ -70,6 +70,7 @@ struct StepParams {
     double delta[6];       // deskew twist log(inv(T[-2]) T[-1])
     double ds1_size;       // first grid
     double ds2_size;       // second grid
+    double ds1_inv, ds2_inv;   // 1 / size (quotient estimates, see trunc_div)
     double max_range, min_range;
     Rigid guess;
     double max_corr;
@@ -98,7 +99,7 @@ struct StepOut {
 // Per-sequence ("lane") device state.
 struct LaneDev {
     // config
-    double voxel_size, max_distance;
+    double voxel_size, max_distance, voxel_inv;
     int maxp, max_iters;
     double eps;
     int cap_points, pool_cap, trace_iters, ng_cap;
@@ -122,6 +123,7 @@ struct LaneDev {
     // icp
     double* part_a; double* part_b;      // [NRED][ng_cap] partial sums (ping-pong)
     double *c_tx, *c_ty, *c_tz, *c_slack; // correspondence cache of blocks too wide for shared memory
+    double *c_px, *c_py, *c_pz;
     u64* c_key; int* c_ord;
     int* trace;                          // [trace_iters][cap_points]
     // dynamic state
@@ -151,11 +153,24 @@ __device__ __forceinline__ u64 pack_key(int kx, int ky, int kz) {
     return ((u64)(u32)(kx + KEY_BIAS) << 42) | ((u64)(u32)(ky + KEY_BIAS) << 21) | (u64)(u32)(kz + KEY_BIAS);
 }
 
-// kiss-icp voxel key: (p / size).cast<int>() - truncation toward zero.
-__device__ __forceinline__ void voxel_key(double x, double y, double z, double size, int& kx, int& ky, int& kz) {
-    kx = (int)(x / size);
-    ky = (int)(y / size);
-    kz = (int)(z / size);
+// kiss-icp voxel key: (p / size).cast<int>() - truncation toward zero of the IEEE quotient.
+// A double division is ~30 instructions, so the quotient is first estimated as x * (1/size)
+// (within 2 ulp of x / size); unless that estimate sits within 1e-11 (relative) of an integer -
+// where the rounding of the true quotient could decide the result - its truncation IS the
+// truncation of x / size.  Only the rare borderline coordinate pays for the exact division.
+__device__ __forceinline__ int trunc_div(double x, double size, double inv) {
+    const double q = x * inv;
+    const double t = trunc(q);
+    const double f = fabs(q - t);
+    const double eps = fabs(q) * 1e-11 + 1e-290;
+    if (f > eps && f < 1.0 - eps && fabs(q) < 2.0e9) return (int)t;
+    return (int)(x / size);
+}
+
+__device__ __forceinline__ void voxel_key(double x, double y, double z, double size, double inv, int& kx, int& ky, int& kz) {
+    kx = trunc_div(x, size, inv);
+    ky = trunc_div(y, size, inv);
+    kz = trunc_div(z, size, inv);
 }
 
 // First-seen table: find-or-insert `key`, keep the minimum `val`; returns the slot.
@@ -233,9 +248,18 @@ __global__ void k_col_motion(const StepParams* params) {
     for (int k = 0; k < 3; ++k) P.col_motion[(9 + k) * P.W + w] = M.t[k];
 }
 
+// kiss-icp Preprocess: min_range < |p| < max_range on the rounded norm.  Away from the two
+// thresholds (by 1e-12 relative, far more than the rounding of the square root) the comparison of
+// the squared norm decides; only borderline points take the square root.
 __device__ __forceinline__ bool range_pass(const StepParams& P, double x, double y, double z) {
     if (!(P.flags & F_RANGE)) return true;
-    double nrm = sqrt((x * x + y * y) + z * z);
+    const double n2 = (x * x + y * y) + z * z;
+    if (P.min_range >= 0.0 && P.max_range > 0.0) {
+        const double mx2 = P.max_range * P.max_range, mn2 = P.min_range * P.min_range;
+        if (n2 < mx2 * (1.0 - 1e-12) && n2 > mn2 * (1.0 + 1e-12)) return true;
+        if (n2 > mx2 * (1.0 + 1e-12) || n2 < mn2 * (1.0 - 1e-12)) return false;
+    }
+    const double nrm = sqrt(n2);
     return nrm < P.max_range && nrm > P.min_range;
 }
 
@@ -245,23 +269,30 @@ __global__ void __launch_bounds__(256) k_scan_insert(LaneDev* lanes, const StepP
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool pass = false, valid = false;
+    bool pass = false, valid = false, ins = false;
+    u64 key = KEY_EMPTY;
     if (i < P.n) {
         double x, y, z;
         valid = load_point(P, i, x, y, z);
         pass = valid && range_pass(P, x, y, z);
-        u32 slot = NONE;
         if (pass) {
             int kx, ky, kz;
-            voxel_key(x, y, z, P.ds1_size, kx, ky, kz);
-            if (key_in_range(kx, ky, kz)) {
-                slot = table_insert_min(L.t1_keys, L.t1_vals, L.t_mask, pack_key(kx, ky, kz), (u32)i);
-            } else {
-                atomicOr(&L.err, ERR_KEYRANGE);
-            }
+            voxel_key(x, y, z, P.ds1_size, P.ds1_inv, kx, ky, kz);
+            if (key_in_range(kx, ky, kz)) { key = pack_key(kx, ky, kz); ins = true; }
+            else atomicOr(&L.err, ERR_KEYRANGE);
         }
-        L.slot1[i] = slot;
     }
+    // neighbouring pixels of a beam mostly fall into the same voxel: one table operation per distinct
+    // key of the warp, issued by the lowest lane (= lowest point index) of each group
+    const u32 am = __ballot_sync(0xffffffffu, ins);
+    u32 slot = NONE;
+    if (ins) {
+        const u32 peers = __match_any_sync(am, key);
+        const int leader = __ffs(peers) - 1;
+        if ((int)(threadIdx.x & 31) == leader) slot = table_insert_min(L.t1_keys, L.t1_vals, L.t_mask, key, (u32)i);
+        slot = __shfl_sync(peers, slot, leader);
+    }
+    if (i < P.n) L.slot1[i] = slot;
     u32 m = __ballot_sync(0xffffffffu, pass);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&L.n_range, __popc(m));
     if (P.range) {          // len(frame) of kiss.py:60: pixels with a return
@@ -365,21 +396,32 @@ __global__ void __launch_bounds__(256) k_compact1(LaneDev* lanes, const StepPara
     int pos = prefix + local;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (!win[k]) continue;
-        int i = i0 + k;
-        double x, y, z;
-        load_point(P, i, x, y, z);
-        L.ds_x[pos] = x; L.ds_y[pos] = y; L.ds_z[pos] = z;
-        L.ds_idx[pos] = (u32)i;
-        if (P.flags & F_SECOND) {
-            int kx, ky, kz;
-            voxel_key(x, y, z, P.ds2_size, kx, ky, kz);
-            u32 s2 = NONE;
-            if (key_in_range(kx, ky, kz)) s2 = table_insert_min(L.t2_keys, L.t2_vals, L.t_mask, pack_key(kx, ky, kz), (u32)pos);
-            else atomicOr(&L.err, ERR_KEYRANGE);
-            L.ds_slot2[pos] = s2;
+        bool ins = false;
+        u64 key = KEY_EMPTY;
+        if (win[k]) {
+            int i = i0 + k;
+            double x, y, z;
+            load_point(P, i, x, y, z);
+            L.ds_x[pos] = x; L.ds_y[pos] = y; L.ds_z[pos] = z;
+            L.ds_idx[pos] = (u32)i;
+            if (P.flags & F_SECOND) {
+                int kx, ky, kz;
+                voxel_key(x, y, z, P.ds2_size, P.ds2_inv, kx, ky, kz);
+                if (key_in_range(kx, ky, kz)) { key = pack_key(kx, ky, kz); ins = true; }
+                else { atomicOr(&L.err, ERR_KEYRANGE); L.ds_slot2[pos] = NONE; }
+            }
         }
-        ++pos;
+        if (P.flags & F_SECOND) {       // one table operation per distinct key of the warp (lowest lane = lowest pos)
+            const u32 am = __ballot_sync(0xffffffffu, ins);
+            if (ins) {
+                const u32 peers = __match_any_sync(am, key);
+                const int leader = __ffs(peers) - 1;
+                u32 s2 = NONE;
+                if ((int)(threadIdx.x & 31) == leader) s2 = table_insert_min(L.t2_keys, L.t2_vals, L.t_mask, key, (u32)pos);
+                L.ds_slot2[pos] = __shfl_sync(peers, s2, leader);
+            }
+        }
+        if (win[k]) ++pos;
     }
     if (tile == ntiles - 1 && threadIdx.x == 0) L.n_ds = prefix + total;
 }
@@ -480,18 +522,16 @@ __device__ __forceinline__ double warp_min_upper(double best) {
     return __longlong_as_double((long long)(((u64)mhi << 32) | 0xffffffffull));
 }
 
-// `slack` (out): how far the query may move, staying in its voxel, before the answer can change:
-// half the gap between the nearest candidate and a lower bound of the distance to every other
-// candidate of the 27 voxels (the runner-up among the visited points, the box distance of every
-// voxel the search skipped), minus a margin far above any rounding involved.  While the accumulated
-// motion stays below it, a full search would return the same map point (strictly nearest, so no
-// tie rule involved) - k_icp uses that to skip the search (see there).  Negative = never skip.
+// `others` (out): a lower bound of the distance from the query to every candidate of the 27 voxels
+// EXCEPT the winner (the runner-up among the visited points, the box distance of every voxel the
+// search skipped), rounded down; negative if nothing was found.  k_icp uses it to prove, for a query
+// that has moved but stayed in its voxel, that a new search would return the same map point.
 __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double sy, double sz, int lane, double max_d2,
-                                             double& bd2, int& bord, double& tx, double& ty, double& tz, double& slack) {
+                                             double& bd2, int& bord, double& tx, double& ty, double& tz, double& others) {
     const u32 FULL = 0xffffffffu;
     const double v = L.voxel_size;
     int kx, ky, kz;
-    voxel_key(sx, sy, sz, v, kx, ky, kz);
+    voxel_key(sx, sy, sz, v, L.voxel_inv, kx, ky, kz);
     u32 id = NONE;
     double lb2 = INFINITY;
     if (lane < 27 && key_in_range(kx, ky, kz)) {
@@ -567,7 +607,7 @@ __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double
     if ((remaining >> lane) & 1u) other = fmin(other, lb2);
     const u32 ohi = __reduce_min_sync(FULL, (u32)((u64)__double_as_longlong(other) >> 32));
     const double d2_other = __longlong_as_double((long long)((u64)ohi << 32));     // low word zero: rounds down
-    slack = found ? (sqrt(d2_other) - sqrt(bd2)) * 0.5 - 1e-9 : -1.0;
+    others = found ? sqrt(d2_other) * (1.0 - 1e-12) : -1.0;
     return found;
 }
 
@@ -803,10 +843,13 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
 // grid = (blocks per lane, lanes), ICP_THREADS threads.  A block owns a contiguous range of
 // 32-point groups and walks it in chunks of ICP_CHUNK groups (= one point per thread).  Per
 // iteration and chunk:
-//   1. thread per point: move the point by the last increment, then try the correspondence cache:
-//      if the point is still in the voxel it was searched from and has moved less than the slack
-//      that search left (see warp_nearest), the nearest map point is provably the cached one and no
-//      search is needed; otherwise the point goes on the block's work list;
+//   1. thread per point: move the point by the last increment, then try the correspondence cache.
+//      The last search of the point, at position p0, left its winner a and a lower bound D of the
+//      distance from p0 to every other candidate (see warp_nearest).  If the point is still in the
+//      same voxel (same 27 candidates voxels; the map does not change during the loop) and
+//      |p - a| + |p - p0| < D, then every other candidate c has |p - c| >= |p0 - c| - |p - p0| >= D - |p - p0|
+//      > |p - a|: a is the strictly nearest candidate, which is what a new search would return (no tie
+//      rule involved), so none is needed; otherwise the point goes on the block's work list;
 //   2. warp per listed point: the pruned 27-voxel search, refreshing the cache entry;
 //   3. thread per point: residual, Geman-McClure weight and the 16 distinct sums (+ count) in
 //      registers; a warp IS a 32-point group, so xor-butterflies give the group partials directly.
@@ -857,9 +900,12 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
 #define C_TZ(i) (*(in_smem ? dyn_smem + 5 * ICP_SRC_CAP + (i) : L.c_tz + goff + (i)))
 #define C_SLACK(i) (*(in_smem ? dyn_smem + 6 * ICP_SRC_CAP + (i) : L.c_slack + goff + (i)))
 #define C_KEY(i) (*(in_smem ? reinterpret_cast<u64*>(dyn_smem + 7 * ICP_SRC_CAP) + (i) : L.c_key + goff + (i)))
-#define C_ORD(i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + 8 * ICP_SRC_CAP) + (i) : L.c_ord + goff + (i)))
+#define C_ORD(i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + 11 * ICP_SRC_CAP) + (i) : L.c_ord + goff + (i)))
+#define C_PX(i) (*(in_smem ? dyn_smem + 8 * ICP_SRC_CAP + (i) : L.c_px + goff + (i)))
+#define C_PY(i) (*(in_smem ? dyn_smem + 9 * ICP_SRC_CAP + (i) : L.c_py + goff + (i)))
+#define C_PZ(i) (*(in_smem ? dyn_smem + 10 * ICP_SRC_CAP + (i) : L.c_pz + goff + (i)))
     if (threadIdx.x == 0) sT = se3q_identity();
-    const double voxel = L.voxel_size;
+    const double voxel = L.voxel_size, voxel_inv = L.voxel_inv;
     // phase clocks of block 0 (thread 0 only; six clock reads per iteration)
     const bool clk = b == 0 && threadIdx.x == 0;
     __shared__ long long s_cyc[6];
@@ -889,13 +935,19 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 if (it > 0) {
                     double xo, yo, zo;
                     rigid_apply(sE, sx, sy, sz, xo, yo, zo);
-                    const double mx = xo - sx, my = yo - sy, mz = zo - sz;
                     sx = xo; sy = yo; sz = zo;
-                    const double slack = C_SLACK(sp) - (sqrt((mx * mx + my * my) + mz * mz) + 1e-10);
-                    C_SLACK(sp) = slack;
-                    int kx, ky, kz;
-                    voxel_key(sx, sy, sz, voxel, kx, ky, kz);
-                    miss = !(slack > 0.0 && key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == C_KEY(sp));
+                    const double others = C_SLACK(sp);
+                    if (others > 0.0) {
+                        const double mx = sx - C_PX(sp), my = sy - C_PY(sp), mz = sz - C_PZ(sp);
+                        const double ex = sx - C_TX(sp), ey = sy - C_TY(sp), ez = sz - C_TZ(sp);
+                        const double moved = sqrt((mx * mx + my * my) + mz * mz);
+                        const double e1 = sqrt((ex * ex + ey * ey) + ez * ez);
+                        if (e1 + moved + 1e-9 < others) {
+                            int kx, ky, kz;
+                            voxel_key(sx, sy, sz, voxel, voxel_inv, kx, ky, kz);
+                            miss = !(key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == C_KEY(sp));
+                        }
+                    }
                 }
                 if (in_smem) { ssx[sp] = sx; ssy[sp] = sy; ssz[sp] = sz; }
                 else if (it > 0) { L.s_x[p] = sx; L.s_y[p] = sy; L.s_z[p] = sz; }
@@ -920,14 +972,15 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 double qx, qy, qz;
                 if (in_smem) { qx = ssx[msp]; qy = ssy[msp]; qz = ssz[msp]; }
                 else { const int mp = g0 * 32 + mq; qx = __ldcg(L.s_x + mp); qy = __ldcg(L.s_y + mp); qz = __ldcg(L.s_z + mp); }
-                double d2, tx, ty, tz, slack;
+                double d2, tx, ty, tz, others;
                 int ord;
-                const bool found = warp_nearest(L, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, slack);
+                const bool found = warp_nearest(L, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others);
                 if (lane == 0) {
                     int kx, ky, kz;
-                    voxel_key(qx, qy, qz, voxel, kx, ky, kz);
+                    voxel_key(qx, qy, qz, voxel, voxel_inv, kx, ky, kz);
                     C_TX(msp) = tx; C_TY(msp) = ty; C_TZ(msp) = tz;
-                    C_SLACK(msp) = slack;
+                    C_PX(msp) = qx; C_PY(msp) = qy; C_PZ(msp) = qz;
+                    C_SLACK(msp) = others;
                     C_KEY(msp) = key_in_range(kx, ky, kz) ? pack_key(kx, ky, kz) : KEY_EMPTY;
                     C_ORD(msp) = found ? ord : -1;
                 }
@@ -995,6 +1048,9 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
 #undef C_SLACK
 #undef C_KEY
 #undef C_ORD
+#undef C_PX
+#undef C_PY
+#undef C_PZ
 }
 
 // ------------------------------------------------------------------------------------
@@ -1055,7 +1111,7 @@ __global__ void __launch_bounds__(256) k_map_insert(LaneDev* lanes, const StepPa
             double x = L.ds_x[j], y = L.ds_y[j], z = L.ds_z[j];
             if (use_pose) { double xo, yo, zo; rigid_apply(T, x, y, z, xo, yo, zo); x = xo; y = yo; z = zo; }
             int kx, ky, kz;
-            voxel_key(x, y, z, L.voxel_size, kx, ky, kz);
+            voxel_key(x, y, z, L.voxel_size, L.voxel_inv, kx, ky, kz);
             if (key_in_range(kx, ky, kz)) key = pack_key(kx, ky, kz);
             else { atomicOr(&L.err, ERR_KEYRANGE); act = false; }
             u32 s2 = L.ds_slot2[j];
@@ -1230,9 +1286,9 @@ __global__ void k_correspondences(LaneDev* lanes, int lane_id, const double* q, 
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n) return;
     double sx = q[3 * (size_t)w], sy = q[3 * (size_t)w + 1], sz = q[3 * (size_t)w + 2];
-    double d2, tx, ty, tz, slack;
+    double d2, tx, ty, tz, others;
     int ord;
-    bool found = L.n_vox > 0 && warp_nearest(L, sx, sy, sz, lane, (max_dist * max_dist) * (1.0 + 1e-9), d2, ord, tx, ty, tz, slack);
+    bool found = L.n_vox > 0 && warp_nearest(L, sx, sy, sz, lane, (max_dist * max_dist) * (1.0 + 1e-9), d2, ord, tx, ty, tz, others);
     bool acc = found && (sqrt(d2) < max_dist);
     if (lane == 0) {
         out_order[w] = acc ? ord : -1;
