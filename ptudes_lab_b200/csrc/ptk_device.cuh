@@ -265,7 +265,7 @@ __device__ __forceinline__ bool range_pass(const StepParams& P, double x, double
 
 // ------------------------------------------------------------------------------------
 // K1: deskew + range filter + voxel key (grid 1) + first-seen atomicMin.
-__global__ void __launch_bounds__(256) k_scan_insert(LaneDev* lanes, const StepParams* params) {
+__global__ void __launch_bounds__(256, 4) k_scan_insert(LaneDev* lanes, const StepParams* params) {
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
