@@ -1,0 +1,92 @@
+"""The ekf-bench scan/IMU loop (ptudes_lab_b200.ekf_bench.run_ekf_ouster, reference
+cli/ekf_bench.py:493-563): plumbing on the CPU with the oracle behind the KissICPWrapper surface,
+and (gpu) the CUDA wrapper against the oracle wrapper under the same loop - config 4 of
+BASELINE.json (ekf-bench ranges min 1 / max 70 -> v = 0.7, 100 Hz IMU)."""
+import numpy as np
+import pytest
+
+from oracle import kiss_oracle as ko
+from ptudes_lab_b200 import synth
+from ptudes_lab_b200.ekf_bench import SynthLidarImuSource, run_ekf_ouster
+from ptudes_lab_b200.ins import ESEKF, IMU, calc_ate
+from ptudes_lab_b200.ouster_compat import ChanField, XYZLut, sensor_info_from_synth
+
+
+class OracleWrapper:
+    """The KissICPWrapper surface (kiss.py:18-166) on the NumPy oracle, LidarScan in."""
+
+    def __init__(self, meta, _min_range=1, _max_range=70):
+        self._lut = XYZLut(meta)
+        w, h = meta.format.columns_per_frame, meta.format.pixels_per_column
+        self._timestamps = np.tile(np.linspace(0, 1.0, w, endpoint=False), (h, 1))
+        self._o = ko.OracleKissICPWrapper(_min_range=_min_range, _max_range=_max_range)
+        self._kiss = self._o._kiss
+
+    def register_frame(self, scan, initial_guess=None):
+        from ptudes_lab_b200.ouster_compat import last_valid_column_ts
+        sel = scan.field(ChanField.RANGE) != 0
+        return self._o.register_points(self._lut(scan)[sel], self._timestamps[sel],
+                                       last_valid_column_ts(scan) * 1e-9, initial_guess=initial_guess)
+
+    @property
+    def pose(self):
+        return self._o.pose
+
+
+def test_source_interleaves_imu_and_scans(tiny_seq):
+    src = SynthLidarImuSource(tiny_seq, 3)
+    items = list(src.withScanIdx())
+    kinds = ["I" if isinstance(d, IMU) else "S" for _, d in items]
+    assert "".join(kinds) == ("I" * 10 + "S") * 3
+    ts = [d.ts for _, d in items if isinstance(d, IMU)]
+    assert np.allclose(np.diff(ts), 0.01)
+    # at rest the accelerometer reads +g on z (specific force), up to the mount-free body tilt
+    first = SynthLidarImuSource(tiny_seq, 1, acc_noise_std=0, gyr_noise_std=0, acc_bias=(0, 0, 0), gyr_bias=(0, 0, 0)).imu_at(0.0)
+    assert abs(np.linalg.norm(first.lacc) - 9.782940329221166) < 0.5 and first.lacc[2] > 9.0
+    assert len(list(src.withScanIdx(start_scan=1, end_scan=1))) == 11
+
+
+@pytest.mark.parametrize("use_imu", [False, True])
+def test_loop_on_the_oracle(tiny_seq, use_imu):
+    n = 12
+    meta = sensor_info_from_synth(tiny_seq.sensor, tiny_seq.dirs)
+    src = SynthLidarImuSource(tiny_seq, n)
+    out = run_ekf_ouster(src, OracleWrapper(meta), ESEKF(), use_imu_prediction=use_imu)
+    assert len(out["kiss_poses"]) == len(out["res_poses"]) == len(out["res_t"]) == n
+    gt = src.gt_poses()
+    ate_r, ate_t = calc_ate(out["kiss_poses"], gt)
+    assert ate_t < 0.15 ** 2 and ate_r < 0.05          # odometry tracks the synthetic ground truth (sparse 32x256 sensor)
+    ekf_r, ekf_t = calc_ate(out["res_poses"], gt)
+    assert ekf_t < 0.2 ** 2                             # and the filter follows its measurements
+    assert all(v is not None and v > 0 for v in out["timings"].values())
+
+
+def test_scan_without_imu_in_between_is_skipped(tiny_seq):
+    meta = sensor_info_from_synth(tiny_seq.sensor, tiny_seq.dirs)
+
+    class Src(SynthLidarImuSource):
+        def withScanIdx(self, **kw):
+            for k, d in super().withScanIdx(**kw):
+                if k == 2 and isinstance(d, IMU):
+                    continue                            # drop the IMU packets of sweep 2
+                yield k, d
+    out = run_ekf_ouster(Src(tiny_seq, 4), OracleWrapper(meta))
+    assert len(out["kiss_poses"]) == 3                  # cli/ekf_bench.py:512-518
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_imu", [False, True])
+def test_config4_cuda_wrapper_equals_oracle_under_the_loop(use_imu):
+    """BASELINE config 4: OS0-128 + 100 Hz IMU, ekf-bench defaults min 1 / max 70, lidar update on the
+    GPU, ESEKF on the host; with --use-imu-prediction the filter's pose is the injected guess."""
+    from ptudes_lab_b200.kiss import KissICPWrapper
+    seq = synth.make_sequence("os0_quad", 0)
+    n = 10
+    meta = sensor_info_from_synth(seq.sensor, seq.dirs)
+    a = run_ekf_ouster(SynthLidarImuSource(seq, n), KissICPWrapper(meta, _min_range=1, _max_range=70, _use_extrinsics=True),
+                       use_imu_prediction=use_imu)
+    b = run_ekf_ouster(SynthLidarImuSource(seq, n), OracleWrapper(meta), use_imu_prediction=use_imu)
+    assert np.array_equal(np.array(a["kiss_poses"]), np.array(b["kiss_poses"]))
+    assert np.array_equal(np.array(a["res_poses"]), np.array(b["res_poses"]))
+    ate_r, ate_t = calc_ate(a["kiss_poses"], SynthLidarImuSource(seq, n).gt_poses())
+    assert ate_t < 0.1 ** 2
