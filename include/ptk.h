@@ -126,6 +126,26 @@ int ptk_register_scan(ptk_ctx* ctx, int lane, const unsigned int* range_mm /* H*
 int ptk_register_scan_batch(ptk_ctx* ctx, const unsigned int* const* range_mm, const double* guesses,
                             const unsigned char* has_guess, double* out_poses, ptk_stats* stats, void* stream);
 
+/* ---- one sequence, voxel map sharded by hash key over several GPUs (one process + context per GPU).
+ * The registration loop of kiss.py:108-114 is driven by the host between its two collectives per
+ * iteration (ptudes_lab_b200/sharded.py): every rank preprocesses the same scan, searches its own
+ * shard of the map, the per-point records are all-gathered, each rank builds the normal-equation
+ * partial of its slice of the source, the [17][32] partial table is all-reduced (NCCL), and every
+ * rank solves.  Sums are combined in the canonical tree order, so poses equal the single-GPU ones
+ * bit for bit.  All buffers are DEVICE pointers of float64:
+ *   records  [5][n_src]         d2, order id, target x, y, z of the nearest LOCAL map point
+ *   gathered [nranks][5][n_src] the records of every rank (all-gather)
+ *   partials [17][32]           column r = slice root of rank r, zero elsewhere (all-reduce SUM) */
+int ptk_shard_config(ptk_ctx* ctx, int rank, int nranks);
+int ptk_shard_begin(ptk_ctx* ctx, int lane, const double* xyz, const double* timestamps, int n,
+                    const unsigned int* range_mm /* alternative input, NULL to use xyz */,
+                    const double* initial_guess, int* n_src, int* n_vox_local, void* stream);
+int ptk_shard_search(ptk_ctx* ctx, int lane, int iteration, double* records, void* stream);
+int ptk_shard_system(ptk_ctx* ctx, int lane, const double* gathered, int iteration, double* partials, void* stream);
+int ptk_shard_solve(ptk_ctx* ctx, int lane, const double* partials, int iteration, int map_empty, int* done,
+                    void* stream);
+int ptk_shard_end(ptk_ctx* ctx, int lane, double* out_pose, ptk_stats* stats, void* stream);
+
 /* ---- state the wrapper exposes (kiss.py:133-166, cli/ekf_bench.py:545-547) --------- */
 int ptk_num_poses(const ptk_ctx* ctx, int lane);
 int ptk_get_pose(const ptk_ctx* ctx, int lane, int index /* <0 from the end */, double* out16);

@@ -53,6 +53,12 @@ SYMBOLS = {
     "ptk_set_sensor": (C.c_int, [_P, C.c_int, C.c_int, _D, _D, _D, C.c_double]),
     "ptk_register_scan": (C.c_int, [_P, C.c_int, _I, _D, _D, C.POINTER(PtkStats), _P]),
     "ptk_register_scan_batch": (C.c_int, [_P, C.POINTER(_I), _D, C.c_char_p, _D, C.POINTER(PtkStats), _P]),
+    "ptk_shard_config": (C.c_int, [_P, C.c_int, C.c_int]),
+    "ptk_shard_begin": (C.c_int, [_P, C.c_int, _D, _D, C.c_int, _I, _D, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "ptk_shard_search": (C.c_int, [_P, C.c_int, C.c_int, _D, _P]),
+    "ptk_shard_system": (C.c_int, [_P, C.c_int, _D, C.c_int, _D, _P]),
+    "ptk_shard_solve": (C.c_int, [_P, C.c_int, _D, C.c_int, C.c_int, C.POINTER(C.c_int), _P]),
+    "ptk_shard_end": (C.c_int, [_P, C.c_int, _D, C.POINTER(PtkStats), _P]),
     "ptk_num_poses": (C.c_int, [_P, C.c_int]),
     "ptk_get_pose": (C.c_int, [_P, C.c_int, C.c_int, _D]),
     "ptk_get_prediction_model": (C.c_int, [_P, C.c_int, _D]),

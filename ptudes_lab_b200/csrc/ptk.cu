@@ -29,6 +29,8 @@ struct LaneHost {
     std::vector<Rigid> poses;
     Threshold thr;
     double last_sigma = 0.0;
+    double pending_sigma = 0.0;       // threshold chosen by step_prepare for the step in flight
+    int pending_nmax = 0, shard_nsrc = 0; // sharded loop state between ptk_shard_begin and ptk_shard_end
     StepParams last_params;
     StepOut last_out;
     bool have_last = false;
@@ -464,15 +466,14 @@ static int maybe_rebuild(ptk_ctx* ctx, int l, const StepOut& O, cudaStream_t st)
     return PTK_OK;
 }
 
-// The whole step for lanes [l0, l0+cnt).
-// `range` non-null selects the range-image input (one H*W uint32 image per lane; xyz/ts/n unused).
-static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, const double* const* ts, const int* n_in,
-                    const unsigned int* const* range, const double* guesses, const unsigned char* has_guess,
-                    double* out_poses, ptk_stats* stats, cudaStream_t st) {
+// First half of the step for lanes [l0, l0+cnt): parameters, upload, deskew + range filter + the two
+// voxel grids (kiss.py:90-105).  Leaves frame_downsample / source on the device.
+static int step_prepare(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, const double* const* ts, const int* n_in,
+                        const unsigned int* const* range, const double* guesses, const unsigned char* has_guess,
+                        int* nmax_out, cudaStream_t st) {
     const ptk_config& c = ctx->cfg;
     CK(cudaSetDevice(ctx->device));
     int nmax = 0;
-    std::vector<double> sigmas(cnt);
     std::vector<int> nv(cnt);
     const int* n = nv.data();
     const int npix = ctx->sen_H * ctx->sen_W;
@@ -518,7 +519,7 @@ static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, con
         P.max_range = c.max_range;
         P.min_range = c.min_range;
         double sigma = has_moved(c, LH) ? compute_threshold(c, LH.thr) : c.initial_threshold;   // kiss.py:99
-        sigmas[k] = sigma;
+        LH.pending_sigma = sigma;
         if (guesses && (!has_guess || has_guess[k])) {
             rigid_from_mat16(guesses + 16 * (size_t)k, P.guess);
         } else {                                                                                // kiss.py:102-105
@@ -552,6 +553,20 @@ static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, con
     LAUNCH(PS_COMPACT1, st, k_compact1<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
     LAUNCH(PS_COMPACT2, st, k_compact2<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
     CK(cudaGetLastError());
+    *nmax_out = nmax;
+    return PTK_OK;
+}
+
+static int step_finish(ptk_ctx* ctx, int l0, int cnt, int nmax, double* out_poses, ptk_stats* stats, cudaStream_t st);
+
+// The whole step for lanes [l0, l0+cnt).
+// `range` non-null selects the range-image input (one H*W uint32 image per lane; xyz/ts/n unused).
+static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, const double* const* ts, const int* n_in,
+                    const unsigned int* const* range, const double* guesses, const unsigned char* has_guess,
+                    double* out_poses, ptk_stats* stats, cudaStream_t st) {
+    int nmax = 0;
+    int rc = step_prepare(ctx, l0, cnt, xyz, ts, n_in, range, guesses, has_guess, &nmax, st);
+    if (rc) return rc;
     // source size changes slowly from scan to scan: size the ICP grid from the last one
     int groups_hint = 0;
     for (int k = 0; k < cnt; ++k) {
@@ -559,9 +574,17 @@ static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, con
         if (!LH.have_last || LH.last_out.n_src <= 0) { groups_hint = 0; break; }
         groups_hint = std::max(groups_hint, (int)(((long long)LH.last_out.n_src * 5 / 4 + 31) / 32) + 1);
     }
-    int rc = launch_icp(ctx, l0, cnt, groups_hint, st);
+    rc = launch_icp(ctx, l0, cnt, groups_hint, st);
     if (rc) return rc;
-    rc = map_update_launch(ctx, l0, cnt, nmax, 1, nullptr, true, true, st);
+    return step_finish(ctx, l0, cnt, nmax, out_poses, stats, st);
+}
+
+// Second half: local-map update with the new pose (kiss.py:129), counters, and the host bookkeeping of
+// kiss.py:116-130 (pose gain metrics, model deviation, pose list).
+static int step_finish(ptk_ctx* ctx, int l0, int cnt, int nmax, double* out_poses, ptk_stats* stats, cudaStream_t st) {
+    LaneDev* dl = ctx->d_lanes + l0;
+    StepOut* dout = ctx->d_outs + l0;
+    int rc = map_update_launch(ctx, l0, cnt, nmax, 1, nullptr, true, true, st);
     if (rc) return rc;
     LAUNCH(PS_FINISH, st, k_finish<<<(cnt + 63) / 64, 64, 0, st>>>(dl, dout, cnt));
     CK(cudaGetLastError());
@@ -586,14 +609,14 @@ static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, con
         so3_log(gain.r, om, theta);
         LH.thr.deviation = gain;                                              // kiss.py:128
         LH.poses.push_back(O.pose);                                           // kiss.py:130
-        LH.last_sigma = sigmas[k];
+        LH.last_sigma = LH.pending_sigma;
         if (out_poses) rigid_to_mat16(O.pose, out_poses + 16 * (size_t)k);
         if (stats) {
             ptk_stats& S = stats[k];
             memset(&S, 0, sizeof(S));
             S.status = O.status; S.n_in = P.range ? O.n_valid : P.n; S.n_range = O.n_range; S.n_ds = O.n_ds; S.n_src = O.n_src;
             S.n_voxels = O.n_vox; S.iterations = O.iterations; S.n_corr = O.n_corr; S.dx_norm = O.dx_norm;
-            S.sigma = sigmas[k]; S.err_dt = dt; S.err_drot = fabs(theta); S.map_points = O.map_points;
+            S.sigma = LH.pending_sigma; S.err_dt = dt; S.err_drot = fabs(theta); S.map_points = O.map_points;
             S.icp_searches = O.icp_searches;
         }
         if (O.status == 2 && !ret) ret = fail(ctx, PTK_E_NUMERIC, "singular normal equations in ICP");
@@ -1083,6 +1106,104 @@ extern "C" int ptk_register_point_cloud(ptk_ctx* ctx, int lane, const double* xy
     }
     if (O.status == 2) return fail(ctx, PTK_E_NUMERIC, "singular normal equations in ICP");
     return PTK_OK;
+}
+
+// ---- hash-sharded map over several GPUs: one process per GPU drives these between its collectives ----
+#include <stddef.h>
+extern "C" int ptk_shard_config(ptk_ctx* ctx, int rank, int nranks) {
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks || nranks > 32) return fail(ctx, PTK_E_ARG, "ptk_shard_config: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    for (size_t l = 0; l < ctx->lanes.size(); ++l) {
+        LaneDev& d = ctx->lanes[l].d;
+        d.shard_rank = rank; d.shard_n = nranks;
+        int v[2] = {rank, nranks};
+        CK(cudaMemcpy((char*)(ctx->d_lanes + l) + offsetof(LaneDev, shard_rank), v, sizeof(v), cudaMemcpyHostToDevice));
+    }
+    return PTK_OK;
+}
+
+extern "C" int ptk_shard_begin(ptk_ctx* ctx, int lane, const double* xyz, const double* timestamps, int n,
+                               const unsigned int* range_mm, const double* initial_guess, int* n_src, int* n_vox_local,
+                               void* stream) {
+    if (!ctx) return PTK_E_ARG;
+    if (lane < 0 || lane >= ctx->B) return fail(ctx, PTK_E_ARG, "lane out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char hg = initial_guess ? 1 : 0;
+    LaneHost& LH = ctx->lanes[lane];
+    int rc = step_prepare(ctx, lane, 1, &xyz, &timestamps, &n, range_mm ? &range_mm : nullptr, initial_guess, &hg,
+                          &LH.pending_nmax, st);
+    if (rc) return rc;
+    int v[2] = {0, 0};
+    CK(cudaMemcpyAsync(&v[0], (char*)(ctx->d_lanes + lane) + offsetof(LaneDev, n_src), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&v[1], (char*)(ctx->d_lanes + lane) + offsetof(LaneDev, n_vox), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    LH.shard_nsrc = v[0];
+    if (n_src) *n_src = v[0];
+    if (n_vox_local) *n_vox_local = v[1];
+    return PTK_OK;
+}
+
+extern "C" int ptk_shard_search(ptk_ctx* ctx, int lane, int it, double* records, void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B || !records) return fail(ctx, PTK_E_ARG, "ptk_shard_search: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    int n = ctx->lanes[lane].shard_nsrc;
+    if (n > 0) {
+        size_t threads = (size_t)n * 32;
+        LAUNCH(PS_ICP, st, k_shard_search<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ctx->d_lanes, lane, ctx->d_params, it, records, n));
+        CK(cudaGetLastError());
+    }
+    return PTK_OK;
+}
+
+static void shard_slice(int n, int G, int rank, int* g_lo, int* g_cnt, int* n_roots) {
+    int n_groups = (n + 31) / 32;
+    int P = 1;
+    while (P < n_groups) P <<= 1;
+    int sg = std::max(1, P / G);
+    *n_roots = P / sg;
+    *g_lo = rank * sg;
+    *g_cnt = rank < *n_roots ? sg : 0;
+}
+
+extern "C" int ptk_shard_system(ptk_ctx* ctx, int lane, const double* gathered, int it, double* partials, void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B || !gathered || !partials) return fail(ctx, PTK_E_ARG, "ptk_shard_system: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    const LaneHost& LH = ctx->lanes[lane];
+    int n = LH.shard_nsrc, G = LH.d.shard_n, rank = LH.d.shard_rank;
+    int g_lo, g_cnt, n_roots;
+    shard_slice(n, G, rank, &g_lo, &g_cnt, &n_roots);
+    CK(cudaMemsetAsync(partials, 0, sizeof(double) * NSUM * 32, st));
+    if (g_cnt > 0 && n > 0) {
+        LAUNCH(PS_ICP, st, k_shard_system<<<(g_cnt + ICP_WARPS - 1) / ICP_WARPS, ICP_THREADS, 0, st>>>(
+                   ctx->d_lanes, lane, ctx->d_params, gathered, G, n, it, g_lo, g_cnt));
+        LAUNCH(PS_ICP, st, k_shard_slice_root<<<1, NSUM * 32, 0, st>>>(ctx->d_lanes, lane, n, g_lo, g_cnt, partials, rank));
+        CK(cudaGetLastError());
+    }
+    return PTK_OK;
+}
+
+extern "C" int ptk_shard_solve(ptk_ctx* ctx, int lane, const double* partials, int it, int map_empty, int* done, void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B || (!map_empty && !partials)) return fail(ctx, PTK_E_ARG, "ptk_shard_solve: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    const LaneHost& LH = ctx->lanes[lane];
+    int g_lo, g_cnt, n_roots;
+    shard_slice(LH.shard_nsrc, LH.d.shard_n, LH.d.shard_rank, &g_lo, &g_cnt, &n_roots);
+    LAUNCH(PS_ICP, st, k_shard_solve<<<1, NSUM * 32, 0, st>>>(ctx->d_lanes, lane, ctx->d_params, ctx->d_outs, partials, n_roots, it, map_empty));
+    CK(cudaGetLastError());
+    int d = 0;
+    CK(cudaMemcpyAsync(&d, (char*)(ctx->d_lanes + lane) + offsetof(LaneDev, icp_done), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (done) *done = d;
+    return PTK_OK;
+}
+
+extern "C" int ptk_shard_end(ptk_ctx* ctx, int lane, double* out_pose, ptk_stats* stats, void* stream) {
+    if (!ctx || lane < 0 || lane >= ctx->B) return fail(ctx, PTK_E_ARG, "ptk_shard_end: bad argument");
+    return step_finish(ctx, lane, 1, ctx->lanes[lane].pending_nmax, out_pose, stats, (cudaStream_t)stream);
 }
 
 extern "C" int ptk_get_icp_phases(const ptk_ctx* ctx, int lane, long long* cycles6) {

@@ -102,6 +102,7 @@ struct LaneDev {
     double voxel_size, max_distance, voxel_inv;
     int maxp, max_iters;
     double eps;
+    int shard_rank, shard_n;             // hash-sharded map: this context keeps voxels with shard_owner(key) == shard_rank
     int cap_points, pool_cap, trace_iters, ng_cap;
     u32 t_mask, m_mask;
     // scan-local tables (first-seen selection), self-cleaning
@@ -134,6 +135,7 @@ struct LaneDev {
     int icp_done, err;
     int icp_searches;
     Rigid icp_E, icp_T;
+    SE3q icp_Tq;                         // T_icp between the launches of the sharded (multi-GPU) loop
 };
 
 // ------------------------------------------------------------------------------------
@@ -142,6 +144,14 @@ __device__ __forceinline__ u32 hash_key(u64 k) {
     k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
     k ^= k >> 33;
     return (u32)k;
+}
+
+// Owner rank of a voxel in the hash-sharded multi-GPU mode (upper hash bits; the table slot uses the lower).
+__device__ __forceinline__ u32 shard_owner(u64 k, int n) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return (u32)(k >> 32) % (u32)n;
 }
 
 __device__ __forceinline__ bool key_in_range(int kx, int ky, int kz) {
@@ -1112,8 +1122,10 @@ __global__ void __launch_bounds__(256) k_map_insert(LaneDev* lanes, const StepPa
             if (use_pose) { double xo, yo, zo; rigid_apply(T, x, y, z, xo, yo, zo); x = xo; y = yo; z = zo; }
             int kx, ky, kz;
             voxel_key(x, y, z, L.voxel_size, L.voxel_inv, kx, ky, kz);
-            if (key_in_range(kx, ky, kz)) key = pack_key(kx, ky, kz);
-            else { atomicOr(&L.err, ERR_KEYRANGE); act = false; }
+            if (key_in_range(kx, ky, kz)) {
+                key = pack_key(kx, ky, kz);
+                if (L.shard_n > 1 && shard_owner(key, L.shard_n) != (u32)L.shard_rank) act = false;   // another rank's voxel
+            } else { atomicOr(&L.err, ERR_KEYRANGE); act = false; }
             u32 s2 = L.ds_slot2[j];
             if (s2 != NONE) { L.t2_keys[s2] = KEY_EMPTY; L.t2_vals[s2] = NONE; L.ds_slot2[j] = NONE; }
         }
@@ -1230,6 +1242,123 @@ __global__ void k_map_rebuild(LaneDev* lanes) {
         B->slot = slot;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) L.n_tomb = 0;
+}
+
+// ---- hash-sharded map over several GPUs ---------------------------------
+// One ICP iteration is split over three launches with two collectives between them (the host drives
+// the loop, ptudes_lab_b200/sharded.py):
+//   k_shard_search      nearest LOCAL map point of every source point -> record (d2, order id, xyz)
+//   [all-gather of the records]
+//   k_shard_system      global nearest = lexicographic min of (d2, order id) over the ranks' records;
+//                       residual terms of this rank's slice of the source; k_shard_slice_root reduces
+//                       the slice with the canonical tree (the slice is an aligned subtree)
+//   [all-reduce of the [17][32] partial table, every rank filling only its own column: x + 0 is exact]
+//   k_shard_solve       canonical tree over the slice roots, 6x6 solve, SE3 exp, T_icp update
+// Every rank ends up with bit-identical sums, hence bit-identical poses - and identical to one GPU.
+constexpr int SHARD_NO_ORD = 1 << 30;
+
+__global__ void k_shard_search(LaneDev* lanes, int lane_id, const StepParams* params, int it, double* rec, int n) {
+    LaneDev& L = lanes[lane_id];
+    const StepParams& P = params[lane_id];
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n) return;
+    double sx = __ldcg(L.s_x + p), sy = __ldcg(L.s_y + p), sz = __ldcg(L.s_z + p);
+    if (it > 0) {
+        double xo, yo, zo;
+        rigid_apply(L.icp_E, sx, sy, sz, xo, yo, zo);
+        sx = xo; sy = yo; sz = zo;
+    }
+    const double max_d2 = (P.max_corr * P.max_corr) * (1.0 + 1e-9);
+    double d2 = INFINITY, tx = 0, ty = 0, tz = 0, others;
+    int ord = SHARD_NO_ORD;
+    const bool found = L.n_vox > 0 && warp_nearest(L, sx, sy, sz, lane, max_d2, d2, ord, tx, ty, tz, others);
+    if (lane == 0) {
+        if (it > 0) { L.s_x[p] = sx; L.s_y[p] = sy; L.s_z[p] = sz; }
+        rec[p] = found ? d2 : INFINITY;
+        rec[(size_t)n + p] = found ? (double)ord : (double)SHARD_NO_ORD;
+        rec[2 * (size_t)n + p] = tx; rec[3 * (size_t)n + p] = ty; rec[4 * (size_t)n + p] = tz;
+    }
+}
+
+__global__ void __launch_bounds__(ICP_THREADS) k_shard_system(LaneDev* lanes, int lane_id, const StepParams* params,
+                                                              const double* gathered, int G, int n, int it, int g_lo, int g_cnt) {
+    LaneDev& L = lanes[lane_id];
+    const StepParams& P = params[lane_id];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gi = blockIdx.x * ICP_WARPS + warp;
+    const int n_groups = (n + 31) >> 5;
+    const int g = g_lo + gi;
+    if (gi >= g_cnt || g >= n_groups) return;
+    const int p = g * 32 + lane;
+    double c[16];
+    bool acc = false;
+    if (p < n) {
+        double bd2 = INFINITY, bord = (double)SHARD_NO_ORD;
+        int br = 0;
+        for (int r = 0; r < G; ++r) {
+            const double* R = gathered + (size_t)r * 5 * n;
+            const double d2 = R[p], ord = R[(size_t)n + p];
+            if (d2 < bd2 || (d2 == bd2 && ord < bord)) { bd2 = d2; bord = ord; br = r; }
+        }
+        const double sx = __ldcg(L.s_x + p), sy = __ldcg(L.s_y + p), sz = __ldcg(L.s_z + p);
+        if (bord < (double)SHARD_NO_ORD) {
+            const double* R = gathered + (size_t)br * 5 * n;
+            const double tx = R[2 * (size_t)n + p], ty = R[3 * (size_t)n + p], tz = R[4 * (size_t)n + p];
+            const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
+            acc = sqrt((dx * dx + dy * dy) + dz * dz) < P.max_corr;
+            if (acc) lin_terms(sx, sy, sz, tx, ty, tz, P.kernel, c);
+        }
+        if (it < L.trace_iters) L.trace[(size_t)it * L.cap_points + p] = acc ? (int)bord : -1;
+    }
+    if (!acc) {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) c[v] = 0.0;
+    }
+    const double mine = warp_reduce16(c, lane);
+    const u32 nacc = __popc(__ballot_sync(0xffffffffu, acc));
+    if (lane < 16) L.part_a[(size_t)(__brev((u32)lane) >> 28) * L.ng_cap + g] = mine;
+    else if (lane == 16) L.part_a[(size_t)16 * L.ng_cap + g] = (double)nacc;
+}
+
+// root of this rank's slice [g_lo, g_lo + g_cnt) of the group partials -> column `col` of out[17][32]
+__global__ void __launch_bounds__(NSUM * 32) k_shard_slice_root(LaneDev* lanes, int lane_id, int n, int g_lo, int g_cnt, double* out, int col) {
+    LaneDev& L = lanes[lane_id];
+    const int v = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_groups = (n + 31) >> 5;
+    const int n_valid = max(0, min(g_cnt, n_groups - g_lo));
+    double x = 0.0;
+    if (n_valid > 0) x = warp_tree_sum(L.part_a + (size_t)v * L.ng_cap + g_lo, n_valid, lane);
+    if (lane == 0) out[v * 32 + col] = x;
+}
+
+__global__ void __launch_bounds__(NSUM * 32) k_shard_solve(LaneDev* lanes, int lane_id, const StepParams* params, StepOut* outs, const double* partials,
+                              int n_roots, int it, int map_empty) {
+    LaneDev& L = lanes[lane_id];
+    const StepParams& P = params[lane_id];
+    StepOut& O = outs[lane_id];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ double red[NSUM];
+    __shared__ Rigid sE;
+    __shared__ SE3q sT;
+    __shared__ SolveSmem sS;
+    __shared__ int s_done;
+    if (map_empty) {          // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
+        if (threadIdx.x == 0) {
+            O.pose = se3q_matrix(se3q_mul(se3q_identity(), se3q_from_rigid(P.guess)));
+            O.iterations = 0; O.n_corr = 0; O.status = 0; O.dx_norm = 0.0;
+            L.icp_done = 1;
+        }
+        return;
+    }
+    if (warp < NSUM) {
+        const double x = warp_tree_sum(partials + warp * 32, n_roots, lane);
+        if (lane == 0) red[warp] = x;
+    }
+    if (threadIdx.x == 0) sT = it == 0 ? se3q_identity() : L.icp_Tq;
+    __syncthreads();
+    if (warp == 0) icp_solve_step(L, P, O, red, &sS, &sE, &sT, &s_done, it, true, lane);
+    __syncthreads();
+    if (threadIdx.x == 0) { L.icp_E = sE; L.icp_Tq = sT; L.icp_done = s_done; }
 }
 
 // ---- stand-alone pieces -------------------------------------------------------------
