@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+RESULT = sys.stdout
 METRIC = "icp_odometry_scans_per_sec"
 UNIT = "scans/s"
 
@@ -39,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ptk", choices=["ptk", "reference"])
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("PTK_BENCH_LANES", "16")),
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("PTK_BENCH_LANES", "32")),
                     help="independent sequences per GPU advanced by one batched step")
     ap.add_argument("--config", default="os0_quad", choices=["os0_quad", "os2_street", "os0_hall"])
     ap.add_argument("--input", default="range", choices=["range", "xyz"],
@@ -278,6 +279,29 @@ def run_ptk(args):
     if not np.array_equal(poses_prof, poses_dev):
         raise SystemExit("bench.py: run-to-run poses differ (non-deterministic step)")
 
+    # ---- the same scans as ONE sequence (configs[1] literally): latency-bound, reported beside the batch
+    single = None
+    if B > 1:
+        odo1 = odometry.Odometry(cfg, device=local, max_points=max_pts, map_capacity=map_cap, batch=1)
+        if use_range:
+            odo1.set_sensor(gens[0].seq.dirs)
+
+        def run1(inp, tsl):
+            odo1.reset()
+            for s_ in range(W):
+                (odo1.register_scan(inp[s_][0], stream=sh) if use_range else odo1.register_frame(inp[s_][0], tsl[s_][0], stream=sh))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for s_ in range(W, T):
+                (odo1.register_scan(inp[s_][0], stream=sh) if use_range else odo1.register_frame(inp[s_][0], tsl[s_][0], stream=sh))
+            torch.cuda.synchronize()
+            return K / (time.perf_counter() - t0)
+        single = {"value": run1(dev_in, tss), "unit": UNIT,
+                  "note": "one sequence, one scan per step (each scan waits for the previous pose): host wall clock"}
+        if not args.no_e2e:
+            single["e2e"] = run1(h_frames, h_ts)
+        odo1.close()
+
     def max_over_ranks(v):
         if world == 1:
             return v
@@ -338,6 +362,8 @@ def run_ptk(args):
     last = stats_acc[-1][0]
     out["counters"] = {k: last[k] for k in ("n_in", "n_range", "n_ds", "n_src", "n_voxels", "map_points",
                                              "iterations", "n_corr")}
+    if single is not None:
+        out["single_sequence"] = single
     out["counters"]["mean_icp_iterations"] = float(np.mean([st["iterations"] for ss in stats_acc for st in ss]))
     queries = sum(st["iterations"] * st["n_src"] for ss in stats_acc for st in ss)
     searches = sum(st["icp_searches"] for ss in stats_acc for st in ss)
@@ -366,7 +392,7 @@ def run_ptk(args):
         dist.destroy_process_group()
     odo.close()
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), file=RESULT, flush=True)
 
 
 def cpu_port_fleet(scans, min_r, max_r, warmup, budget_s, cores):
@@ -452,10 +478,20 @@ def run_reference(args):
                       "lanes": L},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    print(json.dumps(out), file=RESULT, flush=True)
+
+
+def _guard_stdout():
+    """Libraries (NCCL's version banner, for one) write to fd 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the whole run and keep the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
 
 
 if __name__ == "__main__":
+    RESULT = _guard_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)
