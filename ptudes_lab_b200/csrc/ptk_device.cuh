@@ -735,6 +735,96 @@ __constant__ signed char kJtJMap[36] = {
 __constant__ unsigned char kPairA[15] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4};
 __constant__ unsigned char kPairB[15] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4};
 
+// LDL^T with diagonal pivoting of the 6x6 normal equations, oracle/canon.py ldlt_solve6 operation
+// for operation (explicit row/column swaps, same divisions, same order of subtractions), but laid
+// out for latency: lane j (< 6) keeps column j of the symmetric matrix in registers, values travel
+// by shuffles, the independent divisions / trailing updates of a step run on separate lanes, and
+// nothing touches shared memory until the result.  Both copies of every off-diagonal entry are
+// updated with the operand roles of the canonical (row >= column) form, so they stay bit-equal.
+// Writes x to dx_out[6] (shared memory) and returns whether the solve is finite; warp-uniform.
+__device__ __forceinline__ bool ldlt_solve6_warp(const double* red, int lane, double* dx_out) {
+    const u32 FULL = 0xffffffffu;
+    const int j = lane < 6 ? lane : 5;          // lanes >= 6 shadow lane 5
+    double c[6], b[6];
+    int perm[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int m = kJtJMap[i * 6 + j];
+        c[i] = m > 0 ? red[m - 1] : (m < 0 ? -red[-m - 1] : 0.0);
+        b[i] = -red[10 + i];
+        perm[i] = i;
+    }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double dj = c[0];
+#pragma unroll
+        for (int i = 1; i < 6; ++i) if (j == i) dj = c[i];
+        const double adj = fabs(dj);
+        int p = k;
+        double best = __shfl_sync(FULL, adj, k);
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            const double v = __shfl_sync(FULL, adj, i);
+            if (v > best) { best = v; p = i; }
+        }
+        if (p != k) {
+            const double tc = c[k], tb = b[k];
+            const int tp = perm[k];
+#pragma unroll
+            for (int r = k + 1; r < 6; ++r)
+                if (r == p) { c[k] = c[r]; c[r] = tc; b[k] = b[r]; b[r] = tb; perm[k] = perm[r]; perm[r] = tp; }
+            const int src = (j == k) ? p : ((j == p) ? k : j);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) c[i] = __shfl_sync(FULL, c[i], src);
+        }
+        const double d = __shfl_sync(FULL, c[k], k);
+        if (d == 0.0 || d != d) { ok = false; break; }
+        const double l = c[k] / d;                  // lane i > k: a[k][i] == a[i][k]  ->  L(i,k)
+        if (j > k) c[k] = l;
+        double li[6];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) li[i] = __shfl_sync(FULL, l, i);
+        if (j == k) {
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) c[i] = li[i];
+        } else if (j > k) {
+            const double ljd = l * d;
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) {
+                if (i >= j) c[i] = c[i] - li[i] * ljd;          // a[i][j] -= a[i][k] * (a[j][k] * d)
+                else c[i] = c[i] - l * (li[i] * d);             // mirror a[j][i] -= a[j][k] * (a[i][k] * d)
+            }
+        }
+    }
+    if (!ok) return false;
+    double y = b[0], dj = c[0];
+    int pj = perm[0];
+#pragma unroll
+    for (int i = 1; i < 6; ++i) if (j == i) { y = b[i]; dj = c[i]; pj = perm[i]; }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {                   // L z = P b (column sweep = the same subtraction order per row)
+        const double yq = __shfl_sync(FULL, y, q);
+        if (j > q) y = y - c[q] * yq;
+    }
+    y = y / dj;
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {                  // L^T v = w, rows 4..0, subtractions in ascending column order
+        double yv[6];
+#pragma unroll
+        for (int q = i + 1; q < 6; ++q) yv[q] = __shfl_sync(FULL, y, q);
+        if (j == i) {
+#pragma unroll
+            for (int q = i + 1; q < 6; ++q) y = y - c[q] * yv[q];
+        }
+    }
+    const bool fin = fabs(y) <= 1.7976931348623157e308;
+    ok = (__ballot_sync(FULL, fin || lane >= 6) == FULL);
+    if (lane < 6) dx_out[pj] = y;
+    __syncwarp();
+    return ok;
+}
+
 struct SolveSmem {
     double A[36];
     double y[6];
@@ -749,6 +839,13 @@ struct SolveSmem {
 __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, StepOut& O, const double* red, SolveSmem* S,
                                             Rigid* sE, SE3q* sT, int* s_done, int it, bool writer, int lane) {
     const u32 FULL = 0xffffffffu;
+#ifdef PTK_SOLVE_CLOCKS
+    __shared__ long long s_sc[6];
+    long long tl_ = clock64();
+#define SOLVE_TICK(k) do { if (lane == 0) { long long t_ = clock64(); s_sc[k] = (it == 0 ? 0 : s_sc[k]) + (t_ - tl_); tl_ = t_; } } while (0)
+#else
+#define SOLVE_TICK(k) do { } while (0)
+#endif
     const int n_corr = (int)red[16];
     int done = 0, status = 0;
     double nrm = 0.0;
@@ -756,76 +853,9 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
     if (n_corr == 0) {
         status = 1; done = 1;            // B.5
     } else {
-        for (int e = lane; e < 36; e += 32) {
-            int m = kJtJMap[e];
-            S->A[e] = m > 0 ? red[m - 1] : (m < 0 ? -red[-m - 1] : 0.0);
-        }
-        if (lane < 6) S->y[lane] = -red[10 + lane];
-        __syncwarp();
-        u32 perm = 0;                    // virtual index i -> physical index, 3 bits each
-#pragma unroll
-        for (int i = 0; i < 6; ++i) perm |= (u32)i << (3 * i);
-#define PERM(i) ((int)((perm >> (3 * (i))) & 7u))
-        ok = true;
-        for (int k = 0; k < 6; ++k) {
-            int p = k;
-            double best = fabs(S->A[PERM(k) * 7]);
-            for (int i = k + 1; i < 6; ++i) {
-                double v = fabs(S->A[PERM(i) * 7]);
-                if (v > best) { best = v; p = i; }
-            }
-            if (p != k) {
-                u32 a = (perm >> (3 * k)) & 7u, c = (perm >> (3 * p)) & 7u;
-                perm = (perm & ~((7u << (3 * k)) | (7u << (3 * p)))) | (c << (3 * k)) | (a << (3 * p));
-            }
-            const int pk = PERM(k);
-            const double d = S->A[pk * 7];
-            if (d == 0.0 || d != d) { ok = false; break; }
-            if (lane < 5 - k) {
-                int pi = PERM(k + 1 + lane);
-                S->A[pi * 6 + pk] = S->A[pi * 6 + pk] / d;
-            }
-            __syncwarp();
-            const int m = 5 - k;
-            if (lane < (m * (m + 1)) / 2) {
-                int pi = PERM(k + 1 + kPairA[lane]), pj = PERM(k + 1 + kPairB[lane]);
-                double ljd = S->A[pj * 6 + pk] * d;
-                double v = S->A[pi * 6 + pj] - S->A[pi * 6 + pk] * ljd;
-                S->A[pi * 6 + pj] = v;
-                S->A[pj * 6 + pi] = v;
-            }
-            __syncwarp();
-        }
-        if (ok && lane == 0) {
-            double y[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) y[i] = S->y[PERM(i)];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                double acc = y[i];
-#pragma unroll
-                for (int j = 0; j < i; ++j) acc = acc - S->A[PERM(i) * 6 + PERM(j)] * y[j];
-                y[i] = acc;
-            }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) y[i] = y[i] / S->A[PERM(i) * 7];
-#pragma unroll
-            for (int i = 5; i >= 0; --i) {
-                double acc = y[i];
-#pragma unroll
-                for (int j = i + 1; j < 6; ++j) acc = acc - S->A[PERM(j) * 6 + PERM(i)] * y[j];
-                y[i] = acc;
-            }
-            bool fin = true;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                S->dx[PERM(i)] = y[i];
-                if (!(fabs(y[i]) <= 1.7976931348623157e308)) fin = false;
-            }
-            ok = fin;
-        }
-#undef PERM
-        ok = __shfl_sync(FULL, ok ? 1 : 0, 0) != 0;
+        ok = ldlt_solve6_warp(red, lane, S->dx);
+        SOLVE_TICK(1);
+        SOLVE_TICK(2);
         if (!ok) { status = 2; done = 1; }
     }
     if (lane == 0) {
@@ -835,7 +865,9 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
             SE3q Eq;
             Enew = se3_exp_q(dx, &Eq.q);
             Eq.t[0] = Enew.t[0]; Eq.t[1] = Enew.t[1]; Eq.t[2] = Enew.t[2];
+            SOLVE_TICK(3);
             *sT = se3q_mul(Eq, *sT);
+            SOLVE_TICK(4);
             nrm = sqrt(((((dx[0] * dx[0] + dx[1] * dx[1]) + dx[2] * dx[2]) + dx[3] * dx[3]) + dx[4] * dx[4]) + dx[5] * dx[5]);
             if (nrm < L.eps) done = 1;
         }
@@ -846,7 +878,12 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
             O.pose = se3q_matrix(se3q_mul(*sT, se3q_from_rigid(P.guess)));
             O.iterations = it + 1; O.n_corr = n_corr; O.status = status; O.dx_norm = nrm;
         }
+        SOLVE_TICK(5);
+#ifdef PTK_SOLVE_CLOCKS
+        if (done && writer) for (int k = 0; k < 6; ++k) O.icp_cyc[k] = s_sc[k];
+#endif
     }
+#undef SOLVE_TICK
 }
 
 // K4: the whole ICP loop (kiss-icp RegisterFrame) in one persistent cooperative kernel.
@@ -1048,10 +1085,12 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
     }
 #undef ICP_TICK
     if (threadIdx.x == 0 && s_searches) atomicAdd(&L.icp_searches, s_searches);
+#ifndef PTK_SOLVE_CLOCKS
     if (clk) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) O.icp_cyc[k] = s_cyc[k];
     }
+#endif
 #undef C_TX
 #undef C_TY
 #undef C_TZ
