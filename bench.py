@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: do not overlap the next scans' H2D copy")
     ap.add_argument("--profile-pass", action="store_true", default=True)
     return ap.parse_args()
 
@@ -202,6 +203,8 @@ def run_ptk(args):
 
     def step(odo, fr, ts, s):
         if use_range:
+            if isinstance(fr[s][0], np.ndarray) and s + 1 < len(fr) and not args.no_prefetch:
+                odo.prefetch_scan_batch(fr[s + 1])      # host buffers: copy scan s+1 while scan s computes
             return odo.register_scan_batch(fr[s], stream=sh)
         return odo.register_frame_batch(fr[s], ts[s], stream=sh)
 

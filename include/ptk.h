@@ -125,6 +125,11 @@ int ptk_register_scan(ptk_ctx* ctx, int lane, const unsigned int* range_mm /* H*
                       ptk_stats* stats /* nullable */, void* stream);
 int ptk_register_scan_batch(ptk_ctx* ctx, const unsigned int* const* range_mm, const double* guesses,
                             const unsigned char* has_guess, double* out_poses, ptk_stats* stats, void* stream);
+/* Announce the host range images of the step AFTER the next one: the next ptk_register_scan[_batch]
+ * call copies them to the device on a side stream while its own kernels run, and the call after it,
+ * given the same host pointers, only waits for that copy.  batch entries, NULL = skip the lane.
+ * Host buffers should be pinned and must stay valid until they have been consumed. */
+int ptk_prefetch_scan_batch(ptk_ctx* ctx, const unsigned int* const* range_mm);
 
 /* ---- one sequence, voxel map sharded by hash key over several GPUs (one process + context per GPU).
  * The registration loop of kiss.py:108-114 is driven by the host between its two collectives per

@@ -59,6 +59,7 @@ SYMBOLS = {
     "ptk_shard_system": (C.c_int, [_P, C.c_int, _D, C.c_int, _D, _P]),
     "ptk_shard_solve": (C.c_int, [_P, C.c_int, _D, C.c_int, C.c_int, C.POINTER(C.c_int), _P]),
     "ptk_shard_end": (C.c_int, [_P, C.c_int, _D, C.POINTER(PtkStats), _P]),
+    "ptk_prefetch_scan_batch": (C.c_int, [_P, C.POINTER(_I)]),
     "ptk_num_poses": (C.c_int, [_P, C.c_int]),
     "ptk_get_pose": (C.c_int, [_P, C.c_int, C.c_int, _D]),
     "ptk_get_prediction_model": (C.c_int, [_P, C.c_int, _D]),

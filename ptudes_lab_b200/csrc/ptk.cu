@@ -38,7 +38,10 @@ struct LaneHost {
     u32 epoch = 0, tbase1 = 0, tbase2 = 0, release_base = 0;
     double* in_xyz = nullptr;         // staging for host inputs
     double* in_ts = nullptr;
-    u32* in_range = nullptr;          // staging for host range images
+    u32* in_range = nullptr;          // staging for host range images (buffer 0)
+    u32* pf_range[2] = {nullptr, nullptr};   // double-buffered staging: one feeds the step, one receives the prefetch
+    const void* pf_src = nullptr;     // host image whose copy into pf_range[pf_buf] is in flight / done
+    int pf_buf = 0, cur_buf = 0;
     double* col_motion = nullptr;     // [12][W] per-column deskew motion (range-image mode)
     std::vector<void*> allocs;
 };
@@ -84,6 +87,9 @@ struct ptk_ctx {
     double* d_lut_off = nullptr;
     double* d_col_ts = nullptr;
     std::vector<void*> sensor_allocs;
+    cudaStream_t copy_stream = nullptr;      // H2D prefetch of the next scans (ptk_prefetch_scan_batch)
+    cudaEvent_t pf_event = nullptr;
+    std::vector<const unsigned int*> pf_pending;   // host images to copy during the next step
     int num_sms = 148;
     int icp_blocks_total = 148;
     std::string err;
@@ -236,6 +242,8 @@ static int lane_alloc(ptk_ctx* ctx, LaneHost& LH, bool scratch) {
     CK(dalloc(A, &LH.in_xyz, N * 3));
     CK(dalloc(A, &LH.in_ts, N));
     CK(dalloc(A, &LH.in_range, N));
+    LH.pf_range[0] = LH.in_range;
+    CK(dalloc(A, &LH.pf_range[1], N));
     d.icp_E = rigid_identity();
     d.icp_T = rigid_identity();
     return PTK_OK;
@@ -317,6 +325,8 @@ extern "C" int ptk_ctx_destroy(ptk_ctx* ctx) {
     for (void* p : ctx->sensor_allocs) cudaFree(p);
     if (ctx->d_big) cudaFree(ctx->d_big);
     for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
+    if (ctx->pf_event) cudaEventDestroy(ctx->pf_event);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->h_params) cudaFreeHost(ctx->h_params);
     if (ctx->h_outs) cudaFreeHost(ctx->h_outs);
     delete ctx;
@@ -365,6 +375,7 @@ extern "C" int ptk_reset(ptk_ctx* ctx, int lane) {
         LH.thr = Threshold();
         LH.last_sigma = 0.0;
         LH.have_last = false;
+        LH.pf_src = nullptr;
         int rc = lane_reset_device(ctx, l, 0, true);
         if (rc) return rc;
     }
@@ -489,10 +500,15 @@ static int step_prepare(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz,
         memset(&P, 0, sizeof(P));
         int rc = PTK_OK;
         if (range) {
-            if (is_device_ptr(range[k])) P.range = range[k];
+            if (LH.pf_src == (const void*)range[k]) {     // prefetched: the copy overlapped the previous step
+                CK(cudaStreamWaitEvent(st, ctx->pf_event, 0));
+                P.range = LH.pf_range[LH.pf_buf];
+                LH.cur_buf = LH.pf_buf;
+                LH.pf_src = nullptr;
+            } else if (is_device_ptr(range[k])) P.range = range[k];
             else {
-                CK(cudaMemcpyAsync(LH.in_range, range[k], (size_t)npix * sizeof(u32), cudaMemcpyHostToDevice, st));
-                P.range = LH.in_range;
+                CK(cudaMemcpyAsync(LH.pf_range[LH.cur_buf], range[k], (size_t)npix * sizeof(u32), cudaMemcpyHostToDevice, st));
+                P.range = LH.pf_range[LH.cur_buf];
             }
             P.lut_dir = ctx->d_lut_dir; P.lut_off = ctx->d_lut_off; P.col_ts = ctx->d_col_ts;
             P.col_motion = LH.col_motion; P.W = ctx->sen_W; P.range_unit = ctx->sen_unit;
@@ -558,6 +574,7 @@ static int step_prepare(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz,
 }
 
 static int step_finish(ptk_ctx* ctx, int l0, int cnt, int nmax, double* out_poses, ptk_stats* stats, cudaStream_t st);
+static int issue_prefetch(ptk_ctx* ctx);
 
 // The whole step for lanes [l0, l0+cnt).
 // `range` non-null selects the range-image input (one H*W uint32 image per lane; xyz/ts/n unused).
@@ -589,6 +606,10 @@ static int step_finish(ptk_ctx* ctx, int l0, int cnt, int nmax, double* out_pose
     LAUNCH(PS_FINISH, st, k_finish<<<(cnt + 63) / 64, 64, 0, st>>>(dl, dout, cnt));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_outs + l0, dout, sizeof(StepOut) * cnt, cudaMemcpyDeviceToHost, st));
+    {   // everything of this step is queued: start moving the next scans while it runs
+        int prc = issue_prefetch(ctx);
+        if (prc) return prc;
+    }
     CK(cudaStreamSynchronize(st));
     prof_collect(ctx);
     int ret = PTK_OK;
@@ -671,6 +692,41 @@ extern "C" int ptk_set_sensor(ptk_ctx* ctx, int H, int W, const double* directio
     if ((rc = up(&ctx->d_col_ts, col_timestamps, (size_t)W))) return rc;
     for (auto& LH : ctx->lanes) CK(dalloc(ctx->sensor_allocs, &LH.col_motion, (size_t)12 * W));
     ctx->sen_H = H; ctx->sen_W = W; ctx->sen_unit = range_unit;
+    return PTK_OK;
+}
+
+// Host-to-device copy of the NEXT step's range images on a side stream, overlapped with the current
+// step: ptk_prefetch_scan_batch only notes the host pointers; the next ptk_register_scan[_batch] issues
+// the copies right after it has launched its own kernels (so they run while the GPU computes) and the
+// call after that recognises the pointers and merely waits for the copy event.
+static int issue_prefetch(ptk_ctx* ctx) {
+    if (ctx->pf_pending.empty()) return PTK_OK;
+    const int npix = ctx->sen_H * ctx->sen_W;
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->pf_event, cudaEventDisableTiming));
+    }
+    for (int l = 0; l < ctx->B && l < (int)ctx->pf_pending.size(); ++l) {
+        LaneHost& LH = ctx->lanes[l];
+        const unsigned int* src = ctx->pf_pending[l];
+        LH.pf_src = nullptr;
+        if (!src) continue;
+        const int buf = 1 - LH.cur_buf;          // the buffer the step in flight does not read
+        CK(cudaMemcpyAsync(LH.pf_range[buf], src, (size_t)npix * sizeof(u32), cudaMemcpyHostToDevice, ctx->copy_stream));
+        LH.pf_src = src;
+        LH.pf_buf = buf;
+    }
+    ctx->pf_pending.clear();
+    CK(cudaEventRecord(ctx->pf_event, ctx->copy_stream));
+    return PTK_OK;
+}
+
+extern "C" int ptk_prefetch_scan_batch(ptk_ctx* ctx, const unsigned int* const* range_mm) {
+    if (!ctx || !range_mm) return PTK_E_ARG;
+    if (ctx->sen_H * ctx->sen_W <= 0) return fail(ctx, PTK_E_STATE, "ptk_set_sensor has not been called");
+    ctx->pf_pending.assign(range_mm, range_mm + ctx->B);
+    for (auto& p : ctx->pf_pending)
+        if (p && is_device_ptr(p)) p = nullptr;
     return PTK_OK;
 }
 

@@ -507,10 +507,11 @@ __global__ void k_clean_tables(LaneDev* lanes, int which) {
 // (kiss-icp VoxelHashMap::GetCorrespondences).
 //
 // Lanes 0..26 probe one voxel each (one 16 B slot load, usually a first-probe hit) and compute a
-// conservative lower bound of the distance from the query to that voxel's box.  The query's own
-// voxel is scanned first, then the remaining hits four per round (lanes = slots, the 12 row
-// loads of a round are independent), skipping every voxel whose box is farther than the best
-// distance so far (or than `max_d2`, beyond which a match would be rejected anyway).  A skipped
+// conservative lower bound of the distance from the query to that voxel's box.  Voxels are scanned
+// four per round (lanes = slots, the 12 row loads of a round are independent): first the query's
+// own voxel together with the three nearest boxes, then whatever still qualifies, skipping every
+// voxel whose box is farther than the best distance so far (or than `max_d2`, beyond which a match
+// would be rejected anyway).  A skipped
 // voxel holds only points STRICTLY farther than the current best, so the result - including
 // ties, which go to the first candidate in upstream's (i,j,l)-then-stored order through the
 // lexicographic (d2, order id) compare - is the same as scanning all 27.  Unused slots of a
@@ -571,20 +572,31 @@ __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double
     const int sl = lane < MAXP ? lane : 0;
     double bound = max_d2;
     u32 remaining = __ballot_sync(FULL, id != NONE);
-    if (remaining & (1u << 13)) {        // the query's own voxel first: it usually holds the answer
-        const VoxelBlock* B = L.blocks + __shfl_sync(FULL, id, 13);
-        if (lane < MAXP) nn_visit(B, 13, lane, sl, sx, sy, sz, best, sec, ord, bx, by, bz);
-        remaining &= ~(1u << 13);
-        bound = fmin(bound, warp_min_upper(best));
-    }
+    bool first = true;
     while (true) {
         u32 mask = __ballot_sync(FULL, lb2 <= bound) & remaining;
         if (!mask) break;
-        int v0 = __ffs(mask) - 1; mask &= mask - 1;
-        int v1 = v0, v2 = v0, v3 = v0;
-        if (mask) { v1 = __ffs(mask) - 1; mask &= mask - 1; }
-        if (mask) { v2 = __ffs(mask) - 1; mask &= mask - 1; }
-        if (mask) { v3 = __ffs(mask) - 1; }
+        int v0, v1, v2, v3;
+        if (first) {
+            // first round: the query's own voxel (box distance 0) and the three other voxels whose boxes are
+            // nearest - they are the likeliest to be needed at all, and fetching them together with the own
+            // voxel saves a dependent round trip; later rounds take what still qualifies, in index order
+            first = false;
+            const u32 kbits = ((u32)((u64)__double_as_longlong(lb2) >> 32) & ~31u) | (u32)lane;
+            u32 m = mask;
+            u32 k0 = __reduce_min_sync(FULL, (m >> lane) & 1u ? kbits : 0xffffffffu);
+            v0 = (int)(k0 & 31u); m &= ~(1u << v0);
+            v1 = v2 = v3 = v0;
+            if (m) { u32 k1 = __reduce_min_sync(FULL, (m >> lane) & 1u ? kbits : 0xffffffffu); v1 = (int)(k1 & 31u); m &= ~(1u << v1); }
+            if (m) { u32 k2 = __reduce_min_sync(FULL, (m >> lane) & 1u ? kbits : 0xffffffffu); v2 = (int)(k2 & 31u); m &= ~(1u << v2); }
+            if (m) { u32 k3 = __reduce_min_sync(FULL, (m >> lane) & 1u ? kbits : 0xffffffffu); v3 = (int)(k3 & 31u); }
+        } else {
+            v0 = __ffs(mask) - 1; mask &= mask - 1;
+            v1 = v0; v2 = v0; v3 = v0;
+            if (mask) { v1 = __ffs(mask) - 1; mask &= mask - 1; }
+            if (mask) { v2 = __ffs(mask) - 1; mask &= mask - 1; }
+            if (mask) { v3 = __ffs(mask) - 1; }
+        }
         remaining &= ~((1u << v0) | (1u << v1) | (1u << v2) | (1u << v3));
         const VoxelBlock* B0 = L.blocks + __shfl_sync(FULL, id, v0);
         const VoxelBlock* B1 = L.blocks + __shfl_sync(FULL, id, v1);

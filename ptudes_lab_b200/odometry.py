@@ -182,6 +182,14 @@ class Odometry:
         self._check(self._lib.ptk_register_scan(self._h, lane, addr(r), addr(g), addr(pose), C.byref(st), stream))
         return pose, st.as_dict()
 
+    def prefetch_scan_batch(self, ranges):
+        """Start the H2D copy of the next step's (pinned host) range images; see ptk_prefetch_scan_batch."""
+        B = self.batch
+        assert len(ranges) == B
+        self._pf_keep = [None if r is None else self._u32(r) for r in ranges]     # keep the arrays alive
+        ptrs = (C.c_void_p * B)(*[None if r is None else addr(r) for r in self._pf_keep])
+        self._check(self._lib.ptk_prefetch_scan_batch(self._h, ptrs))
+
     def register_scan_batch(self, ranges, guesses=None, stream=0):
         B = self.batch
         assert len(ranges) == B
