@@ -37,10 +37,10 @@ UNIT = "scans/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ptk", choices=["ptk", "reference"])
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("PTK_BENCH_LANES", "32")),
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("PTK_BENCH_LANES", "48")),
                     help="independent sequences per GPU advanced by one batched step")
     ap.add_argument("--config", default="os0_quad", choices=["os0_quad", "os2_street", "os0_hall"])
     ap.add_argument("--input", default="range", choices=["range", "xyz"],

@@ -406,3 +406,41 @@ def test_register_scan_batch_matches_single(tiny_seq):
         ob.close()
         for o in singles:
             o.close()
+
+
+def test_prefetched_host_scans_give_the_same_poses(tiny_seq):
+    """ptk_prefetch_scan_batch: the next step's H2D copy overlaps the running step; results unchanged,
+    also when a prefetched image is not the one registered next (falls back to the in-line copy)."""
+    from ptudes_lab_b200 import _ffi, odometry, synth
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    B = 2
+    seqs = [synth.make_sequence("tiny", s) for s in range(B)]
+    a = odometry.Odometry(cfg, max_points=16384, map_capacity=32768, batch=B)
+    b = odometry.Odometry(cfg, max_points=16384, map_capacity=32768, batch=B)
+    try:
+        for o in (a, b):
+            o.set_sensor(seqs[0].dirs)
+        scans = []
+        for k in range(6):
+            row = []
+            for s in seqs:
+                h = _ffi.pinned_empty((s.sensor.H, s.sensor.W), dtype=np.uint32)
+                h[...] = s.scan(k).range_mm
+                row.append(h)
+            scans.append(row)
+        for k in range(6):
+            if k + 1 < 6 and k != 2:
+                a.prefetch_scan_batch(scans[k + 1])
+            if k == 2:
+                a.prefetch_scan_batch([scans[5][0], None])          # a wrong guess for lane 0, nothing for lane 1
+            pa, _ = a.register_scan_batch(scans[k])
+            pb, _ = b.register_scan_batch([torch_u32(x) for x in scans[k]])
+            assert np.array_equal(pa, pb), k
+    finally:
+        a.close()
+        b.close()
+
+
+def torch_u32(host):
+    import torch
+    return torch.as_tensor(host.astype(np.int64), device="cuda").to(torch.int32).contiguous()
