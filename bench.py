@@ -115,6 +115,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows), "power_w_max": max(pw) if pw else None}
 
 
+def recorded_traffic(kernel, config, lanes, inp):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, if it was taken on this very
+    configuration (profiles/r1_traffic.json); None otherwise - never a guess."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        if t["config"] == config and t["lanes"] == lanes and t["input"] == inp:
+            return t["kernels"].get(kernel)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -355,7 +368,7 @@ def run_ptk(args):
     total_algo = sum(algo.values())
     out["roofline"] = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": recorded_traffic(dom, args.config, B, args.input), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": dms / dn,
         "kernel_share_of_step": dms / ms_prof,
         "step_algorithmic_bytes_per_scan": total_algo / (B * K),

@@ -117,3 +117,18 @@ def run_ekf_ouster(data_source, kiss_icp, ekf: Optional[ESEKF] = None, *, use_im
                "esekf_update_s_per_update": t_corr / n_corr if n_corr else None,
                "kiss_register_frame_s_per_frame": t_kiss / n_corr if n_corr else None}
     return {"res_t": res_t, "kiss_poses": kiss_poses, "res_poses": res_poses, "ekf": ekf, "timings": timings}
+
+
+# ---- trajectory files: the KITTI pose format ekf-bench writes (utils.py:189-194, cli/ekf_bench.py:579-581)
+def save_poses_kitti_format(filename: str, poses, header: str = "") -> None:
+    """One line per pose: the 12 entries of the top three rows, row-major (what `ptudes flyby` and
+    `ekf-bench cmp` read back)."""
+    rows = np.array([np.asarray(p, dtype=np.float64)[:3, :].reshape(12) for p in poses]).reshape(-1, 12)
+    np.savetxt(fname=filename, X=rows, header=header)
+
+
+def load_poses_kitti_format(filename: str):
+    rows = np.loadtxt(filename).reshape(-1, 12)
+    out = np.tile(np.eye(4), (rows.shape[0], 1, 1))
+    out[:, :3, :] = rows.reshape(-1, 3, 4)
+    return list(out)

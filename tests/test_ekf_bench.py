@@ -90,3 +90,15 @@ def test_config4_cuda_wrapper_equals_oracle_under_the_loop(use_imu):
     assert np.array_equal(np.array(a["res_poses"]), np.array(b["res_poses"]))
     ate_r, ate_t = calc_ate(a["kiss_poses"], SynthLidarImuSource(seq, n).gt_poses())
     assert ate_t < 0.1 ** 2
+
+
+def test_kitti_pose_file_round_trip(tmp_path):
+    from ptudes_lab_b200.ekf_bench import load_poses_kitti_format, save_poses_kitti_format
+    from oracle import canon
+    rng = np.random.default_rng(0)
+    poses = [canon.se3_exp_mat(rng.normal(0, 1, 6)) for _ in range(5)]
+    f = str(tmp_path / "poses.txt")
+    save_poses_kitti_format(f, poses, header="ptk")
+    back = load_poses_kitti_format(f)
+    assert len(back) == 5 and all(np.array_equal(a, b) for a, b in zip(poses, back))
+    assert open(f).readline().startswith("# ptk")

@@ -444,3 +444,38 @@ def test_prefetched_host_scans_give_the_same_poses(tiny_seq):
 def torch_u32(host):
     import torch
     return torch.as_tensor(host.astype(np.int64), device="cuda").to(torch.int32).contiguous()
+
+
+def test_100_scan_trajectory_equals_the_cpu_port():
+    """north_star: per-frame poses and the trajectory ATE over 100 scans.  100 scans of the OS0-128 1024x10
+    sequence through the range-image entry against the C port of the oracle: every pose bit-identical,
+    hence ATE (reference definition, ins/data.py:124-153) of exactly zero between the two, and both
+    close to the synthetic ground truth."""
+    import torch
+    from oracle import port
+    from ptudes_lab_b200 import odometry, synth
+    from ptudes_lab_b200.ins import calc_ate
+    seq = synth.make_sequence("os0_quad", 0)
+    gen = synth.TorchScanGenerator(seq, torch.device("cuda", 0))
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    o = odometry.Odometry(cfg, max_points=131072, map_capacity=65536)
+    o.set_sensor(seq.dirs)
+    ref = port.PortKissICP(threads=8)
+    gpu, gts = [], []
+    try:
+        for k in range(100):
+            rng, _, gt = gen.range_image(k)
+            pose, st = o.register_scan(rng)
+            xyz, ts = synth.project_scan(rng.cpu().numpy().astype(np.uint32), seq.dirs)
+            ref.register_points(xyz, ts, 0.1 * (k + 1))
+            assert np.array_equal(pose, ref.pose), k
+            assert st["iterations"] == ref.last_stats["iterations"], k
+            gpu.append(pose)
+            gts.append(gt)
+    finally:
+        o.close()
+    assert calc_ate(gpu, ref.poses) == (0.0, 0.0)
+    g0 = np.linalg.inv(gts[0])
+    ate_r, ate_t = calc_ate(gpu, [g0 @ g for g in gts])
+    assert ate_t < 0.1 ** 2, (ate_r, ate_t)
+    ref.close()
