@@ -479,3 +479,29 @@ def test_100_scan_trajectory_equals_the_cpu_port():
     ate_r, ate_t = calc_ate(gpu, [g0 @ g for g in gts])
     assert ate_t < 0.1 ** 2, (ate_r, ate_t)
     ref.close()
+
+
+def test_wide_batch_uses_one_block_per_lane_and_the_global_cache(tiny_seq):
+    """300 lanes > the co-resident block budget: the ICP launch is split into chunks with ONE block per
+    lane, whose 34 groups (> 1024 points) no longer fit the shared-memory cache, so the global-memory
+    cache arrays and the multi-chunk walk are exercised.  Every lane gets the same scans and must
+    produce the oracle's poses."""
+    from ptudes_lab_b200 import odometry
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    B = 300
+    o = odometry.Odometry(cfg, max_points=8192, map_capacity=4096, batch=B, trace_iterations=0)
+    ref = ko.OracleKissICPWrapper()
+    try:
+        o.set_sensor(tiny_seq.dirs)
+        for k in range(4):
+            sc = tiny_seq.scan(k)
+            xyz, ts, tsec, _ = tiny_seq.points(k)
+            ref.register_points(xyz, ts, tsec)
+            poses, stats = o.register_scan_batch([sc.range_mm] * B)
+            assert ref.last_counts["n_src"] > 1024
+            for l in (0, 1, 147, 295, 296, 299):
+                assert np.array_equal(poses[l], ref.pose), (k, l)
+                assert stats[l]["iterations"] == ref.last_stats["iterations"]
+            assert all(np.array_equal(poses[l], poses[0]) for l in range(B))
+    finally:
+        o.close()
