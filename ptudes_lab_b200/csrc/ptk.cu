@@ -547,7 +547,7 @@ static int step_prepare(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz,
         P.epoch = ++LH.epoch;
         nmax = std::max(nmax, n[k]);
     }
-    int g1 = std::max(1, (nmax + 255) / 256);
+    int g1 = std::max(1, (nmax + 256 * SI_TILES - 1) / (256 * SI_TILES));
     int gt = std::max(1, (nmax + TILE - 1) / TILE);
     for (int k = 0; k < cnt; ++k) {
         LaneHost& LH = ctx->lanes[l0 + k];
@@ -823,7 +823,7 @@ static int scratch_select(ptk_ctx* ctx, StepParams P, bool voxel, double* out_xy
     if (rc) return rc;
     LaneDev* dl = ctx->d_lanes + S;
     StepParams* dp = ctx->d_params + S;
-    int g1 = std::max(1, (P.n + 255) / 256), gt = std::max(1, (P.n + TILE - 1) / TILE);
+    int g1 = std::max(1, (P.n + 256 * SI_TILES - 1) / (256 * SI_TILES)), gt = std::max(1, (P.n + TILE - 1) / TILE);
     if (voxel) LAUNCH(PS_OTHER, st, k_scan_insert<<<dim3(g1, 1), 256, 0, st>>>(dl, dp));
     LAUNCH(PS_OTHER, st, k_compact1<<<dim3(gt, 1), 256, 0, st>>>(dl, dp));
     if (voxel) LAUNCH(PS_OTHER, st, k_clean_tables<<<dim3(ctx->num_sms, 1), 256, 0, st>>>(dl, 1));

@@ -275,39 +275,50 @@ __device__ __forceinline__ bool range_pass(const StepParams& P, double x, double
 
 // ------------------------------------------------------------------------------------
 // K1: deskew + range filter + voxel key (grid 1) + first-seen atomicMin.
+#ifndef PTK_SI_TILES
+#define PTK_SI_TILES 4
+#endif
+constexpr int SI_TILES = PTK_SI_TILES;      // 256-pixel tiles a block of k_scan_insert walks
+
 __global__ void __launch_bounds__(256, 4) k_scan_insert(LaneDev* lanes, const StepParams* params) {
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool pass = false, valid = false, ins = false;
-    u64 key = KEY_EMPTY;
-    if (i < P.n) {
-        double x, y, z;
-        valid = load_point(P, i, x, y, z);
-        pass = valid && range_pass(P, x, y, z);
-        if (pass) {
-            int kx, ky, kz;
-            voxel_key(x, y, z, P.ds1_size, P.ds1_inv, kx, ky, kz);
-            if (key_in_range(kx, ky, kz)) { key = pack_key(kx, ky, kz); ins = true; }
-            else atomicOr(&L.err, ERR_KEYRANGE);
+    int n_pass = 0, n_valid = 0;
+#pragma unroll 1
+    for (int t = 0; t < SI_TILES; ++t) {
+        const int i = (blockIdx.x * SI_TILES + t) * blockDim.x + threadIdx.x;
+        if (i - (int)threadIdx.x >= P.n) break;          // block-uniform
+        bool pass = false, valid = false, ins = false;
+        u64 key = KEY_EMPTY;
+        if (i < P.n) {
+            double x, y, z;
+            valid = load_point(P, i, x, y, z);
+            pass = valid && range_pass(P, x, y, z);
+            if (pass) {
+                int kx, ky, kz;
+                voxel_key(x, y, z, P.ds1_size, P.ds1_inv, kx, ky, kz);
+                if (key_in_range(kx, ky, kz)) { key = pack_key(kx, ky, kz); ins = true; }
+                else atomicOr(&L.err, ERR_KEYRANGE);
+            }
         }
+        // neighbouring pixels of a beam mostly fall into the same voxel: one table operation per distinct
+        // key of the warp, issued by the lowest lane (= lowest point index) of each group
+        const u32 am = __ballot_sync(0xffffffffu, ins);
+        u32 slot = NONE;
+        if (ins) {
+            const u32 peers = __match_any_sync(am, key);
+            const int leader = __ffs(peers) - 1;
+            if ((int)(threadIdx.x & 31) == leader) slot = table_insert_min(L.t1_keys, L.t1_vals, L.t_mask, key, (u32)i);
+            slot = __shfl_sync(peers, slot, leader);
+        }
+        if (i < P.n) L.slot1[i] = slot;
+        n_pass += __popc(__ballot_sync(0xffffffffu, pass));
+        n_valid += __popc(__ballot_sync(0xffffffffu, valid));
     }
-    // neighbouring pixels of a beam mostly fall into the same voxel: one table operation per distinct
-    // key of the warp, issued by the lowest lane (= lowest point index) of each group
-    const u32 am = __ballot_sync(0xffffffffu, ins);
-    u32 slot = NONE;
-    if (ins) {
-        const u32 peers = __match_any_sync(am, key);
-        const int leader = __ffs(peers) - 1;
-        if ((int)(threadIdx.x & 31) == leader) slot = table_insert_min(L.t1_keys, L.t1_vals, L.t_mask, key, (u32)i);
-        slot = __shfl_sync(peers, slot, leader);
-    }
-    if (i < P.n) L.slot1[i] = slot;
-    u32 m = __ballot_sync(0xffffffffu, pass);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&L.n_range, __popc(m));
-    if (P.range) {          // len(frame) of kiss.py:60: pixels with a return
-        m = __ballot_sync(0xffffffffu, valid);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&L.n_valid, __popc(m));
+    // counters: one atomic per warp and kernel (len(frame) of kiss.py:60 = pixels with a return)
+    if ((threadIdx.x & 31) == 0) {
+        if (n_pass) atomicAdd(&L.n_range, n_pass);
+        if (P.range && n_valid) atomicAdd(&L.n_valid, n_valid);
     }
 }
 
@@ -935,6 +946,7 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
     __shared__ SolveSmem sS;
     __shared__ int s_done;
     __shared__ int s_nmiss;
+    __shared__ int s_cnt;
     __shared__ unsigned short s_miss[ICP_CHUNK * 32];
 
     if (L.n_vox == 0) {   // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
@@ -970,7 +982,7 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
     __shared__ long long s_cyc[6];
     __shared__ int s_searches;
     if (threadIdx.x < 6) s_cyc[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_searches = 0;
+    if (threadIdx.x == 0) { s_searches = 0; s_cnt = 0; }
     long long tlast = clk ? clock64() : 0;
 #define ICP_TICK(slot) do { if (clk) { const long long t_ = clock64(); s_cyc[slot] += t_ - tlast; tlast = t_; } } while (0)
 
@@ -1084,13 +1096,25 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
         }
         __syncthreads();
         ICP_TICK(3);
-        for (int v = warp; v < NSUM; v += ICP_WARPS) {
-            double x = warp_tree_sum(part + (size_t)v * L.ng_cap, n_groups, lane);
-            if (lane == 0) red[v] = x;
+        // 16 sums, one warp each, with the canonical tree; the 17th (correspondence count) is a sum of
+        // small integers - exact in any order - so all warps share it instead of one warp doing two trees
+        if (warp < 16) {
+            const double x = warp_tree_sum(part + (size_t)warp * L.ng_cap, n_groups, lane);
+            if (lane == 0) red[warp] = x;
+        }
+        {
+            int cnt = 0;
+            for (int g = threadIdx.x; g < n_groups; g += ICP_THREADS) cnt += (int)__ldcg(part + (size_t)16 * L.ng_cap + g);
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
         }
         __syncthreads();
         ICP_TICK(4);
-        if (warp == 0) icp_solve_step(L, P, O, red, &sS, &sE, &sT, &s_done, it, b == 0, lane);
+        if (warp == 0) {
+            if (lane == 0) { red[16] = (double)s_cnt; s_cnt = 0; }
+            __syncwarp();
+            icp_solve_step(L, P, O, red, &sS, &sE, &sT, &s_done, it, b == 0, lane);
+        }
         __syncthreads();
         ICP_TICK(5);
         if (s_done) break;
