@@ -63,56 +63,94 @@ CONFIGS = {
 
 # --------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons of one GPU sampled DURING the timed region: NVML polled from a thread
+    every few milliseconds (the timed region of a 40-step run is ~0.1 s, too short for `nvidia-smi -lms`)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index, period_s=0.004):
+        self.gpu, self.period = gpu_index, period_s
+        self.samples = []            # (sm_mhz, reasons bitmask, power_w)
+        self.h = None
+        self._stop = threading.Event()
+        self.t = None
+        self.sm_max = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.h = None
+            self.t = threading.Thread(target=self._poll_smi, daemon=True)     # fallback: nvidia-smi one-shots
+            self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_power_cap,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.hw_thermal_slowdown")
+        names = ["hw_slowdown", "sw_power_cap", "sw_thermal_slowdown", "hw_thermal_slowdown"]
+        while not self._stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                bits = 0
+                for n_, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        bits |= self.REASONS[n_]
+                self.sm_max = float(r[1])
+                self.samples.append((float(r[0]), bits, float(r[2])))
+            except Exception:
+                self._stop.wait(0.05)
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((sm, rs, pw))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def mark(self):
-        return len(self.lines)
+        return len(self.samples)
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        if self.t is not None:
+            self.t.join(timeout=1)
 
     def summary(self, lo=0, hi=None):
-        rows = [l.split(",") for l in self.lines[lo:hi] if l.count(",") >= 8]
+        window = "timed region"
+        rows = self.samples[lo:hi]
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in rows if r[2].strip().replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            for name, v in zip(names, r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
-        pw = [float(r[3]) for r in rows if r[3].strip().replace(".", "").isdigit()]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(rows), "power_w_max": max(pw) if pw else None}
+            rows, window = self.samples, "whole run (no sample fell into the timed region)"
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0}
+        bits = 0
+        for _, r, _ in rows:
+            bits |= r
+        pw = [p for _, _, p in rows if p is not None]
+        return {"sm_mhz": float(np.median([r[0] for r in rows])), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(k for k, m in self.REASONS.items() if bits & m), "samples": len(rows),
+                "power_w_max": max(pw) if pw else None, "window": window}
 
 
 def recorded_traffic(kernel, config, lanes, inp):

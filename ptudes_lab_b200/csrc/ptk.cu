@@ -547,13 +547,15 @@ static int step_prepare(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz,
         P.epoch = ++LH.epoch;
         nmax = std::max(nmax, n[k]);
     }
-    int g1 = std::max(1, (nmax + 256 * SI_TILES - 1) / (256 * SI_TILES));
-    int gt = std::max(1, (nmax + TILE - 1) / TILE);
+    // wide batches: fewer, longer-lived blocks (block dispatch limits the rate); a few lanes: all the blocks we can get
+    const int si_tiles = cnt >= 8 ? SI_TILES : 1;
+    int g1 = std::max(1, (nmax + 256 * si_tiles - 1) / (256 * si_tiles));
+    int gt = std::max(1, ((nmax + TILE - 1) / TILE + CT_TILES - 1) / CT_TILES);     // blocks; each takes CT_TILES tickets
     for (int k = 0; k < cnt; ++k) {
         LaneHost& LH = ctx->lanes[l0 + k];
         StepParams& P = ctx->h_params[l0 + k];
         P.tbase1 = LH.tbase1; P.tbase2 = LH.tbase2; P.release_base = LH.release_base;
-        LH.tbase1 += (u32)gt; LH.tbase2 += (u32)gt; LH.release_base += (u32)c.max_iterations + 1u;
+        LH.tbase1 += (u32)(gt * CT_TILES); LH.tbase2 += (u32)(gt * CT_TILES); LH.release_base += (u32)c.max_iterations + 1u;
         LH.last_params = P;
     }
     CK(cudaMemcpyAsync(ctx->d_params + l0, ctx->h_params + l0, sizeof(StepParams) * cnt, cudaMemcpyHostToDevice, st));
@@ -565,7 +567,7 @@ static int step_prepare(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz,
         for (int k = 0; k < cnt; ++k) any = any || (ctx->h_params[l0 + k].flags & F_DESKEW);
         if (any) LAUNCH(PS_COL_MOTION, st, k_col_motion<<<dim3((ctx->sen_W + 127) / 128, cnt), 128, 0, st>>>(dp));
     }
-    LAUNCH(PS_SCAN_INSERT, st, k_scan_insert<<<dim3(g1, cnt), 256, 0, st>>>(dl, dp));
+    LAUNCH(PS_SCAN_INSERT, st, k_scan_insert<<<dim3(g1, cnt), 256, 0, st>>>(dl, dp, si_tiles));
     LAUNCH(PS_COMPACT1, st, k_compact1<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
     LAUNCH(PS_COMPACT2, st, k_compact2<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
     CK(cudaGetLastError());
@@ -776,10 +778,10 @@ static int scratch_params(ptk_ctx* ctx, StepParams& P, cudaStream_t st, bool k2,
     int S = ctx->B;
     LaneHost& LH = ctx->lanes[S];
     P.epoch = ++LH.epoch;
-    int gt = std::max(1, (P.n + TILE - 1) / TILE);
+    int gt = std::max(1, ((P.n + TILE - 1) / TILE + CT_TILES - 1) / CT_TILES);
     P.tbase1 = LH.tbase1; P.tbase2 = LH.tbase2;
-    if (k2) LH.tbase1 += (u32)gt;
-    if (k3) LH.tbase2 += (u32)gt;
+    if (k2) LH.tbase1 += (u32)(gt * CT_TILES);
+    if (k3) LH.tbase2 += (u32)(gt * CT_TILES);
     ctx->h_params[S] = P;
     CK(cudaMemcpyAsync(ctx->d_params + S, ctx->h_params + S, sizeof(StepParams), cudaMemcpyHostToDevice, st));
     return PTK_OK;
@@ -823,8 +825,8 @@ static int scratch_select(ptk_ctx* ctx, StepParams P, bool voxel, double* out_xy
     if (rc) return rc;
     LaneDev* dl = ctx->d_lanes + S;
     StepParams* dp = ctx->d_params + S;
-    int g1 = std::max(1, (P.n + 256 * SI_TILES - 1) / (256 * SI_TILES)), gt = std::max(1, (P.n + TILE - 1) / TILE);
-    if (voxel) LAUNCH(PS_OTHER, st, k_scan_insert<<<dim3(g1, 1), 256, 0, st>>>(dl, dp));
+    int g1 = std::max(1, (P.n + 255) / 256), gt = std::max(1, ((P.n + TILE - 1) / TILE + CT_TILES - 1) / CT_TILES);
+    if (voxel) LAUNCH(PS_OTHER, st, k_scan_insert<<<dim3(g1, 1), 256, 0, st>>>(dl, dp, 1));
     LAUNCH(PS_OTHER, st, k_compact1<<<dim3(gt, 1), 256, 0, st>>>(dl, dp));
     if (voxel) LAUNCH(PS_OTHER, st, k_clean_tables<<<dim3(ctx->num_sms, 1), 256, 0, st>>>(dl, 1));
     LAUNCH(PS_OTHER, st, k_finish<<<1, 64, 0, st>>>(dl, ctx->d_outs + S, 1));

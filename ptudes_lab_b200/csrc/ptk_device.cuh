@@ -278,15 +278,20 @@ __device__ __forceinline__ bool range_pass(const StepParams& P, double x, double
 #ifndef PTK_SI_TILES
 #define PTK_SI_TILES 4
 #endif
-constexpr int SI_TILES = PTK_SI_TILES;      // 256-pixel tiles a block of k_scan_insert walks
+constexpr int SI_TILES = PTK_SI_TILES;      // 256-pixel tiles a block of k_scan_insert walks in wide batches
+#ifndef PTK_CT_TILES
+#define PTK_CT_TILES 1
+#endif
+constexpr int CT_TILES = PTK_CT_TILES;      // 1024-item tiles a block of k_compact1 / k_compact2 walks (1: walking
+                                            // several lengthens the look-back chain and measured slower)
 
-__global__ void __launch_bounds__(256, 4) k_scan_insert(LaneDev* lanes, const StepParams* params) {
+__global__ void __launch_bounds__(256, 4) k_scan_insert(LaneDev* lanes, const StepParams* params, int tiles) {
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
     int n_pass = 0, n_valid = 0;
 #pragma unroll 1
-    for (int t = 0; t < SI_TILES; ++t) {
-        const int i = (blockIdx.x * SI_TILES + t) * blockDim.x + threadIdx.x;
+    for (int t = 0; t < tiles; ++t) {
+        const int i = (blockIdx.x * tiles + t) * blockDim.x + threadIdx.x;
         if (i - (int)threadIdx.x >= P.n) break;          // block-uniform
         bool pass = false, valid = false, ins = false;
         u64 key = KEY_EMPTY;
@@ -386,13 +391,17 @@ __device__ __forceinline__ int lookback_prefix(u64* agg, u32 tile, int total, u3
 __global__ void __launch_bounds__(256) k_compact1(LaneDev* lanes, const StepParams* params) {
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
+    // a block walks CT_TILES tiles (fewer, longer-lived blocks: block dispatch is not free); every block
+    // takes exactly CT_TILES tickets whether or not they are in range, so the host knows the next base
+#pragma unroll 1
+  for (int rep = 0; rep < CT_TILES; ++rep) {
     u32 tile = take_ticket(&L.ticket1, P.tbase1);
     u32 ntiles = (u32)((P.n + TILE - 1) / TILE);
     if (ntiles == 0) {
         if (tile == 0 && threadIdx.x == 0) L.n_ds = 0;
-        return;
+        continue;
     }
-    if (tile >= ntiles) return;
+    if (tile >= ntiles) continue;
     int i0 = (int)tile * TILE + threadIdx.x * 4;
     bool win[4];
     int cnt = 0;
@@ -445,6 +454,7 @@ __global__ void __launch_bounds__(256) k_compact1(LaneDev* lanes, const StepPara
         if (win[k]) ++pos;
     }
     if (tile == ntiles - 1 && threadIdx.x == 0) L.n_ds = prefix + total;
+  }
 }
 
 // K3: stable compaction of the grid-2 winners into `source` (sensor frame + guess-transformed),
@@ -452,15 +462,17 @@ __global__ void __launch_bounds__(256) k_compact1(LaneDev* lanes, const StepPara
 __global__ void __launch_bounds__(256) k_compact2(LaneDev* lanes, const StepParams* params) {
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
+#pragma unroll 1
+  for (int rep = 0; rep < CT_TILES; ++rep) {
     u32 tile = take_ticket(&L.ticket2, P.tbase2);
     if (tile == 0 && threadIdx.x == 0) L.icp_arrive = 0;    // barrier counter of the k_icp that follows
     int n_ds = L.n_ds;
     u32 ntiles = (u32)((n_ds + TILE - 1) / TILE);
     if (ntiles == 0) {
         if (tile == 0 && threadIdx.x == 0) L.n_src = 0;
-        return;
+        continue;
     }
-    if (tile >= ntiles) return;
+    if (tile >= ntiles) continue;
     int j0 = (int)tile * TILE + threadIdx.x * 4;
     bool win[4];
     int cnt = 0;
@@ -495,6 +507,7 @@ __global__ void __launch_bounds__(256) k_compact2(LaneDev* lanes, const StepPara
         ++pos;
     }
     if (tile == ntiles - 1 && threadIdx.x == 0) L.n_src = prefix + total;
+  }
 }
 
 // Clear the scan tables after a stand-alone downsample (the step cleans them on the way).
