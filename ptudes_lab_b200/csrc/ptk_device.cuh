@@ -766,11 +766,6 @@ __constant__ signed char kJtJMap[36] = {
     0, -4, 3, 5, 6, 7,
     4, 0, -2, 6, 8, 9,
     -3, 2, 0, 7, 9, 10};
-// lower-triangle pairs (a >= b) in row-major order: the trailing-block update of step k uses the
-// first m(m+1)/2 of them, m = 5 - k
-__constant__ unsigned char kPairA[15] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4};
-__constant__ unsigned char kPairB[15] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4};
-
 // LDL^T with diagonal pivoting of the 6x6 normal equations, oracle/canon.py ldlt_solve6 operation
 // for operation (explicit row/column swaps, same divisions, same order of subtractions), but laid
 // out for latency: lane j (< 6) keeps column j of the symmetric matrix in registers, values travel
@@ -862,19 +857,13 @@ __device__ __forceinline__ bool ldlt_solve6_warp(const double* red, int lane, do
 }
 
 struct SolveSmem {
-    double A[36];
-    double y[6];
     double dx[6];
 };
 
-// Warp 0 of every block: expand the 17 sums into the 6x6 system, solve it, update T_icp, decide
-// termination (kiss-icp RegisterFrame loop body after BuildLinearSystem).  The LDL^T with
-// diagonal pivoting is ptk_canon.cuh's ldlt_solve6 operation for operation, but the matrix sits
-// in shared memory, rows/columns are permuted virtually (a packed permutation instead of data
-// movement) and the independent divisions / trailing updates of a step run on separate lanes.
+// Warp 0 of every block: expand the 17 sums into the 6x6 system, solve it (ldlt_solve6_warp), update
+// T_icp, decide termination (kiss-icp RegisterFrame loop body after BuildLinearSystem).
 __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, StepOut& O, const double* red, SolveSmem* S,
                                             Rigid* sE, SE3q* sT, int* s_done, int it, bool writer, int lane) {
-    const u32 FULL = 0xffffffffu;
 #ifdef PTK_SOLVE_CLOCKS
     __shared__ long long s_sc[6];
     long long tl_ = clock64();
