@@ -388,7 +388,7 @@ __device__ __forceinline__ int lookback_prefix(u64* agg, u32 tile, int total, u3
 // K2: stable compaction of the grid-1 winners (ascending input index) into frame_downsample,
 // and (F_SECOND) first-seen insert of every kept point into the grid-2 table.
 // With F_SELECT_RANGE the selection is "passes the range filter" instead (Preprocess).
-__global__ void __launch_bounds__(256) k_compact1(LaneDev* lanes, const StepParams* params) {
+__global__ void __launch_bounds__(256, 4) k_compact1(LaneDev* lanes, const StepParams* params) {
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
     // a block walks CT_TILES tiles (fewer, longer-lived blocks: block dispatch is not free); every block
@@ -562,11 +562,13 @@ __device__ __forceinline__ double warp_min_upper(double best) {
 // search skipped), rounded down; negative if nothing was found.  k_icp uses it to prove, for a query
 // that has moved but stayed in its voxel, that a new search would return the same map point.
 __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double sy, double sz, int lane, double max_d2,
-                                             double& bd2, int& bord, double& tx, double& ty, double& tz, double& others) {
+                                             double& bd2, int& bord, double& tx, double& ty, double& tz, double& others,
+                                             u64* qkey = nullptr) {
     const u32 FULL = 0xffffffffu;
     const double v = L.voxel_size;
     int kx, ky, kz;
     voxel_key(sx, sy, sz, v, L.voxel_inv, kx, ky, kz);
+    if (qkey) *qkey = key_in_range(kx, ky, kz) ? pack_key(kx, ky, kz) : KEY_EMPTY;
     u32 id = NONE;
     double lb2 = INFINITY;
     if (lane < 27 && key_in_range(kx, ky, kz)) {
@@ -1047,14 +1049,13 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 else { const int mp = g0 * 32 + mq; qx = __ldcg(L.s_x + mp); qy = __ldcg(L.s_y + mp); qz = __ldcg(L.s_z + mp); }
                 double d2, tx, ty, tz, others;
                 int ord;
-                const bool found = warp_nearest(L, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others);
+                u64 qkey;
+                const bool found = warp_nearest(L, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey);
                 if (lane == 0) {
-                    int kx, ky, kz;
-                    voxel_key(qx, qy, qz, voxel, voxel_inv, kx, ky, kz);
                     C_TX(msp) = tx; C_TY(msp) = ty; C_TZ(msp) = tz;
                     C_PX(msp) = qx; C_PY(msp) = qy; C_PZ(msp) = qz;
                     C_SLACK(msp) = others;
-                    C_KEY(msp) = key_in_range(kx, ky, kz) ? pack_key(kx, ky, kz) : KEY_EMPTY;
+                    C_KEY(msp) = qkey;
                     C_ORD(msp) = found ? ord : -1;
                 }
             }
