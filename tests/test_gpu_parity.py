@@ -505,3 +505,56 @@ def test_wide_batch_uses_one_block_per_lane_and_the_global_cache(tiny_seq):
             assert all(np.array_equal(poses[l], poses[0]) for l in range(B))
     finally:
         o.close()
+
+
+def test_error_paths_and_reset(tiny_seq):
+    """Errors come back as PtkError with the library's code; a reset lane starts a fresh sequence
+    (error behaviour of the reference: exceptions propagate out of register_frame, kiss.py:54-74)."""
+    from ptudes_lab_b200 import odometry
+    from ptudes_lab_b200._ffi import PtkError
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    xyz, ts, tsec, _ = tiny_seq.points(0)
+    # the local map does not fit: PTK_E_CAPACITY (-3)
+    small = odometry.Odometry(cfg, max_points=16384, map_capacity=64)
+    try:
+        with pytest.raises(PtkError) as e:
+            small.register_frame(xyz, ts)
+        assert e.value.code == -3
+    finally:
+        small.close()
+    o = odometry.Odometry(cfg, max_points=16384, map_capacity=16384, batch=2)
+    try:
+        # voxel coordinate beyond +-2^20: PTK_E_KEYRANGE (-4); the oracle raises as well
+        far = np.array([[3.0e6, 0.0, 0.0], [1.0, 2.0, 3.0]])
+        with pytest.raises(PtkError) as e:
+            o.voxel_down_sample(far, 1.0)
+        assert e.value.code == -4
+        with pytest.raises(ValueError):
+            ko.voxel_down_sample(far, 1.0)
+        # bad arguments: PTK_E_ARG (-1)
+        with pytest.raises(PtkError) as e:
+            o.register_frame(xyz, ts, lane=5)
+        assert e.value.code == -1
+        with pytest.raises(PtkError):
+            o.voxel_down_sample(xyz, -1.0)
+        with pytest.raises(PtkError):
+            o.get_pose(0)                      # no pose yet
+        # lanes are independent and resettable
+        ref = ko.OracleKissICPWrapper()
+        for k in range(3):
+            f, t, _, _ = tiny_seq.points(k)
+            ref.register_points(f, t, 0.1)
+            poses, _ = o.register_frame_batch([f, f], [t, t])
+            assert np.array_equal(poses[0], ref.pose) and np.array_equal(poses[1], ref.pose)
+        o.reset(1)
+        assert o.num_poses(1) == 0 and o.num_poses(0) == 3
+        assert odometry.VoxelHashMap(o, 1).empty() and not odometry.VoxelHashMap(o, 0).empty()
+        ref2 = ko.OracleKissICPWrapper()
+        f, t, _, _ = tiny_seq.points(3)
+        ref.register_points(f, t, 0.1)
+        ref2.register_points(f, t, 0.1)
+        poses, _ = o.register_frame_batch([f, f], [t, t])
+        assert np.array_equal(poses[0], ref.pose) and np.array_equal(poses[1], ref2.pose)
+        assert np.array_equal(o.get_pose(-1, lane=0), ref.pose) and np.array_equal(o.get_prediction_model(lane=1), np.eye(4))
+    finally:
+        o.close()
