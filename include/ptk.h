@@ -225,6 +225,25 @@ long long ptk_launch_count(const ptk_ctx* ctx);
  * uploaded before the launches and the result record (pose, counters) read back after them */
 void ptk_control_bytes(int* h2d_per_lane, int* d2h_per_lane);
 
+/* ---- consumer of the poses: the 18-state error-state EKF of `ptudes ekf-bench`, host-native -------
+ * ESEKF of src/ptudes/ins/es_ekf.py:57-329: ptk_ekf_create = ESEKF(init_grav=, init_bacc=, init_bgyr=)
+ * (NULL = the reference defaults), ptk_ekf_process_imu = processImu (:191-257; the sample's dt is
+ * ts - previous ts, the first sample only sets the clock), ptk_ekf_process_pose = processPose
+ * (:259-329; meas_cov 6x6 row-major or NULL for the default 2 cm / 0.01 rad), ptk_ekf_get_nav / _pose =
+ * .nav / .nav.pose_mat(), ptk_ekf_ts = .ts.  Plain host code (no GPU needed); one filter per sequence. */
+typedef struct ptk_ekf ptk_ekf;
+int ptk_ekf_create(ptk_ekf** out, const double* init_grav3, const double* init_bacc3, const double* init_bgyr3);
+int ptk_ekf_destroy(ptk_ekf* f);
+int ptk_ekf_process_imu(ptk_ekf* f, const double* lacc3, const double* avel3, double ts);
+int ptk_ekf_process_imu_batch(ptk_ekf* f, const double* lacc /* n,3 */, const double* avel /* n,3 */,
+                              const double* ts /* n */, int n);
+int ptk_ekf_process_pose(ptk_ekf* f, const double* pose16, const double* meas_cov36 /* nullable */);
+int ptk_ekf_get_nav(const ptk_ekf* f, double* pos3, double* att9, double* vel3, double* bias_gyr3,
+                    double* bias_acc3, double* grav3);
+int ptk_ekf_get_pose(const ptk_ekf* f, double* pose16);
+int ptk_ekf_get_cov(const ptk_ekf* f, double* cov324);
+double ptk_ekf_ts(const ptk_ekf* f);
+
 /* pinned host memory for callers that want fast H2D of scans */
 int ptk_host_alloc(void** out, unsigned long long bytes);
 int ptk_host_free(void* p);

@@ -88,6 +88,15 @@ SYMBOLS = {
     "ptk_launch_count": (C.c_longlong, [_P]),
     "ptk_get_icp_phases": (C.c_int, [_P, C.c_int, _I]),
     "ptk_control_bytes": (None, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ptk_ekf_create": (C.c_int, [C.POINTER(_P), _D, _D, _D]),
+    "ptk_ekf_destroy": (C.c_int, [_P]),
+    "ptk_ekf_process_imu": (C.c_int, [_P, _D, _D, C.c_double]),
+    "ptk_ekf_process_imu_batch": (C.c_int, [_P, _D, _D, _D, C.c_int]),
+    "ptk_ekf_process_pose": (C.c_int, [_P, _D, _D]),
+    "ptk_ekf_get_nav": (C.c_int, [_P, _D, _D, _D, _D, _D, _D]),
+    "ptk_ekf_get_pose": (C.c_int, [_P, _D]),
+    "ptk_ekf_get_cov": (C.c_int, [_P, _D]),
+    "ptk_ekf_ts": (C.c_double, [_P]),
     "ptk_host_alloc": (C.c_int, [C.POINTER(_P), C.c_ulonglong]),
     "ptk_host_free": (C.c_int, [_P]),
 }

@@ -540,6 +540,20 @@ __global__ void k_clean_tables(LaneDev* lanes, int which) {
 // ties, which go to the first candidate in upstream's (i,j,l)-then-stored order through the
 // lexicographic (d2, order id) compare - is the same as scanning all 27.  Unused slots of a
 // block hold +inf (set when the voxel is created), so no per-voxel count is needed.
+// What a search needs of the lane, read once (the kernel keeps it in shared memory): going through
+// `LaneDev&` would reload every field from global memory at each use, on the latency path of a search.
+struct MapView {
+    const MapSlot* slots;
+    const VoxelBlock* blocks;
+    u32 mask;
+    double voxel, voxel_inv;
+};
+__device__ __forceinline__ MapView map_view(const LaneDev& L) {
+    MapView m;
+    m.slots = L.m_slots; m.blocks = L.blocks; m.mask = L.m_mask; m.voxel = L.voxel_size; m.voxel_inv = L.voxel_inv;
+    return m;
+}
+
 __device__ __forceinline__ void nn_visit(const VoxelBlock* B, int v, int lane, int sl, double sx, double sy, double sz,
                                          double& best, double& sec, int& ord, double& bx, double& by, double& bz) {
     double x = __ldg(&B->x[sl]), y = __ldg(&B->y[sl]), z = __ldg(&B->z[sl]);
@@ -561,11 +575,11 @@ __device__ __forceinline__ double warp_min_upper(double best) {
 // EXCEPT the winner (the runner-up among the visited points, the box distance of every voxel the
 // search skipped), rounded down; negative if nothing was found.  k_icp uses it to prove, for a query
 // that has moved but stayed in its voxel, that a new search would return the same map point.
-__device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double sy, double sz, int lane, double max_d2,
+__device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double sy, double sz, int lane, double max_d2,
                                              double& bd2, int& bord, double& tx, double& ty, double& tz, double& others,
                                              u64* qkey = nullptr) {
     const u32 FULL = 0xffffffffu;
-    const double v = L.voxel_size;
+    const double v = L.voxel;
     int kx, ky, kz;
     voxel_key(sx, sy, sz, v, L.voxel_inv, kx, ky, kz);
     if (qkey) *qkey = key_in_range(kx, ky, kz) ? pack_key(kx, ky, kz) : KEY_EMPTY;
@@ -575,12 +589,12 @@ __device__ __forceinline__ bool warp_nearest(const LaneDev& L, double sx, double
         int di = lane / 9 - 1, dj = (lane / 3) % 3 - 1, dk = lane % 3 - 1;
         int nx = kx + di, ny = ky + dj, nz = kz + dk;
         u64 key = pack_key(nx, ny, nz);
-        u32 slot = hash_key(key) & L.m_mask;
+        u32 slot = hash_key(key) & L.mask;
         while (true) {
-            const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2*>(L.m_slots + slot));
+            const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2*>(L.slots + slot));
             if (raw.x == key) { id = (u32)raw.y; break; }
             if (raw.x == KEY_EMPTY) break;
-            slot = (slot + 1) & L.m_mask;
+            slot = (slot + 1) & L.mask;
         }
         // voxel n covers [n v, (n+1) v) for n > 0, (-v, v) for n == 0 and ((n-1) v, n v] for n < 0
         // (keys truncate toward zero); 1e-7 m of slack per axis covers every rounding involved
@@ -951,6 +965,7 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
     __shared__ int s_done;
     __shared__ int s_nmiss;
     __shared__ int s_cnt;
+    __shared__ MapView s_map;
     __shared__ unsigned short s_miss[ICP_CHUNK * 32];
 
     if (L.n_vox == 0) {   // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
@@ -986,7 +1001,7 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
     __shared__ long long s_cyc[6];
     __shared__ int s_searches;
     if (threadIdx.x < 6) s_cyc[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { s_searches = 0; s_cnt = 0; }
+    if (threadIdx.x == 0) { s_searches = 0; s_cnt = 0; s_map = map_view(L); }
     long long tlast = clk ? clock64() : 0;
 #define ICP_TICK(slot) do { if (clk) { const long long t_ = clock64(); s_cyc[slot] += t_ - tlast; tlast = t_; } } while (0)
 
@@ -1050,7 +1065,7 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 double d2, tx, ty, tz, others;
                 int ord;
                 u64 qkey;
-                const bool found = warp_nearest(L, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey);
+                const bool found = warp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey);
                 if (lane == 0) {
                     C_TX(msp) = tx; C_TY(msp) = ty; C_TZ(msp) = tz;
                     C_PX(msp) = qx; C_PY(msp) = qy; C_PZ(msp) = qz;
@@ -1349,7 +1364,7 @@ __global__ void k_shard_search(LaneDev* lanes, int lane_id, const StepParams* pa
     const double max_d2 = (P.max_corr * P.max_corr) * (1.0 + 1e-9);
     double d2 = INFINITY, tx = 0, ty = 0, tz = 0, others;
     int ord = SHARD_NO_ORD;
-    const bool found = L.n_vox > 0 && warp_nearest(L, sx, sy, sz, lane, max_d2, d2, ord, tx, ty, tz, others);
+    const bool found = L.n_vox > 0 && warp_nearest(map_view(L), sx, sy, sz, lane, max_d2, d2, ord, tx, ty, tz, others);
     if (lane == 0) {
         if (it > 0) { L.s_x[p] = sx; L.s_y[p] = sy; L.s_z[p] = sz; }
         rec[p] = found ? d2 : INFINITY;
@@ -1495,7 +1510,7 @@ __global__ void k_correspondences(LaneDev* lanes, int lane_id, const double* q, 
     double sx = q[3 * (size_t)w], sy = q[3 * (size_t)w + 1], sz = q[3 * (size_t)w + 2];
     double d2, tx, ty, tz, others;
     int ord;
-    bool found = L.n_vox > 0 && warp_nearest(L, sx, sy, sz, lane, (max_dist * max_dist) * (1.0 + 1e-9), d2, ord, tx, ty, tz, others);
+    bool found = L.n_vox > 0 && warp_nearest(map_view(L), sx, sy, sz, lane, (max_dist * max_dist) * (1.0 + 1e-9), d2, ord, tx, ty, tz, others);
     bool acc = found && (sqrt(d2) < max_dist);
     if (lane == 0) {
         out_order[w] = acc ? ord : -1;

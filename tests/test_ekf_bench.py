@@ -102,3 +102,15 @@ def test_kitti_pose_file_round_trip(tmp_path):
     back = load_poses_kitti_format(f)
     assert len(back) == 5 and all(np.array_equal(a, b) for a, b in zip(poses, back))
     assert open(f).readline().startswith("# ptk")
+
+
+def test_loop_with_the_native_filter_matches_the_python_one(tiny_seq):
+    """run_ekf_ouster with libptk's host-native ESEKF (ptk_ekf_*) in place of the Python filter; with
+    --use-imu-prediction the filter's pose is the ICP initial guess, so the odometry depends on it too."""
+    from ptudes_lab_b200.ins import ESEKFNative
+    meta = sensor_info_from_synth(tiny_seq.sensor, tiny_seq.dirs)
+    a = run_ekf_ouster(SynthLidarImuSource(tiny_seq, 8), OracleWrapper(meta), ESEKF(), use_imu_prediction=True)
+    b = run_ekf_ouster(SynthLidarImuSource(tiny_seq, 8), OracleWrapper(meta), ESEKFNative(), use_imu_prediction=True)
+    assert np.abs(np.array(a["res_poses"]) - np.array(b["res_poses"])).max() < 1e-6
+    assert np.abs(np.array(a["kiss_poses"]) - np.array(b["kiss_poses"])).max() < 1e-6
+    assert a["res_t"] == b["res_t"]
