@@ -36,8 +36,8 @@ constexpr int NRED = NSUM;
 constexpr int ICP_THREADS = PTK_ICP_THREADS;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 constexpr int ICP_CHUNK = ICP_WARPS;        // 32-point groups a block handles at a time: one point per thread
-constexpr int ICP_SRC_CAP = 1024;           // source points (+ their cache entries) a block keeps in shared memory
-constexpr int ICP_SMEM = ICP_SRC_CAP * (3 * 8 + 4 * 8 + 8 + 4 + 3 * 8);
+constexpr int ICP_SRC_CAP = 768;            // source points (+ their cache entries) a block keeps in shared memory
+constexpr int ICP_SMEM = ICP_SRC_CAP * (3 * 8 + 4 * 8 + 8 + 3 * 8 + 3 * 8 + 2 * 4);
 
 enum StepFlags : int { F_DESKEW = 1, F_RANGE = 2, F_SECOND = 4, F_SELECT_RANGE = 8 };
 enum ErrFlags : int { ERR_KEYRANGE = 1, ERR_POOL = 2, ERR_TABLE = 4 };
@@ -124,7 +124,8 @@ struct LaneDev {
     // icp
     double* part_a; double* part_b;      // [NRED][ng_cap] partial sums (ping-pong)
     double *c_tx, *c_ty, *c_tz, *c_slack; // correspondence cache of blocks too wide for shared memory
-    double *c_px, *c_py, *c_pz;
+    double *c_px, *c_py, *c_pz, *c_t2x, *c_t2y, *c_t2z;
+    int* c_ord2;
     u64* c_key; int* c_ord;
     int* trace;                          // [trace_iters][cap_points]
     // dynamic state
@@ -555,13 +556,16 @@ __device__ __forceinline__ MapView map_view(const LaneDev& L) {
 }
 
 __device__ __forceinline__ void nn_visit(const VoxelBlock* B, int v, int lane, int sl, double sx, double sy, double sz,
-                                         double& best, double& sec, int& ord, double& bx, double& by, double& bz) {
+                                         double& best, double& sec, double& thr, int& ord, int& sord,
+                                         double& bx, double& by, double& bz) {
     double x = __ldg(&B->x[sl]), y = __ldg(&B->y[sl]), z = __ldg(&B->z[sl]);
     double dx = x - sx, dy = y - sy, dz = z - sz;
     double d2 = (dx * dx + dy * dy) + dz * dz;
     int o = v * MAXP + lane;
-    if (d2 < best || (d2 == best && o < ord)) { sec = best; best = d2; ord = o; bx = x; by = y; bz = z; }
-    else sec = fmin(sec, d2);
+    // this lane's nearest (with the tie rule), its runner-up, and a lower bound of everything after those
+    if (d2 < best || (d2 == best && o < ord)) { thr = sec; sec = best; sord = ord; best = d2; ord = o; bx = x; by = y; bz = z; }
+    else if (d2 < sec) { thr = sec; sec = d2; sord = o; }
+    else thr = fmin(thr, d2);
 }
 
 __device__ __forceinline__ double warp_min_upper(double best) {
@@ -571,13 +575,14 @@ __device__ __forceinline__ double warp_min_upper(double best) {
     return __longlong_as_double((long long)(((u64)mhi << 32) | 0xffffffffull));
 }
 
-// `others` (out): a lower bound of the distance from the query to every candidate of the 27 voxels
-// EXCEPT the winner (the runner-up among the visited points, the box distance of every voxel the
-// search skipped), rounded down; negative if nothing was found.  k_icp uses it to prove, for a query
-// that has moved but stayed in its voxel, that a new search would return the same map point.
+// Beside the winner the search reports a runner-up (t2, ord2; ord2 < 0 if there is none) and `others`:
+// a lower bound of the distance from the query to every candidate of the 27 voxels EXCEPT those two
+// (third-nearest among the visited points, box distance of every voxel the search skipped), rounded
+// down; negative if nothing was found.  k_icp uses them to prove, for a query that has moved but stayed
+// in its voxel, which map point a new search would return.
 __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double sy, double sz, int lane, double max_d2,
                                              double& bd2, int& bord, double& tx, double& ty, double& tz, double& others,
-                                             u64* qkey = nullptr) {
+                                             u64* qkey = nullptr, double* t2 = nullptr, int* ord2 = nullptr) {
     const u32 FULL = 0xffffffffu;
     const double v = L.voxel;
     int kx, ky, kz;
@@ -607,8 +612,8 @@ __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double
         az = fmax(fmax(lo - sz, sz - hi) - 1e-7, 0.0);
         lb2 = ((ax * ax + ay * ay) + az * az) * (1.0 - 1e-9);
     }
-    double best = INFINITY, sec = INFINITY, bx = 0, by = 0, bz = 0;
-    int ord = 0x7fffffff;
+    double best = INFINITY, sec = INFINITY, thr = INFINITY, bx = 0, by = 0, bz = 0;
+    int ord = 0x7fffffff, sord = 0x7fffffff;
     const int sl = lane < MAXP ? lane : 0;
     double bound = max_d2;
     u32 remaining = __ballot_sync(FULL, id != NONE);
@@ -643,10 +648,10 @@ __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double
         const VoxelBlock* B2 = L.blocks + __shfl_sync(FULL, id, v2);
         const VoxelBlock* B3 = L.blocks + __shfl_sync(FULL, id, v3);
         if (lane < MAXP) {
-            nn_visit(B0, v0, lane, sl, sx, sy, sz, best, sec, ord, bx, by, bz);
-            if (v1 != v0) nn_visit(B1, v1, lane, sl, sx, sy, sz, best, sec, ord, bx, by, bz);
-            if (v2 != v0) nn_visit(B2, v2, lane, sl, sx, sy, sz, best, sec, ord, bx, by, bz);
-            if (v3 != v0) nn_visit(B3, v3, lane, sl, sx, sy, sz, best, sec, ord, bx, by, bz);
+            nn_visit(B0, v0, lane, sl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
+            if (v1 != v0) nn_visit(B1, v1, lane, sl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
+            if (v2 != v0) nn_visit(B2, v2, lane, sl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
+            if (v3 != v0) nn_visit(B3, v3, lane, sl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
         }
         bound = fmin(bound, warp_min_upper(best));
     }
@@ -664,8 +669,31 @@ __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double
     tz = __shfl_sync(FULL, bz, owner);
     bd2 = __longlong_as_double((long long)(((u64)mhi << 32) | (u64)mlo));
     bord = (int)mord;
-    // lower bound of the squared distance to every candidate but the winner
-    double other = (found && lane == owner) ? sec : best;
+    // runner-up: the nearest of what is left (the owner lane has its own second, every other lane its best)
+    const bool own = found && lane == owner;
+    const double r = own ? sec : best;
+    const int rord = own ? sord : ord;
+    const u64 rbits = (u64)__double_as_longlong(r);
+    const u32 rhi = (u32)(rbits >> 32), rlo = (u32)rbits;
+    const u32 mrhi = __reduce_min_sync(FULL, rhi);
+    const u32 mrlo = __reduce_min_sync(FULL, rhi == mrhi ? rlo : 0xffffffffu);
+    const bool has2 = found && mrhi < 0x7ff00000u;
+    const int owner2 = __ffs(__ballot_sync(FULL, rhi == mrhi && rlo == mrlo)) - 1;
+    const bool own2 = has2 && lane == owner2;
+    if (t2 != nullptr) {
+        int o2 = __shfl_sync(FULL, rord, owner2);
+        if (!has2) o2 = -1;
+        *ord2 = o2;
+        t2[0] = t2[1] = t2[2] = 0.0;
+        if (has2) {      // its coordinates: one more (cache-hot) read of the voxel it sits in
+            const VoxelBlock* B2 = L.blocks + __shfl_sync(FULL, id, o2 / MAXP);
+            const int s2 = o2 % MAXP;
+            t2[0] = __ldg(&B2->x[s2]); t2[1] = __ldg(&B2->y[s2]); t2[2] = __ldg(&B2->z[s2]);
+        }
+    }
+    // lower bound of the squared distance to every candidate but those two
+    double other = (own && own2) ? thr : ((own || own2) ? sec : best);
+    if (t2 == nullptr) other = own ? sec : best;        // callers without a runner-up slot: all but the winner
     if ((remaining >> lane) & 1u) other = fmin(other, lb2);
     const u32 ohi = __reduce_min_sync(FULL, (u32)((u64)__double_as_longlong(other) >> 32));
     const double d2_other = __longlong_as_double((long long)((u64)ohi << 32));     // low word zero: rounds down
@@ -932,12 +960,13 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
 // 32-point groups and walks it in chunks of ICP_CHUNK groups (= one point per thread).  Per
 // iteration and chunk:
 //   1. thread per point: move the point by the last increment, then try the correspondence cache.
-//      The last search of the point, at position p0, left its winner a and a lower bound D of the
-//      distance from p0 to every other candidate (see warp_nearest).  If the point is still in the
-//      same voxel (same 27 candidates voxels; the map does not change during the loop) and
-//      |p - a| + |p - p0| < D, then every other candidate c has |p - c| >= |p0 - c| - |p - p0| >= D - |p - p0|
-//      > |p - a|: a is the strictly nearest candidate, which is what a new search would return (no tie
-//      rule involved), so none is needed; otherwise the point goes on the block's work list;
+//      The last search of the point, at position p0, left its winner a, a runner-up b and a lower bound D
+//      of the distance from p0 to every OTHER candidate (see warp_nearest).  If the point is still in the
+//      same voxel (same 27 candidate voxels; the map does not change during the loop) and, with w the
+//      lexicographically smaller of a and b in (distance^2, order id) - the search's own comparison -,
+//      |p - w| + |p - p0| < D, then every other candidate c has |p - c| >= |p0 - c| - |p - p0| >= D - |p - p0|
+//      > |p - w|: w is what a new search would return, so none is needed (a and b swap places in the cache
+//      when b has become the nearer one); otherwise the point goes on the block's work list;
 //   2. warp per listed point: the pruned 27-voxel search, refreshing the cache entry;
 //   3. thread per point: residual, Geman-McClure weight and the 16 distinct sums (+ count) in
 //      registers; a warp IS a 32-point group, so xor-butterflies give the group partials directly.
@@ -990,7 +1019,11 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
 #define C_TZ(i) (*(in_smem ? dyn_smem + 5 * ICP_SRC_CAP + (i) : L.c_tz + goff + (i)))
 #define C_SLACK(i) (*(in_smem ? dyn_smem + 6 * ICP_SRC_CAP + (i) : L.c_slack + goff + (i)))
 #define C_KEY(i) (*(in_smem ? reinterpret_cast<u64*>(dyn_smem + 7 * ICP_SRC_CAP) + (i) : L.c_key + goff + (i)))
-#define C_ORD(i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + 11 * ICP_SRC_CAP) + (i) : L.c_ord + goff + (i)))
+#define C_T2X(i) (*(in_smem ? dyn_smem + 11 * ICP_SRC_CAP + (i) : L.c_t2x + goff + (i)))
+#define C_T2Y(i) (*(in_smem ? dyn_smem + 12 * ICP_SRC_CAP + (i) : L.c_t2y + goff + (i)))
+#define C_T2Z(i) (*(in_smem ? dyn_smem + 13 * ICP_SRC_CAP + (i) : L.c_t2z + goff + (i)))
+#define C_ORD(i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + 14 * ICP_SRC_CAP) + (i) : L.c_ord + goff + (i)))
+#define C_ORD2(i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + 14 * ICP_SRC_CAP) + ICP_SRC_CAP + (i) : L.c_ord2 + goff + (i)))
 #define C_PX(i) (*(in_smem ? dyn_smem + 8 * ICP_SRC_CAP + (i) : L.c_px + goff + (i)))
 #define C_PY(i) (*(in_smem ? dyn_smem + 9 * ICP_SRC_CAP + (i) : L.c_py + goff + (i)))
 #define C_PZ(i) (*(in_smem ? dyn_smem + 10 * ICP_SRC_CAP + (i) : L.c_pz + goff + (i)))
@@ -1029,10 +1062,23 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                     const double others = C_SLACK(sp);
                     if (others > 0.0) {
                         const double mx = sx - C_PX(sp), my = sy - C_PY(sp), mz = sz - C_PZ(sp);
-                        const double ex = sx - C_TX(sp), ey = sy - C_TY(sp), ez = sz - C_TZ(sp);
                         const double moved = sqrt((mx * mx + my * my) + mz * mz);
-                        const double e1 = sqrt((ex * ex + ey * ey) + ez * ez);
-                        if (e1 + moved + 1e-9 < others) {
+                        const double ax = C_TX(sp), ay = C_TY(sp), az = C_TZ(sp);
+                        double ex = ax - sx, ey = ay - sy, ez = az - sz;
+                        double da2 = (ex * ex + ey * ey) + ez * ez;              // as the search computes it
+                        const int o2 = C_ORD2(sp);
+                        if (o2 >= 0) {
+                            const double bx = C_T2X(sp), by = C_T2Y(sp), bz = C_T2Z(sp);
+                            ex = bx - sx; ey = by - sy; ez = bz - sz;
+                            const double db2 = (ex * ex + ey * ey) + ez * ez;
+                            const int o1 = C_ORD(sp);
+                            if (db2 < da2 || (db2 == da2 && o2 < o1)) {          // the runner-up has become the nearer one
+                                C_TX(sp) = bx; C_TY(sp) = by; C_TZ(sp) = bz; C_ORD(sp) = o2;
+                                C_T2X(sp) = ax; C_T2Y(sp) = ay; C_T2Z(sp) = az; C_ORD2(sp) = o1;
+                                da2 = db2;
+                            }
+                        }
+                        if (sqrt(da2) + moved + 1e-9 < others) {
                             int kx, ky, kz;
                             voxel_key(sx, sy, sz, voxel, voxel_inv, kx, ky, kz);
                             miss = !(key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == C_KEY(sp));
@@ -1065,9 +1111,12 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 double d2, tx, ty, tz, others;
                 int ord;
                 u64 qkey;
-                const bool found = warp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey);
+                double t2[3];
+                int ord2;
+                const bool found = warp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey, t2, &ord2);
                 if (lane == 0) {
                     C_TX(msp) = tx; C_TY(msp) = ty; C_TZ(msp) = tz;
+                    C_T2X(msp) = t2[0]; C_T2Y(msp) = t2[1]; C_T2Z(msp) = t2[2]; C_ORD2(msp) = ord2;
                     C_PX(msp) = qx; C_PY(msp) = qy; C_PZ(msp) = qz;
                     C_SLACK(msp) = others;
                     C_KEY(msp) = qkey;
@@ -1151,6 +1200,10 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
 #undef C_SLACK
 #undef C_KEY
 #undef C_ORD
+#undef C_ORD2
+#undef C_T2X
+#undef C_T2Y
+#undef C_T2Z
 #undef C_PX
 #undef C_PY
 #undef C_PZ
