@@ -241,7 +241,7 @@ static int lane_alloc(ptk_ctx* ctx, LaneHost& LH, bool scratch) {
     CK(dalloc(A, &d.c_tx, N)); CK(dalloc(A, &d.c_ty, N)); CK(dalloc(A, &d.c_tz, N)); CK(dalloc(A, &d.c_slack, N));
     CK(dalloc(A, &d.c_key, N)); CK(dalloc(A, &d.c_ord, N));
     CK(dalloc(A, &d.c_px, N)); CK(dalloc(A, &d.c_py, N)); CK(dalloc(A, &d.c_pz, N));
-    CK(dalloc(A, &d.c_t2x, N)); CK(dalloc(A, &d.c_t2y, N)); CK(dalloc(A, &d.c_t2z, N)); CK(dalloc(A, &d.c_ord2, N));
+    CK(dalloc(A, &d.c_t2, N * 3 * ICP_KX)); CK(dalloc(A, &d.c_ord2, N * ICP_KX));
     CK(dalloc(A, &d.trace, (size_t)std::max(d.trace_iters, 1) * N, 0xFF));
     CK(dalloc(A, &LH.in_xyz, N * 3));
     CK(dalloc(A, &LH.in_ts, N));

@@ -36,8 +36,12 @@ constexpr int NRED = NSUM;
 constexpr int ICP_THREADS = PTK_ICP_THREADS;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 constexpr int ICP_CHUNK = ICP_WARPS;        // 32-point groups a block handles at a time: one point per thread
-constexpr int ICP_SRC_CAP = 768;            // source points (+ their cache entries) a block keeps in shared memory
-constexpr int ICP_SMEM = ICP_SRC_CAP * (3 * 8 + 4 * 8 + 8 + 3 * 8 + 3 * 8 + 2 * 4);
+#ifndef PTK_ICP_KX
+#define PTK_ICP_KX 2
+#endif
+constexpr int ICP_KX = PTK_ICP_KX;          // runner-ups a correspondence cache entry keeps beside the winner
+constexpr int ICP_SRC_CAP = ICP_KX <= 1 ? 768 : (ICP_KX == 2 ? 640 : 512);   // source points (+ cache entries) per block in smem
+constexpr int ICP_SMEM = ICP_SRC_CAP * (3 * 8 + 4 * 8 + 8 + 3 * 8 + ICP_KX * (3 * 8 + 4) + 4) + 8;
 
 enum StepFlags : int { F_DESKEW = 1, F_RANGE = 2, F_SECOND = 4, F_SELECT_RANGE = 8 };
 enum ErrFlags : int { ERR_KEYRANGE = 1, ERR_POOL = 2, ERR_TABLE = 4 };
@@ -124,8 +128,9 @@ struct LaneDev {
     // icp
     double* part_a; double* part_b;      // [NRED][ng_cap] partial sums (ping-pong)
     double *c_tx, *c_ty, *c_tz, *c_slack; // correspondence cache of blocks too wide for shared memory
-    double *c_px, *c_py, *c_pz, *c_t2x, *c_t2y, *c_t2z;
-    int* c_ord2;
+    double *c_px, *c_py, *c_pz;
+    double* c_t2;                        // [3 * ICP_KX][cap_points] runner-up coordinates
+    int* c_ord2;                         // [ICP_KX][cap_points]
     u64* c_key; int* c_ord;
     int* trace;                          // [trace_iters][cap_points]
     // dynamic state
@@ -575,10 +580,10 @@ __device__ __forceinline__ double warp_min_upper(double best) {
     return __longlong_as_double((long long)(((u64)mhi << 32) | 0xffffffffull));
 }
 
-// Beside the winner the search reports a runner-up (t2, ord2; ord2 < 0 if there is none) and `others`:
-// a lower bound of the distance from the query to every candidate of the 27 voxels EXCEPT those two
-// (third-nearest among the visited points, box distance of every voxel the search skipped), rounded
-// down; negative if nothing was found.  k_icp uses them to prove, for a query that has moved but stayed
+// Beside the winner the search reports ICP_KX runner-ups (t2[3*j..], ord2[j]; ord2[j] < 0 if there is
+// none) and `others`: a lower bound of the distance from the query to every candidate of the 27 voxels
+// EXCEPT the ones reported (the nearest visited point not handed out, the box distance of every voxel
+// the search skipped), rounded down; negative if nothing was found.  k_icp uses them to prove, for a query that has moved but stayed
 // in its voxel, which map point a new search would return.
 __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double sy, double sz, int lane, double max_d2,
                                              double& bd2, int& bord, double& tx, double& ty, double& tz, double& others,
@@ -669,31 +674,34 @@ __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double
     tz = __shfl_sync(FULL, bz, owner);
     bd2 = __longlong_as_double((long long)(((u64)mhi << 32) | (u64)mlo));
     bord = (int)mord;
-    // runner-up: the nearest of what is left (the owner lane has its own second, every other lane its best)
-    const bool own = found && lane == owner;
-    const double r = own ? sec : best;
-    const int rord = own ? sord : ord;
-    const u64 rbits = (u64)__double_as_longlong(r);
-    const u32 rhi = (u32)(rbits >> 32), rlo = (u32)rbits;
-    const u32 mrhi = __reduce_min_sync(FULL, rhi);
-    const u32 mrlo = __reduce_min_sync(FULL, rhi == mrhi ? rlo : 0xffffffffu);
-    const bool has2 = found && mrhi < 0x7ff00000u;
-    const int owner2 = __ffs(__ballot_sync(FULL, rhi == mrhi && rlo == mrlo)) - 1;
-    const bool own2 = has2 && lane == owner2;
+    // runner-ups: ICP_KX more rounds of "nearest of what is left".  A lane knows its two nearest candidates
+    // exactly and a lower bound (thr) of the rest; `cons` counts how many of them have been handed out.
+    int cons = (found && lane == owner) ? 1 : 0;
     if (t2 != nullptr) {
-        int o2 = __shfl_sync(FULL, rord, owner2);
-        if (!has2) o2 = -1;
-        *ord2 = o2;
-        t2[0] = t2[1] = t2[2] = 0.0;
-        if (has2) {      // its coordinates: one more (cache-hot) read of the voxel it sits in
-            const VoxelBlock* B2 = L.blocks + __shfl_sync(FULL, id, o2 / MAXP);
-            const int s2 = o2 % MAXP;
-            t2[0] = __ldg(&B2->x[s2]); t2[1] = __ldg(&B2->y[s2]); t2[2] = __ldg(&B2->z[s2]);
+#pragma unroll
+        for (int j = 0; j < ICP_KX; ++j) {
+            const double r = cons == 0 ? best : (cons == 1 ? sec : INFINITY);
+            const int rord = cons == 0 ? ord : sord;
+            const u64 rbits = (u64)__double_as_longlong(r);
+            const u32 rhi = (u32)(rbits >> 32), rlo = (u32)rbits;
+            const u32 mrhi = __reduce_min_sync(FULL, rhi);
+            const u32 mrlo = __reduce_min_sync(FULL, rhi == mrhi ? rlo : 0xffffffffu);
+            const bool has = found && mrhi < 0x7ff00000u;
+            const int ownj = __ffs(__ballot_sync(FULL, rhi == mrhi && rlo == mrlo)) - 1;
+            int oj = __shfl_sync(FULL, rord, ownj);
+            if (!has) oj = -1;
+            ord2[j] = oj;
+            t2[3 * j] = t2[3 * j + 1] = t2[3 * j + 2] = 0.0;
+            if (has) {      // its coordinates: one more (cache-hot) read of the voxel it sits in
+                if (lane == ownj) ++cons;
+                const VoxelBlock* Bj = L.blocks + __shfl_sync(FULL, id, oj / MAXP);
+                const int sj = oj % MAXP;
+                t2[3 * j] = __ldg(&Bj->x[sj]); t2[3 * j + 1] = __ldg(&Bj->y[sj]); t2[3 * j + 2] = __ldg(&Bj->z[sj]);
+            }
         }
     }
-    // lower bound of the squared distance to every candidate but those two
-    double other = (own && own2) ? thr : ((own || own2) ? sec : best);
-    if (t2 == nullptr) other = own ? sec : best;        // callers without a runner-up slot: all but the winner
+    // lower bound of the squared distance to every candidate that was not handed out
+    double other = cons == 0 ? best : (cons == 1 ? sec : thr);
     if ((remaining >> lane) & 1u) other = fmin(other, lb2);
     const u32 ohi = __reduce_min_sync(FULL, (u32)((u64)__double_as_longlong(other) >> 32));
     const double d2_other = __longlong_as_double((long long)((u64)ohi << 32));     // low word zero: rounds down
@@ -965,8 +973,9 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
 //      same voxel (same 27 candidate voxels; the map does not change during the loop) and, with w the
 //      lexicographically smaller of a and b in (distance^2, order id) - the search's own comparison -,
 //      |p - w| + |p - p0| < D, then every other candidate c has |p - c| >= |p0 - c| - |p - p0| >= D - |p - p0|
-//      > |p - w|: w is what a new search would return, so none is needed (a and b swap places in the cache
-//      when b has become the nearer one); otherwise the point goes on the block's work list;
+//      > |p - w|: w is what a new search would return, so none is needed (a runner-up that has become the
+//      nearest swaps places with a in the cache; ICP_KX runner-ups are kept); otherwise the point goes on
+//      the block's work list;
 //   2. warp per listed point: the pruned 27-voxel search, refreshing the cache entry;
 //   3. thread per point: residual, Geman-McClure weight and the 16 distinct sums (+ count) in
 //      registers; a warp IS a 32-point group, so xor-butterflies give the group partials directly.
@@ -1019,11 +1028,12 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
 #define C_TZ(i) (*(in_smem ? dyn_smem + 5 * ICP_SRC_CAP + (i) : L.c_tz + goff + (i)))
 #define C_SLACK(i) (*(in_smem ? dyn_smem + 6 * ICP_SRC_CAP + (i) : L.c_slack + goff + (i)))
 #define C_KEY(i) (*(in_smem ? reinterpret_cast<u64*>(dyn_smem + 7 * ICP_SRC_CAP) + (i) : L.c_key + goff + (i)))
-#define C_T2X(i) (*(in_smem ? dyn_smem + 11 * ICP_SRC_CAP + (i) : L.c_t2x + goff + (i)))
-#define C_T2Y(i) (*(in_smem ? dyn_smem + 12 * ICP_SRC_CAP + (i) : L.c_t2y + goff + (i)))
-#define C_T2Z(i) (*(in_smem ? dyn_smem + 13 * ICP_SRC_CAP + (i) : L.c_t2z + goff + (i)))
-#define C_ORD(i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + 14 * ICP_SRC_CAP) + (i) : L.c_ord + goff + (i)))
-#define C_ORD2(i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + 14 * ICP_SRC_CAP) + ICP_SRC_CAP + (i) : L.c_ord2 + goff + (i)))
+    // runner-up j: coordinate c (0..2) at [11 + 3 j + c] * CAP; then the ints: ord, ord2[0..KX)
+#define C_T2(j, c, i) (*(in_smem ? dyn_smem + (11 + 3 * (j) + (c)) * ICP_SRC_CAP + (i) \
+                                 : L.c_t2 + ((size_t)(3 * (j) + (c)) * L.cap_points) + goff + (i)))
+#define C_ORD(i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + (11 + 3 * ICP_KX) * ICP_SRC_CAP) + (i) : L.c_ord + goff + (i)))
+#define C_ORD2(j, i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + (11 + 3 * ICP_KX) * ICP_SRC_CAP) + ((j) + 1) * ICP_SRC_CAP + (i) \
+                                : L.c_ord2 + (size_t)(j) * L.cap_points + goff + (i)))
 #define C_PX(i) (*(in_smem ? dyn_smem + 8 * ICP_SRC_CAP + (i) : L.c_px + goff + (i)))
 #define C_PY(i) (*(in_smem ? dyn_smem + 9 * ICP_SRC_CAP + (i) : L.c_py + goff + (i)))
 #define C_PZ(i) (*(in_smem ? dyn_smem + 10 * ICP_SRC_CAP + (i) : L.c_pz + goff + (i)))
@@ -1063,18 +1073,20 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                     if (others > 0.0) {
                         const double mx = sx - C_PX(sp), my = sy - C_PY(sp), mz = sz - C_PZ(sp);
                         const double moved = sqrt((mx * mx + my * my) + mz * mz);
-                        const double ax = C_TX(sp), ay = C_TY(sp), az = C_TZ(sp);
-                        double ex = ax - sx, ey = ay - sy, ez = az - sz;
+                        double ex = C_TX(sp) - sx, ey = C_TY(sp) - sy, ez = C_TZ(sp) - sz;
                         double da2 = (ex * ex + ey * ey) + ez * ez;              // as the search computes it
-                        const int o2 = C_ORD2(sp);
-                        if (o2 >= 0) {
-                            const double bx = C_T2X(sp), by = C_T2Y(sp), bz = C_T2Z(sp);
+#pragma unroll
+                        for (int j = 0; j < ICP_KX; ++j) {
+                            const int oj = C_ORD2(j, sp);
+                            if (oj < 0) continue;
+                            const double bx = C_T2(j, 0, sp), by = C_T2(j, 1, sp), bz = C_T2(j, 2, sp);
                             ex = bx - sx; ey = by - sy; ez = bz - sz;
                             const double db2 = (ex * ex + ey * ey) + ez * ez;
                             const int o1 = C_ORD(sp);
-                            if (db2 < da2 || (db2 == da2 && o2 < o1)) {          // the runner-up has become the nearer one
-                                C_TX(sp) = bx; C_TY(sp) = by; C_TZ(sp) = bz; C_ORD(sp) = o2;
-                                C_T2X(sp) = ax; C_T2Y(sp) = ay; C_T2Z(sp) = az; C_ORD2(sp) = o1;
+                            if (db2 < da2 || (db2 == da2 && oj < o1)) {          // this runner-up has become the nearest
+                                const double wx = C_TX(sp), wy = C_TY(sp), wz = C_TZ(sp);
+                                C_TX(sp) = bx; C_TY(sp) = by; C_TZ(sp) = bz; C_ORD(sp) = oj;
+                                C_T2(j, 0, sp) = wx; C_T2(j, 1, sp) = wy; C_T2(j, 2, sp) = wz; C_ORD2(j, sp) = o1;
                                 da2 = db2;
                             }
                         }
@@ -1111,12 +1123,16 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 double d2, tx, ty, tz, others;
                 int ord;
                 u64 qkey;
-                double t2[3];
-                int ord2;
-                const bool found = warp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey, t2, &ord2);
+                double t2[3 * ICP_KX];
+                int ord2[ICP_KX];
+                const bool found = warp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey, t2, ord2);
                 if (lane == 0) {
                     C_TX(msp) = tx; C_TY(msp) = ty; C_TZ(msp) = tz;
-                    C_T2X(msp) = t2[0]; C_T2Y(msp) = t2[1]; C_T2Z(msp) = t2[2]; C_ORD2(msp) = ord2;
+#pragma unroll
+                    for (int j = 0; j < ICP_KX; ++j) {
+                        C_T2(j, 0, msp) = t2[3 * j]; C_T2(j, 1, msp) = t2[3 * j + 1]; C_T2(j, 2, msp) = t2[3 * j + 2];
+                        C_ORD2(j, msp) = ord2[j];
+                    }
                     C_PX(msp) = qx; C_PY(msp) = qy; C_PZ(msp) = qz;
                     C_SLACK(msp) = others;
                     C_KEY(msp) = qkey;
@@ -1201,9 +1217,7 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
 #undef C_KEY
 #undef C_ORD
 #undef C_ORD2
-#undef C_T2X
-#undef C_T2Y
-#undef C_T2Z
+#undef C_T2
 #undef C_PX
 #undef C_PY
 #undef C_PZ
