@@ -1347,7 +1347,7 @@ __global__ void __launch_bounds__(256) k_map_prune(LaneDev* lanes, const StepOut
     double ox, oy, oz;
     if (origin_override) { ox = origin_override[0]; oy = origin_override[1]; oz = origin_override[2]; }
     else { const Rigid& T = outs[blockIdx.y].pose; ox = T.t[0]; oy = T.t[1]; oz = T.t[2]; }
-    const int bump = L.bump;
+    const int bump = min(L.bump, L.pool_cap);    // failed allocations push the counter past the pool (ERR_POOL)
     const double r2max = L.max_distance * L.max_distance;
     const int stride = gridDim.x * blockDim.x;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < bump; u += stride) {
@@ -1386,7 +1386,7 @@ __global__ void k_finish(LaneDev* lanes, StepOut* outs, int n_lanes) {
 // Rebuild the map table without tombstones.
 __global__ void k_map_rebuild(LaneDev* lanes) {
     LaneDev& L = lanes[blockIdx.y];
-    const int bump = L.bump;
+    const int bump = min(L.bump, L.pool_cap);    // failed allocations push the counter past the pool (ERR_POOL)
     const int stride = gridDim.x * blockDim.x;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < bump; u += stride) {
         VoxelBlock* B = L.blocks + u;
@@ -1593,7 +1593,8 @@ __global__ void k_map_dump(LaneDev* lanes, int lane_id, int* keys, int* counts, 
                            int capacity, int* n_out, int* n_pts_out) {
     LaneDev& L = lanes[lane_id];
     const int stride = gridDim.x * blockDim.x;
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < L.bump; u += stride) {
+    const int bump = min(L.bump, L.pool_cap);
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < bump; u += stride) {
         const VoxelBlock* B = L.blocks + u;
         int c = (int)B->count;
         if (c == 0) continue;
