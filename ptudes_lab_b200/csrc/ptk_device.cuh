@@ -1181,9 +1181,9 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
         ICP_TICK(3);
         // 16 sums, one warp each, with the canonical tree; the 17th (correspondence count) is a sum of
         // small integers - exact in any order - so all warps share it instead of one warp doing two trees
-        if (warp < 16) {
-            const double x = warp_tree_sum(part + (size_t)warp * L.ng_cap, n_groups, lane);
-            if (lane == 0) red[warp] = x;
+        for (int v = warp; v < 16; v += ICP_WARPS) {
+            const double x = warp_tree_sum(part + (size_t)v * L.ng_cap, n_groups, lane);
+            if (lane == 0) red[v] = x;
         }
         {
             int cnt = 0;
