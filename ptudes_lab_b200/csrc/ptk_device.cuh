@@ -1014,29 +1014,29 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
         return;
     }
     const int n_groups = (n_src + 31) >> 5;
-    // contiguous range of groups of this block
-    const int gper = (n_groups + nblk - 1) / nblk;
-    const int g_begin = min(b * gper, n_groups), g_end = min(g_begin + gper, n_groups);
+    // groups of this block: b, b + nblk, b + 2 nblk, ... (interleaved: the source is in beam order, and how far a
+    // point moves per iteration - hence how often its cache entry misses - varies with the beam; dealing the
+    // groups round-robin gives every block the same mix, so the blocks reach the barrier together)
+    const int n_local = b < n_groups ? (n_groups - b + nblk - 1) / nblk : 0;
     const double max_corr = P.max_corr, kern = P.kernel;
     const double max_d2 = (max_corr * max_corr) * (1.0 + 1e-9);   // farther candidates are rejected anyway
     // the moving copy of this block's source points and their cache entries live in shared memory when they fit
-    const bool in_smem = (g_end - g_begin) * 32 <= ICP_SRC_CAP;
+    const bool in_smem = n_local * 32 <= ICP_SRC_CAP;
     // cache entry arrays: computed where used (one base + constants) instead of six live pointers
-    const int goff = g_begin * 32;
-#define C_TX(i) (*(in_smem ? dyn_smem + 3 * ICP_SRC_CAP + (i) : L.c_tx + goff + (i)))
-#define C_TY(i) (*(in_smem ? dyn_smem + 4 * ICP_SRC_CAP + (i) : L.c_ty + goff + (i)))
-#define C_TZ(i) (*(in_smem ? dyn_smem + 5 * ICP_SRC_CAP + (i) : L.c_tz + goff + (i)))
-#define C_SLACK(i) (*(in_smem ? dyn_smem + 6 * ICP_SRC_CAP + (i) : L.c_slack + goff + (i)))
-#define C_KEY(i) (*(in_smem ? reinterpret_cast<u64*>(dyn_smem + 7 * ICP_SRC_CAP) + (i) : L.c_key + goff + (i)))
+#define C_TX(i, g) (*(in_smem ? dyn_smem + 3 * ICP_SRC_CAP + (i) : L.c_tx + (g)))
+#define C_TY(i, g) (*(in_smem ? dyn_smem + 4 * ICP_SRC_CAP + (i) : L.c_ty + (g)))
+#define C_TZ(i, g) (*(in_smem ? dyn_smem + 5 * ICP_SRC_CAP + (i) : L.c_tz + (g)))
+#define C_SLACK(i, g) (*(in_smem ? dyn_smem + 6 * ICP_SRC_CAP + (i) : L.c_slack + (g)))
+#define C_KEY(i, g) (*(in_smem ? reinterpret_cast<u64*>(dyn_smem + 7 * ICP_SRC_CAP) + (i) : L.c_key + (g)))
     // runner-up j: coordinate c (0..2) at [11 + 3 j + c] * CAP; then the ints: ord, ord2[0..KX)
-#define C_T2(j, c, i) (*(in_smem ? dyn_smem + (11 + 3 * (j) + (c)) * ICP_SRC_CAP + (i) \
-                                 : L.c_t2 + ((size_t)(3 * (j) + (c)) * L.cap_points) + goff + (i)))
-#define C_ORD(i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + (11 + 3 * ICP_KX) * ICP_SRC_CAP) + (i) : L.c_ord + goff + (i)))
-#define C_ORD2(j, i) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + (11 + 3 * ICP_KX) * ICP_SRC_CAP) + ((j) + 1) * ICP_SRC_CAP + (i) \
-                                : L.c_ord2 + (size_t)(j) * L.cap_points + goff + (i)))
-#define C_PX(i) (*(in_smem ? dyn_smem + 8 * ICP_SRC_CAP + (i) : L.c_px + goff + (i)))
-#define C_PY(i) (*(in_smem ? dyn_smem + 9 * ICP_SRC_CAP + (i) : L.c_py + goff + (i)))
-#define C_PZ(i) (*(in_smem ? dyn_smem + 10 * ICP_SRC_CAP + (i) : L.c_pz + goff + (i)))
+#define C_T2(j, c, i, g) (*(in_smem ? dyn_smem + (11 + 3 * (j) + (c)) * ICP_SRC_CAP + (i) \
+                                    : L.c_t2 + ((size_t)(3 * (j) + (c)) * L.cap_points) + (g)))
+#define C_ORD(i, g) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + (11 + 3 * ICP_KX) * ICP_SRC_CAP) + (i) : L.c_ord + (g)))
+#define C_ORD2(j, i, g) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + (11 + 3 * ICP_KX) * ICP_SRC_CAP) + ((j) + 1) * ICP_SRC_CAP + (i) \
+                                   : L.c_ord2 + (size_t)(j) * L.cap_points + (g)))
+#define C_PX(i, g) (*(in_smem ? dyn_smem + 8 * ICP_SRC_CAP + (i) : L.c_px + (g)))
+#define C_PY(i, g) (*(in_smem ? dyn_smem + 9 * ICP_SRC_CAP + (i) : L.c_py + (g)))
+#define C_PZ(i, g) (*(in_smem ? dyn_smem + 10 * ICP_SRC_CAP + (i) : L.c_pz + (g)))
     if (threadIdx.x == 0) sT = se3q_identity();
     const double voxel = L.voxel_size, voxel_inv = L.voxel_inv;
     // phase clocks of block 0 (thread 0 only; six clock reads per iteration)
@@ -1050,11 +1050,12 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
 
     for (int it = 0;; ++it) {
         double* part = (it & 1) ? L.part_b : L.part_a;
-        for (int g0 = g_begin; g0 < g_end; g0 += ICP_CHUNK) {
-            const int gc = min(ICP_CHUNK, g_end - g0);
+        for (int k0 = 0; k0 < n_local; k0 += ICP_CHUNK) {
+            const int gc = min(ICP_CHUNK, n_local - k0);   // local groups k0 .. k0 + gc, one per warp
             const int q = threadIdx.x;                     // point of this thread within the chunk
-            const int p = g0 * 32 + q;                     // ... within the lane's source
-            const int sp = (g0 - g_begin) * 32 + q;        // ... within the block
+            const int grp = b + (k0 + warp) * nblk;        // this warp's group within the lane's source
+            const int p = grp * 32 + lane;                 // this thread's point within the lane's source
+            const int sp = k0 * 32 + q;                    // ... within the block
             const bool live = q < gc * 32 && p < n_src;
             if (threadIdx.x == 0) s_nmiss = 0;
             __syncthreads();                               // also: previous chunk / iteration fully consumed
@@ -1069,31 +1070,31 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                     double xo, yo, zo;
                     rigid_apply(sE, sx, sy, sz, xo, yo, zo);
                     sx = xo; sy = yo; sz = zo;
-                    const double others = C_SLACK(sp);
+                    const double others = C_SLACK(sp, p);
                     if (others > 0.0) {
-                        const double mx = sx - C_PX(sp), my = sy - C_PY(sp), mz = sz - C_PZ(sp);
+                        const double mx = sx - C_PX(sp, p), my = sy - C_PY(sp, p), mz = sz - C_PZ(sp, p);
                         const double moved = sqrt((mx * mx + my * my) + mz * mz);
-                        double ex = C_TX(sp) - sx, ey = C_TY(sp) - sy, ez = C_TZ(sp) - sz;
+                        double ex = C_TX(sp, p) - sx, ey = C_TY(sp, p) - sy, ez = C_TZ(sp, p) - sz;
                         double da2 = (ex * ex + ey * ey) + ez * ez;              // as the search computes it
 #pragma unroll
                         for (int j = 0; j < ICP_KX; ++j) {
-                            const int oj = C_ORD2(j, sp);
+                            const int oj = C_ORD2(j, sp, p);
                             if (oj < 0) continue;
-                            const double bx = C_T2(j, 0, sp), by = C_T2(j, 1, sp), bz = C_T2(j, 2, sp);
+                            const double bx = C_T2(j, 0, sp, p), by = C_T2(j, 1, sp, p), bz = C_T2(j, 2, sp, p);
                             ex = bx - sx; ey = by - sy; ez = bz - sz;
                             const double db2 = (ex * ex + ey * ey) + ez * ez;
-                            const int o1 = C_ORD(sp);
+                            const int o1 = C_ORD(sp, p);
                             if (db2 < da2 || (db2 == da2 && oj < o1)) {          // this runner-up has become the nearest
-                                const double wx = C_TX(sp), wy = C_TY(sp), wz = C_TZ(sp);
-                                C_TX(sp) = bx; C_TY(sp) = by; C_TZ(sp) = bz; C_ORD(sp) = oj;
-                                C_T2(j, 0, sp) = wx; C_T2(j, 1, sp) = wy; C_T2(j, 2, sp) = wz; C_ORD2(j, sp) = o1;
+                                const double wx = C_TX(sp, p), wy = C_TY(sp, p), wz = C_TZ(sp, p);
+                                C_TX(sp, p) = bx; C_TY(sp, p) = by; C_TZ(sp, p) = bz; C_ORD(sp, p) = oj;
+                                C_T2(j, 0, sp, p) = wx; C_T2(j, 1, sp, p) = wy; C_T2(j, 2, sp, p) = wz; C_ORD2(j, sp, p) = o1;
                                 da2 = db2;
                             }
                         }
                         if (sqrt(da2) + moved + 1e-9 < others) {
                             int kx, ky, kz;
                             voxel_key(sx, sy, sz, voxel, voxel_inv, kx, ky, kz);
-                            miss = !(key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == C_KEY(sp));
+                            miss = !(key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == C_KEY(sp, p));
                         }
                     }
                 }
@@ -1116,10 +1117,11 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
             if (threadIdx.x == 0) s_searches += nmiss;
             for (int i = warp; i < nmiss; i += ICP_WARPS) {
                 const int mq = s_miss[i];
-                const int msp = (g0 - g_begin) * 32 + mq;
+                const int msp = k0 * 32 + mq;
+                const int mp = (b + (k0 + (mq >> 5)) * nblk) * 32 + (mq & 31);
                 double qx, qy, qz;
                 if (in_smem) { qx = ssx[msp]; qy = ssy[msp]; qz = ssz[msp]; }
-                else { const int mp = g0 * 32 + mq; qx = __ldcg(L.s_x + mp); qy = __ldcg(L.s_y + mp); qz = __ldcg(L.s_z + mp); }
+                else { qx = __ldcg(L.s_x + mp); qy = __ldcg(L.s_y + mp); qz = __ldcg(L.s_z + mp); }
                 double d2, tx, ty, tz, others;
                 int ord;
                 u64 qkey;
@@ -1127,16 +1129,16 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 int ord2[ICP_KX];
                 const bool found = warp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey, t2, ord2);
                 if (lane == 0) {
-                    C_TX(msp) = tx; C_TY(msp) = ty; C_TZ(msp) = tz;
+                    C_TX(msp, mp) = tx; C_TY(msp, mp) = ty; C_TZ(msp, mp) = tz;
 #pragma unroll
                     for (int j = 0; j < ICP_KX; ++j) {
-                        C_T2(j, 0, msp) = t2[3 * j]; C_T2(j, 1, msp) = t2[3 * j + 1]; C_T2(j, 2, msp) = t2[3 * j + 2];
-                        C_ORD2(j, msp) = ord2[j];
+                        C_T2(j, 0, msp, mp) = t2[3 * j]; C_T2(j, 1, msp, mp) = t2[3 * j + 1]; C_T2(j, 2, msp, mp) = t2[3 * j + 2];
+                        C_ORD2(j, msp, mp) = ord2[j];
                     }
-                    C_PX(msp) = qx; C_PY(msp) = qy; C_PZ(msp) = qz;
-                    C_SLACK(msp) = others;
-                    C_KEY(msp) = qkey;
-                    C_ORD(msp) = found ? ord : -1;
+                    C_PX(msp, mp) = qx; C_PY(msp, mp) = qy; C_PZ(msp, mp) = qz;
+                    C_SLACK(msp, mp) = others;
+                    C_KEY(msp, mp) = qkey;
+                    C_ORD(msp, mp) = found ? ord : -1;
                 }
             }
             __syncthreads();
@@ -1147,9 +1149,9 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 bool acc = false;
                 int ord = -1;
                 if (live) {
-                    ord = C_ORD(sp);
+                    ord = C_ORD(sp, p);
                     if (ord >= 0) {
-                        const double tx = C_TX(sp), ty = C_TY(sp), tz = C_TZ(sp);
+                        const double tx = C_TX(sp, p), ty = C_TY(sp, p), tz = C_TZ(sp, p);
                         const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
                         const double d2 = (dx * dx + dy * dy) + dz * dz;
                         acc = sqrt(d2) < max_corr;
@@ -1163,8 +1165,8 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 }
                 const double mine = warp_reduce16(c, lane);
                 const u32 nacc = __popc(__ballot_sync(0xffffffffu, acc));   // a sum of 1.0s is exact in any order
-                if (lane < 16) part[(size_t)(__brev((u32)lane) >> 28) * L.ng_cap + g0 + warp] = mine;
-                else if (lane == 16) part[(size_t)16 * L.ng_cap + g0 + warp] = (double)nacc;
+                if (lane < 16) part[(size_t)(__brev((u32)lane) >> 28) * L.ng_cap + grp] = mine;
+                else if (lane == 16) part[(size_t)16 * L.ng_cap + grp] = (double)nacc;
             }
         }
         // ---- one barrier over the lane's blocks (icp_arrive was zeroed by the previous kernel)
