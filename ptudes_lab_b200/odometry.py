@@ -42,6 +42,30 @@ def _mat16(T):
     return np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(4, 4))
 
 
+class StatsBatch:
+    """The per-lane ptk_stats of one batched step.  Behaves like a list of dicts, but the dicts are only
+    built when asked for: converting 48 structs x 16 fields eagerly costs more host time per step than
+    the launches do, and the GPU idles meanwhile."""
+
+    def __init__(self, raw):
+        self._raw = raw
+
+    def __len__(self):
+        return len(self._raw)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._raw[k].as_dict() for k in range(*i.indices(len(self._raw)))]
+        return self._raw[i].as_dict()
+
+    def __iter__(self):
+        return (self._raw[k].as_dict() for k in range(len(self._raw)))
+
+    def field(self, name):
+        """One field of every lane as a list (no dicts)."""
+        return [getattr(self._raw[k], name) for k in range(len(self._raw))]
+
+
 class Odometry:
     """A ptk context with `batch` lanes.  Lane 0 is the default sequence."""
 
@@ -154,7 +178,7 @@ class Odometry:
         stats = (PtkStats * B)()
         rc = self._lib.ptk_register_frame_batch(self._h, xs, ts, ns, addr(gbuf), hg, addr(poses), stats, stream)
         self._check(rc)
-        return poses, [s.as_dict() for s in stats]
+        return poses, StatsBatch(stats)
 
     # -- the step fed with range images (kiss.py:54-74 incl. the XYZLut projection) ---------
     def set_sensor(self, direction, offset=None, col_timestamps=None, range_unit=0.001):
@@ -207,7 +231,7 @@ class Odometry:
         poses = np.empty((B, 4, 4))
         stats = (PtkStats * B)()
         self._check(self._lib.ptk_register_scan_batch(self._h, ptrs, addr(gbuf), hg, addr(poses), stats, stream))
-        return poses, [s.as_dict() for s in stats]
+        return poses, StatsBatch(stats)
 
     # -- KissICP state -------------------------------------------------------------
     def num_poses(self, lane=0):
