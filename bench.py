@@ -213,6 +213,15 @@ def run_ptk(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # one rank = one GPU = its own slice of host cores: a step has ~0.1 ms of host work between the pose
+        # read-back and the next launches, and ranks migrating over each other's cores show up in the max over ranks
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local * per:(local + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+        except Exception:
+            pass
 
     B, K, W = args.lanes, args.steps, args.warmup
     T = W + K
