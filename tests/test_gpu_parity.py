@@ -558,3 +558,59 @@ def test_error_paths_and_reset(tiny_seq):
         assert np.array_equal(o.get_pose(-1, lane=0), ref.pose) and np.array_equal(o.get_prediction_model(lane=1), np.eye(4))
     finally:
         o.close()
+
+
+def test_tombstones_and_table_rebuild(tiny_seq):
+    """A platform that keeps moving erases as many voxels as it adds: erased table slots become tombstones
+    and the table is rebuilt when they pile up.  Ten hops of 300 m with a small map (table of 16384 slots),
+    map contents and nearest-neighbour answers checked against the oracle after every hop."""
+    from ptudes_lab_b200 import odometry
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    o = odometry.Odometry(cfg, max_points=16384, map_capacity=4096)
+    gm = odometry.VoxelHashMap(o, 0)
+    rm = ko.VoxelHashMap(1.0, 100.0, 20)
+    rng = np.random.default_rng(2)
+    try:
+        xyz, _, _, _ = tiny_seq.points(0)
+        ds = ko.voxel_down_sample(ko.preprocess(xyz, 100.0, 5.0), 0.5)[:3000]
+        total_erased = 0
+        for hop in range(10):
+            pose = canon.se3_exp_mat(np.concatenate([[300.0 * hop, 40.0 * (hop % 3), 0.0], rng.normal(0, 0.2, 3)]))
+            before = rm.num_voxels()
+            gm.update(ds, pose)
+            rm.update(ds, pose)
+            if hop:
+                total_erased += before               # 300 m away with max_range 100: every old voxel goes
+                assert rm.num_voxels() < 1.5 * before
+            _map_equal(gm, rm)
+            x, y, z = canon.transform_points(pose, ds[::7, 0], ds[::7, 1], ds[::7, 2])
+            q = np.stack([x, y, z], 1) + 0.03
+            acc, tgt, order = gm.get_correspondences(q, 2.0, return_index=True)
+            racc, rtgt, rorder = rm.get_correspondences(q, 2.0, return_index=True)
+            assert np.array_equal(acc, racc) and np.array_equal(order[acc], rorder[racc]) and np.array_equal(tgt[acc], rtgt[racc])
+        assert total_erased > 8192          # more slots were erased than half the table: a rebuild must have run
+    finally:
+        o.close()
+
+
+def test_iteration_cap(os0_seq):
+    """MAX_NUM_ITERATIONS_ reached before convergence: the loop stops there and returns T_icp * guess."""
+    from ptudes_lab_b200 import odometry
+    from ptudes_lab_b200.odometry import VoxelHashMap, register_frame
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    o = odometry.Odometry(cfg, max_points=140000, map_capacity=65536, max_iterations=3)
+    try:
+        gm = VoxelHashMap(o, 0)
+        rm = ko.VoxelHashMap(1.0, 100.0, 20)
+        xyz, _, _, _ = os0_seq.points(0)
+        ds = ko.voxel_down_sample(ko.preprocess(xyz, 100.0, 5.0), 0.5)
+        gm.update(ds, np.eye(4))
+        rm.update(ds, np.eye(4))
+        src = ko.voxel_down_sample(ds, 1.5)
+        guess = canon.se3_exp_mat(np.array([0.2, -0.1, 0.05, 0.02, -0.01, 0.03]))
+        rpose, rst = ko.register_point_cloud(src, rm, guess, 6.0, 2.0 / 3.0, max_iters=3)
+        pose, st = register_frame(src, gm, guess, 6.0, 2.0 / 3.0, return_stats=True)
+        assert rst["iterations"] == 3 and st["iterations"] == 3 and st["dx_norm"] > 1e-4
+        assert np.array_equal(pose, rpose)
+    finally:
+        o.close()
