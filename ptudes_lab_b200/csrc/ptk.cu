@@ -93,6 +93,7 @@ struct ptk_ctx {
     std::vector<const unsigned int*> pf_pending;   // host images to copy during the next step
     int num_sms = 148;
     int icp_blocks_total = 148;
+    int icp_max_blocks_per_lane = 1 << 20;   // PTK_ICP_MAX_BLOCKS_PER_LANE: fewer blocks = cheaper barrier, slower searches
     int icp_cluster = 0;              // blocks per lane of the cluster launch of wide batches (0: not available)
     int icp_cluster_min_lanes = 56;   // batch width from which the cluster launch is used
     std::string err;
@@ -294,6 +295,7 @@ extern "C" int ptk_ctx_create(ptk_ctx** out, int device, const ptk_config* cfg_i
     }
     ctx->icp_blocks_total = occ * ctx->num_sms;
     {   // cluster size for wide batches: PTK_ICP_CLUSTER (1 disables), default 8 = the portable maximum
+        if (const char* mb = getenv("PTK_ICP_MAX_BLOCKS_PER_LANE")) ctx->icp_max_blocks_per_lane = std::max(1, atoi(mb));
         const char* e = getenv("PTK_ICP_CLUSTER");
         int want = e ? atoi(e) : 8;
         if (const char* m = getenv("PTK_ICP_CLUSTER_MIN_LANES")) ctx->icp_cluster_min_lanes = atoi(m);
@@ -491,6 +493,7 @@ static int launch_icp(ptk_ctx* ctx, int l0, int cnt, int groups_hint, cudaStream
         int chunk = std::min(cnt - done, ctx->icp_blocks_total);
         int per = std::max(1, ctx->icp_blocks_total / chunk);
         if (groups_hint > 0) per = std::max(1, std::min(per, groups_hint));
+        per = std::min(per, ctx->icp_max_blocks_per_lane);
         LaneDev* dl = ctx->d_lanes + l0 + done;
         StepParams* dp = ctx->d_params + l0 + done;
         StepOut* dout = ctx->d_outs + l0 + done;
