@@ -63,8 +63,8 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_sharded_loop_and_fleet_helpers_world2(tmp_path):
-    world = 2
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_loop_and_fleet_helpers(tmp_path, world):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
 
