@@ -268,6 +268,8 @@ def run_ptk(args):
             return odo.register_scan_batch(fr[s], stream=sh)
         return odo.register_frame_batch(fr[s], ts[s], stream=sh)
 
+    icp_phase_cycles = None
+
     def timed_run(odo, fr, ts, profiling, clocks=None):
         odo.reset()
         stats_acc = []
@@ -295,6 +297,8 @@ def run_ptk(args):
         launches = odo.launch_count() - l0
         prof = odo.get_profile() if profiling else None
         if profiling:
+            nonlocal icp_phase_cycles
+            icp_phase_cycles = odo.icp_phases(0)
             odo.set_profiling(False)
         return ms, launches, prof, stats_acc, np.stack(poses), (c0, c1)
 
@@ -432,7 +436,7 @@ def run_ptk(args):
     searches = sum(st["icp_searches"] for ss in stats_acc for st in ss)
     out["icp"] = {"nn_queries": int(queries), "full_searches": int(searches),
                   "cache_hit_rate": 1.0 - searches / max(queries, 1),
-                  "block0_phase_cycles_last_scan": odo.icp_phases(0)}
+                  "warp_cycles_profiled_pass": icp_phase_cycles}
 
     if rank == 0:
         time.sleep(0.2)

@@ -17,6 +17,14 @@ rules of Appendix B where upstream is implementation defined:
  B.6 NN ties -> first in (i,j,l) voxel order then stored order
  B.7 JtJ/Jtr reduced by a fixed adjacent-pairs binary tree over source index
  B.8 point_cloud order unspecified (compare as sets)
+
+order="robin_map" (second mode, used only to MEASURE what rules B.1/B.2/B.4 cost against upstream):
+emulates the iteration order of the tsl::robin_map upstream keeps its voxels in - power-of-two
+bucket count, reserve(frame.size()) in VoxelDownsample, the 20-bit upstream voxel hash of
+SURVEY A.5, robin-hood linear probing (whose layout is the stable sort of the entries by ideal
+bucket) and the erase-while-iterating skip of RemovePointsFarFromLocation (backward-shift
+deletion).  Still UPSTREAM-UNVERIFIED: it restates published behaviour of kiss-icp 0.2.10 and
+tsl::robin_map 1.x from memory; nothing here was compared with the real packages.
 """
 import math
 
@@ -89,19 +97,128 @@ def preprocess(frame, max_range, min_range):
     return frame[range_mask(frame, max_range, min_range)]
 
 
-def voxel_down_sample_idx(frame, voxel_size):
-    """Indices (ascending) of the first point of every voxel (A.5 + B.1)."""
+def upstream_voxel_hash(keys):
+    """kiss-icp VoxelHash (A.5): ((1 << 20) - 1) & (x*73856093 ^ y*19349663 ^ z*83492791) on the int32
+    lanes reinterpreted as uint32.  Known answers: (1,2,3) -> 363078, (-1,0,0) -> 592803."""
+    k = np.asarray(keys).reshape(-1, 3).astype(np.int64) & 0xFFFFFFFF
+    h = ((k[:, 0] * 73856093) & 0xFFFFFFFF) ^ ((k[:, 1] * 19349663) & 0xFFFFFFFF) ^ ((k[:, 2] * 83492791) & 0xFFFFFFFF)
+    return (h & ((1 << 20) - 1)).astype(np.int64)
+
+
+ROBIN_DIST_LIMIT = 4096     # tsl::robin_map grows when an entry sits farther than this from its ideal bucket
+
+
+def robin_bucket_count_reserve(n):
+    """bucket_count() after tsl::robin_map::reserve(n): next power of two >= ceil(n / max_load_factor 0.5)."""
+    want = 2 * int(n)
+    b = 1
+    while b < want:
+        b <<= 1
+    return b if n > 0 else 0
+
+
+class RobinTable:
+    """tsl::robin_map as far as ITERATION ORDER goes: power-of-two bucket count, max_load_factor 0.5, linear
+    probing with robin-hood swaps (an entry being inserted or displaced takes a bucket only from a resident that
+    is strictly closer to its own ideal bucket - so a displaced entry travels past its equals), growth by
+    doubling with re-insertion in old bucket order, backward-shift deletion.  Values are opaque ids."""
+
+    def __init__(self, reserve=0):
+        self.bc = robin_bucket_count_reserve(reserve)
+        self.slot = {}                  # bucket -> [id, hash, distance from ideal bucket]
+        self.where = {}                 # id -> bucket
+        self.grow_next = False
+
+    def __len__(self):
+        return len(self.slot)
+
+    def _place(self, cur, h, b, d):
+        mask = self.bc - 1
+        slot, where = self.slot, self.where
+        while True:
+            r = slot.get(b)
+            if r is None:
+                slot[b] = [cur, h, d]
+                where[cur] = b
+                return
+            if r[2] < d:                # resident is richer: it moves on, the traveller settles here
+                if d > ROBIN_DIST_LIMIT:
+                    self.grow_next = True
+                slot[b] = [cur, h, d]
+                where[cur] = b
+                cur, h, d = r
+            b = (b + 1) & mask
+            d += 1
+
+    def _grow(self):
+        old = [self.slot[b] for b in sorted(self.slot)]
+        self.bc = 2 if self.bc == 0 else self.bc * 2
+        self.slot, self.where = {}, {}
+        self.grow_next = False
+        for cur, h, _ in old:           # rehash_impl: re-insert in the old table's bucket order
+            self._place(cur, h, h & (self.bc - 1), 0)
+
+    def insert_new(self, ident, h):
+        """insert() of a key known to be absent."""
+        h = int(h)
+        if self.grow_next or len(self.slot) >= self.bc // 2:
+            self._grow()
+        self._place(ident, h, h & (self.bc - 1), 0)
+
+    def erase(self, ident):
+        """erase(key): backward-shift deletion.  Returns True if an entry slid into the erased bucket."""
+        mask = self.bc - 1
+        b = self.where.pop(ident)
+        del self.slot[b]
+        shifted = False
+        nb = (b + 1) & mask
+        while True:
+            r = self.slot.get(nb)
+            if r is None or r[2] == 0:
+                return shifted
+            del self.slot[nb]
+            r[2] -= 1
+            self.slot[b] = r
+            self.where[r[0]] = b
+            shifted = True
+            b, nb = nb, (nb + 1) & mask
+
+    def iteration(self):
+        """ids in begin()..end() order (bucket order)."""
+        return [self.slot[b][0] for b in sorted(self.slot)]
+
+
+def robin_layout(hashes, bucket_count):
+    """Entries (given in insertion order, distinct keys) of a robin_map with `bucket_count` buckets that never
+    grows: (ids in iteration order, their buckets)."""
+    t = RobinTable()
+    t.bc = int(bucket_count)
+    for e, h in enumerate(np.asarray(hashes).tolist()):
+        t._place(e, h, h & (t.bc - 1), 0)
+    bs = sorted(t.slot)
+    return np.array([t.slot[b][0] for b in bs], dtype=np.int64), np.array(bs, dtype=np.int64)
+
+
+def voxel_down_sample_idx(frame, voxel_size, order="index"):
+    """Indices of the first point of every voxel (A.5): ascending (B.1, order="index") or in the iteration
+    order of upstream's `tsl::robin_map grid; grid.reserve(frame.size())` (order="robin_map")."""
     frame = np.asarray(frame, dtype=np.float64).reshape(-1, 3)
     if frame.shape[0] == 0:
         return np.zeros(0, dtype=np.int64)
-    packed = pack_keys(voxel_keys(frame, voxel_size))
+    keys = voxel_keys(frame, voxel_size)
+    packed = pack_keys(keys)
     _, first = np.unique(packed, return_index=True)
-    return np.sort(first)
+    first = np.sort(first)                 # insertion order of the voxels = order of first appearance
+    if order == "index":
+        return first
+    assert order == "robin_map", order
+    it, _ = robin_layout(upstream_voxel_hash(keys[first]), robin_bucket_count_reserve(frame.shape[0]))
+    return first[it]
 
 
-def voxel_down_sample(frame, voxel_size):
+def voxel_down_sample(frame, voxel_size, order="index"):
     frame = np.asarray(frame, dtype=np.float64).reshape(-1, 3)
-    return frame[voxel_down_sample_idx(frame, voxel_size)]
+    return frame[voxel_down_sample_idx(frame, voxel_size, order)]
 
 
 # ---------------------------------------------------------------------------
@@ -112,16 +229,21 @@ _OFFSETS = np.array([(i, j, k) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in 
 
 
 class VoxelHashMap:
-    def __init__(self, voxel_size, max_distance, max_points_per_voxel=20):
+    def __init__(self, voxel_size, max_distance, max_points_per_voxel=20, order="index"):
         self.voxel_size = float(voxel_size)
         self.max_distance = float(max_distance)
         self.max_points = int(max_points_per_voxel)
+        self.order = order
         self.clear()
 
     def clear(self):
         self.keys = np.zeros(0, dtype=np.int64)                    # sorted packed keys
         self.pts = np.zeros((0, self.max_points, 3), dtype=np.float64)
         self.cnt = np.zeros(0, dtype=np.int32)
+        self.seq = np.zeros(0, dtype=np.int64)                     # creation sequence number of every voxel
+        self._next_seq = 0
+        self.table = RobinTable() if self.order == "robin_map" else None   # upstream's map_, ids = packed keys
+        self.skipped_last_prune = 0
 
     def empty(self):
         return self.keys.shape[0] == 0
@@ -155,11 +277,22 @@ class VoxelHashMap:
         posc, found = self._lookup(uniq)
         new_keys = uniq[~found]
         if new_keys.shape[0]:
+            # creation order = order in which the scan's points first touch the new voxels
+            first_touch = order[gstart[~found]]
+            new_seq = np.empty(new_keys.shape[0], dtype=np.int64)
+            new_seq[np.argsort(first_touch, kind="stable")] = self._next_seq + np.arange(new_keys.shape[0])
+            self._next_seq += new_keys.shape[0]
             keys = np.concatenate([self.keys, new_keys])
             pts = np.concatenate([self.pts, np.zeros((new_keys.shape[0], self.max_points, 3))])
             cnt = np.concatenate([self.cnt, np.zeros(new_keys.shape[0], dtype=np.int32)])
+            seq = np.concatenate([self.seq, new_seq])
             o = np.argsort(keys, kind="stable")
-            self.keys, self.pts, self.cnt = keys[o], pts[o], cnt[o]
+            self.keys, self.pts, self.cnt, self.seq = keys[o], pts[o], cnt[o], seq[o]
+            if self.table is not None:                               # map_.insert in the order the voxels are created
+                created = new_keys[np.argsort(new_seq, kind="stable")]
+                hs = upstream_voxel_hash(unpack_keys(created))
+                for kk, hh in zip(created.tolist(), hs.tolist()):
+                    self.table.insert_new(kk, hh)
         vid, f = self._lookup(packed)
         assert f.all()
         slot = self.cnt[vid].astype(np.int64) + rank
@@ -175,8 +308,33 @@ class VoxelHashMap:
         dy = self.pts[:, 0, 1] - o[1]
         dz = self.pts[:, 0, 2] - o[2]
         d2 = (dx * dx + dy * dy) + dz * dz
-        keep = ~(d2 > self.max_distance * self.max_distance)
-        self.keys, self.pts, self.cnt = self.keys[keep], self.pts[keep], self.cnt[keep]
+        far = d2 > self.max_distance * self.max_distance
+        self.skipped_last_prune = 0
+        if self.order == "robin_map" and far.any():
+            far = self._robin_erase_while_iterating(far)
+        keep = ~far
+        self.keys, self.pts, self.cnt, self.seq = self.keys[keep], self.pts[keep], self.cnt[keep], self.seq[keep]
+
+    def _robin_erase_while_iterating(self, far):
+        """Which voxels upstream 0.2.x really erases: `for (auto& [voxel, block] : map_) if (far) map_.erase(voxel);`
+        over a tsl::robin_map.  erase() shifts the rest of the cluster back by one bucket, so the entry that
+        slides into the erased bucket is stepped over by the ++ of the range-for and survives this call (A.6)."""
+        t = self.table
+        far_of = dict(zip(self.keys.tolist(), far.tolist()))
+        erased_keys = set()
+        b, last = 0, t.bc
+        while b < last:                                 # the iterator is a bucket pointer
+            r = t.slot.get(b)
+            if r is not None and far_of[r[0]]:
+                kk = r[0]
+                slid = t.erase(kk)
+                erased_keys.add(kk)
+                if slid:
+                    nxt = t.slot.get(b)
+                    if nxt is not None and far_of[nxt[0]]:
+                        self.skipped_last_prune += 1
+            b += 1
+        return np.array([k in erased_keys for k in self.keys.tolist()], dtype=bool)
 
     def update(self, points, pose):
         """VoxelHashMap::Update(points, pose) (/root/reference/src/ptudes/kiss.py:129)."""
@@ -389,23 +547,24 @@ class KissICP:
     kiss_icp.kiss_icp.KissICP: poses, config, compensator, preprocess, voxelize,
     get_adaptive_threshold, get_prediction_model, adaptive_threshold, local_map."""
 
-    def __init__(self, config):
+    def __init__(self, config, order="index"):
         self.poses = []
+        self.order = order
         self.config = config
         self.compensator = _Compensator()
         self.adaptive_threshold = AdaptiveThreshold(config.adaptive_threshold.initial_threshold,
                                                     config.adaptive_threshold.min_motion_th,
                                                     config.data.max_range)
         self.local_map = VoxelHashMap(config.mapping.voxel_size, config.data.max_range,
-                                      config.mapping.max_points_per_voxel)
+                                      config.mapping.max_points_per_voxel, order=order)
 
     def preprocess(self, frame):
         return preprocess(frame, self.config.data.max_range, self.config.data.min_range)
 
     def voxelize(self, frame):
         v = self.config.mapping.voxel_size
-        frame_downsample = voxel_down_sample(frame, v * 0.5)
-        source = voxel_down_sample(frame_downsample, v * 1.5)
+        frame_downsample = voxel_down_sample(frame, v * 0.5, self.order)
+        source = voxel_down_sample(frame_downsample, v * 1.5, self.order)
         return source, frame_downsample
 
     def has_moved(self):
@@ -430,12 +589,12 @@ class KissICP:
 class OracleKissICPWrapper:
     """The ouster-free part of /root/reference/src/ptudes/kiss.py:18-166 on the oracle."""
 
-    def __init__(self, *, _min_range=5, _max_range=100):
+    def __init__(self, *, _min_range=5, _max_range=100, order="index"):
         self._max_range = _max_range
         self._min_range = _min_range
         self._kiss_config = load_config(None, deskew=True, max_range=self._max_range)
         self._kiss_config.data.min_range = self._min_range          # kiss.py:43
-        self._kiss = KissICP(config=self._kiss_config)
+        self._kiss = KissICP(config=self._kiss_config, order=order)
         self._poses_ts = []
         self._err_dt = []
         self._err_drot = []

@@ -148,11 +148,27 @@ def addr(a):
     raise TypeError(type(a))
 
 
+def _check_tensor(a, dtypes, what):
+    """A torch tensor is handed to the C ABI by address: refuse anything the library would misread."""
+    name = str(getattr(a, "dtype", "")).replace("torch.", "")
+    if name not in dtypes:
+        raise TypeError(f"{what}: tensor dtype {name} not accepted (need {' or '.join(dtypes)})")
+    if hasattr(a, "is_contiguous") and not a.is_contiguous():
+        raise TypeError(f"{what}: tensor must be contiguous")
+    return a
+
+
 def f64(a, shape_last=None):
-    """C-contiguous float64 ndarray view/copy of array-like `a` (torch tensors pass through)."""
+    """C-contiguous float64 ndarray view/copy of array-like `a`; torch tensors pass through by address after a
+    dtype / contiguity / shape check (`shape_last`: required size of the last dimension)."""
     if hasattr(a, "data_ptr") and not isinstance(a, np.ndarray):
+        _check_tensor(a, ("float64",), "f64 input")
+        if shape_last is not None and (a.dim() < 1 or int(a.shape[-1]) != shape_last):
+            raise TypeError(f"f64 input: last dimension must be {shape_last}, got shape {tuple(a.shape)}")
         return a
     a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape_last is not None and (a.ndim < 1 or a.shape[-1] != shape_last):
+        raise TypeError(f"f64 input: last dimension must be {shape_last}, got shape {a.shape}")
     return a
 
 

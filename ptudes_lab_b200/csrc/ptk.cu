@@ -4,6 +4,7 @@
 // /root/reference/src/ptudes/kiss.py:83-131 computes around the kiss-icp calls (initial guess,
 // pose gain metrics); all per-point work runs in the kernels of ptk_device.cuh.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,6 +36,7 @@ struct LaneHost {
     StepParams last_params;
     StepOut last_out;
     bool have_last = false;
+    bool failed = false;              // a capacity error left the local map incomplete: the lane refuses steps until ptk_reset
     int last_reg_iters = 0, last_reg_nsrc = 0;
     u32 epoch = 0, tbase1 = 0, tbase2 = 0, release_base = 0;
     double* in_xyz = nullptr;         // staging for host inputs
@@ -92,10 +94,9 @@ struct ptk_ctx {
     cudaEvent_t pf_event = nullptr;
     std::vector<const unsigned int*> pf_pending;   // host images to copy during the next step
     int num_sms = 148;
-    int icp_blocks_total = 148;
-    int icp_max_blocks_per_lane = 1 << 20;   // PTK_ICP_MAX_BLOCKS_PER_LANE: fewer blocks = cheaper barrier, slower searches
-    int icp_cluster = 0;              // blocks per lane of the cluster launch of wide batches (0: not available)
-    int icp_cluster_min_lanes = 56;   // batch width from which the cluster launch is used
+    int icp_blocks_total = 148;       // blocks of k_icp the device holds at once (occupancy x SMs)
+    IcpQueue* d_icp_queue = nullptr;  // task ring of the ICP dataflow kernel
+    int icp_prof = 0;                 // accumulate warp cycles per ICP phase (ptk_set_profiling)
     std::string err;
     std::vector<void*> allocs;
 };
@@ -288,32 +289,12 @@ extern "C" int ptk_ctx_create(ptk_ctx** out, int device, const ptk_config* cfg_i
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; return bail(PTK_E_CUDA); }
     ctx->num_sms = prop.multiProcessorCount;
     int occ = 0;
-    if (cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_SMEM) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, ICP_THREADS, ICP_SMEM) != cudaSuccess || occ < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, IQ_THREADS, 0) != cudaSuccess || occ < 1) {
         ctx->err = std::string("k_icp not launchable on this device: ") + cudaGetErrorString(cudaGetLastError());
         return bail(PTK_E_CUDA);
     }
     ctx->icp_blocks_total = occ * ctx->num_sms;
-    {   // cluster size for wide batches: PTK_ICP_CLUSTER (1 disables), default 8 = the portable maximum
-        if (const char* mb = getenv("PTK_ICP_MAX_BLOCKS_PER_LANE")) ctx->icp_max_blocks_per_lane = std::max(1, atoi(mb));
-        const char* e = getenv("PTK_ICP_CLUSTER");
-        int want = e ? atoi(e) : 8;
-        if (const char* m = getenv("PTK_ICP_CLUSTER_MIN_LANES")) ctx->icp_cluster_min_lanes = atoi(m);
-        ctx->icp_cluster = 0;
-        if (want > 8 && cudaFuncSetAttribute(k_icp, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) want = 8;
-        if (want > 1) {
-            cudaLaunchConfig_t qc;
-            memset(&qc, 0, sizeof(qc));
-            qc.gridDim = dim3(want, 1); qc.blockDim = dim3(ICP_THREADS); qc.dynamicSmemBytes = ICP_SMEM;
-            cudaLaunchAttribute qa[1];
-            qa[0].id = cudaLaunchAttributeClusterDimension;
-            qa[0].val.clusterDim.x = want; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-            qc.attrs = qa; qc.numAttrs = 1;
-            int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, k_icp, &qc) == cudaSuccess && ncl >= 1) ctx->icp_cluster = want;
-        }
-        cudaGetLastError();
-    }
+    if (const char* mb = getenv("PTK_ICP_MAX_BLOCKS")) ctx->icp_blocks_total = std::max(1, std::min(ctx->icp_blocks_total, atoi(mb)));
     ctx->lanes.resize(ctx->B + 1);
     for (int l = 0; l <= ctx->B; ++l) {
         int rc = lane_alloc(ctx, ctx->lanes[l], l == ctx->B);
@@ -327,6 +308,7 @@ extern "C" int ptk_ctx_create(ptk_ctx** out, int device, const ptk_config* cfg_i
     if (!ck(dalloc(ctx->allocs, &ctx->d_lanes, nl), "alloc lanes")) return bail(PTK_E_CUDA);
     if (!ck(dalloc(ctx->allocs, &ctx->d_params, nl, 0), "alloc params")) return bail(PTK_E_CUDA);
     if (!ck(dalloc(ctx->allocs, &ctx->d_outs, nl, 0), "alloc outs")) return bail(PTK_E_CUDA);
+    if (!ck(dalloc(ctx->allocs, &ctx->d_icp_queue, 1, 0), "alloc icp queue")) return bail(PTK_E_CUDA);
     if (!ck(dalloc(ctx->allocs, &ctx->d_tmp, (size_t)cfg.max_points * 3 + 64), "alloc tmp")) return bail(PTK_E_CUDA);
     if (!ck(dalloc(ctx->allocs, &ctx->d_tmp_i, (size_t)cfg.max_points + 64, 0), "alloc tmp_i")) return bail(PTK_E_CUDA);
     if (!ck(cudaMallocHost((void**)&ctx->h_params, sizeof(StepParams) * nl), "pinned params")) return bail(PTK_E_CUDA);
@@ -400,6 +382,7 @@ extern "C" int ptk_reset(ptk_ctx* ctx, int lane) {
         LH.thr = Threshold();
         LH.last_sigma = 0.0;
         LH.have_last = false;
+        LH.failed = false;
         LH.pf_src = nullptr;
         int rc = lane_reset_device(ctx, l, 0, true);
         if (rc) return rc;
@@ -455,52 +438,25 @@ static Rigid prediction_model(const LaneHost& LH) {
 }
 
 // ---- kernel launch helpers -----------------------------------------------------------
-// `groups_hint`: upper estimate of the 32-point source groups per lane (0 = unknown); blocks beyond
-// one per group would only add arrivals to the per-iteration barrier.
+// One launch of the ICP dataflow kernel for lanes [l0, l0+cnt).  `groups_hint`: upper estimate of the 32-point
+// source groups per lane (0 = unknown).  The grid is sized to the work (idle warps only poll the ring) and never
+// exceeds what the device holds at once; the kernel itself does not depend on co-residency.
 static int launch_icp(ptk_ctx* ctx, int l0, int cnt, int groups_hint, cudaStream_t st) {
-    // Wide batches: one THREAD-BLOCK CLUSTER per lane.  The only thing the lane's blocks need from each other
-    // is to be running at the same time (their per-iteration barrier spins on a counter), which is exactly
-    // what a cluster guarantees - so the launch needs no grid-wide co-residency, the grid may hold more
-    // clusters than fit at once, and the lanes that converge early (iterations per scan vary 2-4x between
-    // lanes) hand their SMs to queued lanes instead of leaving them idle until the slowest lane ends.
-    // (measured: pays off from ~56 lanes on - 64 lanes 19.7k -> 21.1k scans/s; at 48 the cooperative launch is faster)
-    if (ctx->icp_cluster > 1 && cnt >= ctx->icp_cluster_min_lanes) {
-        int cl = ctx->icp_cluster;
-        if (groups_hint > 0) while (cl > 1 && cl / 2 >= groups_hint) cl /= 2;
-        LaneDev* dl = ctx->d_lanes + l0;
-        const StepParams* dp = ctx->d_params + l0;
-        StepOut* dout = ctx->d_outs + l0;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(cl, cnt);
-        cfg.blockDim = dim3(ICP_THREADS);
-        cfg.dynamicSmemBytes = ICP_SMEM;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaError_t le = cudaSuccess;
-        LAUNCH(PS_ICP, st, le = cudaLaunchKernelEx(&cfg, k_icp, dl, dp, dout));
-        CK(le);
-        return PTK_OK;
-    }
-    // Few lanes: a cooperative launch with as many blocks per lane as the device holds
-    // (all blocks of a cooperative launch must be co-resident: split wide batches)
+    const int max_groups = (ctx->cfg.max_points + 31) / 32;
+    const int groups = groups_hint > 0 ? std::min(groups_hint, max_groups) : max_groups;
+    const int warps_cap = ctx->icp_blocks_total * IQ_WARPS;
     int done = 0;
     while (done < cnt) {
-        int chunk = std::min(cnt - done, ctx->icp_blocks_total);
-        int per = std::max(1, ctx->icp_blocks_total / chunk);
-        if (groups_hint > 0) per = std::max(1, std::min(per, groups_hint));
-        per = std::min(per, ctx->icp_max_blocks_per_lane);
-        LaneDev* dl = ctx->d_lanes + l0 + done;
-        StepParams* dp = ctx->d_params + l0 + done;
-        StepOut* dout = ctx->d_outs + l0 + done;
-        void* args[] = {&dl, &dp, &dout};
-        cudaError_t le = cudaSuccess;
-        LAUNCH(PS_ICP, st, le = cudaLaunchCooperativeKernel((void*)k_icp, dim3(per, chunk), dim3(ICP_THREADS), args, ICP_SMEM, st));
-        CK(le);
+        // a lane whose publishing warp waits on a full ring occupies one warp: keep lanes well below the warps
+        const int chunk = std::min(cnt - done, std::max(1, warps_cap / 4));
+        const long long total_groups = (long long)groups * chunk;
+        long long want_warps = total_groups;
+        int blocks = (int)std::min<long long>(ctx->icp_blocks_total, (want_warps + IQ_WARPS - 1) / IQ_WARPS);
+        blocks = std::max(blocks, std::min(ctx->icp_blocks_total, (chunk + IQ_WARPS - 1) / IQ_WARPS));
+        blocks = std::max(blocks, 1);
+        LAUNCH(PS_ICP, st, k_icp<<<blocks, IQ_THREADS, 0, st>>>(ctx->d_lanes + l0 + done, ctx->d_params + l0 + done,
+                                                               ctx->d_outs + l0 + done, chunk, ctx->d_icp_queue));
+        CK(cudaGetLastError());
         done += chunk;
     }
     return PTK_OK;
@@ -548,6 +504,7 @@ static int step_prepare(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz,
         int l = l0 + k;
         LaneHost& LH = ctx->lanes[l];
         nv[k] = range ? npix : n_in[k];
+        if (LH.failed) return fail(ctx, PTK_E_STATE, "lane hit a capacity error: its local map is incomplete, ptk_reset it first");
         if (n[k] < 0 || n[k] > c.max_points) return fail(ctx, PTK_E_CAPACITY, "scan larger than cfg.max_points");
         if (!range && n[k] > 0 && !xyz[k]) return fail(ctx, PTK_E_ARG, "xyz is null");
         if (range && !range[k]) return fail(ctx, PTK_E_ARG, "range image is null");
@@ -560,8 +517,9 @@ static int step_prepare(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz,
                 P.range = LH.pf_range[LH.pf_buf];
                 LH.cur_buf = LH.pf_buf;
                 LH.pf_src = nullptr;
-            } else if (is_device_ptr(range[k])) P.range = range[k];
+            } else if (is_device_ptr(range[k])) { P.range = range[k]; LH.pf_src = nullptr; }
             else {
+                LH.pf_src = nullptr;     // any other image invalidates an earlier prefetch (its host buffer may be refilled)
                 CK(cudaMemcpyAsync(LH.pf_range[LH.cur_buf], range[k], (size_t)npix * sizeof(u32), cudaMemcpyHostToDevice, st));
                 P.range = LH.pf_range[LH.cur_buf];
             }
@@ -679,7 +637,14 @@ static int step_finish(ptk_ctx* ctx, int l0, int cnt, int nmax, double* out_pose
         LH.last_reg_iters = O.iterations;
         LH.last_reg_nsrc = O.n_src;
         int ec = err_to_code(ctx, O.err);
-        if (ec && !ret) ret = ec;
+        if (ec) {
+            // points of this scan are missing from the local map (or a key overflowed): the pose is not committed
+            // (the Python wrapper raises before it records anything, kiss.py:54-74 lets exceptions propagate) and
+            // the lane stays unusable until it is reset
+            if (!ret) ret = ec;
+            if (ec == PTK_E_CAPACITY) LH.failed = true;
+            continue;
+        }
         Rigid gain = rigid_mul(rigid_inv(P.guess), O.pose);                   // kiss.py:116
         double dt = sqrt((gain.t[0] * gain.t[0] + gain.t[1] * gain.t[1]) + gain.t[2] * gain.t[2]);
         double om[3], theta;
@@ -1221,7 +1186,6 @@ extern "C" int ptk_register_point_cloud(ptk_ctx* ctx, int lane, const double* xy
 }
 
 // ---- hash-sharded map over several GPUs: one process per GPU drives these between its collectives ----
-#include <stddef.h>
 extern "C" int ptk_shard_config(ptk_ctx* ctx, int rank, int nranks) {
     if (!ctx || nranks < 1 || rank < 0 || rank >= nranks || nranks > 32) return fail(ctx, PTK_E_ARG, "ptk_shard_config: bad argument");
     CK(cudaSetDevice(ctx->device));
@@ -1320,9 +1284,13 @@ extern "C" int ptk_shard_end(ptk_ctx* ctx, int lane, double* out_pose, ptk_stats
 
 extern "C" int ptk_get_icp_phases(const ptk_ctx* ctx, int lane, long long* cycles6) {
     if (!ctx || lane < 0 || lane >= ctx->B || !cycles6) return PTK_E_ARG;
-    const LaneHost& LH = ctx->lanes[lane];
-    if (!LH.have_last) return PTK_E_STATE;
-    for (int k = 0; k < 6; ++k) cycles6[k] = LH.last_out.icp_cyc[k];
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return PTK_E_CUDA;
+    unsigned long long c[8];
+    if (cudaMemcpy(c, (const char*)ctx->d_icp_queue + offsetof(IcpQueue, cyc), sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return PTK_E_CUDA;
+    }
+    for (int k = 0; k < 6; ++k) cycles6[k] = (long long)c[k];
     return PTK_OK;
 }
 
@@ -1332,6 +1300,12 @@ extern "C" int ptk_set_profiling(ptk_ctx* ctx, int on) {
     CK(cudaDeviceSynchronize());
     prof_collect(ctx);
     ctx->prof.on = on != 0;
+    {   // ICP phase accounting (warp cycles summed over the device) follows the profiling switch; reset on every call
+        u32 flag = on ? 1u : 0u;
+        unsigned long long zero[8] = {0};
+        CK(cudaMemcpy((char*)ctx->d_icp_queue + offsetof(IcpQueue, prof), &flag, sizeof(flag), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy((char*)ctx->d_icp_queue + offsetof(IcpQueue, cyc), zero, sizeof(zero), cudaMemcpyHostToDevice));
+    }
     for (int k = 0; k < PTK_PROF_SLOTS; ++k) { ctx->prof.ms[k] = 0.0; ctx->prof.n[k] = 0; }
     return PTK_OK;
 }

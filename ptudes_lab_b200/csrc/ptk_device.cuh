@@ -27,21 +27,12 @@ constexpr int KEY_BIAS = 1 << 20;
 constexpr int TILE = 1024;                 // items per compaction tile (256 threads x 4)
 constexpr int NSUM = 17;                   // distinct normal-equation sums (16) + correspondence count
 constexpr int NRED = NSUM;
-#ifndef PTK_ICP_THREADS
-#define PTK_ICP_THREADS 512
-#endif
-#ifndef PTK_ICP_MINBLOCKS
-#define PTK_ICP_MINBLOCKS 2
-#endif
-constexpr int ICP_THREADS = PTK_ICP_THREADS;
+constexpr int ICP_THREADS = 512;            // block size of the sharded-mode system kernel (one warp per 32-point group)
 constexpr int ICP_WARPS = ICP_THREADS / 32;
-constexpr int ICP_CHUNK = ICP_WARPS;        // 32-point groups a block handles at a time: one point per thread
 #ifndef PTK_ICP_KX
 #define PTK_ICP_KX 2
 #endif
 constexpr int ICP_KX = PTK_ICP_KX;          // runner-ups a correspondence cache entry keeps beside the winner
-constexpr int ICP_SRC_CAP = ICP_KX <= 1 ? 768 : (ICP_KX == 2 ? 640 : 512);   // source points (+ cache entries) per block in smem
-constexpr int ICP_SMEM = ICP_SRC_CAP * (3 * 8 + 4 * 8 + 8 + 3 * 8 + ICP_KX * (3 * 8 + 4) + 4) + 8;
 
 enum StepFlags : int { F_DESKEW = 1, F_RANGE = 2, F_SECOND = 4, F_SELECT_RANGE = 8 };
 enum ErrFlags : int { ERR_KEYRANGE = 1, ERR_POOL = 2, ERR_TABLE = 4 };
@@ -97,7 +88,6 @@ struct StepOut {
     double dx_norm;
     int status, n_range, n_ds, n_src, n_vox, n_tomb, iterations, n_corr, map_points, err, bump, icp_searches;
     int n_valid, pad;
-    long long icp_cyc[6];      // block 0's clock64 spent in: cache pass, searches, sums, barrier, tree, solve
 };
 
 // Per-sequence ("lane") device state.
@@ -126,8 +116,8 @@ struct LaneDev {
     u32* vidx;                           // [pool_cap*MAXP] insertion scratch, NONE when idle
     u32* freelist;
     // icp
-    double* part_a; double* part_b;      // [NRED][ng_cap] partial sums (ping-pong)
-    double *c_tx, *c_ty, *c_tz, *c_slack; // correspondence cache of blocks too wide for shared memory
+    double* part_a; double* part_b;      // [NRED][ng_cap] group partial sums (part_b: unused spare)
+    double *c_tx, *c_ty, *c_tz, *c_slack; // correspondence cache: winner, bound on every other candidate
     double *c_px, *c_py, *c_pz;
     double* c_t2;                        // [3 * ICP_KX][cap_points] runner-up coordinates
     int* c_ord2;                         // [ICP_KX][cap_points]
@@ -139,7 +129,7 @@ struct LaneDev {
     u32 ticket1, ticket2;
     u32 icp_arrive; u32 icp_release;
     int icp_done, err;
-    int icp_searches;
+    int icp_searches, icp_it;
     Rigid icp_E, icp_T;
     SE3q icp_Tq;                         // T_icp between the launches of the sharded (multi-GPU) loop
 };
@@ -150,6 +140,15 @@ __device__ __forceinline__ u32 hash_key(u64 k) {
     k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
     k ^= k >> 33;
     return (u32)k;
+}
+
+// Hash of the LOCAL MAP table: separable in the three voxel coordinates (the classic spatial hash, upstream's
+// multipliers, plus one xor-shift), so the 27 neighbours of a query cost two XORs each instead of a 64-bit mix.
+__device__ __forceinline__ u32 hash_mix(u32 h) { return h ^ (h >> 15); }
+constexpr u32 HASH_A = 73856093u, HASH_B = 19349663u, HASH_C = 83492791u;
+__device__ __forceinline__ u32 hash_map_key(u64 k) {
+    const u32 x = (u32)(k >> 42) & 0x1FFFFFu, y = (u32)(k >> 21) & 0x1FFFFFu, z = (u32)k & 0x1FFFFFu;   // biased coordinates
+    return hash_mix((x * HASH_A) ^ (y * HASH_B) ^ (z * HASH_C));
 }
 
 // Owner rank of a voxel in the hash-sharded multi-GPU mode (upper hash bits; the table slot uses the lower).
@@ -599,7 +598,7 @@ __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double
         int di = lane / 9 - 1, dj = (lane / 3) % 3 - 1, dk = lane % 3 - 1;
         int nx = kx + di, ny = ky + dj, nz = kz + dk;
         u64 key = pack_key(nx, ny, nz);
-        u32 slot = hash_key(key) & L.mask;
+        u32 slot = hash_map_key(key) & L.mask;
         while (true) {
             const ulonglong2 raw = __ldg(reinterpret_cast<const ulonglong2*>(L.slots + slot));
             if (raw.x == key) { id = (u32)raw.y; break; }
@@ -707,6 +706,153 @@ __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double
     const double d2_other = __longlong_as_double((long long)((u64)ohi << 32));     // low word zero: rounds down
     others = found ? sqrt(d2_other) * (1.0 - 1e-12) : -1.0;
     return found;
+}
+
+// ---- the same search with ONE THREAD per query (the ICP kernel's form) -------------------------------------
+// Every lane of a warp carries its own query (or none: active = false), so all missed points of a 32-point group
+// are searched at the same time and the latency of a group's searches is that of one search.  Result semantics
+// are those of warp_nearest: winner = lexicographic minimum of (d2, order id) over the 27 voxels (B.6), ICP_KX
+// runner-ups, and `others` = a lower bound of the distance to every candidate not handed out.
+//   1. 27 table probes, issued nine at a time; voxel ids and a rounded-down float of the box distance go to this
+//      warp's shared-memory scratch (ids/lbs [27][32], one column per lane);
+//   2. the query's own voxel, then each lane walks ITS OWN list of voxels whose box is not farther than the best
+//      so far (a skipped voxel holds only strictly farther points); lanes = queries, so there is no divergence
+//      in the visit itself, only in how many voxels a lane needs;
+//   3. coordinates of the winner and the runner-ups are re-read through their order ids (cache-hot).
+struct NearestOut {
+    double tx, ty, tz, others;
+    double t2[3 * ICP_KX];
+    u64 qkey;
+    int ord;
+    int ord2[ICP_KX];
+};
+
+__device__ __forceinline__ void thread_nearest(const MapView& M, u32* ids, float* lbs, int lane, bool active, double sx, double sy,
+                                               double sz, double max_d2, NearestOut& R) {
+    int kx, ky, kz;
+    voxel_key(sx, sy, sz, M.voxel, M.voxel_inv, kx, ky, kz);
+    const bool inr = active && key_in_range(kx, ky, kz);
+    R.qkey = inr ? pack_key(kx, ky, kz) : KEY_EMPTY;
+    const double v = M.voxel;
+    u32 present = 0;
+    if (inr) {
+        const u64 base = pack_key(kx - 1, ky - 1, kz - 1);
+        const u32 bx = (u32)(kx - 1 + KEY_BIAS), by = (u32)(ky - 1 + KEY_BIAS), bz = (u32)(kz - 1 + KEY_BIAS);
+        u32 hy[3], hz[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { hy[j] = (by + (u32)j) * HASH_B; hz[j] = (bz + (u32)j) * HASH_C; }
+#pragma unroll 1
+        for (int i = 0; i < 3; ++i) {
+            const u32 hxi = (bx + (u32)i) * HASH_A;
+            const u64 keyi = base + ((u64)i << 42);
+            ulonglong2 raw[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const u32 slot = hash_mix(hxi ^ hy[q / 3] ^ hz[q % 3]) & M.mask;
+                raw[q] = __ldg(reinterpret_cast<const ulonglong2*>(M.slots + slot));
+            }
+            // voxel n covers [n v, (n+1) v) for n > 0, (-v, v) for n == 0 and ((n-1) v, n v] for n < 0
+            // (keys truncate toward zero); 1e-7 m of slack per axis covers every rounding involved
+            const int nx = kx - 1 + i;
+            double lo = (double)(nx > 0 ? nx : nx - 1) * v, hi = (double)(nx < 0 ? nx : nx + 1) * v;
+            const double ax = fmax(fmax(lo - sx, sx - hi) - 1e-7, 0.0);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const u64 key = keyi + ((u64)(q / 3) << 21) + (u64)(q % 3);
+                u32 id = NONE;
+                if (raw[q].x == key) id = (u32)raw[q].y;
+                else if (raw[q].x != KEY_EMPTY) {          // collision or tombstone: keep probing
+                    u32 slot = (hash_mix(hxi ^ hy[q / 3] ^ hz[q % 3]) + 1u) & M.mask;
+                    while (true) {
+                        const ulonglong2 r2 = __ldg(reinterpret_cast<const ulonglong2*>(M.slots + slot));
+                        if (r2.x == key) { id = (u32)r2.y; break; }
+                        if (r2.x == KEY_EMPTY) break;
+                        slot = (slot + 1) & M.mask;
+                    }
+                }
+                const int c = i * 9 + q;
+                ids[c * 32 + lane] = id;
+                if (id != NONE) {
+                    const int ny = ky - 1 + q / 3, nz = kz - 1 + q % 3;
+                    lo = (double)(ny > 0 ? ny : ny - 1) * v; hi = (double)(ny < 0 ? ny : ny + 1) * v;
+                    const double ay = fmax(fmax(lo - sy, sy - hi) - 1e-7, 0.0);
+                    lo = (double)(nz > 0 ? nz : nz - 1) * v; hi = (double)(nz < 0 ? nz : nz + 1) * v;
+                    const double az = fmax(fmax(lo - sz, sz - hi) - 1e-7, 0.0);
+                    const double lb2 = ((ax * ax + ay * ay) + az * az) * (1.0 - 1e-9);
+                    lbs[c * 32 + lane] = __double2float_rd(lb2);
+                    present |= 1u << c;
+                }
+            }
+        }
+    }
+    // top three candidates in the search's lexicographic (d2, order id) order + the nearest of all the others
+    double d0 = INFINITY, d1 = INFINITY, d2 = INFINITY, rest = INFINITY;
+    int o0 = -1, o1 = -1, o2 = -1;
+    double bound = max_d2;
+    u32 todo = present;
+    int vv = (present >> 13) & 1u ? 13 : -1;     // the query's own voxel first
+    todo &= ~(1u << 13);
+    while (true) {
+        if (vv < 0) {
+            while (todo) {
+                const int c = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float lb = lbs[c * 32 + lane];
+                if ((double)lb <= bound) { vv = c; break; }
+                rest = fmin(rest, (double)lb);
+            }
+            if (vv < 0) break;
+        }
+        const double2* rows = reinterpret_cast<const double2*>(M.blocks + ids[vv * 32 + lane]);
+        const int obase = vv * MAXP;
+#pragma unroll
+        for (int h = 0; h < MAXP / 4; ++h) {
+            const double2 xa = __ldg(rows + 2 * h), xb = __ldg(rows + 2 * h + 1);
+            const double2 ya = __ldg(rows + MAXP / 2 + 2 * h), yb = __ldg(rows + MAXP / 2 + 2 * h + 1);
+            const double2 za = __ldg(rows + MAXP + 2 * h), zb = __ldg(rows + MAXP + 2 * h + 1);
+            const double xs[4] = {xa.x, xa.y, xb.x, xb.y}, ys[4] = {ya.x, ya.y, yb.x, yb.y}, zs[4] = {za.x, za.y, zb.x, zb.y};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double dx = xs[k] - sx, dy = ys[k] - sy, dz = zs[k] - sz;
+                const double d = (dx * dx + dy * dy) + dz * dz;
+                const int o = obase + 4 * h + k;
+                if (d < d2 || (d == d2 && o < o2)) {                 // beats the third (unused slots hold +inf: never)
+                    rest = fmin(rest, d2);
+                    if (d < d1 || (d == d1 && o < o1)) {
+                        d2 = d1; o2 = o1;
+                        if (d < d0 || (d == d0 && o < o0)) { d1 = d0; o1 = o0; d0 = d; o0 = o; }
+                        else { d1 = d; o1 = o; }
+                    } else { d2 = d; o2 = o; }
+                } else rest = fmin(rest, d);
+            }
+        }
+        bound = fmin(bound, d0);
+        vv = -1;
+    }
+    R.ord = o0;
+    R.tx = R.ty = R.tz = 0.0;
+    if (o0 >= 0) {
+        const VoxelBlock* B = M.blocks + ids[(o0 / MAXP) * 32 + lane];
+        const int sl = o0 % MAXP;
+        R.tx = __ldg(&B->x[sl]); R.ty = __ldg(&B->y[sl]); R.tz = __ldg(&B->z[sl]);
+    }
+    const int oj[2] = {o1, o2};
+    const double dj[2] = {d1, d2};
+    double other = rest;
+#pragma unroll
+    for (int j = 0; j < ICP_KX; ++j) {
+        const int o = j < 2 ? oj[j] : -1;
+        R.ord2[j] = o;
+        R.t2[3 * j] = R.t2[3 * j + 1] = R.t2[3 * j + 2] = 0.0;
+        if (o >= 0) {
+            const VoxelBlock* B = M.blocks + ids[(o / MAXP) * 32 + lane];
+            const int sl = o % MAXP;
+            R.t2[3 * j] = __ldg(&B->x[sl]); R.t2[3 * j + 1] = __ldg(&B->y[sl]); R.t2[3 * j + 2] = __ldg(&B->z[sl]);
+        }
+    }
+#pragma unroll
+    for (int j = ICP_KX; j < 2; ++j) other = fmin(other, dj[j]);      // runner-ups the cache does not keep count as "others"
+    R.others = o0 >= 0 ? sqrt(other) * (1.0 - 1e-12) : -1.0;
 }
 
 // The distinct sums behind the 27 normal-equation terms: the 27 columns the oracle
@@ -956,274 +1102,419 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
             O.iterations = it + 1; O.n_corr = n_corr; O.status = status; O.dx_norm = nrm;
         }
         SOLVE_TICK(5);
-#ifdef PTK_SOLVE_CLOCKS
-        if (done && writer) for (int k = 0; k < 6; ++k) O.icp_cyc[k] = s_sc[k];
-#endif
     }
 #undef SOLVE_TICK
 }
 
-// K4: the whole ICP loop (kiss-icp RegisterFrame) in one persistent cooperative kernel.
-// grid = (blocks per lane, lanes), ICP_THREADS threads.  A block owns a contiguous range of
-// 32-point groups and walks it in chunks of ICP_CHUNK groups (= one point per thread).  Per
-// iteration and chunk:
-//   1. thread per point: move the point by the last increment, then try the correspondence cache.
-//      The last search of the point, at position p0, left its winner a, a runner-up b and a lower bound D
-//      of the distance from p0 to every OTHER candidate (see warp_nearest).  If the point is still in the
-//      same voxel (same 27 candidate voxels; the map does not change during the loop) and, with w the
-//      lexicographically smaller of a and b in (distance^2, order id) - the search's own comparison -,
-//      |p - w| + |p - p0| < D, then every other candidate c has |p - c| >= |p0 - c| - |p - p0| >= D - |p - p0|
-//      > |p - w|: w is what a new search would return, so none is needed (a runner-up that has become the
-//      nearest swaps places with a in the cache; ICP_KX runner-ups are kept); otherwise the point goes on
-//      the block's work list;
-//   2. warp per listed point: the pruned 27-voxel search, refreshing the cache entry;
-//   3. thread per point: residual, Geman-McClure weight and the 16 distinct sums (+ count) in
-//      registers; a warp IS a 32-point group, so xor-butterflies give the group partials directly.
-// A counter barrier over the lane's blocks follows; after it EVERY block reduces the group partials
-// with the same fixed tree, solves the 6x6 system and updates its copy of T_icp (identical code,
-// identical bits), so one grid-wide hop per iteration is all the synchronisation there is.
-// The cache changes which points are searched, never what a search would have returned, so the
-// per-iteration correspondence sets stay bit-exact (tests compare them with the oracle's).
-__global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs) {
-    LaneDev& L = lanes[blockIdx.y];
-    const StepParams& P = params[blockIdx.y];
-    StepOut& O = outs[blockIdx.y];
-    const int nblk = gridDim.x, b = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_src = L.n_src;
+// K4: the ICP loop (kiss-icp RegisterFrame) as a warp-level DATAFLOW over all lanes of the launch.
+//
+// There is no block, cluster or grid barrier anywhere: the unit of work is a task for ONE WARP - "iteration `it`
+// of the 32-point group g of lane l" -, tasks of every lane go through one ticketed ring in global memory, and a
+// warp that has nothing to do for one lane simply takes the next task of whatever lane has one.  The serial part
+// of a lane's iteration (tree reduction, 6x6 solve) occupies one warp of the whole device while every other warp
+// keeps working on other lanes.  A task, thread per point:
+//   1. move the point by the last increment and test the exact correspondence cache (iteration 0: every point
+//      needs a search);
+//   2. thread_nearest for the lanes that missed, all at the same time;
+//   3. residual, Geman-McClure weight and the 16 distinct sums (a warp IS a 32-point group, so butterflies give
+//      the canonical group partial), then the arrival on the lane's counter;
+//   4. the LAST group of an iteration to arrive reduces the group partials with the canonical tree, solves,
+//      updates T_icp and either publishes the next iteration's tasks or writes the pose.
+//
+// The correspondence cache: a search at position p0 leaves its winner a, ICP_KX runner-ups and a lower bound D of
+// the distance from p0 to every OTHER candidate.  If the point is still in the same voxel (same 27 candidate
+// voxels; the map does not change during the loop) and, with w the lexicographically smallest of the kept
+// candidates in (distance^2, order id) - the search's own comparison -, |p - w| + |p - p0| < D, then every other
+// candidate c has |p - c| >= |p0 - c| - |p - p0| > |p - w|: w is what a new search would return.  The cache changes
+// which points are searched, never what a search would have returned, so the per-iteration correspondence sets
+// stay bit-exact (tests compare them with the oracle's).  Cache entries and moving points live in global memory
+// (L2-resident: 150 B per source point) and are read with ld.cg, because consecutive iterations of a group run on
+// different SMs.
+//
+// Scheduling never changes a result: group partials are combined by the fixed tree, whichever warp computes them.
+constexpr int IQ_THREADS = 128;
+constexpr int IQ_WARPS = IQ_THREADS / 32;
+#ifndef PTK_IQ_MINBLOCKS
+#define PTK_IQ_MINBLOCKS 6
+#endif
+constexpr u32 IQ_CAP = 1u << 16;            // ring entries (power of two)
+constexpr u64 IQ_EMPTY = 0ull;
+constexpr u64 IQ_EXIT = ~0ull;
+static_assert(ICP_KX <= 2, "thread_nearest keeps the three nearest candidates");
 
-    extern __shared__ double dyn_smem[];         // source points + cache entries of this block
-    double* const ssx = dyn_smem;
-    double* const ssy = ssx + ICP_SRC_CAP;
-    double* const ssz = ssy + ICP_SRC_CAP;
-    __shared__ double red[NSUM];
-    __shared__ Rigid sE;
-    __shared__ SE3q sT;
-    __shared__ SolveSmem sS;
-    __shared__ int s_done;
-    __shared__ int s_nmiss;
-    __shared__ int s_cnt;
-    __shared__ MapView s_map;
-    __shared__ unsigned short s_miss[ICP_CHUNK * 32];
+struct IcpQueue {
+    u32 head; u32 pad0[31];                 // consumer tickets handed out
+    u32 tail; u32 pad1[31];                 // producer reservations
+    u32 lanes_done; u32 exited; u32 prof; u32 pad2[29];
+    unsigned long long cyc[8];              // warp cycles per phase (prof != 0): cache pass, searches, sums, queue wait, tree, solve
+    u64 slots[IQ_CAP];
+};
 
-    if (L.n_vox == 0) {   // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
-        if (b == 0 && threadIdx.x == 0) {
-            O.pose = se3q_matrix(se3q_mul(se3q_identity(), se3q_from_rigid(P.guess)));
-            O.iterations = 0; O.n_corr = 0; O.status = 0; O.dx_norm = 0.0;
-        }
-        return;
+struct IcpWarpScratch {
+    double red[NSUM];
+    SolveSmem S;
+    Rigid E;
+    SE3q T;
+    int done;
+    int pad;
+};
+
+__device__ __forceinline__ u64 icp_task(int lane_id, int grp) {
+    return (1ull << 56) | ((u64)(u32)lane_id << 32) | (u64)(u32)grp;
+}
+
+// Publish the n_groups tasks of one lane's next iteration.  Every lane of the warp fences its earlier stores first.
+__device__ __forceinline__ void icp_push(IcpQueue* Q, int lane_id, int n_groups, int lane) {
+    const u32 FULL = 0xffffffffu;
+    const u32 n = (u32)n_groups;
+    __threadfence();
+    __syncwarp();
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(&Q->tail, n);
+    base = __shfl_sync(FULL, base, 0);
+    for (u32 i = (u32)lane; i < n; i += 32u) {
+        const u64 t = icp_task(lane_id, (int)i);
+        u64* s = Q->slots + ((base + i) & (IQ_CAP - 1u));
+        while (atomicCAS(s, IQ_EMPTY, t) != IQ_EMPTY) { }      // ring full: wait for the consumer of the older entry
     }
-    const int n_groups = (n_src + 31) >> 5;
-    // groups of this block: b, b + nblk, b + 2 nblk, ... (interleaved: the source is in beam order, and how far a
-    // point moves per iteration - hence how often its cache entry misses - varies with the beam; dealing the
-    // groups round-robin gives every block the same mix, so the blocks reach the barrier together)
-    const int n_local = b < n_groups ? (n_groups - b + nblk - 1) / nblk : 0;
-    const double max_corr = P.max_corr, kern = P.kernel;
-    const double max_d2 = (max_corr * max_corr) * (1.0 + 1e-9);   // farther candidates are rejected anyway
-    // the moving copy of this block's source points and their cache entries live in shared memory when they fit
-    const bool in_smem = n_local * 32 <= ICP_SRC_CAP;
-    // cache entry arrays: computed where used (one base + constants) instead of six live pointers
-#define C_TX(i, g) (*(in_smem ? dyn_smem + 3 * ICP_SRC_CAP + (i) : L.c_tx + (g)))
-#define C_TY(i, g) (*(in_smem ? dyn_smem + 4 * ICP_SRC_CAP + (i) : L.c_ty + (g)))
-#define C_TZ(i, g) (*(in_smem ? dyn_smem + 5 * ICP_SRC_CAP + (i) : L.c_tz + (g)))
-#define C_SLACK(i, g) (*(in_smem ? dyn_smem + 6 * ICP_SRC_CAP + (i) : L.c_slack + (g)))
-#define C_KEY(i, g) (*(in_smem ? reinterpret_cast<u64*>(dyn_smem + 7 * ICP_SRC_CAP) + (i) : L.c_key + (g)))
-    // runner-up j: coordinate c (0..2) at [11 + 3 j + c] * CAP; then the ints: ord, ord2[0..KX)
-#define C_T2(j, c, i, g) (*(in_smem ? dyn_smem + (11 + 3 * (j) + (c)) * ICP_SRC_CAP + (i) \
-                                    : L.c_t2 + ((size_t)(3 * (j) + (c)) * L.cap_points) + (g)))
-#define C_ORD(i, g) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + (11 + 3 * ICP_KX) * ICP_SRC_CAP) + (i) : L.c_ord + (g)))
-#define C_ORD2(j, i, g) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + (11 + 3 * ICP_KX) * ICP_SRC_CAP) + ((j) + 1) * ICP_SRC_CAP + (i) \
-                                   : L.c_ord2 + (size_t)(j) * L.cap_points + (g)))
-#define C_PX(i, g) (*(in_smem ? dyn_smem + 8 * ICP_SRC_CAP + (i) : L.c_px + (g)))
-#define C_PY(i, g) (*(in_smem ? dyn_smem + 9 * ICP_SRC_CAP + (i) : L.c_py + (g)))
-#define C_PZ(i, g) (*(in_smem ? dyn_smem + 10 * ICP_SRC_CAP + (i) : L.c_pz + (g)))
-    if (threadIdx.x == 0) sT = se3q_identity();
-    const double voxel = L.voxel_size, voxel_inv = L.voxel_inv;
-    // phase clocks of block 0 (thread 0 only; six clock reads per iteration)
-    const bool clk = b == 0 && threadIdx.x == 0;
-    __shared__ long long s_cyc[6];
-    __shared__ int s_searches;
-    if (threadIdx.x < 6) s_cyc[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { s_searches = 0; s_cnt = 0; s_map = map_view(L); }
-    long long tlast = clk ? clock64() : 0;
-#define ICP_TICK(slot) do { if (clk) { const long long t_ = clock64(); s_cyc[slot] += t_ - tlast; tlast = t_; } } while (0)
+}
 
-    for (int it = 0;; ++it) {
-        double* part = (it & 1) ? L.part_b : L.part_a;
-        for (int k0 = 0; k0 < n_local; k0 += ICP_CHUNK) {
-            const int gc = min(ICP_CHUNK, n_local - k0);   // local groups k0 .. k0 + gc, one per warp
-            const int q = threadIdx.x;                     // point of this thread within the chunk
-            const int grp = b + (k0 + warp) * nblk;        // this warp's group within the lane's source
-            const int p = grp * 32 + lane;                 // this thread's point within the lane's source
-            const int sp = k0 * 32 + q;                    // ... within the block
-            const bool live = q < gc * 32 && p < n_src;
-            if (threadIdx.x == 0) s_nmiss = 0;
-            __syncthreads();                               // also: previous chunk / iteration fully consumed
-            // ---- 1. move the point, consult the cache
-            double sx = 0, sy = 0, sz = 0;
-            bool miss = false;
-            if (live) {
-                if (it == 0 || !in_smem) { sx = __ldcg(L.s_x + p); sy = __ldcg(L.s_y + p); sz = __ldcg(L.s_z + p); }
-                else { sx = ssx[sp]; sy = ssy[sp]; sz = ssz[sp]; }
-                miss = true;
-                if (it > 0) {
-                    double xo, yo, zo;
-                    rigid_apply(sE, sx, sy, sz, xo, yo, zo);
-                    sx = xo; sy = yo; sz = zo;
-                    const double others = C_SLACK(sp, p);
-                    if (others > 0.0) {
-                        const double mx = sx - C_PX(sp, p), my = sy - C_PY(sp, p), mz = sz - C_PZ(sp, p);
-                        const double moved = sqrt((mx * mx + my * my) + mz * mz);
-                        double ex = C_TX(sp, p) - sx, ey = C_TY(sp, p) - sy, ez = C_TZ(sp, p) - sz;
-                        double da2 = (ex * ex + ey * ey) + ez * ez;              // as the search computes it
+__device__ __forceinline__ Rigid ldcg_rigid(const Rigid* p) {
+    Rigid T;
 #pragma unroll
-                        for (int j = 0; j < ICP_KX; ++j) {
-                            const int oj = C_ORD2(j, sp, p);
-                            if (oj < 0) continue;
-                            const double bx = C_T2(j, 0, sp, p), by = C_T2(j, 1, sp, p), bz = C_T2(j, 2, sp, p);
-                            ex = bx - sx; ey = by - sy; ez = bz - sz;
-                            const double db2 = (ex * ex + ey * ey) + ez * ez;
-                            const int o1 = C_ORD(sp, p);
-                            if (db2 < da2 || (db2 == da2 && oj < o1)) {          // this runner-up has become the nearest
-                                const double wx = C_TX(sp, p), wy = C_TY(sp, p), wz = C_TZ(sp, p);
-                                C_TX(sp, p) = bx; C_TY(sp, p) = by; C_TZ(sp, p) = bz; C_ORD(sp, p) = oj;
-                                C_T2(j, 0, sp, p) = wx; C_T2(j, 1, sp, p) = wy; C_T2(j, 2, sp, p) = wz; C_ORD2(j, sp, p) = o1;
-                                da2 = db2;
-                            }
-                        }
-                        if (sqrt(da2) + moved + 1e-9 < others) {
-                            int kx, ky, kz;
-                            voxel_key(sx, sy, sz, voxel, voxel_inv, kx, ky, kz);
-                            miss = !(key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == C_KEY(sp, p));
-                        }
+    for (int k = 0; k < 9; ++k) T.r[k] = __ldcg(p->r + k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) T.t[k] = __ldcg(p->t + k);
+    return T;
+}
+
+// 16 partials of super-group `sg` (32 consecutive groups), lane = group within the super-group
+__device__ __forceinline__ void icp_load_sg(const double* part, int ngc, int sg, int n_groups, int lane, double* c) {
+    const int g = sg * 32 + lane;
+#pragma unroll
+    for (int v = 0; v < 16; ++v) c[v] = g < n_groups ? __ldcg(part + (size_t)v * ngc + g) : 0.0;
+}
+
+// Canonical tree over the group partials of all 16 sums at once (oracle/canon.py pairwise_tree_sum, exactly the
+// additions of warp_tree_sum): level 1 = butterfly over the 32 groups of a super-group (transposed, 16 sums per
+// pass), level 2 = adjacent-pairs tree over 32 super-groups (zero padded), level 3 = the fixed 8-chunk tree.
+// Returns the total of sum bitrev4(lane & 15).
+__device__ __forceinline__ double icp_tree16(const double* part, int ngc, int n_groups, int lane) {
+    const int n_sg = (n_groups + 31) >> 5;
+    double cur[16], nxt[16];
+    icp_load_sg(part, ngc, 0, n_groups, lane, cur);
+    if (n_sg <= 1) return warp_reduce16(cur, lane);
+    int m = 1;
+    while (m * 32 < n_groups) m <<= 1;
+    const int mc = m <= 32 ? 1 : (m >> 5);
+    double U[8];
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+        double tot = 0.0;
+        if (c < mc) {
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;      // pending left subtrees of the 32-leaf tree
+#pragma unroll 1
+            for (int i = 0; i < 32; ++i) {
+                const int sg = c * 32 + i;
+                double x = 0.0;
+                if (sg < n_sg) {
+                    if (sg + 1 < n_sg) icp_load_sg(part, ngc, sg + 1, n_groups, lane, nxt);
+                    x = warp_reduce16(cur, lane);
+                    if (sg + 1 < n_sg) {
+#pragma unroll
+                        for (int v = 0; v < 16; ++v) cur[v] = nxt[v];
                     }
                 }
-                if (in_smem) { ssx[sp] = sx; ssy[sp] = sy; ssz[sp] = sz; }
-                else if (it > 0) { L.s_x[p] = sx; L.s_y[p] = sy; L.s_z[p] = sz; }
+                if (i & 1) {
+                    x = a0 + x;
+                    if (i & 2) {
+                        x = a1 + x;
+                        if (i & 4) {
+                            x = a2 + x;
+                            if (i & 8) {
+                                x = a3 + x;
+                                if (i & 16) tot = a4 + x; else a4 = x;
+                            } else a3 = x;
+                        } else a2 = x;
+                    } else a1 = x;
+                } else a0 = x;
             }
-            {
-                const u32 mm = __ballot_sync(0xffffffffu, miss);
-                if (mm) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_nmiss, __popc(mm));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (miss) s_miss[base + __popc(mm & ((1u << lane) - 1u))] = (unsigned short)q;
-                }
-            }
-            __syncthreads();
-            ICP_TICK(0);
-            // ---- 2. full search of the listed points, one warp each
-            const int nmiss = s_nmiss;
-            if (threadIdx.x == 0) s_searches += nmiss;
-            for (int i = warp; i < nmiss; i += ICP_WARPS) {
-                const int mq = s_miss[i];
-                const int msp = k0 * 32 + mq;
-                const int mp = (b + (k0 + (mq >> 5)) * nblk) * 32 + (mq & 31);
-                double qx, qy, qz;
-                if (in_smem) { qx = ssx[msp]; qy = ssy[msp]; qz = ssz[msp]; }
-                else { qx = __ldcg(L.s_x + mp); qy = __ldcg(L.s_y + mp); qz = __ldcg(L.s_z + mp); }
-                double d2, tx, ty, tz, others;
-                int ord;
-                u64 qkey;
-                double t2[3 * ICP_KX];
-                int ord2[ICP_KX];
-                const bool found = warp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey, t2, ord2);
+        }
+        // static indexing of U: c is a loop counter of a non-unrolled loop, so select explicitly
+        if (c == 0) U[0] = tot; else if (c == 1) U[1] = tot; else if (c == 2) U[2] = tot; else if (c == 3) U[3] = tot;
+        else if (c == 4) U[4] = tot; else if (c == 5) U[5] = tot; else if (c == 6) U[6] = tot; else U[7] = tot;
+    }
+    if (mc == 1) return U[0];
+    return ((U[0] + U[1]) + (U[2] + U[3])) + ((U[4] + U[5]) + (U[6] + U[7]));
+}
+
+#define IQ_TICK(slot)                                                                    \
+    do {                                                                                 \
+        if (prof && lane == 0) {                                                         \
+            const long long t_ = clock64();                                              \
+            atomicAdd(&Q->cyc[slot], (unsigned long long)(t_ - tlast));                  \
+            tlast = t_;                                                                  \
+        }                                                                                \
+    } while (0)
+
+// All groups of iteration `it` have arrived: reduce, solve, publish (kiss-icp RegisterFrame loop body after
+// BuildLinearSystem).  Runs in one warp.
+__device__ __noinline__ void icp_lane_solve(LaneDev& L, const StepParams& P, StepOut& O, IcpQueue* Q, IcpWarpScratch* ws,
+                                            int lane_id, int it, int n_groups, int n_lanes, int total_warps, int lane) {
+    const u32 FULL = 0xffffffffu;
+    const bool prof = Q->prof != 0;
+    long long tlast = prof ? clock64() : 0;
+    if (lane == 0) L.icp_arrive = 0;
+    const double* part = L.part_a;
+    const int ngc = L.ng_cap;
+    const double tot = icp_tree16(part, ngc, n_groups, lane);
+    int cnt = 0;
+    for (int g = lane; g < n_groups; g += 32) cnt += (int)__ldcg(part + (size_t)16 * ngc + g);
+    cnt = __reduce_add_sync(FULL, cnt);           // a sum of small integers is exact in any order
+    if (lane < 16) ws->red[__brev((u32)lane) >> 28] = tot;
+    if (lane == 0) {
+        ws->red[16] = (double)cnt;
+        SE3q T = se3q_identity();
+        if (it > 0) {
+            T.q.w = __ldcg(&L.icp_Tq.q.w); T.q.x = __ldcg(&L.icp_Tq.q.x); T.q.y = __ldcg(&L.icp_Tq.q.y); T.q.z = __ldcg(&L.icp_Tq.q.z);
+            T.t[0] = __ldcg(&L.icp_Tq.t[0]); T.t[1] = __ldcg(&L.icp_Tq.t[1]); T.t[2] = __ldcg(&L.icp_Tq.t[2]);
+        }
+        ws->T = T;
+    }
+    __syncwarp();
+    IQ_TICK(4);
+    icp_solve_step(L, P, O, ws->red, &ws->S, &ws->E, &ws->T, &ws->done, it, true, lane);
+    __syncwarp();
+    const int done = ws->done;
+    if (!done) {
+        if (lane == 0) {
+            L.icp_E = ws->E;
+            L.icp_Tq = ws->T;
+            L.icp_it = it + 1;
+        }
+        icp_push(Q, lane_id, n_groups, lane);
+    } else {
+        u32 fin = 0;
+        if (lane == 0) {
+            L.icp_done = 1;
+            __threadfence();
+            fin = atomicAdd(&Q->lanes_done, 1u) + 1u;
+        }
+        fin = __shfl_sync(FULL, fin, 0);
+        if (fin == (u32)n_lanes) {
+            // every task of every lane has been consumed: the ring is empty, hand every warp its exit token
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(&Q->tail, (u32)total_warps);
+            base = __shfl_sync(FULL, base, 0);
+            for (u32 i = (u32)lane; i < (u32)total_warps; i += 32u)
+                *((volatile u64*)(Q->slots + ((base + i) & (IQ_CAP - 1u)))) = IQ_EXIT;
+        }
+    }
+    IQ_TICK(5);
+}
+
+// Residual, weight, the group's 16 sums, arrival; the last group of the iteration goes on to the solve.
+__device__ __forceinline__ void icp_group_sums(LaneDev& L, const StepParams& P, StepOut& O, IcpQueue* Q, IcpWarpScratch* ws,
+                                               int lane_id, int g, int it, int n_groups, int n_lanes, int total_warps, int lane,
+                                               bool live, double sx, double sy, double sz, double tx, double ty, double tz, int ord) {
+    const u32 FULL = 0xffffffffu;
+    const double max_corr = P.max_corr;
+    double c[16];
+    bool acc = false;
+    if (live && ord >= 0) {
+        const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
+        const double d2 = (dx * dx + dy * dy) + dz * dz;
+        acc = sqrt(d2) < max_corr;
+        if (acc) lin_terms(sx, sy, sz, tx, ty, tz, P.kernel, c);
+    }
+    if (live && it < L.trace_iters) L.trace[(size_t)it * L.cap_points + (g * 32 + lane)] = acc ? ord : -1;
+    if (!acc) {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) c[v] = 0.0;
+    }
+    const double mine = warp_reduce16(c, lane);
+    const u32 nacc = __popc(__ballot_sync(FULL, acc));
+    double* part = L.part_a;
+    if (lane < 16) __stcg(part + (size_t)(__brev((u32)lane) >> 28) * L.ng_cap + g, mine);
+    else if (lane == 16) __stcg(part + (size_t)16 * L.ng_cap + g, (double)nacc);
+    __threadfence();          // every lane: partials, moved point, cache entry before the arrival becomes visible
+    __syncwarp();
+    u32 arrived = 0;
+    if (lane == 0) arrived = atomicAdd(&L.icp_arrive, 1u) + 1u;
+    arrived = __shfl_sync(FULL, arrived, 0);
+    if (arrived != (u32)n_groups) return;
+    __threadfence();
+    icp_lane_solve(L, P, O, Q, ws, lane_id, it, n_groups, n_lanes, total_warps, lane);
+}
+
+__global__ void __launch_bounds__(IQ_THREADS, PTK_IQ_MINBLOCKS) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs,
+                                                                    int n_lanes, IcpQueue* Q) {
+    const u32 FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_warps = gridDim.x * IQ_WARPS;
+    const int gw = blockIdx.x * IQ_WARPS + warp;
+    __shared__ IcpWarpScratch s_ws[IQ_WARPS];
+    __shared__ u32 s_ids[IQ_WARPS][27 * 32];
+    __shared__ float s_lbs[IQ_WARPS][27 * 32];
+    IcpWarpScratch* ws = &s_ws[warp];
+    const bool prof = Q->prof != 0;
+    long long tlast = prof ? clock64() : 0;
+
+    // ---- seed: the first warps of the grid open the lanes (one warp per lane)
+    const int seeders = min(total_warps, 64 * IQ_WARPS);
+    if (gw < seeders) {
+        for (int l = gw; l < n_lanes; l += seeders) {
+            LaneDev& L = lanes[l];
+            const StepParams& P = params[l];
+            StepOut& O = outs[l];
+            const int n_groups = (L.n_src + 31) >> 5;
+            if (L.n_vox == 0) {       // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
+                u32 fin = 0;
                 if (lane == 0) {
-                    C_TX(msp, mp) = tx; C_TY(msp, mp) = ty; C_TZ(msp, mp) = tz;
+                    O.pose = se3q_matrix(se3q_mul(se3q_identity(), se3q_from_rigid(P.guess)));
+                    O.iterations = 0; O.n_corr = 0; O.status = 0; O.dx_norm = 0.0;
+                    L.icp_done = 1;
+                    __threadfence();
+                    fin = atomicAdd(&Q->lanes_done, 1u) + 1u;
+                }
+                fin = __shfl_sync(FULL, fin, 0);
+                if (fin == (u32)n_lanes) {
+                    u32 base = 0;
+                    if (lane == 0) base = atomicAdd(&Q->tail, (u32)total_warps);
+                    base = __shfl_sync(FULL, base, 0);
+                    for (u32 i = (u32)lane; i < (u32)total_warps; i += 32u)
+                        *((volatile u64*)(Q->slots + ((base + i) & (IQ_CAP - 1u)))) = IQ_EXIT;
+                }
+                continue;
+            }
+            if (lane == 0) { L.icp_it = 0; L.icp_arrive = 0; L.icp_done = 0; }
+            if (n_groups == 0) {      // no source point: zero correspondences (B.5)
+                __syncwarp();
+                icp_lane_solve(L, P, O, Q, ws, l, 0, 0, n_lanes, total_warps, lane);
+                continue;
+            }
+            icp_push(Q, l, n_groups, lane);
+        }
+    }
+
+    // ---- consume
+    while (true) {
+        u64 task = IQ_EMPTY;
+        if (lane == 0) {
+            const u32 t = atomicAdd(&Q->head, 1u);
+            volatile u64* s = Q->slots + (t & (IQ_CAP - 1u));
+            while ((task = *s) == IQ_EMPTY) { }
+            *s = IQ_EMPTY;
+        }
+        task = __shfl_sync(FULL, task, 0);
+        if (task == IQ_EXIT) break;
+        __threadfence();
+        IQ_TICK(3);
+        const int lane_id = (int)((task >> 32) & 0xffffffu), g = (int)(task & 0xffffffffu);
+        LaneDev& L = lanes[lane_id];
+        const StepParams& P = params[lane_id];
+        StepOut& O = outs[lane_id];
+        const int n_src = L.n_src;
+        const int n_groups = (n_src + 31) >> 5;
+        const double max_corr = P.max_corr;
+        const double max_d2 = (max_corr * max_corr) * (1.0 + 1e-9);   // farther candidates are rejected anyway
+        const int p = g * 32 + lane;
+        const bool live = p < n_src;
+        const size_t cap = (size_t)L.cap_points;
+        double sx = 0, sy = 0, sz = 0, tx = 0, ty = 0, tz = 0;
+        int ord = -1;
+        bool miss = false;
+        const int it = __ldcg(&L.icp_it);
+        if (it == 0) {
+            if (live) { sx = L.s_x[p]; sy = L.s_y[p]; sz = L.s_z[p]; }
+            miss = live;          // every point starts with a search
+        } else {
+            // ---- 1. move the point, consult the cache
+            const Rigid E = ldcg_rigid(&L.icp_E);
+            if (live) {
+                const double x0 = __ldcg(L.s_x + p), y0 = __ldcg(L.s_y + p), z0 = __ldcg(L.s_z + p);
+                const double others = __ldcg(L.c_slack + p);
+                tx = __ldcg(L.c_tx + p); ty = __ldcg(L.c_ty + p); tz = __ldcg(L.c_tz + p);
+                ord = __ldcg(L.c_ord + p);
+                const double px = __ldcg(L.c_px + p), py = __ldcg(L.c_py + p), pz = __ldcg(L.c_pz + p);
+                const u64 ckey = __ldcg(L.c_key + p);
+                double b2[3 * ICP_KX];
+                int o2[ICP_KX];
+#pragma unroll
+                for (int j = 0; j < ICP_KX; ++j) {
+                    o2[j] = __ldcg(L.c_ord2 + (size_t)j * cap + p);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) b2[3 * j + c] = __ldcg(L.c_t2 + (size_t)(3 * j + c) * cap + p);
+                }
+                rigid_apply(E, x0, y0, z0, sx, sy, sz);
+                __stcg(L.s_x + p, sx); __stcg(L.s_y + p, sy); __stcg(L.s_z + p, sz);
+                miss = true;
+                if (others > 0.0) {
+                    const double mx = sx - px, my = sy - py, mz = sz - pz;
+                    const double moved = sqrt((mx * mx + my * my) + mz * mz);
+                    double ex = tx - sx, ey = ty - sy, ez = tz - sz;
+                    double da2 = (ex * ex + ey * ey) + ez * ez;              // as the search computes it
 #pragma unroll
                     for (int j = 0; j < ICP_KX; ++j) {
-                        C_T2(j, 0, msp, mp) = t2[3 * j]; C_T2(j, 1, msp, mp) = t2[3 * j + 1]; C_T2(j, 2, msp, mp) = t2[3 * j + 2];
-                        C_ORD2(j, msp, mp) = ord2[j];
+                        const int oj = o2[j];
+                        if (oj < 0) continue;
+                        const double bx = b2[3 * j], by = b2[3 * j + 1], bz = b2[3 * j + 2];
+                        ex = bx - sx; ey = by - sy; ez = bz - sz;
+                        const double db2 = (ex * ex + ey * ey) + ez * ez;
+                        if (db2 < da2 || (db2 == da2 && oj < ord)) {          // this runner-up has become the nearest
+                            __stcg(L.c_tx + p, bx); __stcg(L.c_ty + p, by); __stcg(L.c_tz + p, bz); __stcg(L.c_ord + p, oj);
+                            __stcg(L.c_t2 + (size_t)(3 * j) * cap + p, tx); __stcg(L.c_t2 + (size_t)(3 * j + 1) * cap + p, ty);
+                            __stcg(L.c_t2 + (size_t)(3 * j + 2) * cap + p, tz); __stcg(L.c_ord2 + (size_t)j * cap + p, ord);
+                            tx = bx; ty = by; tz = bz; ord = oj;
+                            da2 = db2;
+                        }
                     }
-                    C_PX(msp, mp) = qx; C_PY(msp, mp) = qy; C_PZ(msp, mp) = qz;
-                    C_SLACK(msp, mp) = others;
-                    C_KEY(msp, mp) = qkey;
-                    C_ORD(msp, mp) = found ? ord : -1;
+                    if (sqrt(da2) + moved + 1e-9 < others) {
+                        int kx, ky, kz;
+                        voxel_key(sx, sy, sz, L.voxel_size, L.voxel_inv, kx, ky, kz);
+                        miss = !(key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == ckey);
+                    }
                 }
             }
-            __syncthreads();
-            ICP_TICK(1);
-            // ---- 3. residual + weights, group partials by warp butterflies
-            if (warp < gc) {
-                double c[16];
-                bool acc = false;
-                int ord = -1;
-                if (live) {
-                    ord = C_ORD(sp, p);
-                    if (ord >= 0) {
-                        const double tx = C_TX(sp, p), ty = C_TY(sp, p), tz = C_TZ(sp, p);
-                        const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
-                        const double d2 = (dx * dx + dy * dy) + dz * dz;
-                        acc = sqrt(d2) < max_corr;
-                        if (acc) lin_terms(sx, sy, sz, tx, ty, tz, kern, c);
-                    }
-                    if (it < L.trace_iters) L.trace[(size_t)it * L.cap_points + p] = acc ? ord : -1;
-                }
-                if (!acc) {
+        }
+        IQ_TICK(0);
+        // ---- 2. the group's missed points, every one on its own thread
+        const u32 mm = __ballot_sync(FULL, miss);
+        if (mm) {
+            const MapView M = map_view(L);
+            NearestOut R;
+            thread_nearest(M, s_ids[warp], s_lbs[warp], lane, miss, sx, sy, sz, max_d2, R);
+            if (miss) {
+                tx = R.tx; ty = R.ty; tz = R.tz; ord = R.ord;
+                __stcg(L.c_tx + p, tx); __stcg(L.c_ty + p, ty); __stcg(L.c_tz + p, tz);
 #pragma unroll
-                    for (int v = 0; v < 16; ++v) c[v] = 0.0;
+                for (int j = 0; j < ICP_KX; ++j) {
+                    __stcg(L.c_t2 + (size_t)(3 * j) * cap + p, R.t2[3 * j]);
+                    __stcg(L.c_t2 + (size_t)(3 * j + 1) * cap + p, R.t2[3 * j + 1]);
+                    __stcg(L.c_t2 + (size_t)(3 * j + 2) * cap + p, R.t2[3 * j + 2]);
+                    __stcg(L.c_ord2 + (size_t)j * cap + p, R.ord2[j]);
                 }
-                const double mine = warp_reduce16(c, lane);
-                const u32 nacc = __popc(__ballot_sync(0xffffffffu, acc));   // a sum of 1.0s is exact in any order
-                if (lane < 16) part[(size_t)(__brev((u32)lane) >> 28) * L.ng_cap + grp] = mine;
-                else if (lane == 16) part[(size_t)16 * L.ng_cap + grp] = (double)nacc;
+                __stcg(L.c_px + p, sx); __stcg(L.c_py + p, sy); __stcg(L.c_pz + p, sz);
+                __stcg(L.c_slack + p, R.others);
+                __stcg(L.c_key + p, R.qkey);
+                __stcg(L.c_ord + p, ord);
             }
+            if (lane == 0) atomicAdd(&L.icp_searches, __popc(mm));
         }
-        // ---- one barrier over the lane's blocks (icp_arrive was zeroed by the previous kernel)
-        __syncthreads();
-        ICP_TICK(2);
-        if (threadIdx.x == 0) {
-            __threadfence();
-            atomicAdd(&L.icp_arrive, 1u);
-            const u32 target = (u32)nblk * (u32)(it + 1);
-            while (*((volatile u32*)&L.icp_arrive) < target) { }
-            __threadfence();
-        }
-        __syncthreads();
-        ICP_TICK(3);
-        // 16 sums, one warp each, with the canonical tree; the 17th (correspondence count) is a sum of
-        // small integers - exact in any order - so all warps share it instead of one warp doing two trees
-        for (int v = warp; v < 16; v += ICP_WARPS) {
-            const double x = warp_tree_sum(part + (size_t)v * L.ng_cap, n_groups, lane);
-            if (lane == 0) red[v] = x;
-        }
-        {
-            int cnt = 0;
-            for (int g = threadIdx.x; g < n_groups; g += ICP_THREADS) cnt += (int)__ldcg(part + (size_t)16 * L.ng_cap + g);
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
-        }
-        __syncthreads();
-        ICP_TICK(4);
-        if (warp == 0) {
-            if (lane == 0) { red[16] = (double)s_cnt; s_cnt = 0; }
-            __syncwarp();
-            icp_solve_step(L, P, O, red, &sS, &sE, &sT, &s_done, it, b == 0, lane);
-        }
-        __syncthreads();
-        ICP_TICK(5);
-        if (s_done) break;
+        IQ_TICK(1);
+        icp_group_sums(L, P, O, Q, ws, lane_id, g, it, n_groups, n_lanes, total_warps, lane, live, sx, sy, sz, tx, ty, tz, ord);
+        IQ_TICK(2);
     }
-#undef ICP_TICK
-    if (threadIdx.x == 0 && s_searches) atomicAdd(&L.icp_searches, s_searches);
-#ifndef PTK_SOLVE_CLOCKS
-    if (clk) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) O.icp_cyc[k] = s_cyc[k];
+    // ---- the last warp to leave rewinds the ring for the next launch
+    if (lane == 0) {
+        __threadfence();
+        const u32 gone = atomicAdd(&Q->exited, 1u) + 1u;
+        if (gone == (u32)total_warps) {
+            Q->head = 0; Q->tail = 0; Q->lanes_done = 0; Q->exited = 0;
+        }
     }
-#endif
-#undef C_TX
-#undef C_TY
-#undef C_TZ
-#undef C_SLACK
-#undef C_KEY
-#undef C_ORD
-#undef C_ORD2
-#undef C_T2
-#undef C_PX
-#undef C_PY
-#undef C_PZ
 }
+#undef IQ_TICK
 
 // ------------------------------------------------------------------------------------
 // K5: map insert, pass 1 (kiss-icp AddPoints): transform frame_downsample by the new pose,
@@ -1231,7 +1522,7 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
 // the smallest point indices of this scan in ascending order (= upstream's sequential insertion
 // order under the canonical ordering).  Also clears table 2.
 __device__ __forceinline__ u32 map_find_or_create(LaneDev& L, u64 key) {
-    u32 slot = hash_key(key) & L.m_mask;
+    u32 slot = hash_map_key(key) & L.m_mask;
     u32 probes = 0;
     while (true) {
         volatile MapSlot* S = L.m_slots + slot;
@@ -1244,7 +1535,13 @@ __device__ __forceinline__ u32 map_find_or_create(LaneDev& L, u64 key) {
                 if (t > 0) id = L.freelist[t - 1];
                 else id = (u32)atomicAdd(&L.bump, 1);
                 if (id >= (u32)L.pool_cap) {
+                    // no block left: flag the step, then hand the slot back as a tombstone so that no later
+                    // launch finds a key without a voxel behind it (threads waiting for this slot's id leave
+                    // their loop on ERR_POOL, which is set first)
                     atomicOr(&L.err, ERR_POOL);
+                    __threadfence();
+                    *((volatile u64*)&L.m_slots[slot].key) = KEY_TOMB;
+                    atomicAdd(&L.n_tomb, 1);
                     return NONE;
                 }
                 VoxelBlock* B = L.blocks + id;
@@ -1261,7 +1558,11 @@ __device__ __forceinline__ u32 map_find_or_create(LaneDev& L, u64 key) {
         }
         if (k == key) {
             u32 id;
-            do { id = S->id; } while (id == NONE && !(*((volatile int*)&L.err) & ERR_POOL));
+            u32 spins = 0;
+            do {
+                id = S->id;
+                if (id == NONE && ++spins > (1u << 24)) { atomicOr(&L.err, ERR_TABLE); break; }   // never wait unbounded
+            } while (id == NONE && !(*((volatile int*)&L.err) & ERR_POOL));
             __threadfence();
             return id;
         }
@@ -1394,7 +1695,7 @@ __global__ void k_map_rebuild(LaneDev* lanes) {
         VoxelBlock* B = L.blocks + u;
         if (B->count == 0) continue;
         u64 key = B->key;
-        u32 slot = hash_key(key) & L.m_mask;
+        u32 slot = hash_map_key(key) & L.m_mask;
         while (true) {
             u64 prev = atomicCAS((u64*)&L.m_slots[slot].key, KEY_EMPTY, key);
             if (prev == KEY_EMPTY) break;

@@ -134,10 +134,11 @@ class Odometry:
         return out
 
     def icp_phases(self, lane=0):
-        """clock64 cycles block 0 of the last ICP launch spent per phase (measurement tap)."""
+        """Warp cycles (clock64, summed over every warp of the device) the ICP dataflow kernel spent per phase
+        since profiling was switched on (measurement tap; zeros while profiling is off)."""
         out = np.zeros(6, dtype=np.int64)
         self._check(self._lib.ptk_get_icp_phases(self._h, lane, addr(out)))
-        return dict(zip(("cache_pass", "searches", "sums", "barrier", "tree", "solve"), out.tolist()))
+        return dict(zip(("cache_pass", "searches", "sums", "queue_wait", "tree", "solve"), out.tolist()))
 
     def launch_count(self):
         return int(self._lib.ptk_launch_count(self._h))
@@ -145,9 +146,11 @@ class Odometry:
     # -- the step ------------------------------------------------------------------
     def register_frame(self, frame, timestamps, initial_guess=None, lane=0, stream=0):
         """One odometry step (kiss.py:83-131).  Returns (pose 4x4, stats dict)."""
-        frame = _ffi.f64(frame)
+        frame = _ffi.f64(frame, 3)
         timestamps = _ffi.f64(timestamps)
         n = int(frame.shape[0])
+        if int(np.prod(tuple(timestamps.shape))) != n:
+            raise TypeError(f"timestamps: {tuple(timestamps.shape)} for {n} points")
         g = _mat16(initial_guess) if initial_guess is not None else None
         pose = np.empty((4, 4))
         st = PtkStats()
@@ -160,7 +163,7 @@ class Odometry:
         """Advance every lane by one scan in one set of launches."""
         B = self.batch
         assert len(frames) == B and len(timestamps) == B
-        frames = [_ffi.f64(f) for f in frames]
+        frames = [_ffi.f64(f, 3) for f in frames]
         timestamps = [_ffi.f64(t) for t in timestamps]
         xs = (C.c_void_p * B)(*[addr(f) for f in frames])
         ts = (C.c_void_p * B)(*[addr(t) for t in timestamps])
@@ -191,11 +194,20 @@ class Odometry:
         self._check(self._lib.ptk_set_sensor(self._h, H, W, addr(d), addr(o), addr(t), float(range_unit)))
         self.sensor_shape = (H, W)
 
-    @staticmethod
-    def _u32(a):
+    def _u32(self, a):
+        """RANGE image for the C ABI: a torch tensor goes by address (int32/uint32 storage, contiguous, H*W
+        elements when the sensor is known); anything else becomes a contiguous uint32 ndarray."""
         if hasattr(a, "data_ptr") and not isinstance(a, np.ndarray):
-            return a                      # torch tensor (int32/uint32 storage), already on the device
-        return np.ascontiguousarray(a, dtype=np.uint32)
+            _ffi._check_tensor(a, ("int32", "uint32"), "range image")
+            shape = getattr(self, "sensor_shape", None)
+            if shape is not None and int(a.numel()) != shape[0] * shape[1]:
+                raise TypeError(f"range image: {int(a.numel())} elements, sensor is {shape[0]}x{shape[1]}")
+            return a
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        shape = getattr(self, "sensor_shape", None)
+        if shape is not None and a.size != shape[0] * shape[1]:
+            raise TypeError(f"range image: {a.size} elements, sensor is {shape[0]}x{shape[1]}")
+        return a
 
     def register_scan(self, range_mm, initial_guess=None, lane=0, stream=0):
         """One odometry step from the RANGE field (H, W) uint32 mm.  Returns (pose 4x4, stats)."""

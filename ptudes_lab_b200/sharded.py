@@ -85,6 +85,7 @@ class PtkShardBackend:
         self.device = torch.device("cuda", torch.cuda.current_device())
         odo._check(self.lib.ptk_shard_config(self.h, rank, nranks))
         self.n_src = 0
+        self.max_iterations = int(odo._cfg.max_iterations)
 
     def _stream(self):
         return torch.cuda.current_stream().cuda_stream
@@ -130,11 +131,13 @@ class ShardedOdometry:
     """register_frame over a hash-sharded map: the loop of kiss-icp's RegisterFrame with two
     collectives per iteration.  `backend` does the per-rank work, `group` the exchange."""
 
-    def __init__(self, backend, group=None, max_iterations: int = 500):
+    def __init__(self, backend, group=None, max_iterations: int = None):
         self.b = backend
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.max_iterations = max_iterations
+        # the loop must run exactly as long as the device-side cap (L.max_iters) allows: k_shard_solve only writes
+        # the pose on its last iteration
+        self.max_iterations = max_iterations if max_iterations is not None else int(getattr(backend, "max_iterations", 500))
         self.collectives = 0
 
     def _all_gather(self, rec):

@@ -520,6 +520,18 @@ def test_error_paths_and_reset(tiny_seq):
         with pytest.raises(PtkError) as e:
             small.register_frame(xyz, ts)
         assert e.value.code == -3
+        # the failed step committed nothing, and the lane refuses further steps (its map is incomplete) ...
+        assert small.num_poses(0) == 0
+        with pytest.raises(PtkError) as e:
+            small.register_frame(xyz, ts)
+        assert e.value.code == -6
+        # ... until it is reset; a scan that fits then runs normally (no stale table entry, no hang)
+        small.reset(0)
+        few = xyz[:40]
+        pose, st = small.register_frame(few, ts[:40])
+        assert np.array_equal(pose, np.eye(4)) and small.num_poses(0) == 1
+        pose, st = small.register_frame(few, ts[:40])
+        assert st["n_voxels"] > 0 and small.num_poses(0) == 2
     finally:
         small.close()
     o = odometry.Odometry(cfg, max_points=16384, map_capacity=16384, batch=2)
