@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-side-runs", action="store_true", help="skip the small runs of configs[2..4] (side_runs)")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: do not overlap the next scans' H2D copy")
     ap.add_argument("--profile-pass", action="store_true", default=True)
     return ap.parse_args()
@@ -153,13 +154,24 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "window": window}
 
 
+def source_sha():
+    """sha256 (16 hex digits) of the kernel sources: ties a committed ncu capture to the code that produced it."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("ptk_device.cuh", "ptk_canon.cuh", "ptk.cu"):
+        with open(os.path.join(ROOT, "ptudes_lab_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def recorded_traffic(kernel, config, lanes, inp):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture, if it was taken on this very
-    configuration (profiles/r1_traffic.json); None otherwise - never a guess."""
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/r2_traffic.json),
+    but only if it was taken on this very configuration AND on these very kernel sources (source_sha);
+    None otherwise - never a guess, never a stale number."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             t = json.load(f)
-        if t["config"] == config and t["lanes"] == lanes and t["input"] == inp:
+        if t["config"] == config and t["lanes"] == lanes and t["input"] == inp and t.get("source_sha") == source_sha():
             return t["kernels"].get(kernel)
     except Exception:
         pass
@@ -198,6 +210,150 @@ def algorithmic_bytes(st, n_pixels=0):
 
 
 # --------------------------------------------------------------------------------------
+# Side runs carried in the same JSON line: the other BASELINE.json configs, so that every round's driver-run
+# BENCH/SCALE record holds evidence for them (they are parity-test cases first; tests/test_gpu_parity.py).
+def side_fleet(config, lanes, warmup, steps, local, seed0, sync, min_max=None):
+    """`lanes` sequences of `config` advanced `warmup + steps` scans by batched steps; device-resident range
+    images, CUDA events around the timed steps.  Returns (ms of the timed steps, last-step stats of lane 0)."""
+    import torch
+    from ptudes_lab_b200 import odometry, synth
+    dev = torch.device("cuda", local)
+    min_r, max_r, max_pts, map_cap = CONFIGS[config]
+    if min_max is not None:
+        min_r, max_r = min_max
+    T = warmup + steps
+    gens = [synth.TorchScanGenerator(synth.make_sequence(config, seed0 + l), dev) for l in range(lanes)]
+    ranges = [[g.range_image(s)[0].contiguous() for g in gens] for s in range(T)]
+    cfg = odometry.load_config(None, deskew=True, max_range=max_r)
+    cfg.data.min_range = min_r
+    odo = odometry.Odometry(cfg, device=local, max_points=max_pts, map_capacity=map_cap, batch=lanes)
+    odo.set_sensor(gens[0].seq.dirs)
+    stream = torch.cuda.Stream(device=dev)
+    try:
+        for s in range(warmup):
+            odo.register_scan_batch(ranges[s], stream=stream.cuda_stream)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        vox = []
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for s in range(warmup, T):
+                _, st = odo.register_scan_batch(ranges[s], stream=stream.cuda_stream)
+                vox.append(st[0]["n_voxels"])
+            e1.record(stream)
+        sync()
+        last = st[0]
+        return e0.elapsed_time(e1), {k: last[k] for k in ("n_in", "n_ds", "n_src", "n_voxels", "map_points", "iterations")}
+    finally:
+        odo.close()
+
+
+def side_ekf_fleet(lanes, warmup, steps, local):
+    """configs[3]: the ekf-bench loop (cli/ekf_bench.py:493-563) at fleet scale - per step and lane 10 IMU samples
+    into the host-native ESEKF, the filter's pose as the ICP initial guess (--use-imu-prediction, :533-535), one
+    batched odometry step from pinned HOST range images, the pose into the filter (:554-557).  Host wall clock."""
+    import torch
+    from ptudes_lab_b200 import _ffi, odometry, synth
+    from ptudes_lab_b200.ekf_bench import SynthLidarImuSource
+    from ptudes_lab_b200.ins import ESEKFNative
+    dev = torch.device("cuda", local)
+    T = warmup + steps
+    seqs = [synth.make_sequence("os0_quad", l) for l in range(lanes)]
+    gens = [synth.TorchScanGenerator(s, dev) for s in seqs]
+    scans = []
+    for s in range(T):
+        row = []
+        for g in gens:
+            h = _ffi.pinned_empty((seqs[0].sensor.H, seqs[0].sensor.W), dtype=np.uint32)
+            h[...] = g.range_image(s)[0].cpu().numpy().astype(np.uint32)
+            row.append(h)
+        scans.append(row)
+    srcs = [SynthLidarImuSource(s, T, seed=1 + l) for l, s in enumerate(seqs)]
+    imus = [[[src.imu_at(k * 0.1 + j * 0.01) for j in range(10)] for k in range(T)] for src in srcs]
+    la = np.array([[[i.lacc for i in sc] for sc in lane] for lane in imus])
+    av = np.array([[[i.avel for i in sc] for sc in lane] for lane in imus])
+    ts = np.array([[[i.ts for i in sc] for sc in lane] for lane in imus])
+    cfg = odometry.load_config(None, deskew=True, max_range=70.0)          # ekf-bench defaults (cli/ekf_bench.py:356-363)
+    cfg.data.min_range = 1.0
+    o = odometry.Odometry(cfg, device=local, max_points=131072, map_capacity=65536, batch=lanes)
+    o.set_sensor(seqs[0].dirs)
+    ekfs = [ESEKFNative() for _ in range(lanes)]
+    t_start, t_ekf = None, 0.0
+    try:
+        for s in range(T):
+            if s == warmup:
+                torch.cuda.synchronize()
+                t_start, t_ekf = time.perf_counter(), 0.0
+            t0 = time.perf_counter()
+            guesses = []
+            for l, f in enumerate(ekfs):
+                f.processImuBatch(la[l, s], av[l, s], ts[l, s])
+                guesses.append(f.pose_mat())
+            t1 = time.perf_counter()
+            if s + 1 < T:
+                o.prefetch_scan_batch(scans[s + 1])
+            poses, st = o.register_scan_batch(scans[s], guesses=guesses)
+            t2 = time.perf_counter()
+            for l, f in enumerate(ekfs):
+                f.processPose(poses[l])
+            t_ekf += (t1 - t0) + (time.perf_counter() - t2)
+        dt = time.perf_counter() - t_start
+    finally:
+        o.close()
+    return {"value": lanes * steps / dt, "unit": UNIT, "lanes": lanes, "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "host_filter_ms_per_step": 1e3 * t_ekf / steps, "timing": "host wall clock, pinned host range images",
+            "workload": "configs[3]: ekf-bench loop, OS0-128 1024x10 + 100 Hz IMU, ranges 1/70 (voxel 0.7), ESEKF pose as "
+                        "ICP guess, host-native ESEKF"}
+
+
+def side_sharded(world, rank, local, scans_n=12):
+    """configs[4], second half: ONE sequence whose voxel map is sharded by hash key over the ranks.  Every rank
+    steps the same scans; poses must equal those of an unsharded single-GPU run (rank 0 checks)."""
+    import torch
+    import torch.distributed as dist
+    from ptudes_lab_b200 import odometry, sharded, synth
+    dev = torch.device("cuda", local)
+    seq = synth.make_sequence("os0_quad", 0)
+    gen = synth.TorchScanGenerator(seq, dev)
+    ranges = [gen.range_image(s)[0].contiguous() for s in range(scans_n)]
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    warm = 3
+    so = sharded.make_sharded(cfg, local, rank, world, max_points=131072, map_capacity=32768, dirs=seq.dirs)
+    try:
+        poses = []
+        t0 = None
+        for s in range(scans_n):
+            if s == warm:
+                dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            p, _ = so.register_frame(None, None, range_mm=ranges[s])
+            poses.append(p)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        info = so.describe()
+    finally:
+        so.close()
+    out = {"value": (scans_n - warm) / float(dt.item()), "unit": UNIT, "ranks": world, "scans": scans_n - warm,
+           "timing": "host wall clock, max over ranks", **info}
+    if rank == 0:
+        o1 = odometry.Odometry(cfg, device=local, max_points=131072, map_capacity=32768, batch=1)
+        o1.set_sensor(seq.dirs)
+        ref = [o1.register_scan(r)[0] for r in ranges]
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        o1.reset()
+        for r in ranges:
+            o1.register_scan(r)
+        torch.cuda.synchronize()
+        out["single_gpu_value"] = scans_n / (time.perf_counter() - t1)
+        o1.close()
+        out["bit_identical_to_single_gpu"] = bool(all(np.array_equal(a, b) for a, b in zip(poses, ref)))
+    return out
+
+
+# --------------------------------------------------------------------------------------
 def run_ptk(args):
     import torch
     import torch.distributed as dist
@@ -225,6 +381,9 @@ def run_ptk(args):
 
     B, K, W = args.lanes, args.steps, args.warmup
     T = W + K
+    TG = T + 1      # one scan more than is stepped: the LAST timed step of the host-buffer leg prefetches it, so the
+                    # timed region holds exactly K host-to-device copies (the first timed scan's copy was issued by the
+                    # last warm-up step, outside the region; this one replaces it)
     min_r, max_r, max_pts, map_cap = CONFIGS[args.config]
 
     # ---- synthetic scans, generated on the device (data plumbing) -------------------------
@@ -233,22 +392,22 @@ def run_ptk(args):
     # input = "xyz": the already projected (N,3)+(N,) float64 cloud of _kiss_register_frame (kiss.py:83).
     use_range = args.input == "range"
     gens = [synth.TorchScanGenerator(synth.make_sequence(args.config, rank * B + l), dev) for l in range(B)]
-    frames = [[None] * B for _ in range(T)]
-    tss = [[None] * B for _ in range(T)]
-    ranges = [[None] * B for _ in range(T)]
+    frames = [[None] * B for _ in range(TG)]
+    tss = [[None] * B for _ in range(TG)]
+    ranges = [[None] * B for _ in range(TG)]
     for l, g in enumerate(gens):
-        for s in range(T):
+        for s in range(TG):
             rng, _, _ = g.range_image(s)
             ranges[s][l] = rng.contiguous()
-            if not use_range or l < (os.cpu_count() or 1):      # the CPU baseline needs projected clouds
+            if not use_range:
                 frames[s][l], tss[s][l] = g.project(rng)
     torch.cuda.synchronize()
     if use_range:
         scan_bytes = sum(r.numel() * 4 for r in ranges[W])
-        total_bytes = sum(r.numel() * 4 for s in range(T) for r in ranges[s])
+        total_bytes = sum(r.numel() * 4 for s in range(TG) for r in ranges[s])
     else:
         scan_bytes = sum(f.numel() * 8 + t.numel() * 8 for f, t in zip(frames[W], tss[W]))
-        total_bytes = sum(f.numel() * 8 + t.numel() * 8 for s in range(T) for f, t in zip(frames[s], tss[s]))
+        total_bytes = sum(f.numel() * 8 + t.numel() * 8 for s in range(TG) for f, t in zip(frames[s], tss[s]))
     n_points = int((ranges[W][0] != 0).sum().item())
 
     cfg = odometry.load_config(None, deskew=True, max_range=max_r)
@@ -320,9 +479,9 @@ def run_ptk(args):
     # ---- leg 2: end to end from pinned host buffers ----------------------------------------
     e2e = None
     if not args.no_e2e:
-        h_frames = [[None] * B for _ in range(T)]
-        h_ts = [[None] * B for _ in range(T)]
-        for s in range(T):
+        h_frames = [[None] * B for _ in range(TG)]
+        h_ts = [[None] * B for _ in range(TG)]
+        for s in range(TG):
             for l in range(B):
                 if use_range:
                     hr = _ffi.pinned_empty(tuple(ranges[s][l].shape), dtype=np.uint32)
@@ -375,6 +534,34 @@ def run_ptk(args):
         t = torch.tensor([v], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # ---- the other BASELINE.json configs, small runs (skipped with --no-side-runs) -----------
+    side = {}
+    if not args.no_side_runs:
+        odo.close()
+        odo = None
+        # configs[4], first half, LITERALLY: 64 sequences in total, dealt to the ranks (strong scaling: 64/N per GPU)
+        if 64 % world == 0:
+            per = 64 // world
+            ms64, _ = side_fleet("os0_quad", per, 3, 10, local, rank * per, barrier)
+            ms64 = max_over_ranks(ms64)
+            side["fleet64_strong"] = {"value": 64 * 10 / (ms64 * 1e-3), "unit": UNIT, "sequences_total": 64,
+                                      "lanes_per_gpu": per, "steps": 10, "ms_per_step": ms64 / 10, "scaling": "strong",
+                                      "workload": "configs[4]: 64 independent os0_quad sequences over the ranks"}
+        if world > 1:
+            try:
+                side["sharded_single_sequence"] = side_sharded(world, rank, local)
+            except Exception as e:      # never lose the headline line to a side run
+                side["sharded_single_sequence"] = {"error": f"{type(e).__name__}: {e}"}
+            dist.barrier()
+        if rank == 0:
+            ms2, c2 = side_fleet("os2_street", 16, 3, 10, local, 0, torch.cuda.synchronize)
+            side["os2_street"] = {"value": 16 * 10 / (ms2 * 1e-3), "unit": UNIT, "lanes": 16, "steps": 10,
+                                  "ms_per_step": ms2 / 10, "counters": c2,
+                                  "workload": "configs[2]: OS2-128 2048x10, 262144 pixels/scan, max_range 200 m (voxel 2 m)"}
+            side["ekf_bench"] = side_ekf_fleet(16, 3, 10, local)
+        if world > 1:
+            dist.barrier()
 
     ms_dev_max = max_over_ranks(ms_dev)
     value = world * B * K / (ms_dev_max * 1e-3)
@@ -431,6 +618,8 @@ def run_ptk(args):
                                              "iterations", "n_corr")}
     if single is not None:
         out["single_sequence"] = single
+    if side:
+        out["side_runs"] = side
     out["counters"]["mean_icp_iterations"] = float(np.mean([st["iterations"] for ss in stats_acc for st in ss]))
     queries = sum(st["iterations"] * st["n_src"] for ss in stats_acc for st in ss)
     searches = sum(st["icp_searches"] for ss in stats_acc for st in ss)
@@ -446,31 +635,39 @@ def run_ptk(args):
     # ---- cpu baseline: the oracle on this box's host cores (rank 0, N = 1 only) -------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         C = max(1, min(B, os.cpu_count() or 1))
-        h = [[(frames[s][l].cpu().numpy(), tss[s][l].cpu().numpy()) for s in range(T)] for l in range(C)]
-        # (the reference's CPU path also projects the scan in NumPy inside register_frame, kiss.py:59-61;
-        #  that part is NOT timed here - the baseline is handed ready-made clouds)
-        out["cpu_baseline"], ref_poses = cpu_baseline_leg(args, h, min_r, max_r, T)
+        h = [[ranges[s][l].cpu().numpy().astype(np.uint32) for s in range(T)] for l in range(C)]
+        out["cpu_baseline"], ref_poses = cpu_baseline_leg(args, h, gens[0].seq.dirs, min_r, max_r, T)
         n = min(len(p) for p in ref_poses)
         ref = np.stack([np.stack(p[:n]) for p in ref_poses], axis=1) if n else None       # (n, C, 4, 4)
         out["parity_vs_oracle"] = {"scans": n, "lanes": C,
                                    "max_abs_pose_diff": float(np.abs(ref - poses_dev[:n, :C]).max()) if n else None}
+        if single is not None:      # configs[1] literally on the CPU: ONE sequence, OpenMP over all cores inside it
+            v1, n1, s1, _ = cpu_port_fleet(h[:1], gens[0].seq.dirs, min_r, max_r, W, min(args.cpu_seconds, 8.0),
+                                           os.cpu_count() or 1)
+            single["cpu_port"] = {"value": v1, "unit": UNIT, "cores": os.cpu_count() or 1,
+                                  "sample": f"one sequence, {n1} scans, OpenMP threads = cores ({s1:.1f} s)"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    odo.close()
+    if odo is not None:
+        odo.close()
     if rank == 0:
         print(json.dumps(out), file=RESULT, flush=True)
 
 
-def cpu_port_fleet(scans, min_r, max_r, warmup, budget_s, cores):
-    """The CPU restatement of the reference path (oracle/kiss_port.c: plain C + OpenMP, upstream
-    kiss-icp's structure) on host cores.  `scans[l][s]` = (xyz, ts) of lane l, scan s.  The lanes
-    are independent sequences, so the best use of the cores is one sequence per thread (each C
-    call releases the GIL); with fewer lanes than cores the spare cores go to OpenMP inside a lane.
-    A step advances every lane by one scan, like the CUDA arm.  Returns (scans/s, steps timed,
-    seconds, poses[lane][scan])."""
+def cpu_port_fleet(scans, dirs, min_r, max_r, warmup, budget_s, cores):
+    """The CPU restatement of the reference path on host cores, charged what KissICPWrapper.register_frame
+    does per scan: the NumPy projection of the RANGE image (`sel = range != 0; xyz = xyz_lut(scan)[sel];
+    timestamps = self._timestamps[sel]`, kiss.py:59-61 = synth.project_scan) and then the kiss-icp step
+    (oracle/kiss_port.c: plain C + OpenMP, upstream kiss-icp's structure, gcc -O3 -march=native built on this
+    host).  `scans[l][s]` = (H, W) uint32 range image of lane l, scan s.  The lanes are independent sequences, so
+    the best use of the cores is one sequence per thread (NumPy and the C call release the GIL); with fewer
+    lanes than cores the spare cores go to OpenMP inside a lane.  A step advances every lane by one scan, like
+    the CUDA arm.  Returns (scans/s, steps timed, seconds, poses[lane][scan])."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import port
+    from ptudes_lab_b200 import synth
+    flags = port.use_native()
     L = len(scans)
     inner = max(1, cores // L)
     ctxs = [port.PortKissICP(_min_range=min_r, _max_range=max_r, threads=inner) for _ in range(L)]
@@ -478,7 +675,7 @@ def cpu_port_fleet(scans, min_r, max_r, warmup, budget_s, cores):
 
     def advance(args):
         l, s = args
-        xyz, ts = scans[l][s]
+        xyz, ts = synth.project_scan(scans[l][s], dirs)              # kiss.py:59-61, timed
         poses[l].append(ctxs[l].register_points(xyz, ts, 0.1 * (s + 1)).copy())
 
     T = len(scans[0])
@@ -495,19 +692,21 @@ def cpu_port_fleet(scans, min_r, max_r, warmup, budget_s, cores):
                     break
     for c in ctxs:
         c.close()
+    cpu_port_fleet.flags = flags
     return (L * n_steps / t_used if t_used > 0 else None), n_steps, t_used, poses
 
 
-def cpu_baseline_leg(args, host_scans, min_r, max_r, T):
+def cpu_baseline_leg(args, host_scans, dirs, min_r, max_r, T):
     """cpu_baseline of the own arm: lane 0..C-1 of this very workload on the box's host cores,
     bounded by --cpu-seconds.  The oracle is used here as the reported baseline only."""
     cores = os.cpu_count() or 1
-    val, n_steps, secs, poses = cpu_port_fleet(host_scans, min_r, max_r, args.warmup, args.cpu_seconds, cores)
+    val, n_steps, secs, poses = cpu_port_fleet(host_scans, dirs, min_r, max_r, args.warmup, args.cpu_seconds, cores)
     L = len(host_scans)
     return ({"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-             "sample": f"oracle/kiss_port.c (C restatement of the kiss-icp 0.2.x step, gcc -O2 + OpenMP): {L} of the "
-                       f"lanes' sequences run concurrently, one per host thread, scans {args.warmup}.."
-                       f"{args.warmup + n_steps - 1} timed ({secs:.1f} s of CPU wall time)"}, poses)
+             "sample": f"NumPy projection of the RANGE image (kiss.py:59-61) + oracle/kiss_port.c (C restatement of the "
+                       f"kiss-icp 0.2.x step, gcc {cpu_port_fleet.flags} + OpenMP): {L} of the lanes' sequences run "
+                       f"concurrently, one per host thread, scans {args.warmup}..{args.warmup + n_steps - 1} timed "
+                       f"({secs:.1f} s of CPU wall time)"}, poses)
 
 
 # --------------------------------------------------------------------------------------
@@ -526,17 +725,15 @@ def run_reference(args):
     L = max(1, min(args.lanes, cores))
     dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
     scans = []
+    dirs = None
     for l in range(L):          # same sequences as the CUDA arm's lanes 0..L-1 (synthetic-data plumbing)
         g = synth.TorchScanGenerator(synth.make_sequence(args.config, l), dev)
-        lane = []
-        for s in range(W + K):
-            xyz, tn, _, _ = g.points(s)
-            lane.append((xyz.cpu().numpy(), tn.cpu().numpy()))
-        scans.append(lane)
-    val, n, secs, _ = cpu_port_fleet(scans, min_r, max_r, W, 240.0, cores)
-    sample = (f"oracle/kiss_port.c (C restatement of the kiss-icp 0.2.x step, gcc -O2 + OpenMP) on {cores} host "
-              f"cores: {L} of the workload's {args.lanes} sequences per step, one per thread; {n} of the requested "
-              f"{K} steps timed")
+        dirs = g.seq.dirs
+        scans.append([g.range_image(s)[0].cpu().numpy().astype(np.uint32) for s in range(W + K)])
+    val, n, secs, _ = cpu_port_fleet(scans, dirs, min_r, max_r, W, 240.0, cores)
+    sample = (f"NumPy projection of the RANGE image (kiss.py:59-61) + oracle/kiss_port.c (C restatement of the kiss-icp "
+              f"0.2.x step, gcc {cpu_port_fleet.flags} + OpenMP) on {cores} host cores: {L} of the workload's "
+              f"{args.lanes} sequences per step, one per thread; {n} of the requested {K} steps timed")
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
            "warmup": W, "ms_per_step": 1e3 * secs / max(n, 1), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",

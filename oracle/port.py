@@ -54,6 +54,18 @@ _SIG = {
 }
 
 
+_NATIVE = None
+
+
+def _bind(path):
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIG.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
 def load(build_if_missing=True):
     global _LIB
     if _LIB is not None:
@@ -64,13 +76,24 @@ def load(build_if_missing=True):
         except Exception:
             if not os.path.exists(build_port.LIB):
                 raise
-    lib = C.CDLL(build_port.LIB)
-    for name, (res, args) in _SIG.items():
-        fn = getattr(lib, name)
-        fn.restype = res
-        fn.argtypes = args
-    _LIB = lib
-    return lib
+    _LIB = _bind(build_port.LIB)
+    return _LIB
+
+
+def use_native():
+    """Switch every PortKissICP created from now on to the -march=native build, compiled on this host (the
+    timed CPU baseline of bench.py).  Returns the flags in use; falls back to the portable build on any failure."""
+    global _LIB, _NATIVE
+    if _NATIVE is None:
+        try:
+            _NATIVE = _bind(build_port.build_native())
+        except Exception:
+            _NATIVE = False
+    if _NATIVE:
+        _LIB = _NATIVE
+        return " ".join(build_port.FLAGS_NATIVE[:1] + build_port.FLAGS_NATIVE[-1:])
+    load()
+    return " ".join(build_port.FLAGS[:1] + build_port.FLAGS[-1:])
 
 
 def _f64(a):

@@ -805,12 +805,22 @@ __device__ __forceinline__ void thread_nearest(const MapView& M, u32* ids, float
         }
         const double2* rows = reinterpret_cast<const double2*>(M.blocks + ids[vv * 32 + lane]);
         const int obase = vv * MAXP;
+        // the rows of a block are read four slots at a time, one batch AHEAD of the arithmetic: the five batches of a
+        // visit then cost about one memory round trip instead of five
+        double2 nx[6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { nx[2 * r] = __ldg(rows + r * (MAXP / 2)); nx[2 * r + 1] = __ldg(rows + r * (MAXP / 2) + 1); }
 #pragma unroll
         for (int h = 0; h < MAXP / 4; ++h) {
-            const double2 xa = __ldg(rows + 2 * h), xb = __ldg(rows + 2 * h + 1);
-            const double2 ya = __ldg(rows + MAXP / 2 + 2 * h), yb = __ldg(rows + MAXP / 2 + 2 * h + 1);
-            const double2 za = __ldg(rows + MAXP + 2 * h), zb = __ldg(rows + MAXP + 2 * h + 1);
-            const double xs[4] = {xa.x, xa.y, xb.x, xb.y}, ys[4] = {ya.x, ya.y, yb.x, yb.y}, zs[4] = {za.x, za.y, zb.x, zb.y};
+            const double xs[4] = {nx[0].x, nx[0].y, nx[1].x, nx[1].y}, ys[4] = {nx[2].x, nx[2].y, nx[3].x, nx[3].y},
+                         zs[4] = {nx[4].x, nx[4].y, nx[5].x, nx[5].y};
+            if (h + 1 < MAXP / 4) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    nx[2 * r] = __ldg(rows + r * (MAXP / 2) + 2 * (h + 1));
+                    nx[2 * r + 1] = __ldg(rows + r * (MAXP / 2) + 2 * (h + 1) + 1);
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const double dx = xs[k] - sx, dy = ys[k] - sy, dz = zs[k] - sz;
@@ -1135,7 +1145,10 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
 constexpr int IQ_THREADS = 128;
 constexpr int IQ_WARPS = IQ_THREADS / 32;
 #ifndef PTK_IQ_MINBLOCKS
-#define PTK_IQ_MINBLOCKS 6
+#define PTK_IQ_MINBLOCKS 5
+#endif
+#ifndef PTK_IQ_MAX_SLEEP
+#define PTK_IQ_MAX_SLEEP 256       // ns: longest pause between two polls of an idle warp
 #endif
 constexpr u32 IQ_CAP = 1u << 16;            // ring entries (power of two)
 constexpr u64 IQ_EMPTY = 0ull;
@@ -1150,14 +1163,78 @@ struct IcpQueue {
     u64 slots[IQ_CAP];
 };
 
+// Per-warp shared memory of the ICP kernel.  The phases of a task are separate (__noinline__) functions, each with
+// its own register allocation; what one phase leaves for the next goes through here, one column per lane.  (As one
+// inlined body the task spilled ~800 B per thread; with most of the SM's L1 configured as shared memory those
+// spills missed L1 and every phase ran an order of magnitude slower than its instruction count.)
 struct IcpWarpScratch {
+    // 8704 B used twice: by a task (thread_nearest scratch + the hand-off columns) and, once the last group of an
+    // iteration has arrived, by the solver as two 17 x 32 staging buffers of group partials (TMA destination)
+    double raw[2 * NSUM * 32];
+    unsigned long long mbar[2];         // one mbarrier per staging buffer
+    u32 mbar_phase[2];
+    int ord[32];                        // order ids of the correspondences (-1: none)
     double red[NSUM];
     SolveSmem S;
     Rigid E;
     SE3q T;
     int done;
     int pad;
+    __device__ __forceinline__ u32* ids() { return reinterpret_cast<u32*>(raw); }                 // [27][32] voxel block of every neighbour
+    __device__ __forceinline__ float* lbs() { return reinterpret_cast<float*>(raw) + 27 * 32; }   // [27][32] rounded-down box distance^2
+    __device__ __forceinline__ double* col(int k) { return raw + 27 * 32 + 32 * k; }              // k = 0..5: sx sy sz tx ty tz, one column per lane
 };
+static_assert(2 * NSUM * 32 >= 27 * 32 + 6 * 32, "hand-off columns must fit behind the search scratch");
+
+// Scoped memory operations of the task ring and the arrival counters (PTX memory model, gpu scope).  One lane
+// releases / acquires on behalf of its warp: __syncwarp / shuffles order the other lanes' accesses around it.
+// (Full __threadfence()s - MEMBAR.SC - per task were far more expensive than these scoped operations.)
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64* p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u32 atom_add_acq_rel_u32(u32* p, u32 v) {
+    u32 old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ u32 atom_add_relaxed_u32(u32* p, u32 v) {
+    u32 old;
+    asm volatile("atom.add.relaxed.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ u64 atom_cas_release_u64(u64* p, u64 cmp, u64 val) {
+    u64 old;
+    asm volatile("atom.cas.release.gpu.global.b64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(cmp), "l"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// ---- TMA (1-D bulk copy global -> shared, completion on an mbarrier): how the solver fetches the group partials.
+// One lane issues all the copies of a staging buffer; they are in flight together and cost no registers, where 16
+// dependent-looking ld.cg per super-group serialised into one L2 round trip each.
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* mbar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* mbar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, u32 bytes, unsigned long long* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(mbar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* mbar, u32 phase) {
+    u32 ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_addr(mbar)), "r"(phase) : "memory");
+    } while (!ok);
+}
 
 __device__ __forceinline__ u64 icp_task(int lane_id, int grp) {
     return (1ull << 56) | ((u64)(u32)lane_id << 32) | (u64)(u32)grp;
@@ -1167,16 +1244,24 @@ __device__ __forceinline__ u64 icp_task(int lane_id, int grp) {
 __device__ __forceinline__ void icp_push(IcpQueue* Q, int lane_id, int n_groups, int lane) {
     const u32 FULL = 0xffffffffu;
     const u32 n = (u32)n_groups;
-    __threadfence();
-    __syncwarp();
+    __syncwarp();                 // lane 0's state stores are ordered before every lane's releasing CAS below
     u32 base = 0;
-    if (lane == 0) base = atomicAdd(&Q->tail, n);
+    if (lane == 0) base = atom_add_relaxed_u32(&Q->tail, n);
     base = __shfl_sync(FULL, base, 0);
     for (u32 i = (u32)lane; i < n; i += 32u) {
         const u64 t = icp_task(lane_id, (int)i);
         u64* s = Q->slots + ((base + i) & (IQ_CAP - 1u));
-        while (atomicCAS(s, IQ_EMPTY, t) != IQ_EMPTY) { }      // ring full: wait for the consumer of the older entry
+        while (atom_cas_release_u64(s, IQ_EMPTY, t) != IQ_EMPTY) { __nanosleep(64); }   // ring full: wait for the older entry's consumer
     }
+}
+
+// Every lane has finished, i.e. every task has been consumed and the ring is empty: hand each warp of the grid its
+// exit token (plain relaxed stores - nobody else writes the ring any more).
+__device__ __forceinline__ void icp_push_exit(IcpQueue* Q, int total_warps, int lane) {
+    u32 base = 0;
+    if (lane == 0) base = atom_add_relaxed_u32(&Q->tail, (u32)total_warps);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (u32 i = (u32)lane; i < (u32)total_warps; i += 32u) st_relaxed_u64(Q->slots + ((base + i) & (IQ_CAP - 1u)), IQ_EXIT);
 }
 
 __device__ __forceinline__ Rigid ldcg_rigid(const Rigid* p) {
@@ -1188,26 +1273,36 @@ __device__ __forceinline__ Rigid ldcg_rigid(const Rigid* p) {
     return T;
 }
 
-// 16 partials of super-group `sg` (32 consecutive groups), lane = group within the super-group
-__device__ __forceinline__ void icp_load_sg(const double* part, int ngc, int sg, int n_groups, int lane, double* c) {
-    const int g = sg * 32 + lane;
-#pragma unroll
-    for (int v = 0; v < 16; ++v) c[v] = g < n_groups ? __ldcg(part + (size_t)v * ngc + g) : 0.0;
+// Stage the 17 rows of super-group `sg` (32 consecutive groups) of the partial table into staging buffer `b`.
+// Lane 0 only.  Rows are copied in whole 16 B units; entries past n_groups are masked by the reader.
+__device__ __forceinline__ void icp_stage_sg(IcpWarpScratch* ws, const double* part, int ngc, int sg, int n_groups, int b) {
+    const int g0 = sg * 32;
+    const int n = min(32, n_groups - g0);
+    const u32 bytes = (u32)(((n + 1) & ~1) * 8);
+    mbar_expect_tx(&ws->mbar[b], bytes * NSUM);
+#pragma unroll 1
+    for (int v = 0; v < NSUM; ++v) tma_load_1d(ws->raw + (b * NSUM + v) * 32, part + (size_t)v * ngc + g0, bytes, &ws->mbar[b]);
 }
 
 // Canonical tree over the group partials of all 16 sums at once (oracle/canon.py pairwise_tree_sum, exactly the
 // additions of warp_tree_sum): level 1 = butterfly over the 32 groups of a super-group (transposed, 16 sums per
 // pass), level 2 = adjacent-pairs tree over 32 super-groups (zero padded), level 3 = the fixed 8-chunk tree.
-// Returns the total of sum bitrev4(lane & 15).
-__device__ __forceinline__ double icp_tree16(const double* part, int ngc, int n_groups, int lane) {
+// Returns the total of sum bitrev4(lane & 15); *count = number of correspondences (a sum of small integers is
+// exact in any order).  Super-groups are staged two ahead through TMA.
+__device__ __forceinline__ double icp_tree16(IcpWarpScratch* ws, const double* part, int ngc, int n_groups, int lane, int* count) {
+    const u32 FULL = 0xffffffffu;
     const int n_sg = (n_groups + 31) >> 5;
-    double cur[16], nxt[16];
-    icp_load_sg(part, ngc, 0, n_groups, lane, cur);
-    if (n_sg <= 1) return warp_reduce16(cur, lane);
+    int cnt = 0;
+    if (lane == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");     // the partials were written through the generic proxy
+        if (n_sg > 0) icp_stage_sg(ws, part, ngc, 0, n_groups, 0);
+        if (n_sg > 1) icp_stage_sg(ws, part, ngc, 1, n_groups, 1);
+    }
     int m = 1;
     while (m * 32 < n_groups) m <<= 1;
     const int mc = m <= 32 ? 1 : (m >> 5);
     double U[8];
+    double single = 0.0;
 #pragma unroll 1
     for (int c = 0; c < 8; ++c) {
         double tot = 0.0;
@@ -1218,12 +1313,22 @@ __device__ __forceinline__ double icp_tree16(const double* part, int ngc, int n_
                 const int sg = c * 32 + i;
                 double x = 0.0;
                 if (sg < n_sg) {
-                    if (sg + 1 < n_sg) icp_load_sg(part, ngc, sg + 1, n_groups, lane, nxt);
-                    x = warp_reduce16(cur, lane);
-                    if (sg + 1 < n_sg) {
+                    const int b = sg & 1;
+                    mbar_wait(&ws->mbar[b], ws->mbar_phase[b]);
+                    const bool valid = sg * 32 + lane < n_groups;
+                    const double* buf = ws->raw + b * NSUM * 32;
+                    double cv[16];
 #pragma unroll
-                        for (int v = 0; v < 16; ++v) cur[v] = nxt[v];
+                    for (int v = 0; v < 16; ++v) cv[v] = valid ? buf[v * 32 + lane] : 0.0;
+                    if (valid) cnt += (int)buf[16 * 32 + lane];
+                    __syncwarp();
+                    if (lane == 0) {
+                        ws->mbar_phase[b] ^= 1u;
+                        if (sg + 2 < n_sg) icp_stage_sg(ws, part, ngc, sg + 2, n_groups, b);
                     }
+                    __syncwarp();
+                    x = warp_reduce16(cv, lane);
+                    if (n_sg == 1) single = x;
                 }
                 if (i & 1) {
                     x = a0 + x;
@@ -1244,6 +1349,8 @@ __device__ __forceinline__ double icp_tree16(const double* part, int ngc, int n_
         if (c == 0) U[0] = tot; else if (c == 1) U[1] = tot; else if (c == 2) U[2] = tot; else if (c == 3) U[3] = tot;
         else if (c == 4) U[4] = tot; else if (c == 5) U[5] = tot; else if (c == 6) U[6] = tot; else U[7] = tot;
     }
+    *count = __reduce_add_sync(FULL, cnt);
+    if (n_sg <= 1) return n_sg == 1 ? single : 0.0;      // one super-group: its butterfly IS the sum; none: nothing to add
     if (mc == 1) return U[0];
     return ((U[0] + U[1]) + (U[2] + U[3])) + ((U[4] + U[5]) + (U[6] + U[7]));
 }
@@ -1267,10 +1374,8 @@ __device__ __noinline__ void icp_lane_solve(LaneDev& L, const StepParams& P, Ste
     if (lane == 0) L.icp_arrive = 0;
     const double* part = L.part_a;
     const int ngc = L.ng_cap;
-    const double tot = icp_tree16(part, ngc, n_groups, lane);
     int cnt = 0;
-    for (int g = lane; g < n_groups; g += 32) cnt += (int)__ldcg(part + (size_t)16 * ngc + g);
-    cnt = __reduce_add_sync(FULL, cnt);           // a sum of small integers is exact in any order
+    const double tot = icp_tree16(ws, part, ngc, n_groups, lane, &cnt);
     if (lane < 16) ws->red[__brev((u32)lane) >> 28] = tot;
     if (lane == 0) {
         ws->red[16] = (double)cnt;
@@ -1297,31 +1402,122 @@ __device__ __noinline__ void icp_lane_solve(LaneDev& L, const StepParams& P, Ste
         u32 fin = 0;
         if (lane == 0) {
             L.icp_done = 1;
-            __threadfence();
-            fin = atomicAdd(&Q->lanes_done, 1u) + 1u;
+            fin = atom_add_acq_rel_u32(&Q->lanes_done, 1u) + 1u;
         }
         fin = __shfl_sync(FULL, fin, 0);
-        if (fin == (u32)n_lanes) {
-            // every task of every lane has been consumed: the ring is empty, hand every warp its exit token
-            u32 base = 0;
-            if (lane == 0) base = atomicAdd(&Q->tail, (u32)total_warps);
-            base = __shfl_sync(FULL, base, 0);
-            for (u32 i = (u32)lane; i < (u32)total_warps; i += 32u)
-                *((volatile u64*)(Q->slots + ((base + i) & (IQ_CAP - 1u)))) = IQ_EXIT;
-        }
+        if (fin == (u32)n_lanes) icp_push_exit(Q, total_warps, lane);
     }
     IQ_TICK(5);
 }
 
-// Residual, weight, the group's 16 sums, arrival; the last group of the iteration goes on to the solve.
-__device__ __forceinline__ void icp_group_sums(LaneDev& L, const StepParams& P, StepOut& O, IcpQueue* Q, IcpWarpScratch* ws,
-                                               int lane_id, int g, int it, int n_groups, int n_lanes, int total_warps, int lane,
-                                               bool live, double sx, double sy, double sz, double tx, double ty, double tz, int ord) {
+// ---- phase 1 of a task: move the group's points by the last increment and consult the correspondence cache.
+// Leaves positions and (for hits) correspondences in the warp scratch; returns whether this lane's point needs a search.
+__device__ __noinline__ bool icp_task_front(LaneDev& L, IcpWarpScratch* ws, int g, int lane, int* it_out) {
+    const int n_src = L.n_src;
+    const int p = g * 32 + lane;
+    const bool live = p < n_src;
+    double sx = 0, sy = 0, sz = 0, tx = 0, ty = 0, tz = 0;
+    int ord = -1;
+    bool miss = false;
+    // every load of the phase goes out before anything is looked at (iteration 0 ignores what the cache arrays hold)
+    const size_t cap = (size_t)L.cap_points;
+    const int pl = live ? p : 0;
+    const int it = __ldcg(&L.icp_it);
+    const Rigid E = ldcg_rigid(&L.icp_E);
+    const double x0 = __ldcg(L.s_x + pl), y0 = __ldcg(L.s_y + pl), z0 = __ldcg(L.s_z + pl);
+    const double others = __ldcg(L.c_slack + pl);
+    const double ctx = __ldcg(L.c_tx + pl), cty = __ldcg(L.c_ty + pl), ctz = __ldcg(L.c_tz + pl);
+    const int cord = __ldcg(L.c_ord + pl);
+    const double px = __ldcg(L.c_px + pl), py = __ldcg(L.c_py + pl), pz = __ldcg(L.c_pz + pl);
+    const u64 ckey = __ldcg(L.c_key + pl);
+    double b2[3 * ICP_KX];
+    int o2[ICP_KX];
+#pragma unroll
+    for (int j = 0; j < ICP_KX; ++j) {
+        o2[j] = __ldcg(L.c_ord2 + (size_t)j * cap + pl);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) b2[3 * j + c] = __ldcg(L.c_t2 + (size_t)(3 * j + c) * cap + pl);
+    }
+    if (it == 0) {
+        if (live) { sx = x0; sy = y0; sz = z0; }
+        miss = live;              // every point starts with a search
+    } else if (live) {
+        tx = ctx; ty = cty; tz = ctz; ord = cord;
+        rigid_apply(E, x0, y0, z0, sx, sy, sz);
+        __stcg(L.s_x + p, sx); __stcg(L.s_y + p, sy); __stcg(L.s_z + p, sz);
+        miss = true;
+        if (others > 0.0) {
+            const double mx = sx - px, my = sy - py, mz = sz - pz;
+            const double moved = sqrt((mx * mx + my * my) + mz * mz);
+            double ex = tx - sx, ey = ty - sy, ez = tz - sz;
+            double da2 = (ex * ex + ey * ey) + ez * ez;              // as the search computes it
+#pragma unroll
+            for (int j = 0; j < ICP_KX; ++j) {
+                const int oj = o2[j];
+                if (oj < 0) continue;
+                const double bx = b2[3 * j], by = b2[3 * j + 1], bz = b2[3 * j + 2];
+                ex = bx - sx; ey = by - sy; ez = bz - sz;
+                const double db2 = (ex * ex + ey * ey) + ez * ez;
+                if (db2 < da2 || (db2 == da2 && oj < ord)) {          // this runner-up has become the nearest
+                    __stcg(L.c_tx + p, bx); __stcg(L.c_ty + p, by); __stcg(L.c_tz + p, bz); __stcg(L.c_ord + p, oj);
+                    __stcg(L.c_t2 + (size_t)(3 * j) * cap + p, tx); __stcg(L.c_t2 + (size_t)(3 * j + 1) * cap + p, ty);
+                    __stcg(L.c_t2 + (size_t)(3 * j + 2) * cap + p, tz); __stcg(L.c_ord2 + (size_t)j * cap + p, ord);
+                    tx = bx; ty = by; tz = bz; ord = oj;
+                    da2 = db2;
+                }
+            }
+            if (sqrt(da2) + moved + 1e-9 < others) {
+                int kx, ky, kz;
+                voxel_key(sx, sy, sz, L.voxel_size, L.voxel_inv, kx, ky, kz);
+                miss = !(key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == ckey);
+            }
+        }
+    }
+    ws->col(0)[lane] = sx; ws->col(1)[lane] = sy; ws->col(2)[lane] = sz;
+    ws->col(3)[lane] = tx; ws->col(4)[lane] = ty; ws->col(5)[lane] = tz;
+    ws->ord[lane] = ord;
+    *it_out = it;
+    return miss;
+}
+
+// ---- phase 2: the group's missed points, every one on its own thread; refreshes their cache entries.
+__device__ __noinline__ void icp_task_search(LaneDev& L, IcpWarpScratch* ws, int g, int lane, bool miss, double max_d2) {
+    const MapView M = map_view(L);
+    const int p = g * 32 + lane;
+    const double sx = ws->col(0)[lane], sy = ws->col(1)[lane], sz = ws->col(2)[lane];
+    NearestOut R;
+    thread_nearest(M, ws->ids(), ws->lbs(), lane, miss, sx, sy, sz, max_d2, R);
+    if (miss) {
+        const size_t cap = (size_t)L.cap_points;
+        ws->col(3)[lane] = R.tx; ws->col(4)[lane] = R.ty; ws->col(5)[lane] = R.tz; ws->ord[lane] = R.ord;
+        __stcg(L.c_tx + p, R.tx); __stcg(L.c_ty + p, R.ty); __stcg(L.c_tz + p, R.tz);
+#pragma unroll
+        for (int j = 0; j < ICP_KX; ++j) {
+            __stcg(L.c_t2 + (size_t)(3 * j) * cap + p, R.t2[3 * j]);
+            __stcg(L.c_t2 + (size_t)(3 * j + 1) * cap + p, R.t2[3 * j + 1]);
+            __stcg(L.c_t2 + (size_t)(3 * j + 2) * cap + p, R.t2[3 * j + 2]);
+            __stcg(L.c_ord2 + (size_t)j * cap + p, R.ord2[j]);
+        }
+        __stcg(L.c_px + p, sx); __stcg(L.c_py + p, sy); __stcg(L.c_pz + p, sz);
+        __stcg(L.c_slack + p, R.others);
+        __stcg(L.c_key + p, R.qkey);
+        __stcg(L.c_ord + p, R.ord);
+    }
+}
+
+// ---- phase 3: residual, weight, the group's 16 sums, arrival.  Returns true for the LAST group of the iteration.
+__device__ __noinline__ bool icp_task_sums(LaneDev& L, const StepParams& P, IcpWarpScratch* ws, int g, int it, int lane) {
     const u32 FULL = 0xffffffffu;
+    const int n_src = L.n_src;
+    const int n_groups = (n_src + 31) >> 5;
+    const bool live = g * 32 + lane < n_src;
     const double max_corr = P.max_corr;
+    const int ord = ws->ord[lane];
     double c[16];
     bool acc = false;
     if (live && ord >= 0) {
+        const double sx = ws->col(0)[lane], sy = ws->col(1)[lane], sz = ws->col(2)[lane];
+        const double tx = ws->col(3)[lane], ty = ws->col(4)[lane], tz = ws->col(5)[lane];
         const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
         const double d2 = (dx * dx + dy * dy) + dz * dz;
         acc = sqrt(d2) < max_corr;
@@ -1337,14 +1533,13 @@ __device__ __forceinline__ void icp_group_sums(LaneDev& L, const StepParams& P, 
     double* part = L.part_a;
     if (lane < 16) __stcg(part + (size_t)(__brev((u32)lane) >> 28) * L.ng_cap + g, mine);
     else if (lane == 16) __stcg(part + (size_t)16 * L.ng_cap + g, (double)nacc);
-    __threadfence();          // every lane: partials, moved point, cache entry before the arrival becomes visible
+    // the arrival releases this warp's stores (partials, moved points, cache entries: ordered before it by the
+    // __syncwarp) and, for the last group, acquires everybody else's
     __syncwarp();
     u32 arrived = 0;
-    if (lane == 0) arrived = atomicAdd(&L.icp_arrive, 1u) + 1u;
+    if (lane == 0) arrived = atom_add_acq_rel_u32(&L.icp_arrive, 1u) + 1u;
     arrived = __shfl_sync(FULL, arrived, 0);
-    if (arrived != (u32)n_groups) return;
-    __threadfence();
-    icp_lane_solve(L, P, O, Q, ws, lane_id, it, n_groups, n_lanes, total_warps, lane);
+    return arrived == (u32)n_groups;
 }
 
 __global__ void __launch_bounds__(IQ_THREADS, PTK_IQ_MINBLOCKS) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs,
@@ -1354,9 +1549,14 @@ __global__ void __launch_bounds__(IQ_THREADS, PTK_IQ_MINBLOCKS) k_icp(LaneDev* l
     const int total_warps = gridDim.x * IQ_WARPS;
     const int gw = blockIdx.x * IQ_WARPS + warp;
     __shared__ IcpWarpScratch s_ws[IQ_WARPS];
-    __shared__ u32 s_ids[IQ_WARPS][27 * 32];
-    __shared__ float s_lbs[IQ_WARPS][27 * 32];
     IcpWarpScratch* ws = &s_ws[warp];
+    if (lane == 0) {
+        mbar_init(&ws->mbar[0], 1);
+        mbar_init(&ws->mbar[1], 1);
+        ws->mbar_phase[0] = ws->mbar_phase[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     const bool prof = Q->prof != 0;
     long long tlast = prof ? clock64() : 0;
 
@@ -1374,17 +1574,10 @@ __global__ void __launch_bounds__(IQ_THREADS, PTK_IQ_MINBLOCKS) k_icp(LaneDev* l
                     O.pose = se3q_matrix(se3q_mul(se3q_identity(), se3q_from_rigid(P.guess)));
                     O.iterations = 0; O.n_corr = 0; O.status = 0; O.dx_norm = 0.0;
                     L.icp_done = 1;
-                    __threadfence();
-                    fin = atomicAdd(&Q->lanes_done, 1u) + 1u;
+                    fin = atom_add_acq_rel_u32(&Q->lanes_done, 1u) + 1u;
                 }
                 fin = __shfl_sync(FULL, fin, 0);
-                if (fin == (u32)n_lanes) {
-                    u32 base = 0;
-                    if (lane == 0) base = atomicAdd(&Q->tail, (u32)total_warps);
-                    base = __shfl_sync(FULL, base, 0);
-                    for (u32 i = (u32)lane; i < (u32)total_warps; i += 32u)
-                        *((volatile u64*)(Q->slots + ((base + i) & (IQ_CAP - 1u)))) = IQ_EXIT;
-                }
+                if (fin == (u32)n_lanes) icp_push_exit(Q, total_warps, lane);
                 continue;
             }
             if (lane == 0) { L.icp_it = 0; L.icp_arrive = 0; L.icp_done = 0; }
@@ -1401,114 +1594,39 @@ __global__ void __launch_bounds__(IQ_THREADS, PTK_IQ_MINBLOCKS) k_icp(LaneDev* l
     while (true) {
         u64 task = IQ_EMPTY;
         if (lane == 0) {
-            const u32 t = atomicAdd(&Q->head, 1u);
-            volatile u64* s = Q->slots + (t & (IQ_CAP - 1u));
-            while ((task = *s) == IQ_EMPTY) { }
-            *s = IQ_EMPTY;
+            const u32 t = atom_add_relaxed_u32(&Q->head, 1u);
+            u64* s = Q->slots + (t & (IQ_CAP - 1u));
+            u32 ns = 32;
+            while ((task = ld_relaxed_u64(s)) == IQ_EMPTY) {       // idle: poll gently, the SM's other warps are working
+                __nanosleep(ns);
+                if (ns < PTK_IQ_MAX_SLEEP) ns <<= 1;
+            }
+            st_relaxed_u64(s, IQ_EMPTY);
+            fence_acq_rel_gpu();                                    // acquire what the publisher released
         }
         task = __shfl_sync(FULL, task, 0);
         if (task == IQ_EXIT) break;
-        __threadfence();
         IQ_TICK(3);
         const int lane_id = (int)((task >> 32) & 0xffffffu), g = (int)(task & 0xffffffffu);
         LaneDev& L = lanes[lane_id];
         const StepParams& P = params[lane_id];
-        StepOut& O = outs[lane_id];
-        const int n_src = L.n_src;
-        const int n_groups = (n_src + 31) >> 5;
-        const double max_corr = P.max_corr;
-        const double max_d2 = (max_corr * max_corr) * (1.0 + 1e-9);   // farther candidates are rejected anyway
-        const int p = g * 32 + lane;
-        const bool live = p < n_src;
-        const size_t cap = (size_t)L.cap_points;
-        double sx = 0, sy = 0, sz = 0, tx = 0, ty = 0, tz = 0;
-        int ord = -1;
-        bool miss = false;
-        const int it = __ldcg(&L.icp_it);
-        if (it == 0) {
-            if (live) { sx = L.s_x[p]; sy = L.s_y[p]; sz = L.s_z[p]; }
-            miss = live;          // every point starts with a search
-        } else {
-            // ---- 1. move the point, consult the cache
-            const Rigid E = ldcg_rigid(&L.icp_E);
-            if (live) {
-                const double x0 = __ldcg(L.s_x + p), y0 = __ldcg(L.s_y + p), z0 = __ldcg(L.s_z + p);
-                const double others = __ldcg(L.c_slack + p);
-                tx = __ldcg(L.c_tx + p); ty = __ldcg(L.c_ty + p); tz = __ldcg(L.c_tz + p);
-                ord = __ldcg(L.c_ord + p);
-                const double px = __ldcg(L.c_px + p), py = __ldcg(L.c_py + p), pz = __ldcg(L.c_pz + p);
-                const u64 ckey = __ldcg(L.c_key + p);
-                double b2[3 * ICP_KX];
-                int o2[ICP_KX];
-#pragma unroll
-                for (int j = 0; j < ICP_KX; ++j) {
-                    o2[j] = __ldcg(L.c_ord2 + (size_t)j * cap + p);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) b2[3 * j + c] = __ldcg(L.c_t2 + (size_t)(3 * j + c) * cap + p);
-                }
-                rigid_apply(E, x0, y0, z0, sx, sy, sz);
-                __stcg(L.s_x + p, sx); __stcg(L.s_y + p, sy); __stcg(L.s_z + p, sz);
-                miss = true;
-                if (others > 0.0) {
-                    const double mx = sx - px, my = sy - py, mz = sz - pz;
-                    const double moved = sqrt((mx * mx + my * my) + mz * mz);
-                    double ex = tx - sx, ey = ty - sy, ez = tz - sz;
-                    double da2 = (ex * ex + ey * ey) + ez * ez;              // as the search computes it
-#pragma unroll
-                    for (int j = 0; j < ICP_KX; ++j) {
-                        const int oj = o2[j];
-                        if (oj < 0) continue;
-                        const double bx = b2[3 * j], by = b2[3 * j + 1], bz = b2[3 * j + 2];
-                        ex = bx - sx; ey = by - sy; ez = bz - sz;
-                        const double db2 = (ex * ex + ey * ey) + ez * ez;
-                        if (db2 < da2 || (db2 == da2 && oj < ord)) {          // this runner-up has become the nearest
-                            __stcg(L.c_tx + p, bx); __stcg(L.c_ty + p, by); __stcg(L.c_tz + p, bz); __stcg(L.c_ord + p, oj);
-                            __stcg(L.c_t2 + (size_t)(3 * j) * cap + p, tx); __stcg(L.c_t2 + (size_t)(3 * j + 1) * cap + p, ty);
-                            __stcg(L.c_t2 + (size_t)(3 * j + 2) * cap + p, tz); __stcg(L.c_ord2 + (size_t)j * cap + p, ord);
-                            tx = bx; ty = by; tz = bz; ord = oj;
-                            da2 = db2;
-                        }
-                    }
-                    if (sqrt(da2) + moved + 1e-9 < others) {
-                        int kx, ky, kz;
-                        voxel_key(sx, sy, sz, L.voxel_size, L.voxel_inv, kx, ky, kz);
-                        miss = !(key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == ckey);
-                    }
-                }
-            }
-        }
+        int it;
+        const bool miss = icp_task_front(L, ws, g, lane, &it);
         IQ_TICK(0);
-        // ---- 2. the group's missed points, every one on its own thread
         const u32 mm = __ballot_sync(FULL, miss);
         if (mm) {
-            const MapView M = map_view(L);
-            NearestOut R;
-            thread_nearest(M, s_ids[warp], s_lbs[warp], lane, miss, sx, sy, sz, max_d2, R);
-            if (miss) {
-                tx = R.tx; ty = R.ty; tz = R.tz; ord = R.ord;
-                __stcg(L.c_tx + p, tx); __stcg(L.c_ty + p, ty); __stcg(L.c_tz + p, tz);
-#pragma unroll
-                for (int j = 0; j < ICP_KX; ++j) {
-                    __stcg(L.c_t2 + (size_t)(3 * j) * cap + p, R.t2[3 * j]);
-                    __stcg(L.c_t2 + (size_t)(3 * j + 1) * cap + p, R.t2[3 * j + 1]);
-                    __stcg(L.c_t2 + (size_t)(3 * j + 2) * cap + p, R.t2[3 * j + 2]);
-                    __stcg(L.c_ord2 + (size_t)j * cap + p, R.ord2[j]);
-                }
-                __stcg(L.c_px + p, sx); __stcg(L.c_py + p, sy); __stcg(L.c_pz + p, sz);
-                __stcg(L.c_slack + p, R.others);
-                __stcg(L.c_key + p, R.qkey);
-                __stcg(L.c_ord + p, ord);
-            }
+            const double max_corr = P.max_corr;
+            icp_task_search(L, ws, g, lane, miss, (max_corr * max_corr) * (1.0 + 1e-9));   // farther candidates are rejected anyway
             if (lane == 0) atomicAdd(&L.icp_searches, __popc(mm));
         }
         IQ_TICK(1);
-        icp_group_sums(L, P, O, Q, ws, lane_id, g, it, n_groups, n_lanes, total_warps, lane, live, sx, sy, sz, tx, ty, tz, ord);
+        const bool last = icp_task_sums(L, P, ws, g, it, lane);
         IQ_TICK(2);
+        if (last) icp_lane_solve(L, P, outs[lane_id], Q, ws, lane_id, it, (L.n_src + 31) >> 5, n_lanes, total_warps, lane);
     }
     // ---- the last warp to leave rewinds the ring for the next launch
     if (lane == 0) {
-        __threadfence();
-        const u32 gone = atomicAdd(&Q->exited, 1u) + 1u;
+        const u32 gone = atom_add_acq_rel_u32(&Q->exited, 1u) + 1u;
         if (gone == (u32)total_warps) {
             Q->head = 0; Q->tail = 0; Q->lanes_done = 0; Q->exited = 0;
         }

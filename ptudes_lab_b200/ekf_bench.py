@@ -64,11 +64,22 @@ class SynthLidarImuSource:
         return [T0i @ t for t in T]
 
 
+def reduce_active_beams(ls, beams_num: int) -> None:
+    """utils.py:328-341: keep `beams_num` uniformly spread beams (rows) of a lidar scan by zeroing the RANGE of
+    all the others.  On the CUDA path a zeroed pixel is simply a pixel without return (kiss.py:59), so the row
+    mask costs nothing beyond this host-side write."""
+    from .ouster_compat import ChanField
+    beam_idxs = np.linspace(0, ls.h, num=beams_num, endpoint=False, dtype=int)
+    clean_mask = np.ones(ls.h, dtype=bool)
+    clean_mask[beam_idxs] = 0
+    ls.field(ChanField.RANGE)[clean_mask, :] = 0
+
+
 def run_ekf_ouster(data_source, kiss_icp, ekf: Optional[ESEKF] = None, *, use_imu_prediction: bool = False,
-                   gt_guess=None, start_scan: int = 0, end_scan: Optional[int] = None):
+                   gt_guess=None, start_scan: int = 0, end_scan: Optional[int] = None, beams: int = 0):
     """The scan/IMU loop of ptudes_ekf_ouster (cli/ekf_bench.py:493-563).
 
-    `kiss_icp` is anything with the KissICPWrapper surface (`register_frame(scan, initial_guess=)`,
+    `beams` is the --beams option (:364-368,526-527).  `kiss_icp` is anything with the KissICPWrapper surface (`register_frame(scan, initial_guess=)`,
     `.pose`, `._kiss.poses`, `._kiss.get_prediction_model()`); `gt_guess(ts) -> 4x4` stands in for the
     --use-gt-guess TrajectoryEvaluator (:536-542).  Returns the lists the CLI collects plus the
     per-stage mean timings it prints (:590-595)."""
@@ -91,6 +102,8 @@ def run_ekf_ouster(data_source, kiss_icp, ekf: Optional[ESEKF] = None, *, use_im
             continue
         imus_per_scan = 0
         ls = d
+        if beams:                                                                # :526-527
+            reduce_active_beams(ls, beams)
         ts = last_valid_column_ts(ls) * 1e-09
         if use_imu_prediction:                                                   # :533-535
             pose_guess = ekf.nav.pose_mat()
@@ -132,3 +145,64 @@ def load_poses_kitti_format(filename: str):
     out = np.tile(np.eye(4), (rows.shape[0], 1, 1))
     out[:, :3, :] = rows.reshape(-1, 3, 4)
     return list(out)
+
+
+# ---- the Newer College ground-truth format ekf-bench also writes and `ekf-bench cmp` reads (utils.py:199-252)
+# newer_college_2021/os_imu_lidar_transforms.yaml, as utils.py:20-26 states them
+NC_OS_IMU_TO_OS_SENSOR = np.eye(4)
+NC_OS_IMU_TO_OS_SENSOR[:3, 3] = [-0.014, 0.012, 0.015]
+NC_OS_SENSOR_TO_BASE = np.eye(4)
+NC_OS_SENSOR_TO_BASE[:3, 3] = [0.001, 0.000, 0.091]
+NC_OS_IMU_TO_BASE = NC_OS_SENSOR_TO_BASE @ NC_OS_IMU_TO_OS_SENSOR
+
+
+def save_poses_nc_gt_format(filename: str, t, poses, header: str = "") -> None:
+    """utils.py:199-228: `sec, nsec, x, y, z, qx, qy, qz, qw` per pose, poses moved from the IMU (nav) frame to
+    the BASE frame on the way out (read_newer_college_gt undoes it)."""
+    from scipy.spatial.transform import Rotation
+    t_arr = np.asarray(t, dtype=np.float64)
+    poses_arr = np.asarray(poses, dtype=np.float64).reshape(-1, 4, 4)
+    poses_arr = np.einsum("nij,jk->nik", poses_arr, np.linalg.inv(NC_OS_IMU_TO_BASE))
+    res = np.zeros((len(t_arr), 9))
+    res[:, 0] = np.floor(t_arr)
+    res[:, 1] = np.floor((t_arr - res[:, 0]) * 1e+9)
+    res[:, 2:5] = poses_arr[:, :3, 3]
+    res[:, 5:9] = Rotation.from_matrix(poses_arr[:, :3, :3]).as_quat()
+    if header:
+        header += "\n\n" + "sec,nsec,x,y,z,qx,qy,qz,qw"
+    np.savetxt(fname=filename, X=res, delimiter=", ", header=header)
+
+
+def read_newer_college_gt(data_path: str, to_os_imu: bool = True):
+    """utils.py:231-252: [(ts, pose4x4)] with the poses in the Ouster IMU nav frame (to_os_imu)."""
+    from scipy.spatial.transform import Rotation
+    gt = np.loadtxt(data_path, delimiter=",").reshape(-1, 9)
+    ts = gt[:, 0] + gt[:, 1] * 1e-9
+    pos = np.tile(np.eye(4), reps=(gt.shape[0], 1, 1))
+    pos[:, :3, 3] = gt[:, 2:5]
+    pos[:, :3, :3] = Rotation.from_quat(gt[:, 5:9]).as_matrix()
+    if to_os_imu:
+        pos = np.einsum("nij,jk->nik", pos, NC_OS_IMU_TO_BASE)
+    return [(float(a), p) for a, p in zip(ts, pos)]
+
+
+def calc_ate_fleet(est, gt, device=None):
+    """calc_ate (ins/data.py:124-153) for a whole fleet at once: `est`, `gt` (S, T, 4, 4) trajectories of S
+    sequences -> (ate_rot (S,), ate_trans (S,)), the reference's definition (first poses aligned, mean of the
+    SQUARED errors, rotation term * 180/pi).  Runs as batched torch ops on `device` (the GPU of the rank when the
+    trajectories of a fleet replay live there); float64 throughout."""
+    import torch
+    A = torch.as_tensor(np.asarray(est) if not torch.is_tensor(est) else est, dtype=torch.float64, device=device)
+    G = torch.as_tensor(np.asarray(gt) if not torch.is_tensor(gt) else gt, dtype=torch.float64, device=device)
+    assert A.shape == G.shape and A.dim() == 4 and A.shape[1] > 0
+    align = A[:, 0] @ torch.linalg.inv(G[:, 0])                     # (S,4,4)
+    G = align[:, None] @ G
+    dt = torch.linalg.norm(G[..., :3, 3] - A[..., :3, 3], dim=-1)   # (S,T)
+    R = A[..., :3, :3].transpose(-1, -2) @ G[..., :3, :3]
+    cosang = ((R[..., 0, 0] + R[..., 1, 1] + R[..., 2, 2]) - 1.0) * 0.5
+    # |rotvec| = angle; atan2 of the skew part keeps precision for the tiny angles an ATE is made of
+    sk = torch.stack([R[..., 2, 1] - R[..., 1, 2], R[..., 0, 2] - R[..., 2, 0], R[..., 1, 0] - R[..., 0, 1]], dim=-1)
+    ang = torch.atan2(0.5 * torch.linalg.norm(sk, dim=-1), cosang)
+    ate_r = (ang * ang).mean(dim=1) * (180.0 / np.pi)
+    ate_t = (dt * dt).mean(dim=1)
+    return ate_r.cpu().numpy(), ate_t.cpu().numpy()

@@ -33,11 +33,6 @@ class _Compensator:
         return self._odo.deskew_scan(frame, timestamps, poses[-2], poses[-1])
 
 
-class _AdaptiveThresholdView:
-    def __init__(self, kiss):
-        self._kiss = kiss
-
-
 class _Kiss:
     """The members of kiss_icp.kiss_icp.KissICP that ptudes reads through `wrapper._kiss`."""
 

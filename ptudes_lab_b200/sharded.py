@@ -139,6 +139,7 @@ class ShardedOdometry:
         # the pose on its last iteration
         self.max_iterations = max_iterations if max_iterations is not None else int(getattr(backend, "max_iterations", 500))
         self.collectives = 0
+        self.scans = 0
 
     def _all_gather(self, rec):
         if self.world == 1:
@@ -154,7 +155,19 @@ class ShardedOdometry:
             self.collectives += 1
         return t
 
+    def describe(self):
+        """What the exchange is and how much of it there was (for bench.py's sharded line)."""
+        return {"exchange": "host-driven loop: NCCL all-gather of the per-point records + all-reduce of the [17][32] "
+                            "partial table per ICP iteration",
+                "collectives_per_scan": self.collectives / max(self.scans, 1)}
+
+    def close(self):
+        odo = getattr(self.b, "odo", None)
+        if odo is not None:
+            odo.close()
+
     def register_frame(self, frame, timestamps, initial_guess=None, range_mm=None):
+        self.scans += 1
         n_src, n_vox_local = self.b.begin(frame, timestamps, initial_guess, range_mm=range_mm)
         total_vox = int(self._all_reduce(torch.tensor([n_vox_local], dtype=torch.int64, device=self.b.device)).item())
         if total_vox == 0:                       # RegisterFrame: empty map -> the guess
@@ -168,3 +181,13 @@ class ShardedOdometry:
             if self.b.solve(part, it):
                 break
         return self.b.end()
+
+
+def make_sharded(cfg, device: int, rank: int, world: int, *, max_points: int, map_capacity: int, dirs=None, group=None):
+    """One rank's share of a hash-sharded single-sequence odometry: its own context (the local map holds only
+    the voxels this rank owns) behind the sharded loop.  `dirs`: XYZLut directions for range-image input."""
+    from . import odometry
+    odo = odometry.Odometry(cfg, device=device, max_points=max_points, map_capacity=map_capacity)
+    if dirs is not None:
+        odo.set_sensor(dirs)
+    return ShardedOdometry(PtkShardBackend(odo, rank, world), group=group)

@@ -114,3 +114,71 @@ def test_loop_with_the_native_filter_matches_the_python_one(tiny_seq):
     assert np.abs(np.array(a["res_poses"]) - np.array(b["res_poses"])).max() < 1e-6
     assert np.abs(np.array(a["kiss_poses"]) - np.array(b["kiss_poses"])).max() < 1e-6
     assert a["res_t"] == b["res_t"]
+
+
+def test_nc_gt_pose_file_round_trip(tmp_path):
+    """save_poses_nc_gt_format / read_newer_college_gt (utils.py:199-252): sec, nsec, xyz, quaternion per pose;
+    the writer moves the poses from the IMU frame to BASE, the reader moves them back."""
+    from ptudes_lab_b200.ekf_bench import NC_OS_IMU_TO_BASE, read_newer_college_gt, save_poses_nc_gt_format
+    from oracle import canon
+    rng = np.random.default_rng(3)
+    poses = [canon.se3_exp_mat(rng.normal(0, 0.7, 6)) for _ in range(6)]
+    ts = [1600000000.25 + 0.1 * k for k in range(6)]
+    f = str(tmp_path / "nc_gt.csv")
+    save_poses_nc_gt_format(f, ts, poses, header="ptk traj")
+    back = read_newer_college_gt(f)
+    assert len(back) == 6
+    for (t, p), t0, p0 in zip(back, ts, poses):
+        assert abs(t - t0) < 2e-6                           # nsec column is floor((t - sec) * 1e9) of a double
+        assert np.abs(p - p0).max() < 1e-12
+    raw = np.loadtxt(f, delimiter=",")
+    assert raw.shape == (6, 9) and raw[0, 0] == 1600000000.0
+    in_base = read_newer_college_gt(f, to_os_imu=False)
+    assert np.abs(in_base[2][1] @ NC_OS_IMU_TO_BASE - poses[2]).max() < 1e-12
+    head = open(f).read().splitlines()
+    assert head[0] == "# ptk traj" and head[2] == "# sec,nsec,x,y,z,qx,qy,qz,qw"
+
+
+def test_reduce_active_beams_and_the_beams_option(tiny_seq):
+    """utils.py:328-341 / cli/ekf_bench.py:526-527: --beams N keeps N uniformly spread rows, the rest lose their
+    RANGE; under the loop the odometry then sees only those beams."""
+    from ptudes_lab_b200.ekf_bench import reduce_active_beams
+    src = SynthLidarImuSource(tiny_seq, 1)
+    ls = [d for _, d in src.withScanIdx() if not isinstance(d, IMU)][0]
+    before = ls.field(ChanField.RANGE).copy()
+    reduce_active_beams(ls, 4)
+    after = ls.field(ChanField.RANGE)
+    keep = np.linspace(0, ls.h, num=4, endpoint=False, dtype=int)
+    assert np.array_equal(after[keep], before[keep])
+    mask = np.ones(ls.h, bool)
+    mask[keep] = False
+    assert not after[mask].any()
+    meta = sensor_info_from_synth(tiny_seq.sensor, tiny_seq.dirs)
+    full = run_ekf_ouster(SynthLidarImuSource(tiny_seq, 4), OracleWrapper(meta))
+    half = run_ekf_ouster(SynthLidarImuSource(tiny_seq, 4), OracleWrapper(meta), beams=tiny_seq.sensor.H // 2)
+    assert len(half["kiss_poses"]) == 4 and not np.array_equal(np.array(full["kiss_poses"]), np.array(half["kiss_poses"]))
+
+
+def test_fleet_ate_equals_the_reference_definition():
+    """calc_ate_fleet: calc_ate (ins/data.py:124-153) over S trajectories in one batched call."""
+    from ptudes_lab_b200.ekf_bench import calc_ate_fleet
+    from oracle import canon
+    rng = np.random.default_rng(5)
+    S, T = 5, 12
+    gt = np.array([[canon.se3_exp_mat(np.r_[0.1 * t, 0.02 * s, 0, 0, 0, 0.03 * t]) for t in range(T)] for s in range(S)])
+    est = np.array([[g @ canon.se3_exp_mat(rng.normal(0, 1e-3 * (s + 1), 6)) for g in row] for s, row in enumerate(gt)])
+    r, t = calc_ate_fleet(est, gt)
+    for s in range(S):
+        rr, tt = calc_ate(list(est[s]), list(gt[s]))
+        assert abs(r[s] - rr) <= 1e-9 * max(rr, 1e-12) + 1e-15 and abs(t[s] - tt) <= 1e-12 * max(tt, 1e-12) + 1e-18
+
+
+@pytest.mark.gpu
+def test_beams_option_on_the_cuda_wrapper():
+    """--beams through the CUDA wrapper: zeroed rows are pixels without return, poses equal the oracle's."""
+    from ptudes_lab_b200.kiss import KissICPWrapper
+    seq = synth.make_sequence("tiny", 0)
+    meta = sensor_info_from_synth(seq.sensor, seq.dirs)
+    a = run_ekf_ouster(SynthLidarImuSource(seq, 5), KissICPWrapper(meta, _min_range=1, _max_range=70), beams=seq.sensor.H // 2)
+    b = run_ekf_ouster(SynthLidarImuSource(seq, 5), OracleWrapper(meta), beams=seq.sensor.H // 2)
+    assert np.array_equal(np.array(a["kiss_poses"]), np.array(b["kiss_poses"]))
