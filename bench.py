@@ -625,7 +625,7 @@ def run_ptk(args):
     searches = sum(st["icp_searches"] for ss in stats_acc for st in ss)
     out["icp"] = {"nn_queries": int(queries), "full_searches": int(searches),
                   "cache_hit_rate": 1.0 - searches / max(queries, 1),
-                  "warp_cycles_profiled_pass": icp_phase_cycles}
+                  "block0_phase_cycles_last_scan": icp_phase_cycles}
 
     if rank == 0:
         time.sleep(0.2)

@@ -52,10 +52,11 @@ struct LaneHost {
 }  // namespace
 
 enum ProfSlot { PS_SCAN_INSERT = 0, PS_COMPACT1, PS_COMPACT2, PS_ICP, PS_MAP_INSERT, PS_MAP_COMMIT, PS_MAP_PRUNE,
-                PS_FINISH, PS_REBUILD, PS_OTHER, PS_COL_MOTION, PS_COUNT };
+                PS_FINISH, PS_REBUILD, PS_OTHER, PS_COL_MOTION, PS_SEARCH0, PS_COUNT };
 static_assert(PS_COUNT <= PTK_PROF_SLOTS, "profile slots");
 static const char* const kProfNames[PS_COUNT] = {"k_scan_insert", "k_compact1", "k_compact2", "k_icp", "k_map_insert",
-                                                 "k_map_commit", "k_map_prune", "k_finish", "k_map_rebuild", "other", "k_col_motion"};
+                                                 "k_map_commit", "k_map_prune", "k_finish", "k_map_rebuild", "other", "k_col_motion",
+                                                 "k_icp_search0"};
 
 struct Prof {
     bool on = false;
@@ -94,9 +95,10 @@ struct ptk_ctx {
     cudaEvent_t pf_event = nullptr;
     std::vector<const unsigned int*> pf_pending;   // host images to copy during the next step
     int num_sms = 148;
-    int icp_blocks_total = 148;       // blocks of k_icp the device holds at once (occupancy x SMs)
-    IcpQueue* d_icp_queue = nullptr;  // task ring of the ICP dataflow kernel
-    int icp_prof = 0;                 // accumulate warp cycles per ICP phase (ptk_set_profiling)
+    int icp_blocks_total = 148;
+    int icp_max_blocks_per_lane = 1 << 20;   // PTK_ICP_MAX_BLOCKS_PER_LANE: fewer blocks = cheaper barrier, slower searches
+    int icp_cluster = 0;              // blocks per lane of the cluster launch of wide batches (0: not available)
+    int icp_cluster_min_lanes = 56;   // batch width from which the cluster launch is used
     std::string err;
     std::vector<void*> allocs;
 };
@@ -236,6 +238,7 @@ static int lane_alloc(ptk_ctx* ctx, LaneHost& LH, bool scratch) {
     CK(dalloc(A, &d.s_idx, N, 0));
     CK(dalloc(A, &d.m_slots, mcap, 0xFF));
     CK(dalloc(A, &d.blocks, (size_t)d.pool_cap, 0));
+    CK(dalloc(A, &d.vmeta, (size_t)d.pool_cap, 0));
     CK(dalloc(A, &d.vidx, (size_t)d.pool_cap * MAXP, 0xFF));
     CK(dalloc(A, &d.freelist, (size_t)d.pool_cap, 0));
     CK(dalloc(A, &d.part_a, (size_t)NRED * d.ng_cap, 0));
@@ -289,12 +292,32 @@ extern "C" int ptk_ctx_create(ptk_ctx** out, int device, const ptk_config* cfg_i
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; return bail(PTK_E_CUDA); }
     ctx->num_sms = prop.multiProcessorCount;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, IQ_THREADS, 0) != cudaSuccess || occ < 1) {
+    if (cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, ICP_THREADS, ICP_SMEM) != cudaSuccess || occ < 1) {
         ctx->err = std::string("k_icp not launchable on this device: ") + cudaGetErrorString(cudaGetLastError());
         return bail(PTK_E_CUDA);
     }
     ctx->icp_blocks_total = occ * ctx->num_sms;
-    if (const char* mb = getenv("PTK_ICP_MAX_BLOCKS")) ctx->icp_blocks_total = std::max(1, std::min(ctx->icp_blocks_total, atoi(mb)));
+    {   // cluster size for wide batches: PTK_ICP_CLUSTER (1 disables), default 8 = the portable maximum
+        if (const char* mb = getenv("PTK_ICP_MAX_BLOCKS_PER_LANE")) ctx->icp_max_blocks_per_lane = std::max(1, atoi(mb));
+        const char* e = getenv("PTK_ICP_CLUSTER");
+        int want = e ? atoi(e) : 8;
+        if (const char* m = getenv("PTK_ICP_CLUSTER_MIN_LANES")) ctx->icp_cluster_min_lanes = atoi(m);
+        ctx->icp_cluster = 0;
+        if (want > 8 && cudaFuncSetAttribute(k_icp, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) want = 8;
+        if (want > 1) {
+            cudaLaunchConfig_t qc;
+            memset(&qc, 0, sizeof(qc));
+            qc.gridDim = dim3(want, 1); qc.blockDim = dim3(ICP_THREADS); qc.dynamicSmemBytes = ICP_SMEM;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = want; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, k_icp, &qc) == cudaSuccess && ncl >= 1) ctx->icp_cluster = want;
+        }
+        cudaGetLastError();
+    }
     ctx->lanes.resize(ctx->B + 1);
     for (int l = 0; l <= ctx->B; ++l) {
         int rc = lane_alloc(ctx, ctx->lanes[l], l == ctx->B);
@@ -308,7 +331,6 @@ extern "C" int ptk_ctx_create(ptk_ctx** out, int device, const ptk_config* cfg_i
     if (!ck(dalloc(ctx->allocs, &ctx->d_lanes, nl), "alloc lanes")) return bail(PTK_E_CUDA);
     if (!ck(dalloc(ctx->allocs, &ctx->d_params, nl, 0), "alloc params")) return bail(PTK_E_CUDA);
     if (!ck(dalloc(ctx->allocs, &ctx->d_outs, nl, 0), "alloc outs")) return bail(PTK_E_CUDA);
-    if (!ck(dalloc(ctx->allocs, &ctx->d_icp_queue, 1, 0), "alloc icp queue")) return bail(PTK_E_CUDA);
     if (!ck(dalloc(ctx->allocs, &ctx->d_tmp, (size_t)cfg.max_points * 3 + 64), "alloc tmp")) return bail(PTK_E_CUDA);
     if (!ck(dalloc(ctx->allocs, &ctx->d_tmp_i, (size_t)cfg.max_points + 64, 0), "alloc tmp_i")) return bail(PTK_E_CUDA);
     if (!ck(cudaMallocHost((void**)&ctx->h_params, sizeof(StepParams) * nl), "pinned params")) return bail(PTK_E_CUDA);
@@ -350,6 +372,7 @@ static int lane_reset_device(ptk_ctx* ctx, int l, cudaStream_t st, bool tables) 
     LaneDev& d = LH.d;
     CK(cudaMemsetAsync(d.m_slots, 0xFF, ((size_t)d.m_mask + 1) * sizeof(MapSlot), st));
     CK(cudaMemsetAsync(d.blocks, 0, (size_t)d.pool_cap * sizeof(VoxelBlock), st));
+    CK(cudaMemsetAsync(d.vmeta, 0, (size_t)d.pool_cap * sizeof(VoxelMeta), st));
     CK(cudaMemsetAsync(d.vidx, 0xFF, (size_t)d.pool_cap * MAXP * sizeof(u32), st));
     if (tables) {
         size_t tcap = (size_t)d.t_mask + 1;
@@ -438,25 +461,60 @@ static Rigid prediction_model(const LaneHost& LH) {
 }
 
 // ---- kernel launch helpers -----------------------------------------------------------
-// One launch of the ICP dataflow kernel for lanes [l0, l0+cnt).  `groups_hint`: upper estimate of the 32-point
-// source groups per lane (0 = unknown).  The grid is sized to the work (idle warps only poll the ring) and never
-// exceeds what the device holds at once; the kernel itself does not depend on co-residency.
+// `groups_hint`: upper estimate of the 32-point source groups per lane (0 = unknown); blocks beyond
+// one per group would only add arrivals to the per-iteration barrier.
 static int launch_icp(ptk_ctx* ctx, int l0, int cnt, int groups_hint, cudaStream_t st) {
-    const int max_groups = (ctx->cfg.max_points + 31) / 32;
-    const int groups = groups_hint > 0 ? std::min(groups_hint, max_groups) : max_groups;
-    const int warps_cap = ctx->icp_blocks_total * IQ_WARPS;
+    {   // iteration 0's searches: every source point of every lane, one thread each (k_icp_search0)
+        const int max_groups = (ctx->cfg.max_points + 31) / 32;
+        const int groups = groups_hint > 0 ? std::min(groups_hint, max_groups) : max_groups;
+        const int wpb = S0_THREADS / 32;
+        int gx = std::max(1, std::min((groups + wpb - 1) / wpb, std::max(1, (ctx->num_sms * 16) / cnt)));
+        LAUNCH(PS_SEARCH0, st, k_icp_search0<<<dim3(gx, cnt), S0_THREADS, 0, st>>>(ctx->d_lanes + l0, ctx->d_params + l0));
+        CK(cudaGetLastError());
+    }
+    // Wide batches: one THREAD-BLOCK CLUSTER per lane.  The only thing the lane's blocks need from each other
+    // is to be running at the same time (their per-iteration barrier spins on a counter), which is exactly
+    // what a cluster guarantees - so the launch needs no grid-wide co-residency, the grid may hold more
+    // clusters than fit at once, and the lanes that converge early (iterations per scan vary 2-4x between
+    // lanes) hand their SMs to queued lanes instead of leaving them idle until the slowest lane ends.
+    // (measured: pays off from ~56 lanes on - 64 lanes 19.7k -> 21.1k scans/s; at 48 the cooperative launch is faster)
+    if (ctx->icp_cluster > 1 && cnt >= ctx->icp_cluster_min_lanes) {
+        int cl = ctx->icp_cluster;
+        if (groups_hint > 0) while (cl > 1 && cl / 2 >= groups_hint) cl /= 2;
+        LaneDev* dl = ctx->d_lanes + l0;
+        const StepParams* dp = ctx->d_params + l0;
+        StepOut* dout = ctx->d_outs + l0;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(cl, cnt);
+        cfg.blockDim = dim3(ICP_THREADS);
+        cfg.dynamicSmemBytes = ICP_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaSuccess;
+        LAUNCH(PS_ICP, st, le = cudaLaunchKernelEx(&cfg, k_icp, dl, dp, dout));
+        CK(le);
+        return PTK_OK;
+    }
+    // Few lanes: a cooperative launch with as many blocks per lane as the device holds
+    // (all blocks of a cooperative launch must be co-resident: split wide batches)
     int done = 0;
     while (done < cnt) {
-        // a lane whose publishing warp waits on a full ring occupies one warp: keep lanes well below the warps
-        const int chunk = std::min(cnt - done, std::max(1, warps_cap / 4));
-        const long long total_groups = (long long)groups * chunk;
-        long long want_warps = total_groups;
-        int blocks = (int)std::min<long long>(ctx->icp_blocks_total, (want_warps + IQ_WARPS - 1) / IQ_WARPS);
-        blocks = std::max(blocks, std::min(ctx->icp_blocks_total, (chunk + IQ_WARPS - 1) / IQ_WARPS));
-        blocks = std::max(blocks, 1);
-        LAUNCH(PS_ICP, st, k_icp<<<blocks, IQ_THREADS, 0, st>>>(ctx->d_lanes + l0 + done, ctx->d_params + l0 + done,
-                                                               ctx->d_outs + l0 + done, chunk, ctx->d_icp_queue));
-        CK(cudaGetLastError());
+        int chunk = std::min(cnt - done, ctx->icp_blocks_total);
+        int per = std::max(1, ctx->icp_blocks_total / chunk);
+        if (groups_hint > 0) per = std::max(1, std::min(per, groups_hint));
+        per = std::min(per, ctx->icp_max_blocks_per_lane);
+        LaneDev* dl = ctx->d_lanes + l0 + done;
+        StepParams* dp = ctx->d_params + l0 + done;
+        StepOut* dout = ctx->d_outs + l0 + done;
+        void* args[] = {&dl, &dp, &dout};
+        cudaError_t le = cudaSuccess;
+        LAUNCH(PS_ICP, st, le = cudaLaunchCooperativeKernel((void*)k_icp, dim3(per, chunk), dim3(ICP_THREADS), args, ICP_SMEM, st));
+        CK(le);
         done += chunk;
     }
     return PTK_OK;
@@ -554,6 +612,12 @@ static int step_prepare(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz,
         } else {                                                                                // kiss.py:102-105
             Rigid last = np ? LH.poses.back() : rigid_identity();
             P.guess = rigid_mul(last, prediction_model(LH));
+        }
+        if (LH.have_last && LH.last_out.n_ds > 0) {
+            // the scan tables' front regions: four slots per key the previous scan put there (at least 4096)
+            u32 c1 = next_pow2((u32)std::max(4096, 4 * LH.last_out.n_ds)), c2 = next_pow2((u32)std::max(4096, 4 * LH.last_out.n_src));
+            P.near1 = c1 <= LH.d.t_mask / 2 ? c1 - 1 : 0;
+            P.near2 = c2 <= LH.d.t_mask / 2 ? c2 - 1 : 0;
         }
         P.max_corr = 3 * sigma;                                                                 // kiss.py:112-113
         P.kernel = sigma / 3;
@@ -700,9 +764,20 @@ extern "C" int ptk_set_sensor(ptk_ctx* ctx, int H, int W, const double* directio
         CK(cudaMemcpy(*dst, src, count * sizeof(double), is_device_ptr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
         return PTK_OK;
     };
-    int rc = up(&ctx->d_lut_dir, direction, np * 3);
+    // (H*W,3) tables of the caller -> three planes on the device (coalesced loads in the scan kernels)
+    auto up_planes = [&](double** dst, const double* src) -> int {
+        std::vector<double> aos(np * 3), soa(np * 3);
+        if (is_device_ptr(src)) CK(cudaMemcpy(aos.data(), src, np * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        else memcpy(aos.data(), src, np * 3 * sizeof(double));
+        for (size_t i = 0; i < np; ++i)
+            for (int c = 0; c < 3; ++c) soa[(size_t)c * np + i] = aos[3 * i + c];
+        CK(dalloc(ctx->sensor_allocs, dst, np * 3));
+        CK(cudaMemcpy(*dst, soa.data(), np * 3 * sizeof(double), cudaMemcpyHostToDevice));
+        return PTK_OK;
+    };
+    int rc = up_planes(&ctx->d_lut_dir, direction);
     if (rc) return rc;
-    if (offset && (rc = up(&ctx->d_lut_off, offset, np * 3))) return rc;
+    if (offset && (rc = up_planes(&ctx->d_lut_off, offset))) return rc;
     std::vector<double> cts;
     if (!col_timestamps) {      // np.linspace(0, 1.0, w, endpoint=False) (kiss.py:34)
         cts.resize(W);
@@ -1284,13 +1359,9 @@ extern "C" int ptk_shard_end(ptk_ctx* ctx, int lane, double* out_pose, ptk_stats
 
 extern "C" int ptk_get_icp_phases(const ptk_ctx* ctx, int lane, long long* cycles6) {
     if (!ctx || lane < 0 || lane >= ctx->B || !cycles6) return PTK_E_ARG;
-    if (cudaSetDevice(ctx->device) != cudaSuccess) return PTK_E_CUDA;
-    unsigned long long c[8];
-    if (cudaMemcpy(c, (const char*)ctx->d_icp_queue + offsetof(IcpQueue, cyc), sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) {
-        cudaGetLastError();
-        return PTK_E_CUDA;
-    }
-    for (int k = 0; k < 6; ++k) cycles6[k] = (long long)c[k];
+    const LaneHost& LH = ctx->lanes[lane];
+    if (!LH.have_last) return PTK_E_STATE;
+    for (int k = 0; k < 6; ++k) cycles6[k] = LH.last_out.icp_cyc[k];
     return PTK_OK;
 }
 
@@ -1300,12 +1371,6 @@ extern "C" int ptk_set_profiling(ptk_ctx* ctx, int on) {
     CK(cudaDeviceSynchronize());
     prof_collect(ctx);
     ctx->prof.on = on != 0;
-    {   // ICP phase accounting (warp cycles summed over the device) follows the profiling switch; reset on every call
-        u32 flag = on ? 1u : 0u;
-        unsigned long long zero[8] = {0};
-        CK(cudaMemcpy((char*)ctx->d_icp_queue + offsetof(IcpQueue, prof), &flag, sizeof(flag), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy((char*)ctx->d_icp_queue + offsetof(IcpQueue, cyc), zero, sizeof(zero), cudaMemcpyHostToDevice));
-    }
     for (int k = 0; k < PTK_PROF_SLOTS; ++k) { ctx->prof.ms[k] = 0.0; ctx->prof.n[k] = 0; }
     return PTK_OK;
 }

@@ -27,28 +27,45 @@ constexpr int KEY_BIAS = 1 << 20;
 constexpr int TILE = 1024;                 // items per compaction tile (256 threads x 4)
 constexpr int NSUM = 17;                   // distinct normal-equation sums (16) + correspondence count
 constexpr int NRED = NSUM;
-constexpr int ICP_THREADS = 512;            // block size of the sharded-mode system kernel (one warp per 32-point group)
+#ifndef PTK_ICP_THREADS
+#define PTK_ICP_THREADS 512
+#endif
+#ifndef PTK_ICP_MINBLOCKS
+#define PTK_ICP_MINBLOCKS 2
+#endif
+constexpr int ICP_THREADS = PTK_ICP_THREADS;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
+constexpr int ICP_CHUNK = ICP_WARPS;        // 32-point groups a block handles at a time: one point per thread
 #ifndef PTK_ICP_KX
 #define PTK_ICP_KX 2
 #endif
 constexpr int ICP_KX = PTK_ICP_KX;          // runner-ups a correspondence cache entry keeps beside the winner
+constexpr int ICP_SRC_CAP = ICP_KX <= 1 ? 768 : (ICP_KX == 2 ? 640 : 512);   // source points (+ cache entries) per block in smem
+constexpr int ICP_SMEM = ICP_SRC_CAP * (3 * 8 + 4 * 8 + 8 + 3 * 8 + ICP_KX * (3 * 8 + 4) + 4) + 8;
 
 enum StepFlags : int { F_DESKEW = 1, F_RANGE = 2, F_SECOND = 4, F_SELECT_RANGE = 8 };
 enum ErrFlags : int { ERR_KEYRANGE = 1, ERR_POOL = 2, ERR_TABLE = 4 };
 
-// One voxel of the local map: 20 points SoA + header, 512 B, 16 B aligned so rows of x/y/z can
-// be read with vector loads.  `count` is the number of valid points.
+// One voxel of the local map: 20 points SoA, 512 B, 16 B aligned so rows of x/y/z can be read with vector
+// loads.  Unused slots hold +inf (the searches need no count).
 struct __align__(16) VoxelBlock {
     double x[MAXP];
     double y[MAXP];
     double z[MAXP];
-    u32 count;
-    u32 slot;   // index of this voxel's entry in the map table
     u64 key;
-    u32 pad[4];
+    u32 pad[6];
 };
 static_assert(sizeof(VoxelBlock) == 512, "VoxelBlock must be 512 B");
+
+// What map maintenance needs of a voxel, 32 B beside the block pool: its first point (RemovePointsFarFromLocation
+// tests that one), the number of valid points and the voxel's table slot.  The prune pass streams this array - one
+// sector per voxel - instead of touching four sectors of every 512 B block.
+struct __align__(32) VoxelMeta {
+    double fx, fy, fz;
+    u32 count;
+    u32 slot;
+};
+static_assert(sizeof(VoxelMeta) == 32, "VoxelMeta must be 32 B");
 
 struct __align__(16) MapSlot {
     u64 key;
@@ -72,13 +89,14 @@ struct StepParams {
     double kernel;
     u32 epoch;             // step counter, >= 1
     u32 tbase1, tbase2;    // ticket bases of the two compaction kernels
-    u32 release_base;      // icp barrier epoch base
+    u32 release_base;      // (unused)
+    u32 near1, near2;      // masks of the front regions of the two scan tables (0: whole table), see table_insert_min
     int W;                 // range-image mode: columns per frame (n = H * W pixels)
     // range-image input (kiss.py:59-61 on the device): non-null `range` selects it
     const u32* range;      // (H*W) RANGE field in millimetres, 0 = no return
     double range_unit;     // metres per RANGE count the direction LUT expects (0.001, or 1 if pre-scaled)
-    const double* lut_dir; // (H*W,3) XYZLut direction
-    const double* lut_off; // (H*W,3) XYZLut offset or null
+    const double* lut_dir; // [3][H*W] XYZLut direction, one plane per coordinate
+    const double* lut_off; // [3][H*W] XYZLut offset or null
     const double* col_ts;  // (W) normalised column timestamps (kiss.py:34-35)
     double* col_motion;    // [12][W] deskew motion of every column, written by k_col_motion
 };
@@ -88,6 +106,7 @@ struct StepOut {
     double dx_norm;
     int status, n_range, n_ds, n_src, n_vox, n_tomb, iterations, n_corr, map_points, err, bump, icp_searches;
     int n_valid, pad;
+    long long icp_cyc[6];      // block 0's clock64 spent in: cache pass, searches, sums, barrier, tree, solve
 };
 
 // Per-sequence ("lane") device state.
@@ -112,6 +131,7 @@ struct LaneDev {
     u32* s_idx;
     // local map
     MapSlot* m_slots;
+    VoxelMeta* vmeta;                    // [pool_cap] first point, count, table slot of every voxel block
     VoxelBlock* blocks;
     u32* vidx;                           // [pool_cap*MAXP] insertion scratch, NONE when idle
     u32* freelist;
@@ -189,8 +209,17 @@ __device__ __forceinline__ void voxel_key(double x, double y, double z, double s
 }
 
 // First-seen table: find-or-insert `key`, keep the minimum `val`; returns the slot.
-__device__ __forceinline__ u32 table_insert_min(u64* keys, u32* vals, u32 mask, u64 key, u32 val) {
-    u32 slot = hash_key(key) & mask;
+// The table has room for every point of the largest scan (`mask` + 1 slots), but a scan only fills a few per cent
+// of it, and with dozens of lanes those sparse tables would not stay in L2.  So the first TABLE_NEAR probes of a key
+// stay inside a small region at the front (`near_mask` + 1 slots, sized by the host from the previous scan's
+// counts); only a key that finds all of them taken moves on to the rest of the table (the slots with the bit
+// `near_mask + 1` set).  The probe sequence of a key is fixed, so every thread with that key ends in the same slot
+// whatever the region sizes; correctness never depends on the hint, only the cache footprint does.
+constexpr u32 TABLE_NEAR = 32;
+__device__ __forceinline__ u32 table_insert_min(u64* keys, u32* vals, u32 mask, u32 near_mask, u64 key, u32 val) {
+    const u32 h = hash_key(key);
+    u32 slot = h & near_mask;
+    u32 j = 0;
     while (true) {
         u64 k = *((volatile u64*)(keys + slot));
         if (k == key) break;
@@ -198,7 +227,9 @@ __device__ __forceinline__ u32 table_insert_min(u64* keys, u32* vals, u32 mask, 
             u64 prev = atomicCAS(keys + slot, KEY_EMPTY, key);
             if (prev == KEY_EMPTY || prev == key) break;
         }
-        slot = (slot + 1) & mask;
+        ++j;
+        if (near_mask == mask || j < TABLE_NEAR) slot = (h + j) & near_mask;
+        else slot = ((h + j) & mask) | (near_mask + 1u);
     }
     atomicMin(vals + slot, val);
     return slot;
@@ -214,11 +245,11 @@ __device__ __forceinline__ bool load_point(const StepParams& P, int i, double& x
         const u32 r = __ldg(P.range + i);
         if (r == 0) return false;
         const double rr = (double)r * P.range_unit;
-        const double* d = P.lut_dir + 3 * (size_t)i;
-        x = __ldg(d) * rr; y = __ldg(d + 1) * rr; z = __ldg(d + 2) * rr;
+        // direction / offset LUTs are stored as three planes of n pixels each: consecutive pixels, consecutive words
+        const size_t np = (size_t)P.n;
+        x = __ldg(P.lut_dir + i) * rr; y = __ldg(P.lut_dir + np + i) * rr; z = __ldg(P.lut_dir + 2 * np + i) * rr;
         if (P.lut_off) {
-            const double* o = P.lut_off + 3 * (size_t)i;
-            x = x + __ldg(o); y = y + __ldg(o + 1); z = z + __ldg(o + 2);
+            x = x + __ldg(P.lut_off + i); y = y + __ldg(P.lut_off + np + i); z = z + __ldg(P.lut_off + 2 * np + i);
         }
         if (P.flags & F_DESKEW) {
             const double* m = P.col_motion + (i % P.W);
@@ -318,7 +349,7 @@ __global__ void __launch_bounds__(256, 4) k_scan_insert(LaneDev* lanes, const St
         if (ins) {
             const u32 peers = __match_any_sync(am, key);
             const int leader = __ffs(peers) - 1;
-            if ((int)(threadIdx.x & 31) == leader) slot = table_insert_min(L.t1_keys, L.t1_vals, L.t_mask, key, (u32)i);
+            if ((int)(threadIdx.x & 31) == leader) slot = table_insert_min(L.t1_keys, L.t1_vals, L.t_mask, P.near1 ? P.near1 : L.t_mask, key, (u32)i);
             slot = __shfl_sync(peers, slot, leader);
         }
         if (i < P.n) L.slot1[i] = slot;
@@ -452,7 +483,7 @@ __global__ void __launch_bounds__(256, 4) k_compact1(LaneDev* lanes, const StepP
                 const u32 peers = __match_any_sync(am, key);
                 const int leader = __ffs(peers) - 1;
                 u32 s2 = NONE;
-                if ((int)(threadIdx.x & 31) == leader) s2 = table_insert_min(L.t2_keys, L.t2_vals, L.t_mask, key, (u32)pos);
+                if ((int)(threadIdx.x & 31) == leader) s2 = table_insert_min(L.t2_keys, L.t2_vals, L.t_mask, P.near2 ? P.near2 : L.t_mask, key, (u32)pos);
                 L.ds_slot2[pos] = __shfl_sync(peers, s2, leader);
             }
         }
@@ -1116,523 +1147,328 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
 #undef SOLVE_TICK
 }
 
-// K4: the ICP loop (kiss-icp RegisterFrame) as a warp-level DATAFLOW over all lanes of the launch.
-//
-// There is no block, cluster or grid barrier anywhere: the unit of work is a task for ONE WARP - "iteration `it`
-// of the 32-point group g of lane l" -, tasks of every lane go through one ticketed ring in global memory, and a
-// warp that has nothing to do for one lane simply takes the next task of whatever lane has one.  The serial part
-// of a lane's iteration (tree reduction, 6x6 solve) occupies one warp of the whole device while every other warp
-// keeps working on other lanes.  A task, thread per point:
-//   1. move the point by the last increment and test the exact correspondence cache (iteration 0: every point
-//      needs a search);
-//   2. thread_nearest for the lanes that missed, all at the same time;
-//   3. residual, Geman-McClure weight and the 16 distinct sums (a warp IS a 32-point group, so butterflies give
-//      the canonical group partial), then the arrival on the lane's counter;
-//   4. the LAST group of an iteration to arrive reduces the group partials with the canonical tree, solves,
-//      updates T_icp and either publishes the next iteration's tasks or writes the pose.
-//
-// The correspondence cache: a search at position p0 leaves its winner a, ICP_KX runner-ups and a lower bound D of
-// the distance from p0 to every OTHER candidate.  If the point is still in the same voxel (same 27 candidate
-// voxels; the map does not change during the loop) and, with w the lexicographically smallest of the kept
-// candidates in (distance^2, order id) - the search's own comparison -, |p - w| + |p - p0| < D, then every other
-// candidate c has |p - c| >= |p0 - c| - |p - p0| > |p - w|: w is what a new search would return.  The cache changes
-// which points are searched, never what a search would have returned, so the per-iteration correspondence sets
-// stay bit-exact (tests compare them with the oracle's).  Cache entries and moving points live in global memory
-// (L2-resident: 150 B per source point) and are read with ld.cg, because consecutive iterations of a group run on
-// different SMs.
-//
-// Scheduling never changes a result: group partials are combined by the fixed tree, whichever warp computes them.
-constexpr int IQ_THREADS = 128;
-constexpr int IQ_WARPS = IQ_THREADS / 32;
-#ifndef PTK_IQ_MINBLOCKS
-#define PTK_IQ_MINBLOCKS 5
-#endif
-#ifndef PTK_IQ_MAX_SLEEP
-#define PTK_IQ_MAX_SLEEP 256       // ns: longest pause between two polls of an idle warp
-#endif
-constexpr u32 IQ_CAP = 1u << 16;            // ring entries (power of two)
-constexpr u64 IQ_EMPTY = 0ull;
-constexpr u64 IQ_EXIT = ~0ull;
-static_assert(ICP_KX <= 2, "thread_nearest keeps the three nearest candidates");
-
-struct IcpQueue {
-    u32 head; u32 pad0[31];                 // consumer tickets handed out
-    u32 tail; u32 pad1[31];                 // producer reservations
-    u32 lanes_done; u32 exited; u32 prof; u32 pad2[29];
-    unsigned long long cyc[8];              // warp cycles per phase (prof != 0): cache pass, searches, sums, queue wait, tree, solve
-    u64 slots[IQ_CAP];
-};
-
-// Per-warp shared memory of the ICP kernel.  The phases of a task are separate (__noinline__) functions, each with
-// its own register allocation; what one phase leaves for the next goes through here, one column per lane.  (As one
-// inlined body the task spilled ~800 B per thread; with most of the SM's L1 configured as shared memory those
-// spills missed L1 and every phase ran an order of magnitude slower than its instruction count.)
-struct IcpWarpScratch {
-    // 8704 B used twice: by a task (thread_nearest scratch + the hand-off columns) and, once the last group of an
-    // iteration has arrived, by the solver as two 17 x 32 staging buffers of group partials (TMA destination)
-    double raw[2 * NSUM * 32];
-    unsigned long long mbar[2];         // one mbarrier per staging buffer
-    u32 mbar_phase[2];
-    int ord[32];                        // order ids of the correspondences (-1: none)
-    double red[NSUM];
-    SolveSmem S;
-    Rigid E;
-    SE3q T;
-    int done;
-    int pad;
-    __device__ __forceinline__ u32* ids() { return reinterpret_cast<u32*>(raw); }                 // [27][32] voxel block of every neighbour
-    __device__ __forceinline__ float* lbs() { return reinterpret_cast<float*>(raw) + 27 * 32; }   // [27][32] rounded-down box distance^2
-    __device__ __forceinline__ double* col(int k) { return raw + 27 * 32 + 32 * k; }              // k = 0..5: sx sy sz tx ty tz, one column per lane
-};
-static_assert(2 * NSUM * 32 >= 27 * 32 + 6 * 32, "hand-off columns must fit behind the search scratch");
-
-// Scoped memory operations of the task ring and the arrival counters (PTX memory model, gpu scope).  One lane
-// releases / acquires on behalf of its warp: __syncwarp / shuffles order the other lanes' accesses around it.
-// (Full __threadfence()s - MEMBAR.SC - per task were far more expensive than these scoped operations.)
-__device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
-    u64 v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(u64* p, u64 v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ u32 atom_add_acq_rel_u32(u32* p, u32 v) {
-    u32 old;
-    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-    return old;
-}
-__device__ __forceinline__ u32 atom_add_relaxed_u32(u32* p, u32 v) {
-    u32 old;
-    asm volatile("atom.add.relaxed.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
-    return old;
-}
-__device__ __forceinline__ u64 atom_cas_release_u64(u64* p, u64 cmp, u64 val) {
-    u64 old;
-    asm volatile("atom.cas.release.gpu.global.b64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(cmp), "l"(val) : "memory");
-    return old;
-}
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-
-// ---- TMA (1-D bulk copy global -> shared, completion on an mbarrier): how the solver fetches the group partials.
-// One lane issues all the copies of a staging buffer; they are in flight together and cost no registers, where 16
-// dependent-looking ld.cg per super-group serialised into one L2 round trip each.
-__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* mbar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(mbar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* mbar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(mbar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, u32 bytes, unsigned long long* mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(mbar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* mbar, u32 phase) {
-    u32 ok;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(smem_addr(mbar)), "r"(phase) : "memory");
-    } while (!ok);
-}
-
-__device__ __forceinline__ u64 icp_task(int lane_id, int grp) {
-    return (1ull << 56) | ((u64)(u32)lane_id << 32) | (u64)(u32)grp;
-}
-
-// Publish the n_groups tasks of one lane's next iteration.  Every lane of the warp fences its earlier stores first.
-__device__ __forceinline__ void icp_push(IcpQueue* Q, int lane_id, int n_groups, int lane) {
-    const u32 FULL = 0xffffffffu;
-    const u32 n = (u32)n_groups;
-    __syncwarp();                 // lane 0's state stores are ordered before every lane's releasing CAS below
-    u32 base = 0;
-    if (lane == 0) base = atom_add_relaxed_u32(&Q->tail, n);
-    base = __shfl_sync(FULL, base, 0);
-    for (u32 i = (u32)lane; i < n; i += 32u) {
-        const u64 t = icp_task(lane_id, (int)i);
-        u64* s = Q->slots + ((base + i) & (IQ_CAP - 1u));
-        while (atom_cas_release_u64(s, IQ_EMPTY, t) != IQ_EMPTY) { __nanosleep(64); }   // ring full: wait for the older entry's consumer
-    }
-}
-
-// Every lane has finished, i.e. every task has been consumed and the ring is empty: hand each warp of the grid its
-// exit token (plain relaxed stores - nobody else writes the ring any more).
-__device__ __forceinline__ void icp_push_exit(IcpQueue* Q, int total_warps, int lane) {
-    u32 base = 0;
-    if (lane == 0) base = atom_add_relaxed_u32(&Q->tail, (u32)total_warps);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    for (u32 i = (u32)lane; i < (u32)total_warps; i += 32u) st_relaxed_u64(Q->slots + ((base + i) & (IQ_CAP - 1u)), IQ_EXIT);
-}
-
-__device__ __forceinline__ Rigid ldcg_rigid(const Rigid* p) {
-    Rigid T;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) T.r[k] = __ldcg(p->r + k);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) T.t[k] = __ldcg(p->t + k);
-    return T;
-}
-
-// Stage the 17 rows of super-group `sg` (32 consecutive groups) of the partial table into staging buffer `b`.
-// Lane 0 only.  Rows are copied in whole 16 B units; entries past n_groups are masked by the reader.
-__device__ __forceinline__ void icp_stage_sg(IcpWarpScratch* ws, const double* part, int ngc, int sg, int n_groups, int b) {
-    const int g0 = sg * 32;
-    const int n = min(32, n_groups - g0);
-    const u32 bytes = (u32)(((n + 1) & ~1) * 8);
-    mbar_expect_tx(&ws->mbar[b], bytes * NSUM);
-#pragma unroll 1
-    for (int v = 0; v < NSUM; ++v) tma_load_1d(ws->raw + (b * NSUM + v) * 32, part + (size_t)v * ngc + g0, bytes, &ws->mbar[b]);
-}
-
-// Canonical tree over the group partials of all 16 sums at once (oracle/canon.py pairwise_tree_sum, exactly the
-// additions of warp_tree_sum): level 1 = butterfly over the 32 groups of a super-group (transposed, 16 sums per
-// pass), level 2 = adjacent-pairs tree over 32 super-groups (zero padded), level 3 = the fixed 8-chunk tree.
-// Returns the total of sum bitrev4(lane & 15); *count = number of correspondences (a sum of small integers is
-// exact in any order).  Super-groups are staged two ahead through TMA.
-__device__ __forceinline__ double icp_tree16(IcpWarpScratch* ws, const double* part, int ngc, int n_groups, int lane, int* count) {
-    const u32 FULL = 0xffffffffu;
-    const int n_sg = (n_groups + 31) >> 5;
-    int cnt = 0;
-    if (lane == 0) {
-        asm volatile("fence.proxy.async;" ::: "memory");     // the partials were written through the generic proxy
-        if (n_sg > 0) icp_stage_sg(ws, part, ngc, 0, n_groups, 0);
-        if (n_sg > 1) icp_stage_sg(ws, part, ngc, 1, n_groups, 1);
-    }
-    int m = 1;
-    while (m * 32 < n_groups) m <<= 1;
-    const int mc = m <= 32 ? 1 : (m >> 5);
-    double U[8];
-    double single = 0.0;
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-        double tot = 0.0;
-        if (c < mc) {
-            double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;      // pending left subtrees of the 32-leaf tree
-#pragma unroll 1
-            for (int i = 0; i < 32; ++i) {
-                const int sg = c * 32 + i;
-                double x = 0.0;
-                if (sg < n_sg) {
-                    const int b = sg & 1;
-                    mbar_wait(&ws->mbar[b], ws->mbar_phase[b]);
-                    const bool valid = sg * 32 + lane < n_groups;
-                    const double* buf = ws->raw + b * NSUM * 32;
-                    double cv[16];
-#pragma unroll
-                    for (int v = 0; v < 16; ++v) cv[v] = valid ? buf[v * 32 + lane] : 0.0;
-                    if (valid) cnt += (int)buf[16 * 32 + lane];
-                    __syncwarp();
-                    if (lane == 0) {
-                        ws->mbar_phase[b] ^= 1u;
-                        if (sg + 2 < n_sg) icp_stage_sg(ws, part, ngc, sg + 2, n_groups, b);
-                    }
-                    __syncwarp();
-                    x = warp_reduce16(cv, lane);
-                    if (n_sg == 1) single = x;
-                }
-                if (i & 1) {
-                    x = a0 + x;
-                    if (i & 2) {
-                        x = a1 + x;
-                        if (i & 4) {
-                            x = a2 + x;
-                            if (i & 8) {
-                                x = a3 + x;
-                                if (i & 16) tot = a4 + x; else a4 = x;
-                            } else a3 = x;
-                        } else a2 = x;
-                    } else a1 = x;
-                } else a0 = x;
-            }
-        }
-        // static indexing of U: c is a loop counter of a non-unrolled loop, so select explicitly
-        if (c == 0) U[0] = tot; else if (c == 1) U[1] = tot; else if (c == 2) U[2] = tot; else if (c == 3) U[3] = tot;
-        else if (c == 4) U[4] = tot; else if (c == 5) U[5] = tot; else if (c == 6) U[6] = tot; else U[7] = tot;
-    }
-    *count = __reduce_add_sync(FULL, cnt);
-    if (n_sg <= 1) return n_sg == 1 ? single : 0.0;      // one super-group: its butterfly IS the sum; none: nothing to add
-    if (mc == 1) return U[0];
-    return ((U[0] + U[1]) + (U[2] + U[3])) + ((U[4] + U[5]) + (U[6] + U[7]));
-}
-
-#define IQ_TICK(slot)                                                                    \
-    do {                                                                                 \
-        if (prof && lane == 0) {                                                         \
-            const long long t_ = clock64();                                              \
-            atomicAdd(&Q->cyc[slot], (unsigned long long)(t_ - tlast));                  \
-            tlast = t_;                                                                  \
-        }                                                                                \
-    } while (0)
-
-// All groups of iteration `it` have arrived: reduce, solve, publish (kiss-icp RegisterFrame loop body after
-// BuildLinearSystem).  Runs in one warp.
-__device__ __noinline__ void icp_lane_solve(LaneDev& L, const StepParams& P, StepOut& O, IcpQueue* Q, IcpWarpScratch* ws,
-                                            int lane_id, int it, int n_groups, int n_lanes, int total_warps, int lane) {
-    const u32 FULL = 0xffffffffu;
-    const bool prof = Q->prof != 0;
-    long long tlast = prof ? clock64() : 0;
-    if (lane == 0) L.icp_arrive = 0;
-    const double* part = L.part_a;
-    const int ngc = L.ng_cap;
-    int cnt = 0;
-    const double tot = icp_tree16(ws, part, ngc, n_groups, lane, &cnt);
-    if (lane < 16) ws->red[__brev((u32)lane) >> 28] = tot;
-    if (lane == 0) {
-        ws->red[16] = (double)cnt;
-        SE3q T = se3q_identity();
-        if (it > 0) {
-            T.q.w = __ldcg(&L.icp_Tq.q.w); T.q.x = __ldcg(&L.icp_Tq.q.x); T.q.y = __ldcg(&L.icp_Tq.q.y); T.q.z = __ldcg(&L.icp_Tq.q.z);
-            T.t[0] = __ldcg(&L.icp_Tq.t[0]); T.t[1] = __ldcg(&L.icp_Tq.t[1]); T.t[2] = __ldcg(&L.icp_Tq.t[2]);
-        }
-        ws->T = T;
-    }
-    __syncwarp();
-    IQ_TICK(4);
-    icp_solve_step(L, P, O, ws->red, &ws->S, &ws->E, &ws->T, &ws->done, it, true, lane);
-    __syncwarp();
-    const int done = ws->done;
-    if (!done) {
-        if (lane == 0) {
-            L.icp_E = ws->E;
-            L.icp_Tq = ws->T;
-            L.icp_it = it + 1;
-        }
-        icp_push(Q, lane_id, n_groups, lane);
-    } else {
-        u32 fin = 0;
-        if (lane == 0) {
-            L.icp_done = 1;
-            fin = atom_add_acq_rel_u32(&Q->lanes_done, 1u) + 1u;
-        }
-        fin = __shfl_sync(FULL, fin, 0);
-        if (fin == (u32)n_lanes) icp_push_exit(Q, total_warps, lane);
-    }
-    IQ_TICK(5);
-}
-
-// ---- phase 1 of a task: move the group's points by the last increment and consult the correspondence cache.
-// Leaves positions and (for hits) correspondences in the warp scratch; returns whether this lane's point needs a search.
-__device__ __noinline__ bool icp_task_front(LaneDev& L, IcpWarpScratch* ws, int g, int lane, int* it_out) {
+// K4a: the searches of ICP iteration 0.  The first iteration has to search for EVERY source point (there is no
+// cache entry yet), which made it a third of the loop's time when the points were searched one per warp inside the
+// cooperative kernel.  Here it is an ordinary wide launch: one THREAD per source point (thread_nearest), a warp per
+// 32-point group, every lane of the batch at once.  The cache entries go to the lane's global cache arrays; k_icp
+// starts from them.
+constexpr int S0_THREADS = 128;
+__global__ void __launch_bounds__(S0_THREADS) k_icp_search0(LaneDev* lanes, const StepParams* params) {
+    LaneDev& L = lanes[blockIdx.y];
+    const StepParams& P = params[blockIdx.y];
+    __shared__ u32 s_ids[S0_THREADS / 32][27 * 32];
+    __shared__ float s_lbs[S0_THREADS / 32][27 * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_src = L.n_src;
-    const int p = g * 32 + lane;
-    const bool live = p < n_src;
-    double sx = 0, sy = 0, sz = 0, tx = 0, ty = 0, tz = 0;
-    int ord = -1;
-    bool miss = false;
-    // every load of the phase goes out before anything is looked at (iteration 0 ignores what the cache arrays hold)
+    if (L.n_vox == 0 || n_src == 0) return;
+    const MapView M = map_view(L);
+    const double max_corr = P.max_corr;
+    const double max_d2 = (max_corr * max_corr) * (1.0 + 1e-9);   // farther candidates are rejected anyway
     const size_t cap = (size_t)L.cap_points;
-    const int pl = live ? p : 0;
-    const int it = __ldcg(&L.icp_it);
-    const Rigid E = ldcg_rigid(&L.icp_E);
-    const double x0 = __ldcg(L.s_x + pl), y0 = __ldcg(L.s_y + pl), z0 = __ldcg(L.s_z + pl);
-    const double others = __ldcg(L.c_slack + pl);
-    const double ctx = __ldcg(L.c_tx + pl), cty = __ldcg(L.c_ty + pl), ctz = __ldcg(L.c_tz + pl);
-    const int cord = __ldcg(L.c_ord + pl);
-    const double px = __ldcg(L.c_px + pl), py = __ldcg(L.c_py + pl), pz = __ldcg(L.c_pz + pl);
-    const u64 ckey = __ldcg(L.c_key + pl);
-    double b2[3 * ICP_KX];
-    int o2[ICP_KX];
-#pragma unroll
-    for (int j = 0; j < ICP_KX; ++j) {
-        o2[j] = __ldcg(L.c_ord2 + (size_t)j * cap + pl);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) b2[3 * j + c] = __ldcg(L.c_t2 + (size_t)(3 * j + c) * cap + pl);
-    }
-    if (it == 0) {
-        if (live) { sx = x0; sy = y0; sz = z0; }
-        miss = live;              // every point starts with a search
-    } else if (live) {
-        tx = ctx; ty = cty; tz = ctz; ord = cord;
-        rigid_apply(E, x0, y0, z0, sx, sy, sz);
-        __stcg(L.s_x + p, sx); __stcg(L.s_y + p, sy); __stcg(L.s_z + p, sz);
-        miss = true;
-        if (others > 0.0) {
-            const double mx = sx - px, my = sy - py, mz = sz - pz;
-            const double moved = sqrt((mx * mx + my * my) + mz * mz);
-            double ex = tx - sx, ey = ty - sy, ez = tz - sz;
-            double da2 = (ex * ex + ey * ey) + ez * ez;              // as the search computes it
+    for (int g = blockIdx.x * (S0_THREADS / 32) + warp; g * 32 < n_src; g += gridDim.x * (S0_THREADS / 32)) {
+        const int p = g * 32 + lane;
+        const bool live = p < n_src;
+        double sx = 0, sy = 0, sz = 0;
+        if (live) { sx = L.s_x[p]; sy = L.s_y[p]; sz = L.s_z[p]; }
+        NearestOut R;
+        thread_nearest(M, s_ids[warp], s_lbs[warp], lane, live, sx, sy, sz, max_d2, R);
+        if (live) {
+            L.c_tx[p] = R.tx; L.c_ty[p] = R.ty; L.c_tz[p] = R.tz;
 #pragma unroll
             for (int j = 0; j < ICP_KX; ++j) {
-                const int oj = o2[j];
-                if (oj < 0) continue;
-                const double bx = b2[3 * j], by = b2[3 * j + 1], bz = b2[3 * j + 2];
-                ex = bx - sx; ey = by - sy; ez = bz - sz;
-                const double db2 = (ex * ex + ey * ey) + ez * ez;
-                if (db2 < da2 || (db2 == da2 && oj < ord)) {          // this runner-up has become the nearest
-                    __stcg(L.c_tx + p, bx); __stcg(L.c_ty + p, by); __stcg(L.c_tz + p, bz); __stcg(L.c_ord + p, oj);
-                    __stcg(L.c_t2 + (size_t)(3 * j) * cap + p, tx); __stcg(L.c_t2 + (size_t)(3 * j + 1) * cap + p, ty);
-                    __stcg(L.c_t2 + (size_t)(3 * j + 2) * cap + p, tz); __stcg(L.c_ord2 + (size_t)j * cap + p, ord);
-                    tx = bx; ty = by; tz = bz; ord = oj;
-                    da2 = db2;
-                }
+                L.c_t2[(size_t)(3 * j) * cap + p] = R.t2[3 * j];
+                L.c_t2[(size_t)(3 * j + 1) * cap + p] = R.t2[3 * j + 1];
+                L.c_t2[(size_t)(3 * j + 2) * cap + p] = R.t2[3 * j + 2];
+                L.c_ord2[(size_t)j * cap + p] = R.ord2[j];
             }
-            if (sqrt(da2) + moved + 1e-9 < others) {
-                int kx, ky, kz;
-                voxel_key(sx, sy, sz, L.voxel_size, L.voxel_inv, kx, ky, kz);
-                miss = !(key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == ckey);
-            }
+            L.c_px[p] = sx; L.c_py[p] = sy; L.c_pz[p] = sz;
+            L.c_slack[p] = R.others;
+            L.c_key[p] = R.qkey;
+            L.c_ord[p] = R.ord;
         }
     }
-    ws->col(0)[lane] = sx; ws->col(1)[lane] = sy; ws->col(2)[lane] = sz;
-    ws->col(3)[lane] = tx; ws->col(4)[lane] = ty; ws->col(5)[lane] = tz;
-    ws->ord[lane] = ord;
-    *it_out = it;
-    return miss;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&L.icp_searches, n_src);
 }
 
-// ---- phase 2: the group's missed points, every one on its own thread; refreshes their cache entries.
-__device__ __noinline__ void icp_task_search(LaneDev& L, IcpWarpScratch* ws, int g, int lane, bool miss, double max_d2) {
-    const MapView M = map_view(L);
-    const int p = g * 32 + lane;
-    const double sx = ws->col(0)[lane], sy = ws->col(1)[lane], sz = ws->col(2)[lane];
-    NearestOut R;
-    thread_nearest(M, ws->ids(), ws->lbs(), lane, miss, sx, sy, sz, max_d2, R);
-    if (miss) {
-        const size_t cap = (size_t)L.cap_points;
-        ws->col(3)[lane] = R.tx; ws->col(4)[lane] = R.ty; ws->col(5)[lane] = R.tz; ws->ord[lane] = R.ord;
-        __stcg(L.c_tx + p, R.tx); __stcg(L.c_ty + p, R.ty); __stcg(L.c_tz + p, R.tz);
-#pragma unroll
-        for (int j = 0; j < ICP_KX; ++j) {
-            __stcg(L.c_t2 + (size_t)(3 * j) * cap + p, R.t2[3 * j]);
-            __stcg(L.c_t2 + (size_t)(3 * j + 1) * cap + p, R.t2[3 * j + 1]);
-            __stcg(L.c_t2 + (size_t)(3 * j + 2) * cap + p, R.t2[3 * j + 2]);
-            __stcg(L.c_ord2 + (size_t)j * cap + p, R.ord2[j]);
-        }
-        __stcg(L.c_px + p, sx); __stcg(L.c_py + p, sy); __stcg(L.c_pz + p, sz);
-        __stcg(L.c_slack + p, R.others);
-        __stcg(L.c_key + p, R.qkey);
-        __stcg(L.c_ord + p, R.ord);
-    }
-}
-
-// ---- phase 3: residual, weight, the group's 16 sums, arrival.  Returns true for the LAST group of the iteration.
-__device__ __noinline__ bool icp_task_sums(LaneDev& L, const StepParams& P, IcpWarpScratch* ws, int g, int it, int lane) {
-    const u32 FULL = 0xffffffffu;
-    const int n_src = L.n_src;
-    const int n_groups = (n_src + 31) >> 5;
-    const bool live = g * 32 + lane < n_src;
-    const double max_corr = P.max_corr;
-    const int ord = ws->ord[lane];
-    double c[16];
-    bool acc = false;
-    if (live && ord >= 0) {
-        const double sx = ws->col(0)[lane], sy = ws->col(1)[lane], sz = ws->col(2)[lane];
-        const double tx = ws->col(3)[lane], ty = ws->col(4)[lane], tz = ws->col(5)[lane];
-        const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
-        const double d2 = (dx * dx + dy * dy) + dz * dz;
-        acc = sqrt(d2) < max_corr;
-        if (acc) lin_terms(sx, sy, sz, tx, ty, tz, P.kernel, c);
-    }
-    if (live && it < L.trace_iters) L.trace[(size_t)it * L.cap_points + (g * 32 + lane)] = acc ? ord : -1;
-    if (!acc) {
-#pragma unroll
-        for (int v = 0; v < 16; ++v) c[v] = 0.0;
-    }
-    const double mine = warp_reduce16(c, lane);
-    const u32 nacc = __popc(__ballot_sync(FULL, acc));
-    double* part = L.part_a;
-    if (lane < 16) __stcg(part + (size_t)(__brev((u32)lane) >> 28) * L.ng_cap + g, mine);
-    else if (lane == 16) __stcg(part + (size_t)16 * L.ng_cap + g, (double)nacc);
-    // the arrival releases this warp's stores (partials, moved points, cache entries: ordered before it by the
-    // __syncwarp) and, for the last group, acquires everybody else's
-    __syncwarp();
-    u32 arrived = 0;
-    if (lane == 0) arrived = atom_add_acq_rel_u32(&L.icp_arrive, 1u) + 1u;
-    arrived = __shfl_sync(FULL, arrived, 0);
-    return arrived == (u32)n_groups;
-}
-
-__global__ void __launch_bounds__(IQ_THREADS, PTK_IQ_MINBLOCKS) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs,
-                                                                    int n_lanes, IcpQueue* Q) {
-    const u32 FULL = 0xffffffffu;
+// K4: the whole ICP loop (kiss-icp RegisterFrame) in one persistent cooperative kernel.
+// grid = (blocks per lane, lanes), ICP_THREADS threads.  A block owns a contiguous range of
+// 32-point groups and walks it in chunks of ICP_CHUNK groups (= one point per thread).  Per
+// iteration and chunk:
+//   1. thread per point: move the point by the last increment, then try the correspondence cache.
+//      The last search of the point, at position p0, left its winner a, a runner-up b and a lower bound D
+//      of the distance from p0 to every OTHER candidate (see warp_nearest).  If the point is still in the
+//      same voxel (same 27 candidate voxels; the map does not change during the loop) and, with w the
+//      lexicographically smaller of a and b in (distance^2, order id) - the search's own comparison -,
+//      |p - w| + |p - p0| < D, then every other candidate c has |p - c| >= |p0 - c| - |p - p0| >= D - |p - p0|
+//      > |p - w|: w is what a new search would return, so none is needed (a runner-up that has become the
+//      nearest swaps places with a in the cache; ICP_KX runner-ups are kept); otherwise the point goes on
+//      the block's work list;
+//   2. warp per listed point: the pruned 27-voxel search, refreshing the cache entry;
+//   3. thread per point: residual, Geman-McClure weight and the 16 distinct sums (+ count) in
+//      registers; a warp IS a 32-point group, so xor-butterflies give the group partials directly.
+// A counter barrier over the lane's blocks follows; after it EVERY block reduces the group partials
+// with the same fixed tree, solves the 6x6 system and updates its copy of T_icp (identical code,
+// identical bits), so one grid-wide hop per iteration is all the synchronisation there is.
+// The cache changes which points are searched, never what a search would have returned, so the
+// per-iteration correspondence sets stay bit-exact (tests compare them with the oracle's).
+__global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev* lanes, const StepParams* params, StepOut* outs) {
+    LaneDev& L = lanes[blockIdx.y];
+    const StepParams& P = params[blockIdx.y];
+    StepOut& O = outs[blockIdx.y];
+    const int nblk = gridDim.x, b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_warps = gridDim.x * IQ_WARPS;
-    const int gw = blockIdx.x * IQ_WARPS + warp;
-    __shared__ IcpWarpScratch s_ws[IQ_WARPS];
-    IcpWarpScratch* ws = &s_ws[warp];
-    if (lane == 0) {
-        mbar_init(&ws->mbar[0], 1);
-        mbar_init(&ws->mbar[1], 1);
-        ws->mbar_phase[0] = ws->mbar_phase[1] = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    const bool prof = Q->prof != 0;
-    long long tlast = prof ? clock64() : 0;
+    const int n_src = L.n_src;
 
-    // ---- seed: the first warps of the grid open the lanes (one warp per lane)
-    const int seeders = min(total_warps, 64 * IQ_WARPS);
-    if (gw < seeders) {
-        for (int l = gw; l < n_lanes; l += seeders) {
-            LaneDev& L = lanes[l];
-            const StepParams& P = params[l];
-            StepOut& O = outs[l];
-            const int n_groups = (L.n_src + 31) >> 5;
-            if (L.n_vox == 0) {       // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
-                u32 fin = 0;
-                if (lane == 0) {
-                    O.pose = se3q_matrix(se3q_mul(se3q_identity(), se3q_from_rigid(P.guess)));
-                    O.iterations = 0; O.n_corr = 0; O.status = 0; O.dx_norm = 0.0;
-                    L.icp_done = 1;
-                    fin = atom_add_acq_rel_u32(&Q->lanes_done, 1u) + 1u;
+    extern __shared__ double dyn_smem[];         // source points + cache entries of this block
+    double* const ssx = dyn_smem;
+    double* const ssy = ssx + ICP_SRC_CAP;
+    double* const ssz = ssy + ICP_SRC_CAP;
+    __shared__ double red[NSUM];
+    __shared__ Rigid sE;
+    __shared__ SE3q sT;
+    __shared__ SolveSmem sS;
+    __shared__ int s_done;
+    __shared__ int s_nmiss;
+    __shared__ int s_cnt;
+    __shared__ MapView s_map;
+    __shared__ unsigned short s_miss[ICP_CHUNK * 32];
+
+    if (L.n_vox == 0) {   // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
+        if (b == 0 && threadIdx.x == 0) {
+            O.pose = se3q_matrix(se3q_mul(se3q_identity(), se3q_from_rigid(P.guess)));
+            O.iterations = 0; O.n_corr = 0; O.status = 0; O.dx_norm = 0.0;
+        }
+        return;
+    }
+    const int n_groups = (n_src + 31) >> 5;
+    // groups of this block: b, b + nblk, b + 2 nblk, ... (interleaved: the source is in beam order, and how far a
+    // point moves per iteration - hence how often its cache entry misses - varies with the beam; dealing the
+    // groups round-robin gives every block the same mix, so the blocks reach the barrier together)
+    const int n_local = b < n_groups ? (n_groups - b + nblk - 1) / nblk : 0;
+    const double max_corr = P.max_corr, kern = P.kernel;
+    const double max_d2 = (max_corr * max_corr) * (1.0 + 1e-9);   // farther candidates are rejected anyway
+    // the moving copy of this block's source points and their cache entries live in shared memory when they fit
+    const bool in_smem = n_local * 32 <= ICP_SRC_CAP;
+    // cache entry arrays: computed where used (one base + constants) instead of six live pointers
+#define C_TX(i, g) (*(in_smem ? dyn_smem + 3 * ICP_SRC_CAP + (i) : L.c_tx + (g)))
+#define C_TY(i, g) (*(in_smem ? dyn_smem + 4 * ICP_SRC_CAP + (i) : L.c_ty + (g)))
+#define C_TZ(i, g) (*(in_smem ? dyn_smem + 5 * ICP_SRC_CAP + (i) : L.c_tz + (g)))
+#define C_SLACK(i, g) (*(in_smem ? dyn_smem + 6 * ICP_SRC_CAP + (i) : L.c_slack + (g)))
+#define C_KEY(i, g) (*(in_smem ? reinterpret_cast<u64*>(dyn_smem + 7 * ICP_SRC_CAP) + (i) : L.c_key + (g)))
+    // runner-up j: coordinate c (0..2) at [11 + 3 j + c] * CAP; then the ints: ord, ord2[0..KX)
+#define C_T2(j, c, i, g) (*(in_smem ? dyn_smem + (11 + 3 * (j) + (c)) * ICP_SRC_CAP + (i) \
+                                    : L.c_t2 + ((size_t)(3 * (j) + (c)) * L.cap_points) + (g)))
+#define C_ORD(i, g) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + (11 + 3 * ICP_KX) * ICP_SRC_CAP) + (i) : L.c_ord + (g)))
+#define C_ORD2(j, i, g) (*(in_smem ? reinterpret_cast<int*>(dyn_smem + (11 + 3 * ICP_KX) * ICP_SRC_CAP) + ((j) + 1) * ICP_SRC_CAP + (i) \
+                                   : L.c_ord2 + (size_t)(j) * L.cap_points + (g)))
+#define C_PX(i, g) (*(in_smem ? dyn_smem + 8 * ICP_SRC_CAP + (i) : L.c_px + (g)))
+#define C_PY(i, g) (*(in_smem ? dyn_smem + 9 * ICP_SRC_CAP + (i) : L.c_py + (g)))
+#define C_PZ(i, g) (*(in_smem ? dyn_smem + 10 * ICP_SRC_CAP + (i) : L.c_pz + (g)))
+    if (threadIdx.x == 0) sT = se3q_identity();
+    const double voxel = L.voxel_size, voxel_inv = L.voxel_inv;
+    // phase clocks of block 0 (thread 0 only; six clock reads per iteration)
+    const bool clk = b == 0 && threadIdx.x == 0;
+    __shared__ long long s_cyc[6];
+    __shared__ int s_searches;
+    if (threadIdx.x < 6) s_cyc[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_searches = 0; s_cnt = 0; s_map = map_view(L); }
+    long long tlast = clk ? clock64() : 0;
+#define ICP_TICK(slot) do { if (clk) { const long long t_ = clock64(); s_cyc[slot] += t_ - tlast; tlast = t_; } } while (0)
+
+    for (int it = 0;; ++it) {
+        double* part = (it & 1) ? L.part_b : L.part_a;
+        for (int k0 = 0; k0 < n_local; k0 += ICP_CHUNK) {
+            const int gc = min(ICP_CHUNK, n_local - k0);   // local groups k0 .. k0 + gc, one per warp
+            const int q = threadIdx.x;                     // point of this thread within the chunk
+            const int grp = b + (k0 + warp) * nblk;        // this warp's group within the lane's source
+            const int p = grp * 32 + lane;                 // this thread's point within the lane's source
+            const int sp = k0 * 32 + q;                    // ... within the block
+            const bool live = q < gc * 32 && p < n_src;
+            if (threadIdx.x == 0) s_nmiss = 0;
+            __syncthreads();                               // also: previous chunk / iteration fully consumed
+            // ---- 1. move the point, consult the cache
+            double sx = 0, sy = 0, sz = 0;
+            bool miss = false;
+            if (live) {
+                if (it == 0 || !in_smem) { sx = __ldcg(L.s_x + p); sy = __ldcg(L.s_y + p); sz = __ldcg(L.s_z + p); }
+                else { sx = ssx[sp]; sy = ssy[sp]; sz = ssz[sp]; }
+                miss = true;
+                if (it == 0) {
+                    // every point's first search has been done by k_icp_search0: fetch its cache entry
+                    if (in_smem) {
+                        C_TX(sp, p) = L.c_tx[p]; C_TY(sp, p) = L.c_ty[p]; C_TZ(sp, p) = L.c_tz[p];
+#pragma unroll
+                        for (int j = 0; j < ICP_KX; ++j) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) C_T2(j, c, sp, p) = L.c_t2[(size_t)(3 * j + c) * L.cap_points + p];
+                            C_ORD2(j, sp, p) = L.c_ord2[(size_t)j * L.cap_points + p];
+                        }
+                        C_PX(sp, p) = L.c_px[p]; C_PY(sp, p) = L.c_py[p]; C_PZ(sp, p) = L.c_pz[p];
+                        C_SLACK(sp, p) = L.c_slack[p];
+                        C_KEY(sp, p) = L.c_key[p];
+                        C_ORD(sp, p) = L.c_ord[p];
+                    }
+                    miss = false;
                 }
-                fin = __shfl_sync(FULL, fin, 0);
-                if (fin == (u32)n_lanes) icp_push_exit(Q, total_warps, lane);
-                continue;
+                if (it > 0) {
+                    double xo, yo, zo;
+                    rigid_apply(sE, sx, sy, sz, xo, yo, zo);
+                    sx = xo; sy = yo; sz = zo;
+                    const double others = C_SLACK(sp, p);
+                    if (others > 0.0) {
+                        const double mx = sx - C_PX(sp, p), my = sy - C_PY(sp, p), mz = sz - C_PZ(sp, p);
+                        const double moved = sqrt((mx * mx + my * my) + mz * mz);
+                        double ex = C_TX(sp, p) - sx, ey = C_TY(sp, p) - sy, ez = C_TZ(sp, p) - sz;
+                        double da2 = (ex * ex + ey * ey) + ez * ez;              // as the search computes it
+#pragma unroll
+                        for (int j = 0; j < ICP_KX; ++j) {
+                            const int oj = C_ORD2(j, sp, p);
+                            if (oj < 0) continue;
+                            const double bx = C_T2(j, 0, sp, p), by = C_T2(j, 1, sp, p), bz = C_T2(j, 2, sp, p);
+                            ex = bx - sx; ey = by - sy; ez = bz - sz;
+                            const double db2 = (ex * ex + ey * ey) + ez * ez;
+                            const int o1 = C_ORD(sp, p);
+                            if (db2 < da2 || (db2 == da2 && oj < o1)) {          // this runner-up has become the nearest
+                                const double wx = C_TX(sp, p), wy = C_TY(sp, p), wz = C_TZ(sp, p);
+                                C_TX(sp, p) = bx; C_TY(sp, p) = by; C_TZ(sp, p) = bz; C_ORD(sp, p) = oj;
+                                C_T2(j, 0, sp, p) = wx; C_T2(j, 1, sp, p) = wy; C_T2(j, 2, sp, p) = wz; C_ORD2(j, sp, p) = o1;
+                                da2 = db2;
+                            }
+                        }
+                        if (sqrt(da2) + moved + 1e-9 < others) {
+                            int kx, ky, kz;
+                            voxel_key(sx, sy, sz, voxel, voxel_inv, kx, ky, kz);
+                            miss = !(key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == C_KEY(sp, p));
+                        }
+                    }
+                }
+                if (in_smem) { ssx[sp] = sx; ssy[sp] = sy; ssz[sp] = sz; }
+                else if (it > 0) { L.s_x[p] = sx; L.s_y[p] = sy; L.s_z[p] = sz; }
             }
-            if (lane == 0) { L.icp_it = 0; L.icp_arrive = 0; L.icp_done = 0; }
-            if (n_groups == 0) {      // no source point: zero correspondences (B.5)
-                __syncwarp();
-                icp_lane_solve(L, P, O, Q, ws, l, 0, 0, n_lanes, total_warps, lane);
-                continue;
+            {
+                const u32 mm = __ballot_sync(0xffffffffu, miss);
+                if (mm) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_nmiss, __popc(mm));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (miss) s_miss[base + __popc(mm & ((1u << lane) - 1u))] = (unsigned short)q;
+                }
             }
-            icp_push(Q, l, n_groups, lane);
-        }
-    }
-
-    // ---- consume
-    while (true) {
-        u64 task = IQ_EMPTY;
-        if (lane == 0) {
-            const u32 t = atom_add_relaxed_u32(&Q->head, 1u);
-            u64* s = Q->slots + (t & (IQ_CAP - 1u));
-            u32 ns = 32;
-            while ((task = ld_relaxed_u64(s)) == IQ_EMPTY) {       // idle: poll gently, the SM's other warps are working
-                __nanosleep(ns);
-                if (ns < PTK_IQ_MAX_SLEEP) ns <<= 1;
+            __syncthreads();
+            ICP_TICK(0);
+            // ---- 2. full search of the listed points, one warp each
+            const int nmiss = s_nmiss;
+            if (threadIdx.x == 0) s_searches += nmiss;
+            for (int i = warp; i < nmiss; i += ICP_WARPS) {
+                const int mq = s_miss[i];
+                const int msp = k0 * 32 + mq;
+                const int mp = (b + (k0 + (mq >> 5)) * nblk) * 32 + (mq & 31);
+                double qx, qy, qz;
+                if (in_smem) { qx = ssx[msp]; qy = ssy[msp]; qz = ssz[msp]; }
+                else { qx = __ldcg(L.s_x + mp); qy = __ldcg(L.s_y + mp); qz = __ldcg(L.s_z + mp); }
+                double d2, tx, ty, tz, others;
+                int ord;
+                u64 qkey;
+                double t2[3 * ICP_KX];
+                int ord2[ICP_KX];
+                const bool found = warp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey, t2, ord2);
+                if (lane == 0) {
+                    C_TX(msp, mp) = tx; C_TY(msp, mp) = ty; C_TZ(msp, mp) = tz;
+#pragma unroll
+                    for (int j = 0; j < ICP_KX; ++j) {
+                        C_T2(j, 0, msp, mp) = t2[3 * j]; C_T2(j, 1, msp, mp) = t2[3 * j + 1]; C_T2(j, 2, msp, mp) = t2[3 * j + 2];
+                        C_ORD2(j, msp, mp) = ord2[j];
+                    }
+                    C_PX(msp, mp) = qx; C_PY(msp, mp) = qy; C_PZ(msp, mp) = qz;
+                    C_SLACK(msp, mp) = others;
+                    C_KEY(msp, mp) = qkey;
+                    C_ORD(msp, mp) = found ? ord : -1;
+                }
             }
-            st_relaxed_u64(s, IQ_EMPTY);
-            fence_acq_rel_gpu();                                    // acquire what the publisher released
+            __syncthreads();
+            ICP_TICK(1);
+            // ---- 3. residual + weights, group partials by warp butterflies
+            if (warp < gc) {
+                double c[16];
+                bool acc = false;
+                int ord = -1;
+                if (live) {
+                    ord = C_ORD(sp, p);
+                    if (ord >= 0) {
+                        const double tx = C_TX(sp, p), ty = C_TY(sp, p), tz = C_TZ(sp, p);
+                        const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
+                        const double d2 = (dx * dx + dy * dy) + dz * dz;
+                        acc = sqrt(d2) < max_corr;
+                        if (acc) lin_terms(sx, sy, sz, tx, ty, tz, kern, c);
+                    }
+                    if (it < L.trace_iters) L.trace[(size_t)it * L.cap_points + p] = acc ? ord : -1;
+                }
+                if (!acc) {
+#pragma unroll
+                    for (int v = 0; v < 16; ++v) c[v] = 0.0;
+                }
+                const double mine = warp_reduce16(c, lane);
+                const u32 nacc = __popc(__ballot_sync(0xffffffffu, acc));   // a sum of 1.0s is exact in any order
+                if (lane < 16) part[(size_t)(__brev((u32)lane) >> 28) * L.ng_cap + grp] = mine;
+                else if (lane == 16) part[(size_t)16 * L.ng_cap + grp] = (double)nacc;
+            }
         }
-        task = __shfl_sync(FULL, task, 0);
-        if (task == IQ_EXIT) break;
-        IQ_TICK(3);
-        const int lane_id = (int)((task >> 32) & 0xffffffu), g = (int)(task & 0xffffffffu);
-        LaneDev& L = lanes[lane_id];
-        const StepParams& P = params[lane_id];
-        int it;
-        const bool miss = icp_task_front(L, ws, g, lane, &it);
-        IQ_TICK(0);
-        const u32 mm = __ballot_sync(FULL, miss);
-        if (mm) {
-            const double max_corr = P.max_corr;
-            icp_task_search(L, ws, g, lane, miss, (max_corr * max_corr) * (1.0 + 1e-9));   // farther candidates are rejected anyway
-            if (lane == 0) atomicAdd(&L.icp_searches, __popc(mm));
+        // ---- one barrier over the lane's blocks (icp_arrive was zeroed by the previous kernel)
+        __syncthreads();
+        ICP_TICK(2);
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&L.icp_arrive, 1u);
+            const u32 target = (u32)nblk * (u32)(it + 1);
+            while (*((volatile u32*)&L.icp_arrive) < target) { }
+            __threadfence();
         }
-        IQ_TICK(1);
-        const bool last = icp_task_sums(L, P, ws, g, it, lane);
-        IQ_TICK(2);
-        if (last) icp_lane_solve(L, P, outs[lane_id], Q, ws, lane_id, it, (L.n_src + 31) >> 5, n_lanes, total_warps, lane);
+        __syncthreads();
+        ICP_TICK(3);
+        // 16 sums, one warp each, with the canonical tree; the 17th (correspondence count) is a sum of
+        // small integers - exact in any order - so all warps share it instead of one warp doing two trees
+        for (int v = warp; v < 16; v += ICP_WARPS) {
+            const double x = warp_tree_sum(part + (size_t)v * L.ng_cap, n_groups, lane);
+            if (lane == 0) red[v] = x;
+        }
+        {
+            int cnt = 0;
+            for (int g = threadIdx.x; g < n_groups; g += ICP_THREADS) cnt += (int)__ldcg(part + (size_t)16 * L.ng_cap + g);
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+        }
+        __syncthreads();
+        ICP_TICK(4);
+        if (warp == 0) {
+            if (lane == 0) { red[16] = (double)s_cnt; s_cnt = 0; }
+            __syncwarp();
+            icp_solve_step(L, P, O, red, &sS, &sE, &sT, &s_done, it, b == 0, lane);
+        }
+        __syncthreads();
+        ICP_TICK(5);
+        if (s_done) break;
     }
-    // ---- the last warp to leave rewinds the ring for the next launch
-    if (lane == 0) {
-        const u32 gone = atom_add_acq_rel_u32(&Q->exited, 1u) + 1u;
-        if (gone == (u32)total_warps) {
-            Q->head = 0; Q->tail = 0; Q->lanes_done = 0; Q->exited = 0;
-        }
+#undef ICP_TICK
+    if (threadIdx.x == 0 && s_searches) atomicAdd(&L.icp_searches, s_searches);
+#ifndef PTK_SOLVE_CLOCKS
+    if (clk) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) O.icp_cyc[k] = s_cyc[k];
     }
+#endif
+#undef C_TX
+#undef C_TY
+#undef C_TZ
+#undef C_SLACK
+#undef C_KEY
+#undef C_ORD
+#undef C_ORD2
+#undef C_T2
+#undef C_PX
+#undef C_PY
+#undef C_PZ
 }
-#undef IQ_TICK
+
 
 // ------------------------------------------------------------------------------------
 // K5: map insert, pass 1 (kiss-icp AddPoints): transform frame_downsample by the new pose,
@@ -1666,7 +1502,8 @@ __device__ __forceinline__ u32 map_find_or_create(LaneDev& L, u64 key) {
                 double2* rows = reinterpret_cast<double2*>(B);   // unused slots read as +inf in the NN search
 #pragma unroll
                 for (int k = 0; k < (3 * MAXP) / 2; ++k) rows[k] = make_double2(INFINITY, INFINITY);
-                B->count = 0; B->slot = slot; B->key = key;
+                B->key = key;
+                L.vmeta[id].count = 0; L.vmeta[id].slot = slot;
                 atomicAdd(&L.n_vox, 1);
                 __threadfence();
                 S->id = id;
@@ -1720,7 +1557,7 @@ __global__ void __launch_bounds__(256) k_map_insert(LaneDev* lanes, const StepPa
         }
         if (j < n_ds) L.ds_vid[j] = vid;
         if (act && vid != NONE) {
-            int c0 = (int)*((volatile u32*)&L.blocks[vid].count);
+            int c0 = (int)*((volatile u32*)&L.vmeta[vid].count);
             u32 cur = (u32)j;
             u32* slots = L.vidx + (size_t)vid * MAXP;
             for (int s = c0; s < L.maxp; ++s) {
@@ -1752,8 +1589,9 @@ __global__ void __launch_bounds__(256) k_map_commit(LaneDev* lanes, const StepOu
         if (use_pose) { double xo, yo, zo; rigid_apply(T, x, y, z, xo, yo, zo); x = xo; y = yo; z = zo; }
         VoxelBlock* B = L.blocks + vid;
         B->x[s] = x; B->y[s] = y; B->z[s] = z;
+        if (s == 0) { L.vmeta[vid].fx = x; L.vmeta[vid].fy = y; L.vmeta[vid].fz = z; }
         slots[s] = NONE;
-        atomicAdd(&B->count, 1u);
+        atomicAdd(&L.vmeta[vid].count, 1u);
         ++added;
     }
 #pragma unroll
@@ -1772,14 +1610,14 @@ __global__ void __launch_bounds__(256) k_map_prune(LaneDev* lanes, const StepOut
     const double r2max = L.max_distance * L.max_distance;
     const int stride = gridDim.x * blockDim.x;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < bump; u += stride) {
-        VoxelBlock* B = L.blocks + u;
-        u32 c = B->count;
+        VoxelMeta& V = L.vmeta[u];
+        const u32 c = V.count;
         if (c == 0) continue;
-        double dx = B->x[0] - ox, dy = B->y[0] - oy, dz = B->z[0] - oz;
+        double dx = V.fx - ox, dy = V.fy - oy, dz = V.fz - oz;
         double d2 = (dx * dx + dy * dy) + dz * dz;
         if (d2 > r2max) {
-            L.m_slots[B->slot].key = KEY_TOMB;
-            B->count = 0;
+            L.m_slots[V.slot].key = KEY_TOMB;
+            V.count = 0;
             int t = atomicAdd(&L.free_top, 1);
             L.freelist[t] = (u32)u;
             atomicSub(&L.n_vox, 1);
@@ -1811,7 +1649,7 @@ __global__ void k_map_rebuild(LaneDev* lanes) {
     const int stride = gridDim.x * blockDim.x;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < bump; u += stride) {
         VoxelBlock* B = L.blocks + u;
-        if (B->count == 0) continue;
+        if (L.vmeta[u].count == 0) continue;
         u64 key = B->key;
         u32 slot = hash_map_key(key) & L.m_mask;
         while (true) {
@@ -1820,7 +1658,7 @@ __global__ void k_map_rebuild(LaneDev* lanes) {
             slot = (slot + 1) & L.m_mask;
         }
         L.m_slots[slot].id = (u32)u;
-        B->slot = slot;
+        L.vmeta[u].slot = slot;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) L.n_tomb = 0;
 }
@@ -2017,7 +1855,7 @@ __global__ void k_map_dump(LaneDev* lanes, int lane_id, int* keys, int* counts, 
     const int bump = min(L.bump, L.pool_cap);
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < bump; u += stride) {
         const VoxelBlock* B = L.blocks + u;
-        int c = (int)B->count;
+        int c = (int)L.vmeta[u].count;
         if (c == 0) continue;
         if (cloud) {
             int at = atomicAdd(n_pts_out, c);

@@ -134,11 +134,10 @@ class Odometry:
         return out
 
     def icp_phases(self, lane=0):
-        """Warp cycles (clock64, summed over every warp of the device) the ICP dataflow kernel spent per phase
-        since profiling was switched on (measurement tap; zeros while profiling is off)."""
+        """clock64 cycles block 0 of the lane's last ICP launch spent per phase (measurement tap)."""
         out = np.zeros(6, dtype=np.int64)
         self._check(self._lib.ptk_get_icp_phases(self._h, lane, addr(out)))
-        return dict(zip(("cache_pass", "searches", "sums", "queue_wait", "tree", "solve"), out.tolist()))
+        return dict(zip(("cache_pass", "searches", "sums", "barrier", "tree", "solve"), out.tolist()))
 
     def launch_count(self):
         return int(self._lib.ptk_launch_count(self._h))
