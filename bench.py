@@ -41,10 +41,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ptk", choices=["ptk", "reference"])
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("PTK_BENCH_LANES", "48")),
-                    help="independent sequences per GPU advanced by one batched step")
+                    help="independent sequences per GPU")
+    ap.add_argument("--contexts", type=int, default=int(os.environ.get("PTK_BENCH_CONTEXTS", "3")),
+                    help="contexts the lanes of a GPU are dealt to (each advances its lanes in lock step, on its own thread)")
+    ap.add_argument("--icp-blocks", type=int, default=6, help="ICP blocks per lane when several contexts share the GPU")
     ap.add_argument("--config", default="os0_quad", choices=["os0_quad", "os2_street", "os0_hall"])
-    ap.add_argument("--input", default="range", choices=["range", "xyz"],
-                    help="range: RANGE image as KissICPWrapper.register_frame gets it; xyz: projected cloud")
+    ap.add_argument("--input", default="range", choices=["range"],
+                    help="range: RANGE image as KissICPWrapper.register_frame gets it")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -380,121 +383,121 @@ def run_ptk(args):
             pass
 
     B, K, W = args.lanes, args.steps, args.warmup
+    G = max(1, min(args.contexts, B))
     T = W + K
-    TG = T + 1      # one scan more than is stepped: the LAST timed step of the host-buffer leg prefetches it, so the
-                    # timed region holds exactly K host-to-device copies (the first timed scan's copy was issued by the
-                    # last warm-up step, outside the region; this one replaces it)
     min_r, max_r, max_pts, map_cap = CONFIGS[args.config]
 
     # ---- synthetic scans, generated on the device (data plumbing) -------------------------
-    # input = "range": the scan as KissICPWrapper.register_frame receives it (kiss.py:54-61): the RANGE
-    # image (H, W) uint32 mm; projection + mask + column timestamps run inside the step.
-    # input = "xyz": the already projected (N,3)+(N,) float64 cloud of _kiss_register_frame (kiss.py:83).
-    use_range = args.input == "range"
+    # the scan as KissICPWrapper.register_frame receives it (kiss.py:54-61): the RANGE image (H, W) uint32 mm;
+    # projection + mask + column timestamps run inside the step.
+    use_range = True
     gens = [synth.TorchScanGenerator(synth.make_sequence(args.config, rank * B + l), dev) for l in range(B)]
-    frames = [[None] * B for _ in range(TG)]
-    tss = [[None] * B for _ in range(TG)]
-    ranges = [[None] * B for _ in range(TG)]
+    ranges = [[None] * B for _ in range(T)]
     for l, g in enumerate(gens):
-        for s in range(TG):
-            rng, _, _ = g.range_image(s)
-            ranges[s][l] = rng.contiguous()
-            if not use_range:
-                frames[s][l], tss[s][l] = g.project(rng)
+        for s in range(T):
+            ranges[s][l] = g.range_image(s)[0].contiguous()
     torch.cuda.synchronize()
-    if use_range:
-        scan_bytes = sum(r.numel() * 4 for r in ranges[W])
-        total_bytes = sum(r.numel() * 4 for s in range(TG) for r in ranges[s])
-    else:
-        scan_bytes = sum(f.numel() * 8 + t.numel() * 8 for f, t in zip(frames[W], tss[W]))
-        total_bytes = sum(f.numel() * 8 + t.numel() * 8 for s in range(TG) for f, t in zip(frames[s], tss[s]))
+    scan_bytes = sum(r.numel() * 4 for r in ranges[W])
+    total_bytes = sum(r.numel() * 4 for s in range(T) for r in ranges[s])
     n_points = int((ranges[W][0] != 0).sum().item())
 
     cfg = odometry.load_config(None, deskew=True, max_range=max_r)
     cfg.data.min_range = min_r
-    stream = torch.cuda.Stream(device=dev)
-    sh = stream.cuda_stream
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(odo, fr, ts, s):
-        if use_range:
-            if isinstance(fr[s][0], np.ndarray) and s + 1 < len(fr) and not args.no_prefetch:
-                odo.prefetch_scan_batch(fr[s + 1])      # host buffers: copy scan s+1 while scan s computes
-            return odo.register_scan_batch(fr[s], stream=sh)
-        return odo.register_frame_batch(fr[s], ts[s], stream=sh)
+    # The B sequences of this rank are dealt to G contexts.  The lanes of one context advance in lock step (one
+    # batched call = one step of all of them); the contexts are NOT synchronised with each other: ptk_fleet_replay
+    # runs each on its own host thread and stream, so the latency-bound ICP loop of one context overlaps the
+    # streaming kernels of the others.  G = 1 is the plain lock-step batch.
+    parts = [list(range(g * B // G, (g + 1) * B // G)) for g in range(G)]
+    odos = [odometry.Odometry(cfg, device=local, max_points=max_pts, map_capacity=map_cap, batch=len(p)) for p in parts]
+    for o in odos:
+        o.set_sensor(gens[0].seq.dirs)
+        if G > 1:
+            o.set_icp_blocks_per_lane(args.icp_blocks)
+    streams = [torch.cuda.Stream(device=dev) for _ in odos]
+    sh = [st.cuda_stream for st in streams]
+    stream = streams[0]
+
+    def replay(images, lo, hi, want_stats=False):
+        rg = [[[images[s][l] for l in parts[g]] for s in range(lo, hi)] for g in range(G)]
+        return odometry.fleet_replay(odos, rg, sh, want_stats=want_stats)
+
+    def merge(per_ctx):          # [g] (n, b_g, 4, 4) -> (n, B, 4, 4)
+        out = np.empty((per_ctx[0].shape[0], B, 4, 4))
+        for g, pz in enumerate(per_ctx):
+            out[:, parts[g]] = pz
+        return out
 
     icp_phase_cycles = None
 
-    def timed_run(odo, fr, ts, profiling, clocks=None):
-        odo.reset()
-        stats_acc = []
-        poses = []
-        for s in range(W):
-            p, st = step(odo, fr, ts, s)
-            poses.append(p)
+    def timed_run(images, profiling, clocks=None):
+        """W untimed scans, then K timed ones: one ptk_fleet_replay call each.  Device time = from an event recorded
+        on every context's stream before the call to the last of the events recorded on them after it."""
+        for o in odos:
+            o.reset()
+        poses_w = merge(replay(images, 0, W))
         if profiling:
-            odo.set_profiling(True)
-        l0 = odo.launch_count()
+            for o in odos:
+                o.set_profiling(True)
+        l0 = sum(o.launch_count() for o in odos)
         barrier()
         c0 = clocks.mark() if clocks else 0
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for s in range(W, T):
-                p, st = step(odo, fr, ts, s)
-                poses.append(p)
-                stats_acc.append(st)
-            e1.record(stream)
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in odos]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in odos]
+        for ev, st in zip(e0, streams):
+            ev.record(st)
+        res = replay(images, W, T, want_stats=profiling)
+        for ev, st in zip(e1, streams):
+            ev.record(st)
         barrier()
         c1 = clocks.mark() if clocks else 0
-        ms = e0.elapsed_time(e1)
-        launches = odo.launch_count() - l0
-        prof = odo.get_profile() if profiling else None
+        ms = max(e0[0].elapsed_time(ev) for ev in e1)
+        launches = sum(o.launch_count() for o in odos) - l0
+        prof, stats_acc = None, None
         if profiling:
             nonlocal icp_phase_cycles
-            icp_phase_cycles = odo.icp_phases(0)
-            odo.set_profiling(False)
-        return ms, launches, prof, stats_acc, np.stack(poses), (c0, c1)
+            poses_t, stats_ctx = res
+            icp_phase_cycles = odos[0].icp_phases(0)
+            prof = {}
+            for o in odos:
+                for k, (ms_k, n_k) in o.get_profile().items():
+                    a = prof.get(k, (0.0, 0))
+                    prof[k] = (a[0] + ms_k, a[1] + n_k)
+                o.set_profiling(False)
+            stats_acc = [[stats_ctx[g][s][i] for g in range(G) for i in range(len(parts[g]))] for s in range(K)]
+        else:
+            poses_t = res
+        return ms, launches, prof, stats_acc, np.concatenate([poses_w, merge(poses_t)]), (c0, c1)
 
-    odo = odometry.Odometry(cfg, device=local, max_points=max_pts, map_capacity=map_cap, batch=B)
-    if use_range:
-        odo.set_sensor(gens[0].seq.dirs)
-    dev_in = ranges if use_range else frames
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
 
     # ---- leg 1: inputs resident in HBM ----------------------------------------------------
-    ms_dev, launches, _, stats_acc, poses_dev, cspan = timed_run(odo, dev_in, tss, False, clocks)
-    # per-kernel device times: same steps again with every launch bracketed by CUDA events on
+    ms_dev, launches, _, _, poses_dev, cspan = timed_run(ranges, False, clocks)
+    # per-kernel device times: same scans again with every launch bracketed by CUDA events on
     # the launching stream (separate pass so the events do not sit inside the headline number)
-    ms_prof, _, prof, _, poses_prof, _ = timed_run(odo, dev_in, tss, True)
+    ms_prof, _, prof, stats_acc, poses_prof, _ = timed_run(ranges, True)
 
     # ---- leg 2: end to end from pinned host buffers ----------------------------------------
+    # every timed scan is copied host -> device inside the timed call (the first one synchronously, the others
+    # prefetched one scan ahead on a side stream while the previous scan computes): exactly K copies per lane
     e2e = None
+    h_frames = None
     if not args.no_e2e:
-        h_frames = [[None] * B for _ in range(TG)]
-        h_ts = [[None] * B for _ in range(TG)]
-        for s in range(TG):
+        h_frames = [[None] * B for _ in range(T)]
+        for s in range(T):
             for l in range(B):
-                if use_range:
-                    hr = _ffi.pinned_empty(tuple(ranges[s][l].shape), dtype=np.uint32)
-                    hr[...] = ranges[s][l].cpu().numpy().astype(np.uint32)
-                    h_frames[s][l] = hr
-                else:
-                    n = frames[s][l].shape[0]
-                    hf = _ffi.pinned_empty((n, 3))
-                    ht = _ffi.pinned_empty((n,))
-                    hf[...] = frames[s][l].cpu().numpy()
-                    ht[...] = tss[s][l].cpu().numpy()
-                    h_frames[s][l], h_ts[s][l] = hf, ht
-        ms_e2e, _, _, _, poses_e2e, _ = timed_run(odo, h_frames, h_ts, False)
+                hr = _ffi.pinned_empty(tuple(ranges[s][l].shape), dtype=np.uint32)
+                hr[...] = ranges[s][l].cpu().numpy().astype(np.uint32)
+                h_frames[s][l] = hr
+        ms_e2e, _, _, _, poses_e2e, _ = timed_run(h_frames, False)
         if not np.array_equal(poses_e2e, poses_dev):
             raise SystemExit("bench.py: host-buffer and device-buffer runs disagree")
         import ctypes
@@ -509,23 +512,22 @@ def run_ptk(args):
     single = None
     if B > 1:
         odo1 = odometry.Odometry(cfg, device=local, max_points=max_pts, map_capacity=map_cap, batch=1)
-        if use_range:
-            odo1.set_sensor(gens[0].seq.dirs)
+        odo1.set_sensor(gens[0].seq.dirs)
 
-        def run1(inp, tsl):
+        def run1(inp):
             odo1.reset()
             for s_ in range(W):
-                (odo1.register_scan(inp[s_][0], stream=sh) if use_range else odo1.register_frame(inp[s_][0], tsl[s_][0], stream=sh))
+                odo1.register_scan(inp[s_][0], stream=sh[0])
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for s_ in range(W, T):
-                (odo1.register_scan(inp[s_][0], stream=sh) if use_range else odo1.register_frame(inp[s_][0], tsl[s_][0], stream=sh))
+                odo1.register_scan(inp[s_][0], stream=sh[0])
             torch.cuda.synchronize()
             return K / (time.perf_counter() - t0)
-        single = {"value": run1(dev_in, tss), "unit": UNIT,
+        single = {"value": run1(ranges), "unit": UNIT,
                   "note": "one sequence, one scan per step (each scan waits for the previous pose): host wall clock"}
         if not args.no_e2e:
-            single["e2e"] = run1(h_frames, h_ts)
+            single["e2e"] = run1(h_frames)
         odo1.close()
 
     def max_over_ranks(v):
@@ -537,9 +539,10 @@ def run_ptk(args):
 
     # ---- the other BASELINE.json configs, small runs (skipped with --no-side-runs) -----------
     side = {}
+    for o in odos:
+        o.close()
+    odos = []
     if not args.no_side_runs:
-        odo.close()
-        odo = None
         # configs[4], first half, LITERALLY: 64 sequences in total, dealt to the ranks (strong scaling: 64/N per GPU)
         if 64 % world == 0:
             per = 64 // world
@@ -571,9 +574,11 @@ def run_ptk(args):
         "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": f"configs[1] 100-scan OS0-128 1024x10 sequence shape ({args.config}), full odometry step, "
-                        f"{B} independent sequences (lanes) per GPU advanced by one batched step; scans "
-                        f"{W}..{W + K - 1} of each sequence timed",
-            "lanes_per_gpu": B, "points_per_scan": n_points, "input": args.input, "max_range": max_r,
+                        f"{B} independent sequences (lanes) per GPU in {G} context(s) of {[len(p) for p in parts]} lanes; a "
+                        f"step = every lane advanced by one scan (one batched call per context, contexts free-running "
+                        f"on their own host threads: ptk_fleet_replay); scans {W}..{W + K - 1} of each sequence timed",
+            "lanes_per_gpu": B, "contexts_per_gpu": G, "icp_blocks_per_lane": (args.icp_blocks if G > 1 else "all"),
+            "points_per_scan": n_points, "input": args.input, "max_range": max_r,
             "min_range": min_r, "voxel_size": cfg.mapping.voxel_size,
             "l2": f"every step reads scans never touched before ({total_bytes / 1e9:.2f} GB of scans per GPU, "
                   f"{scan_bytes / 1e6:.1f} MB per step); the local maps are persistent state and stay wherever "
@@ -587,9 +592,8 @@ def run_ptk(args):
         out["e2e"] = {"value": world * B * K / (ms_e2e_max * 1e-3), "unit": UNIT,
                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                       "ms_per_step": ms_e2e_max / K,
-                      "api": ("ptk_register_scan_batch (C ABI, ctypes) with pinned host RANGE images (uint32 mm)"
-                              if use_range else
-                              "ptk_register_frame_batch (C ABI, ctypes) with pinned host xyz/timestamps")}
+                      "api": "ptk_fleet_replay -> ptk_register_scan_batch per context and scan (C ABI, ctypes) with pinned "
+                             "host RANGE images (uint32 mm); poses and counters of every scan read back to the host"}
 
     # ---- roofline of the dominant kernel ---------------------------------------------------
     peak, peak_src = measured_peaks()
@@ -608,7 +612,7 @@ def run_ptk(args):
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": recorded_traffic(dom, args.config, B, args.input), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": dms / dn,
-        "kernel_share_of_step": dms / ms_prof,
+        "kernel_share_of_step": dms / sum(v[0] for v in prof.values()),
         "step_algorithmic_bytes_per_scan": total_algo / (B * K),
         "step_hbm_frac": (total_algo / (ms_dev * 1e-3) / 1e9) / peak,
         "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items() if v[1] > 0},
@@ -649,8 +653,8 @@ def run_ptk(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if odo is not None:
-        odo.close()
+    for o in odos:
+        o.close()
     if rank == 0:
         print(json.dumps(out), file=RESULT, flush=True)
 

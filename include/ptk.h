@@ -131,6 +131,19 @@ int ptk_register_scan_batch(ptk_ctx* ctx, const unsigned int* const* range_mm, c
  * Host buffers should be pinned and must stay valid until they have been consumed. */
 int ptk_prefetch_scan_batch(ptk_ctx* ctx, const unsigned int* const* range_mm);
 
+/* ---- fleet replay over several contexts (BASELINE.json configs[4]: independent sequences) ----------------------
+ * The lanes of one context advance in lock step; a fleet does not have to.  ptk_fleet_replay runs n_ctx contexts,
+ * each on its own host thread (and the stream streams[g], non-default), through n_scans scans:
+ *   range_mm[g][s * batch_g + l]   RANGE image of scan s, lane l of context g (host pinned or device pointers)
+ *   out_poses[g][(s * batch_g + l) * 16], stats[g][s * batch_g + l]   (nullable)
+ * Every step of every context is an ordinary ptk_register_scan_batch (host images are prefetched one scan ahead);
+ * the contexts just are not synchronised with each other, so the ICP loop of one overlaps the streaming kernels of
+ * the others.  ptk_set_icp_blocks_per_lane caps the blocks of the cooperative ICP launch per lane (0 = as many as
+ * the device holds) so that the ICP launches of several contexts fit the device side by side. */
+int ptk_set_icp_blocks_per_lane(ptk_ctx* ctx, int blocks);
+int ptk_fleet_replay(ptk_ctx* const* ctxs, int n_ctx, const unsigned int* const* const* range_mm, int n_scans,
+                     double* const* out_poses, ptk_stats* const* stats, void* const* streams);
+
 /* ---- one sequence, voxel map sharded by hash key over several GPUs (one process + context per GPU).
  * The registration loop of kiss.py:108-114 is driven by the host between its two collectives per
  * iteration (ptudes_lab_b200/sharded.py): every rank preprocesses the same scan, searches its own
@@ -142,6 +155,17 @@ int ptk_prefetch_scan_batch(ptk_ctx* ctx, const unsigned int* const* range_mm);
  *   gathered [nranks][5][n_src] the records of every rank (all-gather)
  *   partials [17][32]           column r = slice root of rank r, zero elsewhere (all-reduce SUM) */
 int ptk_shard_config(ptk_ctx* ctx, int rank, int nranks);
+/* The same mode WITHOUT the host in the loop (the product path on NVLink-connected GPUs): after ptk_shard_config
+ * every rank exports its exchange buffer (a CUDA IPC handle, or the pointer itself for contexts of one process),
+ * attaches every other rank's, and from then on the ordinary step (ptk_register_scan / ptk_register_frame, lane 0,
+ * the SAME scan on every rank) does everything: the ICP kernel of each rank searches its own shard and the blocks
+ * with the same index exchange their per-point (d2, order id, target) records through peer memory with stamp flags,
+ * take the lexicographic minimum over the ranks and build identical normal equations - no collective, no host round
+ * trip per iteration, poses bit-identical to one GPU.  Streams must be non-default (the ranks' kernels spin on each
+ * other).  Replaces nothing in the reference (kiss-icp is single-process); requested by BASELINE.json north_star. */
+int ptk_shard_peer_export(ptk_ctx* ctx, unsigned char* handle64 /* nullable */, void** local_ptr /* nullable */,
+                          unsigned long long* bytes /* nullable */);
+int ptk_shard_peer_attach(ptk_ctx* ctx, int rank, const unsigned char* handle64 /* or NULL */, void* direct_ptr /* or NULL */);
 int ptk_shard_begin(ptk_ctx* ctx, int lane, const double* xyz, const double* timestamps, int n,
                     const unsigned int* range_mm /* alternative input, NULL to use xyz */,
                     const double* initial_guess, int* n_src, int* n_vox_local, void* stream);

@@ -97,6 +97,11 @@ SYMBOLS = {
     "ptk_ekf_get_pose": (C.c_int, [_P, _D]),
     "ptk_ekf_get_cov": (C.c_int, [_P, _D]),
     "ptk_ekf_ts": (C.c_double, [_P]),
+    "ptk_shard_peer_export": (C.c_int, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_ulonglong)]),
+    "ptk_shard_peer_attach": (C.c_int, [_P, C.c_int, C.c_char_p, _P]),
+    "ptk_set_icp_blocks_per_lane": (C.c_int, [_P, C.c_int]),
+    "ptk_fleet_replay": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(C.POINTER(_I)), C.c_int, C.POINTER(_D),
+                                   C.POINTER(C.POINTER(PtkStats)), C.POINTER(_P)]),
     "ptk_host_alloc": (C.c_int, [C.POINTER(_P), C.c_ulonglong]),
     "ptk_host_free": (C.c_int, [_P]),
 }

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -99,6 +100,11 @@ struct ptk_ctx {
     int icp_max_blocks_per_lane = 1 << 20;   // PTK_ICP_MAX_BLOCKS_PER_LANE: fewer blocks = cheaper barrier, slower searches
     int icp_cluster = 0;              // blocks per lane of the cluster launch of wide batches (0: not available)
     int icp_cluster_min_lanes = 56;   // batch width from which the cluster launch is used
+    // hash-sharded mode with in-kernel exchange: this rank's buffer and every rank's buffer as mapped here
+    void* xch_local = nullptr;
+    size_t xch_bytes = 0;
+    void* xch_peer[PTK_MAX_PEERS] = {nullptr};
+    bool xch_ipc[PTK_MAX_PEERS] = {false};
     std::string err;
     std::vector<void*> allocs;
 };
@@ -352,6 +358,9 @@ extern "C" int ptk_ctx_destroy(ptk_ctx* ctx) {
         for (void* p : L.allocs) cudaFree(p);
     for (void* p : ctx->allocs) cudaFree(p);
     for (void* p : ctx->sensor_allocs) cudaFree(p);
+    for (int r = 0; r < PTK_MAX_PEERS; ++r)
+        if (ctx->xch_ipc[r] && ctx->xch_peer[r]) cudaIpcCloseMemHandle(ctx->xch_peer[r]);
+    if (ctx->xch_local) cudaFree(ctx->xch_local);
     if (ctx->d_big) cudaFree(ctx->d_big);
     for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
     if (ctx->pf_event) cudaEventDestroy(ctx->pf_event);
@@ -508,6 +517,7 @@ static int launch_icp(ptk_ctx* ctx, int l0, int cnt, int groups_hint, cudaStream
         int per = std::max(1, ctx->icp_blocks_total / chunk);
         if (groups_hint > 0) per = std::max(1, std::min(per, groups_hint));
         per = std::min(per, ctx->icp_max_blocks_per_lane);
+        if (ctx->xch_local) per = std::min(per, XCH_FLAGS - 2);      // one exchange stamp per block
         LaneDev* dl = ctx->d_lanes + l0 + done;
         StepParams* dp = ctx->d_params + l0 + done;
         StepOut* dout = ctx->d_outs + l0 + done;
@@ -622,6 +632,7 @@ static int step_prepare(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz,
         P.max_corr = 3 * sigma;                                                                 // kiss.py:112-113
         P.kernel = sigma / 3;
         P.epoch = ++LH.epoch;
+        P.xch_epoch = P.epoch;
         nmax = std::max(nmax, n[k]);
     }
     // wide batches: fewer, longer-lived blocks (block dispatch limits the rate); a few lanes: all the blocks we can get
@@ -1274,6 +1285,69 @@ extern "C" int ptk_shard_config(ptk_ctx* ctx, int rank, int nranks) {
     return PTK_OK;
 }
 
+// ---- in-kernel exchange through peer memory ------------------------------------------------------------------
+// Layout of a rank's buffer: records [nranks][2][5][max_points] f64 | stamps [nranks][XCH_FLAGS] u64 | voxel counts [nranks] i32
+static size_t xch_rec_bytes(const ptk_ctx* ctx, int G) { return (size_t)G * 2 * 5 * (size_t)ctx->cfg.max_points * sizeof(double); }
+static size_t xch_flag_bytes(int G) { return (size_t)G * XCH_FLAGS * sizeof(unsigned long long); }
+
+extern "C" int ptk_shard_peer_export(ptk_ctx* ctx, unsigned char* handle64, void** local_ptr, unsigned long long* bytes) {
+    if (!ctx) return PTK_E_ARG;
+    const int G = ctx->lanes[0].d.shard_n;
+    if (G < 2 || G > PTK_MAX_PEERS) return fail(ctx, PTK_E_STATE, "ptk_shard_peer_export: call ptk_shard_config with 2..8 ranks first");
+    if (ctx->cfg.max_iterations > 1000000) return fail(ctx, PTK_E_ARG, "ptk_shard_peer_export: max_iterations too large");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->xch_local) {
+        ctx->xch_bytes = xch_rec_bytes(ctx, G) + xch_flag_bytes(G) + 256;
+        CK(cudaMalloc(&ctx->xch_local, ctx->xch_bytes));
+        CK(cudaMemset(ctx->xch_local, 0, ctx->xch_bytes));
+        CK(cudaDeviceSynchronize());
+    }
+    if (handle64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ctx->xch_local));
+        memcpy(handle64, &h, 64);
+    }
+    if (local_ptr) *local_ptr = ctx->xch_local;
+    if (bytes) *bytes = ctx->xch_bytes;
+    return PTK_OK;
+}
+
+extern "C" int ptk_shard_peer_attach(ptk_ctx* ctx, int rank, const unsigned char* handle64, void* direct_ptr) {
+    if (!ctx) return PTK_E_ARG;
+    const int G = ctx->lanes[0].d.shard_n, me = ctx->lanes[0].d.shard_rank;
+    if (!ctx->xch_local) return fail(ctx, PTK_E_STATE, "ptk_shard_peer_attach: ptk_shard_peer_export first");
+    if (rank < 0 || rank >= G) return fail(ctx, PTK_E_ARG, "ptk_shard_peer_attach: rank out of range");
+    CK(cudaSetDevice(ctx->device));
+    if (rank == me) ctx->xch_peer[rank] = ctx->xch_local;
+    else if (direct_ptr) ctx->xch_peer[rank] = direct_ptr;            // same process (peer access is the caller's business)
+    else if (handle64) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->xch_peer[rank] = p;
+        ctx->xch_ipc[rank] = true;
+    } else return fail(ctx, PTK_E_ARG, "ptk_shard_peer_attach: neither handle nor pointer");
+    ctx->xch_peer[me] = ctx->xch_local;
+    for (int r = 0; r < G; ++r)
+        if (!ctx->xch_peer[r]) return PTK_OK;                         // more ranks to come
+    // every rank is mapped: hand the pointers to the lanes
+    CK(cudaDeviceSynchronize());
+    for (size_t l = 0; l < ctx->lanes.size(); ++l) {
+        LaneDev& d = ctx->lanes[l].d;
+        for (int r = 0; r < G; ++r) {
+            char* base = (char*)ctx->xch_peer[r];
+            d.xch_rec[r] = (double*)base;
+            d.xch_flag[r] = (unsigned long long*)(base + xch_rec_bytes(ctx, G));
+            d.xch_nvox[r] = (int*)(base + xch_rec_bytes(ctx, G) + xch_flag_bytes(G));
+        }
+        CK(cudaMemcpy((char*)(ctx->d_lanes + l) + offsetof(LaneDev, xch_rec), d.xch_rec,
+                      offsetof(LaneDev, n_range) - offsetof(LaneDev, xch_rec), cudaMemcpyHostToDevice));
+    }
+    return PTK_OK;
+}
+
 extern "C" int ptk_shard_begin(ptk_ctx* ctx, int lane, const double* xyz, const double* timestamps, int n,
                                const unsigned int* range_mm, const double* initial_guess, int* n_src, int* n_vox_local,
                                void* stream) {
@@ -1402,5 +1476,46 @@ extern "C" int ptk_host_alloc(void** out, unsigned long long bytes) {
 
 extern "C" int ptk_host_free(void* p) {
     if (p) cudaFreeHost(p);
+    return PTK_OK;
+}
+
+// ---- fleet replay: several contexts, each advanced by its own host thread -----------------------------------------
+// The lanes of ONE context move in lock step (every call waits for all of them), so while its ICP kernel - a chain of
+// dependent iterations that leaves most of the GPU idle - runs, nothing else of that context can.  A fleet of
+// independent sequences does not need the lock step: split it over a few contexts, let every context run through
+// its scans on its own thread and stream, and the ICP of one overlaps the streaming kernels of the others.
+extern "C" int ptk_set_icp_blocks_per_lane(ptk_ctx* ctx, int blocks) {
+    if (!ctx || blocks < 0) return PTK_E_ARG;
+    ctx->icp_max_blocks_per_lane = blocks == 0 ? (1 << 20) : blocks;
+    return PTK_OK;
+}
+
+extern "C" int ptk_fleet_replay(ptk_ctx* const* ctxs, int n_ctx, const unsigned int* const* const* range_mm, int n_scans,
+                                double* const* out_poses, ptk_stats* const* stats, void* const* streams) {
+    if (!ctxs || n_ctx < 1 || !range_mm || n_scans < 0) return PTK_E_ARG;
+    std::vector<int> rcs(n_ctx, PTK_OK);
+    auto work = [&](int g) {
+        ptk_ctx* ctx = ctxs[g];
+        const int B = ctx->B;
+        cudaStream_t st = streams ? (cudaStream_t)streams[g] : nullptr;
+        for (int s = 0; s < n_scans; ++s) {
+            const unsigned int* const* cur = range_mm[g] + (size_t)s * B;
+            if (s + 1 < n_scans && !is_device_ptr(cur[0])) {
+                int prc = ptk_prefetch_scan_batch(ctx, range_mm[g] + (size_t)(s + 1) * B);
+                if (prc) { rcs[g] = prc; return; }
+            }
+            int rc = ptk_register_scan_batch(ctx, cur, nullptr, nullptr, out_poses ? out_poses[g] + (size_t)s * B * 16 : nullptr,
+                                             (stats && stats[g]) ? stats[g] + (size_t)s * B : nullptr, st);
+            if (rc) { rcs[g] = rc; return; }
+        }
+    };
+    if (n_ctx == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < n_ctx; ++g) th.emplace_back(work, g);
+        for (auto& t : th) t.join();
+    }
+    for (int g = 0; g < n_ctx; ++g)
+        if (rcs[g]) return rcs[g];
     return PTK_OK;
 }

@@ -25,6 +25,8 @@ constexpr u64 KEY_TOMB = ~0ull - 1ull;
 constexpr u32 NONE = 0xFFFFFFFFu;
 constexpr int KEY_BIAS = 1 << 20;
 constexpr int TILE = 1024;                 // items per compaction tile (256 threads x 4)
+constexpr int PTK_MAX_PEERS = 8;           // ranks of the peer-memory (in-kernel) exchange of the hash-sharded mode
+constexpr int XCH_FLAGS = 64;              // stamps per source rank: one per k_icp block (< 63) + the voxel count
 constexpr int NSUM = 17;                   // distinct normal-equation sums (16) + correspondence count
 constexpr int NRED = NSUM;
 #ifndef PTK_ICP_THREADS
@@ -90,6 +92,7 @@ struct StepParams {
     u32 epoch;             // step counter, >= 1
     u32 tbase1, tbase2;    // ticket bases of the two compaction kernels
     u32 release_base;      // (unused)
+    u32 xch_epoch;         // hash-sharded mode: step counter the exchange stamps are built from (same on every rank)
     u32 near1, near2;      // masks of the front regions of the two scan tables (0: whole table), see table_insert_min
     int W;                 // range-image mode: columns per frame (n = H * W pixels)
     // range-image input (kiss.py:59-61 on the device): non-null `range` selects it
@@ -143,6 +146,10 @@ struct LaneDev {
     int* c_ord2;                         // [ICP_KX][cap_points]
     u64* c_key; int* c_ord;
     int* trace;                          // [trace_iters][cap_points]
+    // hash-sharded mode, exchange through peer memory: entry r = rank r's buffer as mapped into this process
+    double* xch_rec[PTK_MAX_PEERS];              // [source rank][2][5][cap_points]: d2, order id, target xyz per source point
+    unsigned long long* xch_flag[PTK_MAX_PEERS]; // [source rank][XCH_FLAGS] stamps (epoch << 32 | exchange number)
+    int* xch_nvox[PTK_MAX_PEERS];                // [source rank] voxels in that rank's shard
     // dynamic state
     int n_range, n_ds, n_src, n_valid;
     int free_top, bump, n_vox, n_tomb, map_points;
@@ -1147,6 +1154,8 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
 #undef SOLVE_TICK
 }
 
+constexpr int SHARD_NO_ORD_K = 1 << 30;     // "no candidate" in an exchanged record
+
 // K4a: the searches of ICP iteration 0.  The first iteration has to search for EVERY source point (there is no
 // cache entry yet), which made it a third of the loop's time when the points were searched one per warp inside the
 // cooperative kernel.  Here it is an ordinary wide launch: one THREAD per source point (thread_nearest), a warp per
@@ -1160,7 +1169,7 @@ __global__ void __launch_bounds__(S0_THREADS) k_icp_search0(LaneDev* lanes, cons
     __shared__ float s_lbs[S0_THREADS / 32][27 * 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_src = L.n_src;
-    if (L.n_vox == 0 || n_src == 0) return;
+    if ((L.n_vox == 0 && L.shard_n <= 1) || n_src == 0) return;     // (a rank of a sharded map may own no voxel yet)
     const MapView M = map_view(L);
     const double max_corr = P.max_corr;
     const double max_d2 = (max_corr * max_corr) * (1.0 + 1e-9);   // farther candidates are rejected anyway
@@ -1233,7 +1242,36 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
     __shared__ MapView s_map;
     __shared__ unsigned short s_miss[ICP_CHUNK * 32];
 
-    if (L.n_vox == 0) {   // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
+    // ---- hash-sharded map: this context holds the voxels rank `sh_rank` of `sh_n` owns; the other
+    // ranks run the same kernel on their GPUs and the blocks with the same index trade per-point records through
+    // peer memory (NVLink): every rank writes its records straight into every other rank's buffer, then a stamp.
+    const int sh_n = L.shard_n, sh_rank = L.shard_rank;
+    const bool shard = sh_n > 1 && L.xch_rec[sh_rank] != nullptr;
+    int n_vox_all = L.n_vox;
+    if (shard) {
+        __shared__ int s_nvox;
+        if (threadIdx.x == 0) {
+            const u64 st = ((u64)P.xch_epoch << 32) | 1ull;
+            if (b == 0) {
+                for (int r = 0; r < sh_n; ++r)
+                    if (r != sh_rank) *((volatile int*)(L.xch_nvox[r] + sh_rank)) = L.n_vox;
+                __threadfence_system();
+                for (int r = 0; r < sh_n; ++r)
+                    if (r != sh_rank) *((volatile u64*)(L.xch_flag[r] + sh_rank * XCH_FLAGS + (XCH_FLAGS - 1))) = st;
+            }
+            int tot = L.n_vox;
+            for (int r = 0; r < sh_n; ++r) {
+                if (r == sh_rank) continue;
+                while (*((volatile u64*)(L.xch_flag[sh_rank] + r * XCH_FLAGS + (XCH_FLAGS - 1))) < st) { __nanosleep(100); }
+                tot += *((volatile int*)(L.xch_nvox[sh_rank] + r));
+            }
+            s_nvox = tot;
+        }
+        __syncthreads();
+        n_vox_all = s_nvox;
+    }
+    u32 xcnt = 0;             // exchanges this block has done in this launch
+    if (n_vox_all == 0) {   // RegisterFrame: if (voxel_map.Empty()) return initial_guess;
         if (b == 0 && threadIdx.x == 0) {
             O.pose = se3q_matrix(se3q_mul(se3q_identity(), se3q_from_rigid(P.guess)));
             O.iterations = 0; O.n_corr = 0; O.status = 0; O.dx_norm = 0.0;
@@ -1388,14 +1426,65 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
             __syncthreads();
             ICP_TICK(1);
             // ---- 3. residual + weights, group partials by warp butterflies
+            double wtx = 0, wty = 0, wtz = 0;
+            int word = -1;
+            if (live) {
+                word = C_ORD(sp, p);
+                if (word >= 0) { wtx = C_TX(sp, p); wty = C_TY(sp, p); wtz = C_TZ(sp, p); }
+            }
+            if (shard) {
+                // what this rank found is the nearest point of ITS voxels; the correspondence is the lexicographic
+                // minimum of (d2, order id) over the ranks (tie rule B.6: the order id encodes the voxel offset)
+                const size_t cap = (size_t)L.cap_points;
+                const int par = (int)(xcnt & 1u);
+                double d2l = INFINITY, ordl = (double)SHARD_NO_ORD_K;
+                if (live && word >= 0) {
+                    const double dx = wtx - sx, dy = wty - sy, dz = wtz - sz;
+                    d2l = (dx * dx + dy * dy) + dz * dz;
+                    ordl = (double)word;
+                }
+                if (live) {
+                    for (int r = 0; r < sh_n; ++r) {
+                        if (r == sh_rank) continue;
+                        double* rec = L.xch_rec[r] + (size_t)((sh_rank * 2 + par) * 5) * cap + p;
+                        rec[0] = d2l; rec[cap] = ordl; rec[2 * cap] = wtx; rec[3 * cap] = wty; rec[4 * cap] = wtz;
+                    }
+                }
+                __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const u64 st = ((u64)P.xch_epoch << 32) | (u64)(xcnt + 2u);
+                    for (int r = 0; r < sh_n; ++r)
+                        if (r != sh_rank) *((volatile u64*)(L.xch_flag[r] + sh_rank * XCH_FLAGS + b)) = st;
+                    for (int r = 0; r < sh_n; ++r) {
+                        if (r == sh_rank) continue;
+                        while (*((volatile u64*)(L.xch_flag[sh_rank] + r * XCH_FLAGS + b)) < st) { }
+                    }
+                    __threadfence_system();
+                }
+                __syncthreads();
+                if (live) {
+                    for (int r = 0; r < sh_n; ++r) {
+                        if (r == sh_rank) continue;
+                        const double* rec = L.xch_rec[sh_rank] + (size_t)((r * 2 + par) * 5) * cap + p;
+                        const double d2r = __ldcv(rec), ordr = __ldcv(rec + cap);
+                        if (d2r < d2l || (d2r == d2l && ordr < ordl)) {
+                            d2l = d2r; ordl = ordr;
+                            wtx = __ldcv(rec + 2 * cap); wty = __ldcv(rec + 3 * cap); wtz = __ldcv(rec + 4 * cap);
+                        }
+                    }
+                    word = ordl < (double)SHARD_NO_ORD_K ? (int)ordl : -1;
+                }
+                ++xcnt;
+            }
             if (warp < gc) {
                 double c[16];
                 bool acc = false;
                 int ord = -1;
                 if (live) {
-                    ord = C_ORD(sp, p);
+                    ord = word;
                     if (ord >= 0) {
-                        const double tx = C_TX(sp, p), ty = C_TY(sp, p), tz = C_TZ(sp, p);
+                        const double tx = wtx, ty = wty, tz = wtz;
                         const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
                         const double d2 = (dx * dx + dy * dy) + dz * dz;
                         acc = sqrt(d2) < max_corr;

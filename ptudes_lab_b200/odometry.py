@@ -142,6 +142,11 @@ class Odometry:
     def launch_count(self):
         return int(self._lib.ptk_launch_count(self._h))
 
+    def set_icp_blocks_per_lane(self, blocks: int):
+        """Cap the blocks per lane of the cooperative ICP launch (0: as many as the device holds), so that the
+        ICP launches of several contexts fit the device side by side (fleet replay over several contexts)."""
+        self._check(self._lib.ptk_set_icp_blocks_per_lane(self._h, int(blocks)))
+
     # -- the step ------------------------------------------------------------------
     def register_frame(self, frame, timestamps, initial_guess=None, lane=0, stream=0):
         """One odometry step (kiss.py:83-131).  Returns (pose 4x4, stats dict)."""
@@ -410,3 +415,35 @@ def register_frame(points, voxel_map: VoxelHashMap, initial_guess, max_correspon
     if return_stats:
         return pose, st.as_dict()
     return pose
+
+
+def fleet_replay(odos, ranges, streams, want_stats=False):
+    """ptk_fleet_replay: contexts `odos` (each advanced by its own host thread inside the library, on the
+    non-default stream handle streams[g]) through the scans `ranges[g][s][l]` = RANGE image of scan s, lane l of
+    context g (pinned host arrays or device tensors).  Returns poses[g] (n_scans, batch_g, 4, 4) [, stats[g][s]]."""
+    lib = odos[0]._lib
+    G = len(odos)
+    T = len(ranges[0])
+    keep, ptr_arrays = [], []
+    for g, o in enumerate(odos):
+        assert len(ranges[g]) == T
+        flat = [o._u32(r) for s in range(T) for r in ranges[g][s]]
+        assert len(flat) == T * o.batch
+        keep.append(flat)
+        ptr_arrays.append((C.c_void_p * len(flat))(*[addr(r) for r in flat]))
+    rng = (C.POINTER(C.c_void_p) * G)(*[C.cast(a, C.POINTER(C.c_void_p)) for a in ptr_arrays])
+    poses = [np.empty((T, o.batch, 4, 4)) for o in odos]
+    pp = (C.c_void_p * G)(*[addr(p) for p in poses])
+    stats = [(PtkStats * (T * o.batch))() for o in odos] if want_stats else None
+    sp = (C.POINTER(PtkStats) * G)(*[C.cast(s_, C.POINTER(PtkStats)) for s_ in stats]) if want_stats else None
+    hs = (C.c_void_p * G)(*[o._h for o in odos])
+    st = (C.c_void_p * G)(*[int(x) for x in streams])
+    rc = lib.ptk_fleet_replay(hs, G, rng, T, pp, sp, st)
+    if rc != 0:
+        for o in odos:
+            o._check(rc)
+    if want_stats:
+        out_stats = [[StatsBatch((PtkStats * o.batch).from_buffer(stats[g], s * o.batch * C.sizeof(PtkStats))) for s in range(T)]
+                     for g, o in enumerate(odos)]
+        return poses, out_stats
+    return poses

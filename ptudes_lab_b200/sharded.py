@@ -183,7 +183,80 @@ class ShardedOdometry:
         return self.b.end()
 
 
-def make_sharded(cfg, device: int, rank: int, world: int, *, max_points: int, map_capacity: int, dirs=None, group=None):
+class PeerShardedOdometry:
+    """One rank of a hash-sharded single-sequence odometry whose per-iteration exchange happens INSIDE the ICP kernel,
+    through peer memory (NVLink): every rank steps the same scans with the ordinary register_scan / register_frame
+    calls, the kernels of the ranks trade per-point records and stamps directly - no collective, no host in the loop.
+    torch.distributed is used once, to pass the CUDA IPC handles around (`connect`)."""
+
+    def __init__(self, odo, rank: int, nranks: int):
+        self.odo, self.rank, self.nranks = odo, rank, nranks
+        self.lib, self.h = odo._lib, odo._h
+        odo._check(self.lib.ptk_shard_config(self.h, rank, nranks))
+        self.scans = 0
+        self.connected = nranks == 1
+
+    def export(self):
+        """(IPC handle bytes, device pointer) of this rank's exchange buffer."""
+        handle = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        self.odo._check(self.lib.ptk_shard_peer_export(self.h, handle, C.byref(ptr), None))
+        return handle.raw, ptr.value
+
+    def attach(self, rank: int, handle: bytes = None, pointer: int = None):
+        self.odo._check(self.lib.ptk_shard_peer_attach(self.h, rank, handle, pointer))
+
+    def connect(self, group=None):
+        """Exchange the IPC handles over torch.distributed (one all-gather of 64 bytes per rank) and map every peer."""
+        if self.nranks == 1:
+            return self
+        handle, _ = self.export()
+        t = torch.tensor(list(handle), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        out = [torch.empty_like(t) for _ in range(self.nranks)]
+        dist.all_gather(out, t, group=group)
+        for r, h in enumerate(out):
+            if r != self.rank:
+                self.attach(r, handle=bytes(h.cpu().tolist()))
+        dist.barrier(group=group)
+        self.connected = True
+        return self
+
+    def register_frame(self, frame, timestamps, initial_guess=None, range_mm=None, stream=None):
+        """The ordinary step; `stream` must be a non-default stream (the ranks' ICP kernels wait for each other)."""
+        assert self.connected, "PeerShardedOdometry.connect() first"
+        if stream is None:
+            if not hasattr(self, "_stream"):
+                self._stream = torch.cuda.Stream()
+            stream = self._stream.cuda_stream
+        self.scans += 1
+        if range_mm is not None:
+            return self.odo.register_scan(range_mm, initial_guess=initial_guess, stream=stream)
+        return self.odo.register_frame(frame, timestamps, initial_guess=initial_guess, stream=stream)
+
+    def describe(self):
+        return {"exchange": "inside the ICP kernel: per-point (d2, order id, target) records written straight into the "
+                            "peers' memory (CUDA IPC over NVLink) with stamp flags; no collective, no host round trip",
+                "collectives_per_scan": 0.0}
+
+    def close(self):
+        self.odo.close()
+
+
+def make_sharded(cfg, device: int, rank: int, world: int, *, max_points: int, map_capacity: int, dirs=None, group=None,
+                 mode: str = "peer"):
+    """One rank's share of a hash-sharded single-sequence odometry.  mode="peer": exchange inside the kernel through
+    peer memory (the product path on NVLink-connected GPUs); mode="nccl": the host-driven loop with two NCCL
+    collectives per ICP iteration (kept as the portable comparison point, and what the gloo tests exercise)."""
+    from . import odometry
+    if mode == "peer" and world > 1:
+        odo = odometry.Odometry(cfg, device=device, max_points=max_points, map_capacity=map_capacity)
+        if dirs is not None:
+            odo.set_sensor(dirs)
+        return PeerShardedOdometry(odo, rank, world).connect(group)
+    return _make_sharded_nccl(cfg, device, rank, world, max_points=max_points, map_capacity=map_capacity, dirs=dirs, group=group)
+
+
+def _make_sharded_nccl(cfg, device: int, rank: int, world: int, *, max_points: int, map_capacity: int, dirs=None, group=None):
     """One rank's share of a hash-sharded single-sequence odometry: its own context (the local map holds only
     the voxels this rank owns) behind the sharded loop.  `dirs`: XYZLut directions for range-image input."""
     from . import odometry

@@ -626,3 +626,45 @@ def test_iteration_cap(os0_seq):
         assert np.array_equal(pose, rpose)
     finally:
         o.close()
+
+
+def test_fleet_replay_over_several_contexts(tiny_seq):
+    """ptk_fleet_replay: three contexts (2 + 2 + 1 lanes), each advanced by its own thread inside the library, from
+    pinned host range images (prefetched one scan ahead) and from device images.  Free-running contexts must give
+    exactly the poses of the lock-step batched call, i.e. the oracle's."""
+    import torch
+    from ptudes_lab_b200 import _ffi, odometry
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    n = 6
+    ref = ko.OracleKissICPWrapper()
+    want = []
+    for k in range(n):
+        xyz, ts, tsec, _ = tiny_seq.points(k)
+        want.append(ref.register_points(xyz, ts, tsec).copy())
+    batches = (2, 2, 1)
+    odos = [odometry.Odometry(cfg, max_points=16384, map_capacity=16384, batch=b) for b in batches]
+    try:
+        for o in odos:
+            o.set_sensor(tiny_seq.dirs)
+            o.set_icp_blocks_per_lane(6)
+        streams = [torch.cuda.Stream() for _ in odos]
+        host = []
+        for k in range(n):
+            h = _ffi.pinned_empty(tiny_seq.scan(k).range_mm.shape, dtype=np.uint32)
+            h[...] = tiny_seq.scan(k).range_mm
+            host.append(h)
+        dev = [torch.as_tensor(tiny_seq.scan(k).range_mm.astype(np.int32), device="cuda:0") for k in range(n)]
+        for images in (host, dev):
+            for o in odos:
+                o.reset()
+            ranges = [[[images[k]] * b for k in range(n)] for b in batches]
+            poses, stats = odometry.fleet_replay(odos, ranges, [s.cuda_stream for s in streams], want_stats=True)
+            for g, b in enumerate(batches):
+                assert poses[g].shape == (n, b, 4, 4)
+                for k in range(n):
+                    for l in range(b):
+                        assert np.array_equal(poses[g][k, l], want[k]), (g, k, l)
+                assert stats[g][n - 1][0]["n_src"] == ref.last_counts["n_src"]
+    finally:
+        for o in odos:
+            o.close()
