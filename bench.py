@@ -40,9 +40,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ptk", choices=["ptk", "reference"])
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("PTK_BENCH_LANES", "48")),
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("PTK_BENCH_LANES", "64")),
                     help="independent sequences per GPU")
-    ap.add_argument("--contexts", type=int, default=int(os.environ.get("PTK_BENCH_CONTEXTS", "3")),
+    ap.add_argument("--contexts", type=int, default=int(os.environ.get("PTK_BENCH_CONTEXTS", "8")),
                     help="contexts the lanes of a GPU are dealt to (each advances its lanes in lock step, on its own thread)")
     ap.add_argument("--icp-blocks", type=int, default=6, help="ICP blocks per lane when several contexts share the GPU")
     ap.add_argument("--config", default="os0_quad", choices=["os0_quad", "os2_street", "os0_hall"])

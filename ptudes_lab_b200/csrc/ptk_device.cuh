@@ -746,6 +746,26 @@ __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double
     return found;
 }
 
+// ---- TMA pieces (1-D bulk copy global -> shared, completion counted on an mbarrier) -----------------------------
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* mbar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* mbar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, u32 bytes, unsigned long long* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(mbar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* mbar, u32 phase) {
+    u32 ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_addr(mbar)), "r"(phase) : "memory");
+    } while (!ok);
+}
+
 // ---- the same search with ONE THREAD per query (the ICP kernel's form) -------------------------------------
 // Every lane of a warp carries its own query (or none: active = false), so all missed points of a 32-point group
 // are searched at the same time and the latency of a group's searches is that of one search.  Result semantics
@@ -754,8 +774,11 @@ __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double
 //   1. 27 table probes, issued nine at a time; voxel ids and a rounded-down float of the box distance go to this
 //      warp's shared-memory scratch (ids/lbs [27][32], one column per lane);
 //   2. the query's own voxel, then each lane walks ITS OWN list of voxels whose box is not farther than the best
-//      so far (a skipped voxel holds only strictly farther points); lanes = queries, so there is no divergence
-//      in the visit itself, only in how many voxels a lane needs;
+//      so far (a skipped voxel holds only strictly farther points).  The warp moves in rounds: every lane that
+//      still has a voxel to look at fetches its 480 B of point rows with ONE TMA bulk copy (cp.async.bulk) into
+//      its own slice of the warp's staging buffer, the copies of a round complete on the warp's mbarrier, and the
+//      distances are computed from shared memory.  (Reading the rows with per-thread 16 B loads instead made the
+//      kernel L1-bound: 32 lanes x 30 loads, every one a different cache line, per round.);
 //   3. coordinates of the winner and the runner-ups are re-read through their order ids (cache-hot).
 struct NearestOut {
     double tx, ty, tz, others;
@@ -765,8 +788,11 @@ struct NearestOut {
     int ord2[ICP_KX];
 };
 
-__device__ __forceinline__ void thread_nearest(const MapView& M, u32* ids, float* lbs, int lane, bool active, double sx, double sy,
-                                               double sz, double max_d2, NearestOut& R) {
+constexpr int STAGE_STRIDE = 62;            // doubles per lane in the staging buffer: 496 B (an odd number of 16 B units:
+                                            // the lanes' LDS.128 fall into different banks), 480 B of them used
+__device__ __forceinline__ void thread_nearest(const MapView& M, u32* ids, float* lbs, double* stage, unsigned long long* mbar,
+                                               u32& phase, int lane, bool active, double sx, double sy, double sz, double max_d2,
+                                               NearestOut& R) {
     int kx, ky, kz;
     voxel_key(sx, sy, sz, M.voxel, M.voxel_inv, kx, ky, kz);
     const bool inr = active && key_in_range(kx, ky, kz);
@@ -830,6 +856,7 @@ __device__ __forceinline__ void thread_nearest(const MapView& M, u32* ids, float
     u32 todo = present;
     int vv = (present >> 13) & 1u ? 13 : -1;     // the query's own voxel first
     todo &= ~(1u << 13);
+    double* const mine = stage + lane * STAGE_STRIDE;
     while (true) {
         if (vv < 0) {
             while (todo) {
@@ -839,43 +866,42 @@ __device__ __forceinline__ void thread_nearest(const MapView& M, u32* ids, float
                 if ((double)lb <= bound) { vv = c; break; }
                 rest = fmin(rest, (double)lb);
             }
-            if (vv < 0) break;
         }
-        const double2* rows = reinterpret_cast<const double2*>(M.blocks + ids[vv * 32 + lane]);
-        const int obase = vv * MAXP;
-        // the rows of a block are read four slots at a time, one batch AHEAD of the arithmetic: the five batches of a
-        // visit then cost about one memory round trip instead of five
-        double2 nx[6];
+        const u32 act = __ballot_sync(0xffffffffu, vv >= 0);
+        if (!act) break;
+        if (lane == 0) mbar_expect_tx(mbar, (u32)__popc(act) * (u32)(3 * MAXP * sizeof(double)));
+        __syncwarp();
+        if (vv >= 0) tma_load_1d(mine, M.blocks + ids[vv * 32 + lane], (u32)(3 * MAXP * sizeof(double)), mbar);
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+        if (vv >= 0) {
+            const double2* rows = reinterpret_cast<const double2*>(mine);
+            const int obase = vv * MAXP;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { nx[2 * r] = __ldg(rows + r * (MAXP / 2)); nx[2 * r + 1] = __ldg(rows + r * (MAXP / 2) + 1); }
+            for (int h = 0; h < MAXP / 4; ++h) {
+                const double2 xa = rows[2 * h], xb = rows[2 * h + 1];
+                const double2 ya = rows[MAXP / 2 + 2 * h], yb = rows[MAXP / 2 + 2 * h + 1];
+                const double2 za = rows[MAXP + 2 * h], zb = rows[MAXP + 2 * h + 1];
+                const double xs[4] = {xa.x, xa.y, xb.x, xb.y}, ys[4] = {ya.x, ya.y, yb.x, yb.y}, zs[4] = {za.x, za.y, zb.x, zb.y};
 #pragma unroll
-        for (int h = 0; h < MAXP / 4; ++h) {
-            const double xs[4] = {nx[0].x, nx[0].y, nx[1].x, nx[1].y}, ys[4] = {nx[2].x, nx[2].y, nx[3].x, nx[3].y},
-                         zs[4] = {nx[4].x, nx[4].y, nx[5].x, nx[5].y};
-            if (h + 1 < MAXP / 4) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    nx[2 * r] = __ldg(rows + r * (MAXP / 2) + 2 * (h + 1));
-                    nx[2 * r + 1] = __ldg(rows + r * (MAXP / 2) + 2 * (h + 1) + 1);
+                for (int k = 0; k < 4; ++k) {
+                    const double dx = xs[k] - sx, dy = ys[k] - sy, dz = zs[k] - sz;
+                    const double d = (dx * dx + dy * dy) + dz * dz;
+                    const int o = obase + 4 * h + k;
+                    if (d < d2 || (d == d2 && o < o2)) {                 // beats the third (unused slots hold +inf: never)
+                        rest = fmin(rest, d2);
+                        if (d < d1 || (d == d1 && o < o1)) {
+                            d2 = d1; o2 = o1;
+                            if (d < d0 || (d == d0 && o < o0)) { d1 = d0; o1 = o0; d0 = d; o0 = o; }
+                            else { d1 = d; o1 = o; }
+                        } else { d2 = d; o2 = o; }
+                    } else rest = fmin(rest, d);
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double dx = xs[k] - sx, dy = ys[k] - sy, dz = zs[k] - sz;
-                const double d = (dx * dx + dy * dy) + dz * dz;
-                const int o = obase + 4 * h + k;
-                if (d < d2 || (d == d2 && o < o2)) {                 // beats the third (unused slots hold +inf: never)
-                    rest = fmin(rest, d2);
-                    if (d < d1 || (d == d1 && o < o1)) {
-                        d2 = d1; o2 = o1;
-                        if (d < d0 || (d == d0 && o < o0)) { d1 = d0; o1 = o0; d0 = d; o0 = o; }
-                        else { d1 = d; o1 = o; }
-                    } else { d2 = d; o2 = o; }
-                } else rest = fmin(rest, d);
-            }
+            bound = fmin(bound, d0);
         }
-        bound = fmin(bound, d0);
         vv = -1;
+        __syncwarp();             // everybody is done with the staging buffer before the next round's copies land
     }
     R.ord = o0;
     R.tx = R.ty = R.tz = 0.0;
@@ -1161,13 +1187,21 @@ constexpr int SHARD_NO_ORD_K = 1 << 30;     // "no candidate" in an exchanged re
 // cooperative kernel.  Here it is an ordinary wide launch: one THREAD per source point (thread_nearest), a warp per
 // 32-point group, every lane of the batch at once.  The cache entries go to the lane's global cache arrays; k_icp
 // starts from them.
-constexpr int S0_THREADS = 128;
+constexpr int S0_THREADS = 64;
 __global__ void __launch_bounds__(S0_THREADS) k_icp_search0(LaneDev* lanes, const StepParams* params) {
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
+    __shared__ __align__(16) double s_stage[S0_THREADS / 32][32 * STAGE_STRIDE];      // TMA destination, one slice per lane
     __shared__ u32 s_ids[S0_THREADS / 32][27 * 32];
     __shared__ float s_lbs[S0_THREADS / 32][27 * 32];
+    __shared__ unsigned long long s_mbar[S0_THREADS / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        mbar_init(&s_mbar[warp], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    u32 phase = 0;
     const int n_src = L.n_src;
     if ((L.n_vox == 0 && L.shard_n <= 1) || n_src == 0) return;     // (a rank of a sharded map may own no voxel yet)
     const MapView M = map_view(L);
@@ -1180,7 +1214,7 @@ __global__ void __launch_bounds__(S0_THREADS) k_icp_search0(LaneDev* lanes, cons
         double sx = 0, sy = 0, sz = 0;
         if (live) { sx = L.s_x[p]; sy = L.s_y[p]; sz = L.s_z[p]; }
         NearestOut R;
-        thread_nearest(M, s_ids[warp], s_lbs[warp], lane, live, sx, sy, sz, max_d2, R);
+        thread_nearest(M, s_ids[warp], s_lbs[warp], s_stage[warp], &s_mbar[warp], phase, lane, live, sx, sy, sz, max_d2, R);
         if (live) {
             L.c_tx[p] = R.tx; L.c_ty[p] = R.ty; L.c_tz[p] = R.tz;
 #pragma unroll
