@@ -161,20 +161,21 @@ def source_sha():
     """sha256 (16 hex digits) of the kernel sources: ties a committed ncu capture to the code that produced it."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("ptk_device.cuh", "ptk_canon.cuh", "ptk.cu"):
+    for f in ("ptk_device.cuh", "ptk_canon.cuh"):
         with open(os.path.join(ROOT, "ptudes_lab_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
 
 
-def recorded_traffic(kernel, config, lanes, inp):
+def recorded_traffic(kernel, config, lanes, inp, contexts=1):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/r2_traffic.json),
     but only if it was taken on this very configuration AND on these very kernel sources (source_sha);
     None otherwise - never a guess, never a stale number."""
     try:
         with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             t = json.load(f)
-        if t["config"] == config and t["lanes"] == lanes and t["input"] == inp and t.get("source_sha") == source_sha():
+        if (t["config"] == config and t["lanes"] == lanes and t["input"] == inp and t.get("contexts", 1) == contexts
+                and t.get("source_sha") == source_sha()):
             return t["kernels"].get(kernel)
     except Exception:
         pass
@@ -215,40 +216,49 @@ def algorithmic_bytes(st, n_pixels=0):
 # --------------------------------------------------------------------------------------
 # Side runs carried in the same JSON line: the other BASELINE.json configs, so that every round's driver-run
 # BENCH/SCALE record holds evidence for them (they are parity-test cases first; tests/test_gpu_parity.py).
-def side_fleet(config, lanes, warmup, steps, local, seed0, sync, min_max=None):
-    """`lanes` sequences of `config` advanced `warmup + steps` scans by batched steps; device-resident range
-    images, CUDA events around the timed steps.  Returns (ms of the timed steps, last-step stats of lane 0)."""
+def side_fleet(config, lanes, warmup, steps, local, seed0, sync, contexts=1, icp_blocks=6):
+    """`lanes` sequences of `config` advanced `warmup + steps` scans, dealt to `contexts` free-running contexts
+    (ptk_fleet_replay); device-resident range images, CUDA events around the timed scans.  Returns (ms of the timed
+    scans, last-scan counters of lane 0)."""
     import torch
     from ptudes_lab_b200 import odometry, synth
     dev = torch.device("cuda", local)
     min_r, max_r, max_pts, map_cap = CONFIGS[config]
-    if min_max is not None:
-        min_r, max_r = min_max
     T = warmup + steps
+    G = max(1, min(contexts, lanes))
     gens = [synth.TorchScanGenerator(synth.make_sequence(config, seed0 + l), dev) for l in range(lanes)]
     ranges = [[g.range_image(s)[0].contiguous() for g in gens] for s in range(T)]
     cfg = odometry.load_config(None, deskew=True, max_range=max_r)
     cfg.data.min_range = min_r
-    odo = odometry.Odometry(cfg, device=local, max_points=max_pts, map_capacity=map_cap, batch=lanes)
-    odo.set_sensor(gens[0].seq.dirs)
-    stream = torch.cuda.Stream(device=dev)
+    parts = [list(range(g * lanes // G, (g + 1) * lanes // G)) for g in range(G)]
+    odos = [odometry.Odometry(cfg, device=local, max_points=max_pts, map_capacity=map_cap, batch=len(p)) for p in parts]
+    streams = [torch.cuda.Stream(device=dev) for _ in odos]
+    sh = [st.cuda_stream for st in streams]
     try:
-        for s in range(warmup):
-            odo.register_scan_batch(ranges[s], stream=stream.cuda_stream)
+        for o in odos:
+            o.set_sensor(gens[0].seq.dirs)
+            if G > 1:
+                o.set_icp_blocks_per_lane(icp_blocks)
+
+        def replay(lo, hi, want_stats=False):
+            rg = [[[ranges[s][l] for l in parts[g]] for s in range(lo, hi)] for g in range(G)]
+            return odometry.fleet_replay(odos, rg, sh, want_stats=want_stats)
+        replay(0, warmup)
         sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        vox = []
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for s in range(warmup, T):
-                _, st = odo.register_scan_batch(ranges[s], stream=stream.cuda_stream)
-                vox.append(st[0]["n_voxels"])
-            e1.record(stream)
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in odos]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in odos]
+        for ev, st in zip(e0, streams):
+            ev.record(st)
+        _, stats = replay(warmup, T, want_stats=True)
+        for ev, st in zip(e1, streams):
+            ev.record(st)
         sync()
-        last = st[0]
-        return e0.elapsed_time(e1), {k: last[k] for k in ("n_in", "n_ds", "n_src", "n_voxels", "map_points", "iterations")}
+        last = stats[0][steps - 1][0]
+        return (max(e0[0].elapsed_time(ev) for ev in e1),
+                {k: last[k] for k in ("n_in", "n_ds", "n_src", "n_voxels", "map_points", "iterations")})
     finally:
-        odo.close()
+        for o in odos:
+            o.close()
 
 
 def side_ekf_fleet(lanes, warmup, steps, local):
@@ -546,10 +556,12 @@ def run_ptk(args):
         # configs[4], first half, LITERALLY: 64 sequences in total, dealt to the ranks (strong scaling: 64/N per GPU)
         if 64 % world == 0:
             per = 64 // world
-            ms64, _ = side_fleet("os0_quad", per, 3, 10, local, rank * per, barrier)
+            g64 = max(1, min(G, per // 4))
+            ms64, _ = side_fleet("os0_quad", per, 3, 10, local, rank * per, barrier, contexts=g64, icp_blocks=args.icp_blocks)
             ms64 = max_over_ranks(ms64)
             side["fleet64_strong"] = {"value": 64 * 10 / (ms64 * 1e-3), "unit": UNIT, "sequences_total": 64,
-                                      "lanes_per_gpu": per, "steps": 10, "ms_per_step": ms64 / 10, "scaling": "strong",
+                                      "lanes_per_gpu": per, "contexts_per_gpu": g64, "steps": 10, "ms_per_step": ms64 / 10,
+                                      "scaling": "strong",
                                       "workload": "configs[4]: 64 independent os0_quad sequences over the ranks"}
         if world > 1:
             try:
@@ -558,8 +570,8 @@ def run_ptk(args):
                 side["sharded_single_sequence"] = {"error": f"{type(e).__name__}: {e}"}
             dist.barrier()
         if rank == 0:
-            ms2, c2 = side_fleet("os2_street", 16, 3, 10, local, 0, torch.cuda.synchronize)
-            side["os2_street"] = {"value": 16 * 10 / (ms2 * 1e-3), "unit": UNIT, "lanes": 16, "steps": 10,
+            ms2, c2 = side_fleet("os2_street", 16, 3, 10, local, 0, torch.cuda.synchronize, contexts=4, icp_blocks=args.icp_blocks)
+            side["os2_street"] = {"value": 16 * 10 / (ms2 * 1e-3), "unit": UNIT, "lanes": 16, "contexts": 4, "steps": 10,
                                   "ms_per_step": ms2 / 10, "counters": c2,
                                   "workload": "configs[2]: OS2-128 2048x10, 262144 pixels/scan, max_range 200 m (voxel 2 m)"}
             side["ekf_bench"] = side_ekf_fleet(16, 3, 10, local)
@@ -610,7 +622,7 @@ def run_ptk(args):
     total_algo = sum(algo.values())
     out["roofline"] = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": recorded_traffic(dom, args.config, B, args.input), "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": recorded_traffic(dom, args.config, B, args.input, G), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": dms / dn,
         "kernel_share_of_step": dms / sum(v[0] for v in prof.values()),
         "step_algorithmic_bytes_per_scan": total_algo / (B * K),

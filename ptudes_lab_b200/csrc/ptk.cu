@@ -4,6 +4,7 @@
 // /root/reference/src/ptudes/kiss.py:83-131 computes around the kiss-icp calls (initial guess,
 // pose gain metrics); all per-point work runs in the kernels of ptk_device.cuh.
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -100,6 +101,8 @@ struct ptk_ctx {
     int icp_max_blocks_per_lane = 1 << 20;   // PTK_ICP_MAX_BLOCKS_PER_LANE: fewer blocks = cheaper barrier, slower searches
     int icp_cluster = 0;              // blocks per lane of the cluster launch of wide batches (0: not available)
     int icp_cluster_min_lanes = 56;   // batch width from which the cluster launch is used
+    bool blocking_sync = false;       // wait for a step on a blocking-sync event (the thread sleeps) instead of spinning:
+    cudaEvent_t sync_event = nullptr; // set by ptk_fleet_replay, whose worker threads may outnumber the host cores
     // hash-sharded mode with in-kernel exchange: this rank's buffer and every rank's buffer as mapped here
     void* xch_local = nullptr;
     size_t xch_bytes = 0;
@@ -364,6 +367,7 @@ extern "C" int ptk_ctx_destroy(ptk_ctx* ctx) {
     if (ctx->d_big) cudaFree(ctx->d_big);
     for (cudaEvent_t e : ctx->prof.ev) cudaEventDestroy(e);
     if (ctx->pf_event) cudaEventDestroy(ctx->pf_event);
+    if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->h_params) cudaFreeHost(ctx->h_params);
     if (ctx->h_outs) cudaFreeHost(ctx->h_outs);
@@ -699,7 +703,13 @@ static int step_finish(ptk_ctx* ctx, int l0, int cnt, int nmax, double* out_pose
         int prc = issue_prefetch(ctx);
         if (prc) return prc;
     }
-    CK(cudaStreamSynchronize(st));
+    if (ctx->blocking_sync) {
+        if (!ctx->sync_event) CK(cudaEventCreateWithFlags(&ctx->sync_event, cudaEventBlockingSync | cudaEventDisableTiming));
+        CK(cudaEventRecord(ctx->sync_event, st));
+        CK(cudaEventSynchronize(ctx->sync_event));
+    } else {
+        CK(cudaStreamSynchronize(st));
+    }
     prof_collect(ctx);
     int ret = PTK_OK;
     for (int k = 0; k < cnt; ++k) {
@@ -1494,8 +1504,15 @@ extern "C" int ptk_fleet_replay(ptk_ctx* const* ctxs, int n_ctx, const unsigned 
                                 double* const* out_poses, ptk_stats* const* stats, void* const* streams) {
     if (!ctxs || n_ctx < 1 || !range_mm || n_scans < 0) return PTK_E_ARG;
     std::vector<int> rcs(n_ctx, PTK_OK);
+    // more worker threads than host cores (8 ranks x 8 contexts on a 32-core box, ranks pinned to their share of
+    // the cores): a spinning cudaStreamSynchronize per worker would starve the others, so the workers sleep
+    const unsigned hw = std::thread::hardware_concurrency();
+    cpu_set_t cs;
+    int avail = (sched_getaffinity(0, sizeof(cs), &cs) == 0) ? CPU_COUNT(&cs) : (int)hw;
+    const bool blocking = n_ctx > 1 && n_ctx + 1 > std::max(1, avail);
     auto work = [&](int g) {
         ptk_ctx* ctx = ctxs[g];
+        ctx->blocking_sync = blocking;
         const int B = ctx->B;
         cudaStream_t st = streams ? (cudaStream_t)streams[g] : nullptr;
         for (int s = 0; s < n_scans; ++s) {
@@ -1506,8 +1523,9 @@ extern "C" int ptk_fleet_replay(ptk_ctx* const* ctxs, int n_ctx, const unsigned 
             }
             int rc = ptk_register_scan_batch(ctx, cur, nullptr, nullptr, out_poses ? out_poses[g] + (size_t)s * B * 16 : nullptr,
                                              (stats && stats[g]) ? stats[g] + (size_t)s * B : nullptr, st);
-            if (rc) { rcs[g] = rc; return; }
+            if (rc) { rcs[g] = rc; ctx->blocking_sync = false; return; }
         }
+        ctx->blocking_sync = false;
     };
     if (n_ctx == 1) work(0);
     else {
