@@ -319,6 +319,70 @@ def side_ekf_fleet(lanes, warmup, steps, local):
                         "ICP guess, host-native ESEKF"}
 
 
+def side_ingest(local, frames=96, reps=10):
+    """SURVEY 8f-4, the step before the path: LEGACY lidar packets of `frames` OS0-128 1024x10 scans -> RANGE images.
+    (a) packets resident in HBM, ONE launch of k_decode_packets per repetition, CUDA events; algorithmic bytes = every
+    packet byte read once + every pixel of the image and every column header written once.  (b) the same through the
+    ScanBatcher object with HOST packets pushed one by one (pinned ring -> H2D -> decode), host wall clock."""
+    import ctypes as C
+    import torch
+    from ptudes_lab_b200 import _ffi, ingest, synth
+    dev = torch.device("cuda", local)
+    seq = synth.make_sequence("os0_quad", 0)
+    H, W = seq.sensor.H, seq.sensor.W
+    pf = ingest.PacketFormat(ingest.PROFILE_LIDAR_LEGACY, H, 16, W)
+    gen = synth.TorchScanGenerator(seq, dev)
+    distinct = []
+    for k in range(8):
+        r = gen.range_image(k)[0].cpu().numpy().astype(np.uint32)
+        ts = (np.arange(W) * (100_000_000 // W) + k * 100_000_000).astype(np.uint64)
+        distinct.append((r, ingest.encode_scan_packets(pf, k, r, ts)))
+    host = np.concatenate([distinct[f % 8][1] for f in range(frames)])            # (frames * ppf, packet size)
+    d_packets = torch.from_numpy(host).to(dev)
+    out = ingest.decode_frames(pf, d_packets, frames, device=local)                # warm-up + check
+    torch.cuda.synchronize()
+    for f in (0, frames - 1):
+        assert np.array_equal(out["RANGE"][f].cpu().numpy().view(np.uint32), distinct[f % 8][0]), "ingest: decoded image differs"
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ingest.decode_frames(pf, d_packets, frames, device=local, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    algo = frames * (pf.packets_per_frame * pf.lidar_packet_size + H * W * 4 + W * (8 + 4 + 2))
+    peak, peak_src = measured_peaks()
+    # (b) packet by packet through the batcher
+    lib = _ffi.load()
+    h = C.c_void_p()
+    assert lib.ptk_batcher_create(C.byref(h), local, C.byref(pf.c), 4) == 0
+    ls = ingest.DeviceLidarScan(H, W, ("RANGE",), local)
+    fs = ls._fields_struct()
+    ready, n_done = C.c_int(), 0
+    base = host.ctypes.data
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(host.shape[0]):
+        lib.ptk_batcher_push(h, base + i * pf.lidar_packet_size, C.byref(ready))
+        if ready.value:
+            lib.ptk_batcher_decode(h, C.byref(fs), None, None, None)
+            n_done += 1
+    lib.ptk_batcher_flush(h, C.byref(ready))
+    if ready.value:
+        lib.ptk_batcher_decode(h, C.byref(fs), None, None, None)
+        n_done += 1
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    lib.ptk_batcher_destroy(h)
+    return {"value": frames / (ms * 1e-3), "unit": "scans/s", "frames_per_launch": frames, "ms_per_launch": ms,
+            "roofline": {"bound": "hbm", "kernel": "k_decode_packets", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": algo / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo},
+            "e2e": {"value": n_done / dt, "unit": "scans/s", "h2d_bytes_per_scan": pf.packets_per_frame * pf.lidar_packet_size,
+                    "api": "ptk_batcher_push per packet (host bytes) + ptk_batcher_decode per frame, host wall clock"},
+            "workload": "OS0-128 1024x10 LEGACY lidar packets (64 x 24896 B per scan) -> staggered RANGE image + column headers"}
+
+
 def side_sharded(world, rank, local, scans_n=12):
     """configs[4], second half: ONE sequence whose voxel map is sharded by hash key over the ranks.  Every rank
     steps the same scans; poses must equal those of an unsharded single-GPU run (rank 0 checks)."""
@@ -575,6 +639,10 @@ def run_ptk(args):
                                   "ms_per_step": ms2 / 10, "counters": c2,
                                   "workload": "configs[2]: OS2-128 2048x10, 262144 pixels/scan, max_range 200 m (voxel 2 m)"}
             side["ekf_bench"] = side_ekf_fleet(16, 3, 10, local)
+            try:
+                side["ingest"] = side_ingest(local)
+            except Exception as e:      # never lose the headline line to a side run
+                side["ingest"] = {"error": f"{type(e).__name__}: {e}"}
         if world > 1:
             dist.barrier()
 

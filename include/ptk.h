@@ -268,6 +268,78 @@ int ptk_ekf_get_pose(const ptk_ekf* f, double* pose16);
 int ptk_ekf_get_cov(const ptk_ekf* f, double* cov324);
 double ptk_ekf_ts(const ptk_ekf* f);
 
+/* ---- ingest: raw Ouster UDP packets -> LidarScan fields -------------------------------
+ * The step before the path for recorded data: src/ptudes/data.py:31-77 (`OusterLidarData.withScanIdx`:
+ * `_client.PacketFormat.from_info`, `_client.ScanBatcher(w, pf)`, `batch(packet, ls_write)`), fed by
+ * `pcap.Pcap` / `OusterRawBagSource` (src/ptudes/utils.py:171-187, src/ptudes/bag.py:21-97).  In the
+ * reference the batching is ouster-sdk's C++ ScanBatcher writing HOST LidarScan fields column by column;
+ * here the raw packets of a frame cross the bus once and ONE kernel scatters them into the staggered
+ * (H, W) field images in HBM, where ptk_register_scan reads the RANGE image without a round trip to
+ * the host.  Packet layouts restate the published Ouster sensor UDP formats [UPSTREAM-UNVERIFIED: the
+ * SDK is absent; the packet sizes 24896 / 24832 / 8448 / 33024 B for 128 beams are the known answers]. */
+#define PTK_PROFILE_LEGACY 1                       /* UDPProfileLidar.PROFILE_LIDAR_LEGACY */
+#define PTK_PROFILE_RNG19_RFL8_SIG16_NIR16_DUAL 2  /* dual returns */
+#define PTK_PROFILE_RNG19_RFL8_SIG16_NIR16 3       /* single return */
+#define PTK_PROFILE_RNG15_RFL8_NIR8 4              /* low data rate */
+#define PTK_IMU_PACKET_SIZE 48
+
+/* _client.PacketFormat.from_info(metadata): byte layout of one lidar packet */
+typedef struct ptk_packet_format {
+    int profile, pixels_per_column, columns_per_packet, columns_per_frame;
+    int packet_header_size, col_header_size, channel_data_size, col_footer_size, packet_footer_size;
+    int col_size, lidar_packet_size, packets_per_frame;
+} ptk_packet_format;
+int ptk_packet_format_init(ptk_packet_format* pf, int profile, int pixels_per_column, int columns_per_packet,
+                           int columns_per_frame);
+/* frame id of a packet (packet header, or the first column header of a LEGACY packet) */
+int ptk_packet_frame_id(const ptk_packet_format* pf, const unsigned char* packet);
+
+/* Device pointers of the fields of `n_frames` frames, frame f at element offset f * (H*W) (images) or
+ * f * W (per-column headers).  range/timestamp/status/measurement_id are required, the others nullable. */
+typedef struct ptk_scan_fields {
+    unsigned int* range;               /* ChanField.RANGE, millimetres, staggered (H, W) */
+    unsigned int* range2;              /* ChanField.RANGE2 (dual profile) */
+    unsigned short* reflectivity;      /* ChanField.REFLECTIVITY */
+    unsigned short* signal;            /* ChanField.SIGNAL */
+    unsigned short* near_ir;           /* ChanField.NEAR_IR */
+    unsigned long long* timestamp;     /* LidarScan.timestamp (W) ns */
+    unsigned int* status;              /* LidarScan.status (W), bit 0 = column valid */
+    unsigned short* measurement_id;    /* LidarScan.measurement_id (W) */
+} ptk_scan_fields;
+
+/* ScanBatcher for whole frames: `packets` holds n_frames * pf->packets_per_frame slots of
+ * pf->lidar_packet_size bytes (HOST memory - copied to the device inside the call - or DEVICE memory);
+ * a slot of zero bytes is a lost packet.  Every column with its valid bit set lands in column
+ * measurement_id of its frame; columns no packet covered read 0 in every field (ScanBatcher's zero fill). */
+int ptk_decode_packets(const ptk_packet_format* pf, int device, const unsigned char* packets, int n_frames,
+                       const ptk_scan_fields* out, void* stream);
+
+/* ScanBatcher(w, pf) as an object: push packets in arrival order; a packet of a newer frame closes the
+ * current one (data.py:58 `if batch(packet, ls_write)`), packets of older frames are dropped, a repeated
+ * packet replaces its earlier copy.  Closed frames wait in pinned host memory (`frames` of them at most)
+ * until ptk_batcher_decode moves the oldest to the device and decodes it. */
+typedef struct ptk_batcher ptk_batcher;
+int ptk_batcher_create(ptk_batcher** out, int device /* -1: host-side grouping only */, const ptk_packet_format* pf,
+                       int frames);
+int ptk_batcher_destroy(ptk_batcher* b);
+int ptk_batcher_push(ptk_batcher* b, const unsigned char* packet, int* frames_ready);
+int ptk_batcher_flush(ptk_batcher* b, int* frames_ready);     /* end of the stream: close the partial frame (data.py:52-56) */
+int ptk_batcher_decode(ptk_batcher* b, const ptk_scan_fields* out, int* frame_id, int* n_packets, void* stream);
+/* the oldest closed frame's packet slots as they sit in pinned host memory (tests, host-side consumers) */
+int ptk_batcher_peek(ptk_batcher* b, const unsigned char** packets, int* frame_id, int* n_packets);
+int ptk_batcher_pop(ptk_batcher* b);
+
+/* pcap.Pcap(file, meta) as far as data.py needs it: UDP payloads of a classic pcap file in capture order
+ * (Ethernet / VLAN / Linux cooked / raw IP link types, IPv4 with reassembly of fragmented datagrams -
+ * a 128-beam lidar packet is 17 Ethernet frames). */
+typedef struct ptk_pcap ptk_pcap;
+int ptk_pcap_open(ptk_pcap** out, const char* path);
+int ptk_pcap_close(ptk_pcap* p);
+/* next UDP datagram: payload copied to buf (at most cap bytes), returns 1, 0 at the end of the file */
+int ptk_pcap_next(ptk_pcap* p, unsigned char* buf, int cap, int* len, int* dst_port, double* ts);
+/* text of the last failure of an ingest call on this thread */
+const char* ptk_ingest_last_error(void);
+
 /* pinned host memory for callers that want fast H2D of scans */
 int ptk_host_alloc(void** out, unsigned long long bytes);
 int ptk_host_free(void* p);

@@ -36,6 +36,17 @@ class PtkStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class PtkPacketFormat(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("profile", "pixels_per_column", "columns_per_packet", "columns_per_frame",
+                                       "packet_header_size", "col_header_size", "channel_data_size", "col_footer_size",
+                                       "packet_footer_size", "col_size", "lidar_packet_size", "packets_per_frame")]
+
+
+class PtkScanFields(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("range", "range2", "reflectivity", "signal", "near_ir", "timestamp", "status",
+                                          "measurement_id")]
+
+
 # every symbol include/ptk.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _D = C.c_void_p      # double* that may be host or device: pass raw addresses
@@ -102,6 +113,20 @@ SYMBOLS = {
     "ptk_set_icp_blocks_per_lane": (C.c_int, [_P, C.c_int]),
     "ptk_fleet_replay": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(C.POINTER(_I)), C.c_int, C.POINTER(_D),
                                    C.POINTER(C.POINTER(PtkStats)), C.POINTER(_P)]),
+    "ptk_packet_format_init": (C.c_int, [C.POINTER(PtkPacketFormat), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ptk_packet_frame_id": (C.c_int, [C.POINTER(PtkPacketFormat), C.c_void_p]),
+    "ptk_decode_packets": (C.c_int, [C.POINTER(PtkPacketFormat), C.c_int, C.c_void_p, C.c_int, C.POINTER(PtkScanFields), _P]),
+    "ptk_batcher_create": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(PtkPacketFormat), C.c_int]),
+    "ptk_batcher_destroy": (C.c_int, [_P]),
+    "ptk_batcher_push": (C.c_int, [_P, C.c_void_p, C.POINTER(C.c_int)]),
+    "ptk_batcher_flush": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "ptk_batcher_decode": (C.c_int, [_P, C.POINTER(PtkScanFields), C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "ptk_batcher_peek": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ptk_batcher_pop": (C.c_int, [_P]),
+    "ptk_pcap_open": (C.c_int, [C.POINTER(_P), C.c_char_p]),
+    "ptk_pcap_close": (C.c_int, [_P]),
+    "ptk_pcap_next": (C.c_int, [_P, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "ptk_ingest_last_error": (C.c_char_p, []),
     "ptk_host_alloc": (C.c_int, [C.POINTER(_P), C.c_ulonglong]),
     "ptk_host_free": (C.c_int, [_P]),
 }

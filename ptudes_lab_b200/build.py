@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 # PTK_LIB_SUFFIX / PTK_NVCC_EXTRA: build and load a tuning variant next to the default library
 # (e.g. PTK_LIB_SUFFIX=_mb3 PTK_NVCC_EXTRA="-DPTK_IQ_MINBLOCKS=3")
 LIB = os.path.join(CSRC, "libptk%s.so" % os.environ.get("PTK_LIB_SUFFIX", ""))
-SOURCES = [os.path.join(CSRC, "ptk.cu"), os.path.join(CSRC, "ptk_ekf.cpp")]
+SOURCES = [os.path.join(CSRC, "ptk.cu"), os.path.join(CSRC, "ptk_ingest.cu"), os.path.join(CSRC, "ptk_ekf.cpp")]
 HEADERS = [os.path.join(CSRC, "ptk_device.cuh"), os.path.join(CSRC, "ptk_canon.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "ptk.h")]
 

@@ -42,7 +42,10 @@ constexpr int ICP_CHUNK = ICP_WARPS;        // 32-point groups a block handles a
 #define PTK_ICP_KX 2
 #endif
 constexpr int ICP_KX = PTK_ICP_KX;          // runner-ups a correspondence cache entry keeps beside the winner
-constexpr int ICP_SRC_CAP = ICP_KX <= 1 ? 768 : (ICP_KX == 2 ? 640 : 512);   // source points (+ cache entries) per block in smem
+#ifndef PTK_ICP_SRC_CAP
+#define PTK_ICP_SRC_CAP (ICP_KX <= 1 ? 768 : (ICP_KX == 2 ? 640 : 512))
+#endif
+constexpr int ICP_SRC_CAP = PTK_ICP_SRC_CAP;   // source points (+ cache entries) per block in smem
 constexpr int ICP_SMEM = ICP_SRC_CAP * (3 * 8 + 4 * 8 + 8 + 3 * 8 + ICP_KX * (3 * 8 + 4) + 4) + 8;
 
 enum StepFlags : int { F_DESKEW = 1, F_RANGE = 2, F_SECOND = 4, F_SELECT_RANGE = 8 };

@@ -1,0 +1,549 @@
+// Ingest: raw Ouster UDP packets -> staggered LidarScan field images in HBM (include/ptk.h, "ingest").
+//
+// Reference path: /root/reference/src/ptudes/data.py:31-77 (OusterLidarData.withScanIdx drives ouster-sdk's
+// PacketFormat / ScanBatcher per packet, on the host), fed by pcap.Pcap / OusterRawBagSource
+// (/root/reference/src/ptudes/utils.py:171-187, /root/reference/src/ptudes/bag.py:21-97).
+// Here: packets of a frame are grouped on the host (ptk_batcher: frame-id logic only, no per-pixel work),
+// cross the bus as they came off the wire, and ONE kernel per batch of frames scatters the channel data into
+// the (H, W) images: a block per packet, the packet staged in shared memory by one TMA bulk copy, columns
+// written to their measurement ids.  Byte work, HBM-bound: reads every packet byte once, writes every pixel once.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <deque>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ptk.h"
+
+namespace ptk_ingest {
+
+thread_local std::string g_ingest_err;
+
+#define ICK(x)                                                                                   \
+    do {                                                                                         \
+        cudaError_t e_ = (x);                                                                    \
+        if (e_ != cudaSuccess) {                                                                 \
+            g_ingest_err = std::string(#x) + ": " + cudaGetErrorString(e_);                      \
+            return PTK_E_CUDA;                                                                   \
+        }                                                                                        \
+    } while (0)
+
+// ---- packet layout ---------------------------------------------------------------------------------
+struct DevFormat {
+    int profile, H, cpp, W;
+    int pkt_hdr, col_hdr, ch_size, col_size, pkt_size, ppf;
+};
+
+__host__ __device__ inline uint16_t rd16(const unsigned char* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+__host__ __device__ inline uint32_t rd32(const unsigned char* p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__host__ __device__ inline uint64_t rd64(const unsigned char* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+// column header of column c: timestamp, measurement id, status word (bit 0 = valid)
+__host__ __device__ inline void col_header(const DevFormat& F, const unsigned char* pkt, int c, uint64_t& ts, int& mid, uint32_t& status) {
+    const unsigned char* col = pkt + F.pkt_hdr + (size_t)c * F.col_size;
+    ts = rd64(col);
+    mid = rd16(col + 8);
+    if (F.profile == PTK_PROFILE_LEGACY) status = rd32(col + F.col_size - 4);      // 0xFFFFFFFF valid, 0 not
+    else status = rd16(col + 10);
+}
+
+// ---- TMA (1-D bulk copy global -> shared, completion on an mbarrier) ---------------------------------
+__device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One block per packet slot: blockIdx.x = slot within the frame, blockIdx.y = frame.
+__global__ void __launch_bounds__(256) k_decode_packets(const unsigned char* __restrict__ packets, DevFormat F, ptk_scan_fields out,
+                                                        unsigned int* frame_done, int use_tma) {
+    extern __shared__ __align__(16) unsigned char s_pkt[];
+    __shared__ int s_mid[64];
+    __shared__ unsigned long long s_bar;
+    __shared__ int s_last;
+    const int f = blockIdx.y;
+    const unsigned char* g = packets + ((size_t)f * F.ppf + blockIdx.x) * (size_t)F.pkt_size;
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(&s_bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(&s_bar)), "r"((uint32_t)F.pkt_size) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(saddr(s_pkt)), "l"(g), "r"((uint32_t)F.pkt_size), "r"(saddr(&s_bar)) : "memory");
+        }
+        __syncthreads();            // the barrier is initialised before anybody polls it
+        uint32_t ok;
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(saddr(&s_bar)) : "memory");
+        } while (!ok);
+    } else {
+        for (int i = threadIdx.x; i < F.pkt_size; i += blockDim.x) s_pkt[i] = g[i];
+        __syncthreads();
+    }
+    const size_t img = (size_t)f * F.H * F.W, hdr = (size_t)f * F.W;
+    if ((int)threadIdx.x < F.cpp) {
+        uint64_t ts; int mid; uint32_t st;
+        col_header(F, s_pkt, threadIdx.x, ts, mid, st);
+        const bool valid = (st & 1u) && mid < F.W;
+        s_mid[threadIdx.x] = valid ? mid : -1;
+        if (valid) {
+            out.timestamp[hdr + mid] = ts;
+            out.status[hdr + mid] = st;
+            out.measurement_id[hdr + mid] = (unsigned short)mid;
+        }
+    }
+    __syncthreads();
+    // consecutive threads = consecutive columns of one row: 4*cpp contiguous bytes of the image per row
+    const int n = F.H * F.cpp;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = i % F.cpp, p = i / F.cpp;
+        const int mid = s_mid[c];
+        if (mid < 0) continue;
+        const unsigned char* ch = s_pkt + F.pkt_hdr + (size_t)c * F.col_size + F.col_hdr + (size_t)p * F.ch_size;
+        const size_t o = img + (size_t)p * F.W + mid;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(ch);
+        if (F.profile == PTK_PROFILE_LEGACY) {
+            out.range[o] = w0 & 0x000fffffu;
+            if (out.reflectivity) out.reflectivity[o] = rd16(ch + 4);
+            if (out.signal) out.signal[o] = rd16(ch + 6);
+            if (out.near_ir) out.near_ir[o] = rd16(ch + 8);
+        } else if (F.profile == PTK_PROFILE_RNG19_RFL8_SIG16_NIR16) {
+            out.range[o] = w0 & 0x0007ffffu;
+            if (out.reflectivity) out.reflectivity[o] = ch[4];
+            if (out.signal) out.signal[o] = rd16(ch + 6);
+            if (out.near_ir) out.near_ir[o] = rd16(ch + 8);
+        } else if (F.profile == PTK_PROFILE_RNG15_RFL8_NIR8) {
+            out.range[o] = (w0 & 0x7fffu) << 3;
+            if (out.reflectivity) out.reflectivity[o] = ch[2];
+            if (out.near_ir) out.near_ir[o] = (unsigned short)((unsigned)ch[3] << 4);
+        } else {    // RNG19_RFL8_SIG16_NIR16_DUAL
+            out.range[o] = w0 & 0x0007ffffu;
+            if (out.reflectivity) out.reflectivity[o] = ch[3];
+            if (out.range2) out.range2[o] = rd32(ch + 4) & 0x0007ffffu;
+            if (out.signal) out.signal[o] = rd16(ch + 8);
+            if (out.near_ir) out.near_ir[o] = rd16(ch + 12);
+        }
+    }
+    // ScanBatcher's zero fill: the last block of a frame clears the columns nobody wrote (status still 0)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&frame_done[f], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // (columns checked 256 at a time; the usual frame has none missing and this is one pass of W/256 loads)
+    __shared__ int s_nmiss;
+    __shared__ unsigned short s_misscol[256];
+    for (int w0 = 0; w0 < F.W; w0 += blockDim.x) {
+        if (threadIdx.x == 0) s_nmiss = 0;
+        __syncthreads();
+        const int w = w0 + threadIdx.x;
+        if (w < F.W && !(__ldcg(out.status + hdr + w) & 1u)) {
+            s_misscol[atomicAdd(&s_nmiss, 1)] = (unsigned short)w;
+            out.timestamp[hdr + w] = 0; out.status[hdr + w] = 0; out.measurement_id[hdr + w] = 0;
+        }
+        __syncthreads();
+        const int nm = s_nmiss;
+        for (int i = threadIdx.x; i < nm * F.H; i += blockDim.x) {
+            const size_t o = img + (size_t)(i / nm) * F.W + s_misscol[i % nm];
+            out.range[o] = 0;
+            if (out.range2) out.range2[o] = 0;
+            if (out.reflectivity) out.reflectivity[o] = 0;
+            if (out.signal) out.signal[o] = 0;
+            if (out.near_ir) out.near_ir[o] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+DevFormat dev_format(const ptk_packet_format& pf) {
+    DevFormat F;
+    F.profile = pf.profile; F.H = pf.pixels_per_column; F.cpp = pf.columns_per_packet; F.W = pf.columns_per_frame;
+    F.pkt_hdr = pf.packet_header_size; F.col_hdr = pf.col_header_size; F.ch_size = pf.channel_data_size;
+    F.col_size = pf.col_size; F.pkt_size = pf.lidar_packet_size; F.ppf = pf.packets_per_frame;
+    return F;
+}
+
+bool format_ok(const ptk_packet_format* pf) {
+    if (!pf) return false;
+    ptk_packet_format ref;
+    if (ptk_packet_format_init(&ref, pf->profile, pf->pixels_per_column, pf->columns_per_packet, pf->columns_per_frame) != PTK_OK) return false;
+    return memcmp(&ref, pf, sizeof(ref)) == 0;
+}
+
+// decode `n_frames` frames whose packet slots are in DEVICE memory
+int decode_device(const ptk_packet_format& pf, const unsigned char* d_packets, int n_frames, const ptk_scan_fields& out, cudaStream_t st) {
+    if (n_frames == 0) return PTK_OK;
+    const DevFormat F = dev_format(pf);
+    unsigned int* d_done = nullptr;
+    ICK(cudaMallocAsync((void**)&d_done, sizeof(unsigned int) * n_frames, st));
+    ICK(cudaMemsetAsync(d_done, 0, sizeof(unsigned int) * n_frames, st));
+    // a column counts as written when bit 0 of its status is set: start from "nothing written"
+    ICK(cudaMemsetAsync(out.status, 0, sizeof(unsigned int) * (size_t)n_frames * F.W, st));
+    const int use_tma = (F.pkt_size % 16 == 0) && (((uintptr_t)d_packets) % 16 == 0);
+    const size_t smem = (size_t)F.pkt_size + 16;
+    if (smem > 48 * 1024) ICK(cudaFuncSetAttribute(k_decode_packets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_decode_packets<<<dim3(F.ppf, n_frames), 256, smem, st>>>(d_packets, F, out, d_done, use_tma);
+    ICK(cudaGetLastError());
+    ICK(cudaFreeAsync(d_done, st));
+    return PTK_OK;
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace ptk_ingest
+using namespace ptk_ingest;
+
+// ---- C ABI -------------------------------------------------------------------------------------------
+extern "C" int ptk_packet_format_init(ptk_packet_format* pf, int profile, int pixels_per_column, int columns_per_packet,
+                                      int columns_per_frame) {
+    if (!pf || pixels_per_column < 1 || columns_per_packet < 1 || columns_per_packet > 64 || columns_per_frame < columns_per_packet ||
+        columns_per_frame % columns_per_packet != 0)
+        return PTK_E_ARG;
+    memset(pf, 0, sizeof(*pf));
+    pf->profile = profile;
+    pf->pixels_per_column = pixels_per_column;
+    pf->columns_per_packet = columns_per_packet;
+    pf->columns_per_frame = columns_per_frame;
+    switch (profile) {
+        case PTK_PROFILE_LEGACY:
+            pf->packet_header_size = 0; pf->col_header_size = 16; pf->channel_data_size = 12; pf->col_footer_size = 4; pf->packet_footer_size = 0;
+            break;
+        case PTK_PROFILE_RNG19_RFL8_SIG16_NIR16:
+            pf->packet_header_size = 32; pf->col_header_size = 12; pf->channel_data_size = 12; pf->col_footer_size = 0; pf->packet_footer_size = 32;
+            break;
+        case PTK_PROFILE_RNG15_RFL8_NIR8:
+            pf->packet_header_size = 32; pf->col_header_size = 12; pf->channel_data_size = 4; pf->col_footer_size = 0; pf->packet_footer_size = 32;
+            break;
+        case PTK_PROFILE_RNG19_RFL8_SIG16_NIR16_DUAL:
+            pf->packet_header_size = 32; pf->col_header_size = 12; pf->channel_data_size = 16; pf->col_footer_size = 0; pf->packet_footer_size = 32;
+            break;
+        default:
+            return PTK_E_ARG;
+    }
+    pf->col_size = pf->col_header_size + pixels_per_column * pf->channel_data_size + pf->col_footer_size;
+    pf->lidar_packet_size = pf->packet_header_size + columns_per_packet * pf->col_size + pf->packet_footer_size;
+    pf->packets_per_frame = columns_per_frame / columns_per_packet;
+    return PTK_OK;
+}
+
+extern "C" int ptk_packet_frame_id(const ptk_packet_format* pf, const unsigned char* packet) {
+    if (!pf || !packet) return PTK_E_ARG;
+    if (pf->profile == PTK_PROFILE_LEGACY) return rd16(packet + 10);      // first column header
+    return rd16(packet + 2);                                              // packet header
+}
+
+extern "C" int ptk_decode_packets(const ptk_packet_format* pf, int device, const unsigned char* packets, int n_frames,
+                                  const ptk_scan_fields* out, void* stream) {
+    if (!format_ok(pf) || !packets || n_frames < 0 || !out || !out->range || !out->timestamp || !out->status || !out->measurement_id)
+        return PTK_E_ARG;
+    ICK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_device_ptr(packets)) return decode_device(*pf, packets, n_frames, *out, st);
+    const size_t bytes = (size_t)n_frames * pf->packets_per_frame * pf->lidar_packet_size;
+    unsigned char* d = nullptr;
+    ICK(cudaMallocAsync((void**)&d, std::max(bytes, (size_t)16), st));
+    ICK(cudaMemcpyAsync(d, packets, bytes, cudaMemcpyHostToDevice, st));
+    int rc = decode_device(*pf, d, n_frames, *out, st);
+    cudaFreeAsync(d, st);
+    if (rc == PTK_OK) ICK(cudaStreamSynchronize(st));     // the host buffer is the caller's again
+    return rc;
+}
+
+// ---- ScanBatcher over whole frames --------------------------------------------------------------------
+struct ptk_batcher {
+    ptk_packet_format pf;
+    int device = -1;
+    int frames = 0;
+    size_t frame_bytes = 0;
+    unsigned char* h_ring = nullptr;       // [frames][ppf][packet]: pinned when a device is attached
+    unsigned char* d_ring = nullptr;       // the same slots on the device
+    std::vector<cudaEvent_t> copied;       // per ring slot: its H2D copy has completed
+    std::vector<char> copy_pending;
+    struct Frame { int ring; int frame_id; int n_packets; std::vector<char> present; };
+    std::deque<Frame> closed;
+    bool open = false;
+    Frame cur;
+    int next_ring = 0;
+    long long dropped = 0;
+};
+
+static int batcher_close(ptk_batcher* b) {
+    // lost packets read as zero bytes: no column of theirs has its valid bit set
+    for (int s = 0; s < b->pf.packets_per_frame; ++s)
+        if (!b->cur.present[s])
+            memset(b->h_ring + (size_t)b->cur.ring * b->frame_bytes + (size_t)s * b->pf.lidar_packet_size, 0, b->pf.lidar_packet_size);
+    b->closed.push_back(b->cur);
+    b->open = false;
+    return PTK_OK;
+}
+
+static int batcher_open(ptk_batcher* b, int frame_id) {
+    if ((int)b->closed.size() >= b->frames - 1) { g_ingest_err = "ptk_batcher: every frame slot holds a closed frame; decode or pop first"; return PTK_E_STATE; }
+    const int r = b->next_ring;
+    b->next_ring = (b->next_ring + 1) % b->frames;
+    if (b->device >= 0 && b->copy_pending[r]) {       // the slot's previous frame may still be on its way to the device
+        ICK(cudaEventSynchronize(b->copied[r]));
+        b->copy_pending[r] = 0;
+    }
+    b->cur.ring = r; b->cur.frame_id = frame_id; b->cur.n_packets = 0;
+    b->cur.present.assign(b->pf.packets_per_frame, 0);
+    b->open = true;
+    return PTK_OK;
+}
+
+extern "C" int ptk_batcher_create(ptk_batcher** out, int device, const ptk_packet_format* pf, int frames) {
+    if (!out || !format_ok(pf) || frames < 2) return PTK_E_ARG;
+    ptk_batcher* b = new ptk_batcher();
+    b->pf = *pf; b->device = device; b->frames = frames;
+    b->frame_bytes = (size_t)pf->packets_per_frame * pf->lidar_packet_size;
+    auto fail = [&](int rc) { ptk_batcher_destroy(b); return rc; };
+    if (device >= 0) {
+        if (cudaSetDevice(device) != cudaSuccess) { g_ingest_err = "cudaSetDevice failed"; cudaGetLastError(); return fail(PTK_E_CUDA); }
+        if (cudaMallocHost((void**)&b->h_ring, b->frame_bytes * frames) != cudaSuccess ||
+            cudaMalloc((void**)&b->d_ring, b->frame_bytes * frames) != cudaSuccess) {
+            g_ingest_err = "ptk_batcher: allocation failed"; cudaGetLastError(); return fail(PTK_E_CUDA);
+        }
+        b->copied.resize(frames); b->copy_pending.assign(frames, 0);
+        for (int i = 0; i < frames; ++i)
+            if (cudaEventCreateWithFlags(&b->copied[i], cudaEventDisableTiming) != cudaSuccess) { b->copied.resize(i); return fail(PTK_E_CUDA); }
+    } else {
+        b->h_ring = (unsigned char*)malloc(b->frame_bytes * frames);
+        if (!b->h_ring) return fail(PTK_E_CAPACITY);
+    }
+    *out = b;
+    return PTK_OK;
+}
+
+extern "C" int ptk_batcher_destroy(ptk_batcher* b) {
+    if (!b) return PTK_OK;
+    if (b->device >= 0) {
+        cudaSetDevice(b->device);
+        for (cudaEvent_t e : b->copied) cudaEventDestroy(e);
+        if (b->h_ring) cudaFreeHost(b->h_ring);
+        if (b->d_ring) cudaFree(b->d_ring);
+    } else {
+        free(b->h_ring);
+    }
+    delete b;
+    return PTK_OK;
+}
+
+extern "C" int ptk_batcher_push(ptk_batcher* b, const unsigned char* packet, int* frames_ready) {
+    if (!b || !packet) return PTK_E_ARG;
+    const int fid = ptk_packet_frame_id(&b->pf, packet);
+    if (b->open && b->cur.frame_id != fid) {
+        if (b->cur.frame_id == ((fid + 1) & 0xffff)) {       // a straggler of the previous frame: ScanBatcher drops it
+            ++b->dropped;
+            if (frames_ready) *frames_ready = (int)b->closed.size();
+            return PTK_OK;
+        }
+        int rc = batcher_close(b);
+        if (rc) return rc;
+    }
+    if (!b->open) {
+        int rc = batcher_open(b, fid);
+        if (rc) return rc;
+    }
+    // the slot of a packet is given by its first column (sensors send whole, aligned column groups)
+    DevFormat F = dev_format(b->pf);
+    uint64_t ts; int mid; uint32_t st;
+    col_header(F, packet, 0, ts, mid, st);
+    if (mid % F.cpp != 0 || mid / F.cpp >= F.ppf) {
+        // first column invalid (its header may be blank): place by any valid column
+        bool placed = false;
+        for (int c = 1; c < F.cpp && !placed; ++c) {
+            col_header(F, packet, c, ts, mid, st);
+            if ((st & 1u) && mid >= c && (mid - c) % F.cpp == 0 && (mid - c) / F.cpp < F.ppf) { mid -= c; placed = true; }
+        }
+        if (!placed) { ++b->dropped; if (frames_ready) *frames_ready = (int)b->closed.size(); return PTK_OK; }
+    }
+    const int slot = mid / F.cpp;
+    memcpy(b->h_ring + (size_t)b->cur.ring * b->frame_bytes + (size_t)slot * F.pkt_size, packet, F.pkt_size);
+    if (!b->cur.present[slot]) { b->cur.present[slot] = 1; ++b->cur.n_packets; }
+    if (frames_ready) *frames_ready = (int)b->closed.size();
+    return PTK_OK;
+}
+
+extern "C" int ptk_batcher_flush(ptk_batcher* b, int* frames_ready) {
+    if (!b) return PTK_E_ARG;
+    if (b->open) {
+        int rc = batcher_close(b);
+        if (rc) return rc;
+    }
+    if (frames_ready) *frames_ready = (int)b->closed.size();
+    return PTK_OK;
+}
+
+extern "C" int ptk_batcher_peek(ptk_batcher* b, const unsigned char** packets, int* frame_id, int* n_packets) {
+    if (!b) return PTK_E_ARG;
+    if (b->closed.empty()) { g_ingest_err = "ptk_batcher: no closed frame"; return PTK_E_STATE; }
+    const ptk_batcher::Frame& f = b->closed.front();
+    if (packets) *packets = b->h_ring + (size_t)f.ring * b->frame_bytes;
+    if (frame_id) *frame_id = f.frame_id;
+    if (n_packets) *n_packets = f.n_packets;
+    return PTK_OK;
+}
+
+extern "C" int ptk_batcher_pop(ptk_batcher* b) {
+    if (!b) return PTK_E_ARG;
+    if (b->closed.empty()) { g_ingest_err = "ptk_batcher: no closed frame"; return PTK_E_STATE; }
+    b->closed.pop_front();
+    return PTK_OK;
+}
+
+extern "C" int ptk_batcher_decode(ptk_batcher* b, const ptk_scan_fields* out, int* frame_id, int* n_packets, void* stream) {
+    if (!b || !out || !out->range || !out->timestamp || !out->status || !out->measurement_id) return PTK_E_ARG;
+    if (b->device < 0) { g_ingest_err = "ptk_batcher: created without a device"; return PTK_E_STATE; }
+    if (b->closed.empty()) { g_ingest_err = "ptk_batcher: no closed frame"; return PTK_E_STATE; }
+    ICK(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const ptk_batcher::Frame f = b->closed.front();
+    unsigned char* d = b->d_ring + (size_t)f.ring * b->frame_bytes;
+    ICK(cudaMemcpyAsync(d, b->h_ring + (size_t)f.ring * b->frame_bytes, b->frame_bytes, cudaMemcpyHostToDevice, st));
+    ICK(cudaEventRecord(b->copied[f.ring], st));
+    b->copy_pending[f.ring] = 1;
+    int rc = decode_device(b->pf, d, 1, *out, st);
+    if (rc) return rc;
+    if (frame_id) *frame_id = f.frame_id;
+    if (n_packets) *n_packets = f.n_packets;
+    b->closed.pop_front();
+    return PTK_OK;
+}
+
+// ---- pcap reader (classic libpcap file format) ----------------------------------------------------------
+struct ptk_pcap {
+    FILE* f = nullptr;
+    bool swap = false, nanos = false;
+    uint32_t linktype = 1;
+    struct Key { uint32_t src, dst; uint16_t id; bool operator<(const Key& o) const { return src != o.src ? src < o.src : (dst != o.dst ? dst < o.dst : id < o.id); } };
+    struct Frag { std::vector<unsigned char> data; std::vector<std::pair<int, int>> have; int total = -1; long long seq = 0; };
+    std::map<Key, Frag> frags;
+    long long seq = 0;
+    std::vector<unsigned char> rec;
+};
+
+static uint32_t sw32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24); }
+
+extern "C" int ptk_pcap_open(ptk_pcap** out, const char* path) {
+    if (!out || !path) return PTK_E_ARG;
+    FILE* f = fopen(path, "rb");
+    if (!f) { g_ingest_err = std::string("cannot open ") + path; return PTK_E_ARG; }
+    unsigned char h[24];
+    if (fread(h, 1, 24, f) != 24) { fclose(f); g_ingest_err = "pcap: short file"; return PTK_E_ARG; }
+    uint32_t magic;
+    memcpy(&magic, h, 4);
+    ptk_pcap* p = new ptk_pcap();
+    if (magic == 0xa1b2c3d4u) { }
+    else if (magic == 0xd4c3b2a1u) p->swap = true;
+    else if (magic == 0xa1b23c4du) p->nanos = true;
+    else if (magic == 0x4d3cb2a1u) { p->swap = true; p->nanos = true; }
+    else { fclose(f); delete p; g_ingest_err = "pcap: not a classic pcap file (pcapng is not supported)"; return PTK_E_ARG; }
+    uint32_t lt;
+    memcpy(&lt, h + 20, 4);
+    p->linktype = p->swap ? sw32(lt) : lt;
+    p->f = f;
+    *out = p;
+    return PTK_OK;
+}
+
+extern "C" int ptk_pcap_close(ptk_pcap* p) {
+    if (!p) return PTK_OK;
+    if (p->f) fclose(p->f);
+    delete p;
+    return PTK_OK;
+}
+
+extern "C" int ptk_pcap_next(ptk_pcap* p, unsigned char* buf, int cap, int* len, int* dst_port, double* ts) {
+    if (!p || !buf || !len) return PTK_E_ARG;
+    while (true) {
+        unsigned char rh[16];
+        if (fread(rh, 1, 16, p->f) != 16) return 0;
+        uint32_t sec, frac, incl;
+        memcpy(&sec, rh, 4); memcpy(&frac, rh + 4, 4); memcpy(&incl, rh + 8, 4);
+        if (p->swap) { sec = sw32(sec); frac = sw32(frac); incl = sw32(incl); }
+        if (incl > (1u << 26)) { g_ingest_err = "pcap: corrupt record"; return PTK_E_ARG; }
+        p->rec.resize(incl);
+        if (incl && fread(p->rec.data(), 1, incl, p->f) != incl) return 0;
+        const double t = (double)sec + (double)frac * (p->nanos ? 1e-9 : 1e-6);
+        const unsigned char* d = p->rec.data();
+        int n = (int)incl, off = 0;
+        // link layer -> start of the IP header
+        if (p->linktype == 1) {                       // Ethernet (+ VLAN tags)
+            if (n < 14) continue;
+            int et = (d[12] << 8) | d[13];
+            off = 14;
+            while ((et == 0x8100 || et == 0x88a8) && n >= off + 4) { et = (d[off + 2] << 8) | d[off + 3]; off += 4; }
+            if (et != 0x0800) continue;
+        } else if (p->linktype == 113) {              // Linux cooked capture
+            if (n < 16 || ((d[14] << 8) | d[15]) != 0x0800) continue;
+            off = 16;
+        } else if (p->linktype == 0) {                // BSD loopback: 4-byte family
+            off = 4;
+        } else if (p->linktype == 101 || p->linktype == 228 || p->linktype == 12) {   // raw IP
+            off = 0;
+        } else { g_ingest_err = "pcap: unsupported link type"; return PTK_E_ARG; }
+        if (n < off + 20 || (d[off] >> 4) != 4) continue;
+        const int ihl = (d[off] & 15) * 4;
+        const int tot = std::min((d[off + 2] << 8) | d[off + 3], n - off);
+        if (d[off + 9] != 17 || tot < ihl) continue;
+        const int fl = (d[off + 6] << 8) | d[off + 7];
+        const bool mf = fl & 0x2000;
+        const int foff = (fl & 0x1fff) * 8;
+        const unsigned char* pay = d + off + ihl;
+        int plen = tot - ihl;
+        std::vector<unsigned char>* dgram = nullptr;
+        std::vector<unsigned char> whole;
+        ptk_pcap::Key key{0, 0, 0};
+        if (mf || foff) {                            // a fragment: reassemble
+            memcpy(&key.src, d + off + 12, 4); memcpy(&key.dst, d + off + 16, 4);
+            key.id = (uint16_t)((d[off + 4] << 8) | d[off + 5]);
+            ptk_pcap::Frag& F = p->frags[key];
+            if (F.have.empty()) F.seq = p->seq++;
+            bool dup = false;
+            for (auto& h : F.have) if (h.first == foff) dup = true;
+            if (!dup) {
+                if ((int)F.data.size() < foff + plen) F.data.resize(foff + plen);
+                memcpy(F.data.data() + foff, pay, plen);
+                F.have.push_back({foff, plen});
+            }
+            if (!mf) F.total = foff + plen;
+            int got = 0;
+            for (auto& h : F.have) got += h.second;
+            if (F.total >= 0 && got >= F.total) {
+                whole.swap(F.data);
+                whole.resize(F.total);
+                p->frags.erase(key);
+                dgram = &whole;
+            } else {
+                if (p->frags.size() > 64) {          // forget the oldest incomplete datagram
+                    auto old = p->frags.begin();
+                    for (auto it = p->frags.begin(); it != p->frags.end(); ++it) if (it->second.seq < old->second.seq) old = it;
+                    p->frags.erase(old);
+                }
+                continue;
+            }
+            pay = dgram->data(); plen = (int)dgram->size();
+        }
+        if (plen < 8) continue;
+        const int dport = (pay[2] << 8) | pay[3];
+        const int ulen = std::min((pay[4] << 8) | pay[5], plen);
+        const int body = ulen - 8;
+        if (body < 0) continue;
+        *len = body;
+        if (dst_port) *dst_port = dport;
+        if (ts) *ts = t;
+        memcpy(buf, pay + 8, std::min(body, cap));
+        return 1;
+    }
+}
+
+extern "C" const char* ptk_ingest_last_error(void) { return g_ingest_err.c_str(); }
