@@ -177,8 +177,18 @@ def _bag_record(hdr, data):
     return struct.pack("<I", len(hdr)) + hdr + struct.pack("<I", len(data)) + data
 
 
-def write_bag(path, messages, compression="none", per_chunk=50):
-    """messages: list of (ts seconds, topic, payload bytes) -> ROS bag 2.0 with ouster_ros/PacketMsg messages."""
+def imu_msg(seq, ts, frame_id, avel, lacc):
+    """serialized sensor_msgs/Imu (ROS1)"""
+    sec = int(ts)
+    fid = frame_id.encode()
+    return (struct.pack("<IIII", seq, sec, int(round((ts - sec) * 1e9)), len(fid)) + fid +
+            struct.pack("<37d", 0, 0, 0, 1, *([0.0] * 9), *avel, *([0.0] * 9), *lacc, *([0.0] * 9)))
+
+
+def write_bag(path, messages, compression="none", per_chunk=50, imu_topics=()):
+    """messages: list of (ts seconds, topic, payload bytes) -> ROS bag 2.0.  Topics are ouster_ros/PacketMsg
+    (payload = the packet, wrapped as `uint8[] buf`) unless listed in `imu_topics` (payload = a serialized
+    sensor_msgs/Imu, written as is)."""
     import bz2
     md5 = b"4f7b5949e76f86d01e96b0e33ba9b5e3"
     topics = sorted({m[1] for m in messages})
@@ -194,11 +204,15 @@ def write_bag(path, messages, compression="none", per_chunk=50):
             for ts, topic, payload in messages[i:i + per_chunk]:
                 if topic not in seen:
                     seen.add(topic)
-                    ch = _bag_header(topic=topic.encode(), type=b"ouster_ros/PacketMsg", md5sum=md5, message_definition=b"uint8[] buf\n")
+                    if topic in imu_topics:
+                        ch = _bag_header(topic=topic.encode(), type=b"sensor_msgs/Imu", md5sum=b"6a62c6daae103f4ff57a132d6f95cec2",
+                                         message_definition=b"Header header\n")
+                    else:
+                        ch = _bag_header(topic=topic.encode(), type=b"ouster_ros/PacketMsg", md5sum=md5, message_definition=b"uint8[] buf\n")
                     body += _bag_record(_bag_header(op=b"\x07", conn=struct.pack("<I", cid[topic]), topic=topic.encode()), ch)
                 sec = int(ts)
                 nsec = int(round((ts - sec) * 1e9))
                 body += _bag_record(_bag_header(op=b"\x02", conn=struct.pack("<I", cid[topic]), time=struct.pack("<II", sec, nsec)),
-                                    struct.pack("<I", len(payload)) + payload)
+                                    payload if topic in imu_topics else struct.pack("<I", len(payload)) + payload)
             data = bz2.compress(body) if compression == "bz2" else body
             f.write(_bag_record(_bag_header(op=b"\x05", compression=compression.encode(), size=struct.pack("<I", len(body))), data))

@@ -1,0 +1,17 @@
+#!/bin/bash
+# round-2 experiment batch O: half-warp searches in k_icp (default) against full-warp searches (_fw) and three runner-ups (_kx3)
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > $O/r2o_tests.log 2>&1; echo "tests rc=$?"; tail -3 $O/r2o_tests.log
+run() { # suffix lanes contexts tag
+  PTK_LIB_SUFFIX=$1 timeout 300 python bench.py --lanes $2 --contexts $3 --no-side-runs --no-cpu-baseline --no-e2e \
+     > $O/r2o_v$1_l$2c$3$4.json 2> $O/r2o_v$1_l$2c$3$4.err; echo "v$1 l$2 c$3 $4 rc=$?"
+}
+run "" 64 8
+run _fw 64 8
+run _kx3 64 8
+run "" 48 1
+run _fw 48 1
+run _kx3 48 1
+run "" 64 8 b
+run _fw 64 8 b

@@ -658,7 +658,12 @@ static int step_prepare(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz,
         for (int k = 0; k < cnt; ++k) any = any || (ctx->h_params[l0 + k].flags & F_DESKEW);
         if (any) LAUNCH(PS_COL_MOTION, st, k_col_motion<<<dim3((ctx->sen_W + 127) / 128, cnt), 128, 0, st>>>(dp));
     }
-    LAUNCH(PS_SCAN_INSERT, st, k_scan_insert<<<dim3(g1, cnt), 256, 0, st>>>(dl, dp, si_tiles));
+    if (range) {
+        const int ncb = (ctx->sen_W + 255) / 256, nrb = (ctx->sen_H + SI_ROWS - 1) / SI_ROWS;
+        LAUNCH(PS_SCAN_INSERT, st, k_scan_insert_range<<<dim3(ncb * nrb, cnt), 256, 0, st>>>(dl, dp, ctx->sen_H, ncb));
+    } else {
+        LAUNCH(PS_SCAN_INSERT, st, k_scan_insert<<<dim3(g1, cnt), 256, 0, st>>>(dl, dp, si_tiles));
+    }
     LAUNCH(PS_COMPACT1, st, k_compact1<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
     LAUNCH(PS_COMPACT2, st, k_compact2<<<dim3(gt, cnt), 256, 0, st>>>(dl, dp));
     CK(cudaGetLastError());

@@ -226,12 +226,16 @@ __device__ __forceinline__ void voxel_key(double x, double y, double z, double s
 // `near_mask + 1` set).  The probe sequence of a key is fixed, so every thread with that key ends in the same slot
 // whatever the region sizes; correctness never depends on the hint, only the cache footprint does.
 constexpr u32 TABLE_NEAR = 32;
-__device__ __forceinline__ u32 table_insert_min(u64* keys, u32* vals, u32 mask, u32 near_mask, u64 key, u32 val) {
+// `first`: the key word already read from the key's first slot (callers with several inserts to do issue those
+// reads together, ahead of the dependent atomics).  `lowered`: the value became the slot's minimum at the time of the
+// call - a value that did not can never be the final minimum.
+__device__ __forceinline__ u32 table_insert_min_from(u64* keys, u32* vals, u32 mask, u32 near_mask, u64 key, u32 val,
+                                                     u64 first, bool& lowered) {
     const u32 h = hash_key(key);
     u32 slot = h & near_mask;
     u32 j = 0;
+    u64 k = first;
     while (true) {
-        u64 k = *((volatile u64*)(keys + slot));
         if (k == key) break;
         if (k == KEY_EMPTY) {
             u64 prev = atomicCAS(keys + slot, KEY_EMPTY, key);
@@ -240,9 +244,16 @@ __device__ __forceinline__ u32 table_insert_min(u64* keys, u32* vals, u32 mask, 
         ++j;
         if (near_mask == mask || j < TABLE_NEAR) slot = (h + j) & near_mask;
         else slot = ((h + j) & mask) | (near_mask + 1u);
+        k = *((volatile u64*)(keys + slot));
     }
-    atomicMin(vals + slot, val);
+    lowered = atomicMin(vals + slot, val) > val;
     return slot;
+}
+__device__ __forceinline__ u64 table_first_probe(const u64* keys, u32 near_mask, u64 key) {
+    return *((volatile const u64*)(keys + (hash_key(key) & near_mask)));
+}
+__device__ __forceinline__ u32 table_insert_min(u64* keys, u32* vals, u32 mask, u32 near_mask, u64 key, u32 val, bool& lowered) {
+    return table_insert_min_from(keys, vals, mask, near_mask, key, val, table_first_probe(keys, near_mask, key), lowered);
 }
 
 // Load input point i and apply the per-point deskew (kiss-icp DeSkewScan).  Returns false for a
@@ -354,13 +365,18 @@ __global__ void __launch_bounds__(256, 4) k_scan_insert(LaneDev* lanes, const St
         }
         // neighbouring pixels of a beam mostly fall into the same voxel: one table operation per distinct
         // key of the warp, issued by the lowest lane (= lowest point index) of each group
+        // (slot1 keeps the slot only for a point that may still win its voxel: the lowest index of its warp's
+        // group, and only if it lowered the slot's minimum - every final winner is both)
         const u32 am = __ballot_sync(0xffffffffu, ins);
         u32 slot = NONE;
         if (ins) {
             const u32 peers = __match_any_sync(am, key);
             const int leader = __ffs(peers) - 1;
-            if ((int)(threadIdx.x & 31) == leader) slot = table_insert_min(L.t1_keys, L.t1_vals, L.t_mask, P.near1 ? P.near1 : L.t_mask, key, (u32)i);
-            slot = __shfl_sync(peers, slot, leader);
+            if ((int)(threadIdx.x & 31) == leader) {
+                bool lowered;
+                slot = table_insert_min(L.t1_keys, L.t1_vals, L.t_mask, P.near1 ? P.near1 : L.t_mask, key, (u32)i, lowered);
+                if (!lowered) slot = NONE;
+            }
         }
         if (i < P.n) L.slot1[i] = slot;
         n_pass += __popc(__ballot_sync(0xffffffffu, pass));
@@ -370,6 +386,102 @@ __global__ void __launch_bounds__(256, 4) k_scan_insert(LaneDev* lanes, const St
     if ((threadIdx.x & 31) == 0) {
         if (n_pass) atomicAdd(&L.n_range, n_pass);
         if (P.range && n_valid) atomicAdd(&L.n_valid, n_valid);
+    }
+}
+
+// K1, range-image form.  A thread owns ONE COLUMN of the image for SI_ROWS consecutive rows: the column's deskew
+// motion (12 doubles) is loaded once instead of once per pixel, and everything a pixel needs - its range, its three
+// LUT words - is addressed by the pixel index alone, so all the loads of the thread's pixels are issued before the
+// first use (one memory round trip instead of three per pixel), and so are the first table probes of its inserts.
+// Lanes of a warp are consecutive columns of a row, i.e. ascending pixel indices: the warp-level grouping of equal
+// keys works as in k_scan_insert.  Arithmetic is load_point's, operation for operation.
+#ifndef PTK_SI_ROWS
+#define PTK_SI_ROWS 2          // measured: 2 rows at 64 registers beat 4 rows at 80 and 8 at 128
+#endif
+constexpr int SI_ROWS = PTK_SI_ROWS;
+#ifndef PTK_SI_MINBLOCKS
+#define PTK_SI_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, PTK_SI_MINBLOCKS) k_scan_insert_range(LaneDev* lanes, const StepParams* params, int H, int ncb) {
+    LaneDev& L = lanes[blockIdx.y];
+    const StepParams& P = params[blockIdx.y];
+    const int W = P.W;
+    const int cb = blockIdx.x % ncb, rb = blockIdx.x / ncb;
+    const int w = cb * 256 + threadIdx.x;
+    const int h0 = rb * SI_ROWS;
+    const bool colok = w < W;
+    const int wc = colok ? w : W - 1;
+    const size_t np = (size_t)P.n;
+    const bool deskew = P.flags & F_DESKEW;
+    u32 r[SI_ROWS];
+    double x[SI_ROWS], y[SI_ROWS], z[SI_ROWS];
+#pragma unroll
+    for (int k = 0; k < SI_ROWS; ++k) {
+        const int h = min(h0 + k, H - 1);
+        const size_t i = (size_t)h * W + wc;
+        r[k] = __ldg(P.range + i);
+        x[k] = __ldg(P.lut_dir + i); y[k] = __ldg(P.lut_dir + np + i); z[k] = __ldg(P.lut_dir + 2 * np + i);
+    }
+    double m[12];
+    if (deskew) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) m[q] = P.col_motion[(size_t)q * W + wc];
+    }
+    u64 key[SI_ROWS];
+    bool lead[SI_ROWS];
+    int n_pass = 0, n_valid = 0;
+    const u32 near = P.near1 ? P.near1 : L.t_mask;
+#pragma unroll
+    for (int k = 0; k < SI_ROWS; ++k) {
+        const bool inb = colok && h0 + k < H;
+        const bool valid = inb && r[k] != 0;
+        const double rr = (double)r[k] * P.range_unit;
+        double px = x[k] * rr, py = y[k] * rr, pz = z[k] * rr;
+        if (P.lut_off) {
+            const size_t i = (size_t)min(h0 + k, H - 1) * W + wc;
+            px = px + __ldg(P.lut_off + i); py = py + __ldg(P.lut_off + np + i); pz = pz + __ldg(P.lut_off + 2 * np + i);
+        }
+        if (deskew) {
+            const double xo = ((m[0] * px + m[1] * py) + m[2] * pz) + m[9];
+            const double yo = ((m[3] * px + m[4] * py) + m[5] * pz) + m[10];
+            const double zo = ((m[6] * px + m[7] * py) + m[8] * pz) + m[11];
+            px = xo; py = yo; pz = zo;
+        }
+        const bool pass = valid && range_pass(P, px, py, pz);
+        bool ins = false;
+        key[k] = KEY_EMPTY;
+        if (pass) {
+            int kx, ky, kz;
+            voxel_key(px, py, pz, P.ds1_size, P.ds1_inv, kx, ky, kz);
+            if (key_in_range(kx, ky, kz)) { key[k] = pack_key(kx, ky, kz); ins = true; }
+            else atomicOr(&L.err, ERR_KEYRANGE);
+        }
+        const u32 am = __ballot_sync(0xffffffffu, ins);
+        lead[k] = false;
+        if (ins) {
+            const u32 peers = __match_any_sync(am, key[k]);
+            lead[k] = (int)(threadIdx.x & 31) == __ffs(peers) - 1;
+        }
+        n_pass += __popc(__ballot_sync(0xffffffffu, pass));
+        n_valid += __popc(__ballot_sync(0xffffffffu, valid));
+    }
+    u64 first[SI_ROWS];
+#pragma unroll
+    for (int k = 0; k < SI_ROWS; ++k) first[k] = lead[k] ? table_first_probe(L.t1_keys, near, key[k]) : KEY_EMPTY;
+    u32 slot[SI_ROWS];
+    bool lowered[SI_ROWS];
+#pragma unroll
+    for (int k = 0; k < SI_ROWS; ++k) {      // the atomics of all rows go out before any of their results is looked at
+        slot[k] = NONE;
+        lowered[k] = false;
+        if (lead[k]) slot[k] = table_insert_min_from(L.t1_keys, L.t1_vals, L.t_mask, near, key[k], (u32)((h0 + k) * W + w), first[k], lowered[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < SI_ROWS; ++k)
+        if (colok && h0 + k < H) L.slot1[(h0 + k) * W + w] = lowered[k] ? slot[k] : NONE;
+    if ((threadIdx.x & 31) == 0) {
+        if (n_pass) atomicAdd(&L.n_range, n_pass);
+        if (n_valid) atomicAdd(&L.n_valid, n_valid);
     }
 }
 
@@ -437,6 +549,7 @@ __device__ __forceinline__ int lookback_prefix(u64* agg, u32 tile, int total, u3
 __global__ void __launch_bounds__(256, 4) k_compact1(LaneDev* lanes, const StepParams* params) {
     LaneDev& L = lanes[blockIdx.y];
     const StepParams& P = params[blockIdx.y];
+    __shared__ u32 s_win[TILE];             // the tile's winners (input indices), ascending
     // a block walks CT_TILES tiles (fewer, longer-lived blocks: block dispatch is not free); every block
     // takes exactly CT_TILES tickets whether or not they are in range, so the host knows the next base
 #pragma unroll 1
@@ -448,34 +561,57 @@ __global__ void __launch_bounds__(256, 4) k_compact1(LaneDev* lanes, const StepP
         continue;
     }
     if (tile >= ntiles) continue;
-    int i0 = (int)tile * TILE + threadIdx.x * 4;
+    const int i0 = (int)tile * TILE + threadIdx.x * 4;
     bool win[4];
     int cnt = 0;
+    if (P.flags & F_SELECT_RANGE) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        int i = i0 + k;
-        win[k] = false;
-        if (i < P.n) {
-            if (P.flags & F_SELECT_RANGE) {
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k;
+            win[k] = false;
+            if (i < P.n) {
                 double x, y, z;
                 win[k] = load_point(P, i, x, y, z) && range_pass(P, x, y, z);
-            } else {
-                u32 s = L.slot1[i];
-                win[k] = (s != NONE) && (L.t1_vals[s] == (u32)i);
             }
         }
-        cnt += win[k] ? 1 : 0;
-    }
-    int total;
-    int local = block_excl_scan(cnt, total);
-    int prefix = lookback_prefix(L.agg1, tile, total, P.epoch);
-    int pos = prefix + local;
+    } else {
+        // slot1 holds a slot only for the points that could still win their voxel (k_scan_insert): one 16 B load
+        // for the thread's four points, then the gathers of the few candidates, all in flight together
+        u32 sl[4];
+        if (i0 + 3 < P.n) {
+            const uint4 v = *reinterpret_cast<const uint4*>(L.slot1 + i0);
+            sl[0] = v.x; sl[1] = v.y; sl[2] = v.z; sl[3] = v.w;
+        } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 4; ++k) sl[k] = i0 + k < P.n ? L.slot1[i0 + k] : NONE;
+        }
+        u32 tv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tv[k] = sl[k] != NONE ? L.t1_vals[sl[k]] : NONE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) win[k] = sl[k] != NONE && tv[k] == (u32)(i0 + k);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cnt += win[k] ? 1 : 0;
+    int total;
+    const int local = block_excl_scan(cnt, total);
+    {
+        int q = local;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (win[k]) s_win[q++] = (u32)(i0 + k);
+    }
+    const int prefix = lookback_prefix(L.agg1, tile, total, P.epoch);      // (its barriers also publish s_win)
+    // one winner per thread, whole warps at a time: recompute the point (cheaper than having stored all of them),
+    // write frame_downsample, and insert into the grid-2 table - lanes of a warp hold ascending output positions
+    for (int q0 = 0; q0 < total; q0 += blockDim.x) {
+        const int q = q0 + threadIdx.x;
+        const bool act = q < total;
+        const int pos = prefix + q;
         bool ins = false;
         u64 key = KEY_EMPTY;
-        if (win[k]) {
-            int i = i0 + k;
+        if (act) {
+            const int i = (int)s_win[q];
             double x, y, z;
             load_point(P, i, x, y, z);
             L.ds_x[pos] = x; L.ds_y[pos] = y; L.ds_z[pos] = z;
@@ -484,22 +620,25 @@ __global__ void __launch_bounds__(256, 4) k_compact1(LaneDev* lanes, const StepP
                 int kx, ky, kz;
                 voxel_key(x, y, z, P.ds2_size, P.ds2_inv, kx, ky, kz);
                 if (key_in_range(kx, ky, kz)) { key = pack_key(kx, ky, kz); ins = true; }
-                else { atomicOr(&L.err, ERR_KEYRANGE); L.ds_slot2[pos] = NONE; }
+                else atomicOr(&L.err, ERR_KEYRANGE);
             }
         }
         if (P.flags & F_SECOND) {       // one table operation per distinct key of the warp (lowest lane = lowest pos)
             const u32 am = __ballot_sync(0xffffffffu, ins);
+            u32 s2 = NONE;
             if (ins) {
                 const u32 peers = __match_any_sync(am, key);
-                const int leader = __ffs(peers) - 1;
-                u32 s2 = NONE;
-                if ((int)(threadIdx.x & 31) == leader) s2 = table_insert_min(L.t2_keys, L.t2_vals, L.t_mask, P.near2 ? P.near2 : L.t_mask, key, (u32)pos);
-                L.ds_slot2[pos] = __shfl_sync(peers, s2, leader);
+                if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+                    bool lowered;
+                    s2 = table_insert_min(L.t2_keys, L.t2_vals, L.t_mask, P.near2 ? P.near2 : L.t_mask, key, (u32)pos, lowered);
+                    if (!lowered) s2 = NONE;
+                }
             }
+            if (act) L.ds_slot2[pos] = s2;
         }
-        if (win[k]) ++pos;
     }
     if (tile == ntiles - 1 && threadIdx.x == 0) L.n_ds = prefix + total;
+    __syncthreads();                        // s_win is free again
   }
 }
 
@@ -746,6 +885,164 @@ __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double
     const u32 ohi = __reduce_min_sync(FULL, (u32)((u64)__double_as_longlong(other) >> 32));
     const double d2_other = __longlong_as_double((long long)((u64)ohi << 32));     // low word zero: rounds down
     others = found ? sqrt(d2_other) * (1.0 - 1e-12) : -1.0;
+    return found;
+}
+
+// The same search by HALF a warp (16 lanes): the two halves of a warp carry two independent queries, so a block's
+// missed points are searched 2 x ICP_WARPS at a time - the search phase of an ICP iteration is usually one round
+// instead of two.  A lane probes voxels gl and gl + 16 of the 27 and scans slots gl and gl + 16 (< 20) of a visited
+// voxel; every collective names only the half's lanes, so the halves may diverge freely.  Pruning rule, winner
+// (lexicographic (d2, order id) minimum, tie rule B.6), runner-ups and the `others` bound are those of warp_nearest.
+__device__ __forceinline__ bool halfwarp_nearest(const MapView& L, double sx, double sy, double sz, int lane, double max_d2,
+                                                 double& bd2, int& bord, double& tx, double& ty, double& tz, double& others,
+                                                 u64* qkey, double* t2, int* ord2) {
+    const int gl = lane & 15, gs = lane & 16;
+    const u32 gm = gs ? 0xffff0000u : 0x0000ffffu;
+    const double v = L.voxel;
+    int kx, ky, kz;
+    voxel_key(sx, sy, sz, v, L.voxel_inv, kx, ky, kz);
+    const bool inr = key_in_range(kx, ky, kz);
+    if (qkey) *qkey = inr ? pack_key(kx, ky, kz) : KEY_EMPTY;
+    u32 id[2] = {NONE, NONE};
+    double lb[2] = {INFINITY, INFINITY};
+    {
+        u64 key[2];
+        u32 slot[2];
+        ulonglong2 raw[2];
+        bool have[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = gl + 16 * h;
+            have[h] = inr && c < 27;
+            const int di = c / 9 - 1, dj = (c / 3) % 3 - 1, dk = c % 3 - 1;
+            const int nx = kx + di, ny = ky + dj, nz = kz + dk;
+            key[h] = pack_key(nx, ny, nz);
+            slot[h] = hash_map_key(key[h]) & L.mask;
+            if (have[h]) {
+                raw[h] = __ldg(reinterpret_cast<const ulonglong2*>(L.slots + slot[h]));
+                // voxel n covers [n v, (n+1) v) for n > 0, (-v, v) for n == 0 and ((n-1) v, n v] for n < 0
+                double lo, hi, ax, ay, az;
+                lo = (double)(nx > 0 ? nx : nx - 1) * v; hi = (double)(nx < 0 ? nx : nx + 1) * v;
+                ax = fmax(fmax(lo - sx, sx - hi) - 1e-7, 0.0);
+                lo = (double)(ny > 0 ? ny : ny - 1) * v; hi = (double)(ny < 0 ? ny : ny + 1) * v;
+                ay = fmax(fmax(lo - sy, sy - hi) - 1e-7, 0.0);
+                lo = (double)(nz > 0 ? nz : nz - 1) * v; hi = (double)(nz < 0 ? nz : nz + 1) * v;
+                az = fmax(fmax(lo - sz, sz - hi) - 1e-7, 0.0);
+                lb[h] = ((ax * ax + ay * ay) + az * az) * (1.0 - 1e-9);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (!have[h]) continue;
+            while (true) {
+                if (raw[h].x == key[h]) { id[h] = (u32)raw[h].y; break; }
+                if (raw[h].x == KEY_EMPTY) break;
+                slot[h] = (slot[h] + 1) & L.mask;
+                raw[h] = __ldg(reinterpret_cast<const ulonglong2*>(L.slots + slot[h]));
+            }
+            if (id[h] == NONE) lb[h] = INFINITY;
+        }
+    }
+    // 27-bit masks over the voxels as the whole half sees them: voxel c sits in lane c & 15, element c >> 4
+#define HW_MASK27(p0, p1) ((((__ballot_sync(gm, (p0)) >> gs) & 0xffffu)) | (((__ballot_sync(gm, (p1)) >> gs) & 0x7ffu) << 16))
+#define HW_ID(c) __shfl_sync(gm, ((c) >> 4) ? id[1] : id[0], (c) & 15, 16)
+    double best = INFINITY, sec = INFINITY, thr = INFINITY, bx = 0, by = 0, bz = 0;
+    int ord = 0x7fffffff, sord = 0x7fffffff;
+    double bound = max_d2;
+    u32 remaining = HW_MASK27(id[0] != NONE, id[1] != NONE);
+    bool first = true;
+    while (true) {
+        u32 mask = HW_MASK27(lb[0] <= bound, lb[1] <= bound) & remaining;
+        if (!mask) break;
+        int v0, v1, v2, v3;
+        if (first) {
+            // the query's own voxel (box distance 0) and the three nearest other boxes, fetched together
+            first = false;
+            const u32 k0b = ((u32)((u64)__double_as_longlong(lb[0]) >> 32) & ~31u) | (u32)gl;
+            const u32 k1b = ((u32)((u64)__double_as_longlong(lb[1]) >> 32) & ~31u) | (u32)(gl + 16);
+            u32 m = mask;
+#define HW_PICK(mm) __reduce_min_sync(gm, min(((mm) >> gl) & 1u ? k0b : 0xffffffffu, ((mm) >> (gl + 16)) & 1u ? k1b : 0xffffffffu))
+            v0 = (int)(HW_PICK(m) & 31u); m &= ~(1u << v0);
+            v1 = v2 = v3 = v0;
+            if (m) { v1 = (int)(HW_PICK(m) & 31u); m &= ~(1u << v1); }
+            if (m) { v2 = (int)(HW_PICK(m) & 31u); m &= ~(1u << v2); }
+            if (m) { v3 = (int)(HW_PICK(m) & 31u); }
+#undef HW_PICK
+        } else {
+            v0 = __ffs(mask) - 1; mask &= mask - 1;
+            v1 = v0; v2 = v0; v3 = v0;
+            if (mask) { v1 = __ffs(mask) - 1; mask &= mask - 1; }
+            if (mask) { v2 = __ffs(mask) - 1; mask &= mask - 1; }
+            if (mask) { v3 = __ffs(mask) - 1; }
+        }
+        remaining &= ~((1u << v0) | (1u << v1) | (1u << v2) | (1u << v3));
+        const VoxelBlock* B0 = L.blocks + HW_ID(v0);
+        const VoxelBlock* B1 = L.blocks + HW_ID(v1);
+        const VoxelBlock* B2 = L.blocks + HW_ID(v2);
+        const VoxelBlock* B3 = L.blocks + HW_ID(v3);
+        nn_visit(B0, v0, gl, gl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
+        if (v1 != v0) nn_visit(B1, v1, gl, gl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
+        if (v2 != v0) nn_visit(B2, v2, gl, gl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
+        if (v3 != v0) nn_visit(B3, v3, gl, gl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
+        if (gl < MAXP - 16) {
+            nn_visit(B0, v0, gl + 16, gl + 16, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
+            if (v1 != v0) nn_visit(B1, v1, gl + 16, gl + 16, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
+            if (v2 != v0) nn_visit(B2, v2, gl + 16, gl + 16, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
+            if (v3 != v0) nn_visit(B3, v3, gl + 16, gl + 16, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
+        }
+        {   // an upper bound of the half-wide minimum of the non-negative bests with one redux
+            const u32 mhi = __reduce_min_sync(gm, (u32)((u64)__double_as_longlong(best) >> 32));
+            bound = fmin(bound, __longlong_as_double((long long)(((u64)mhi << 32) | 0xffffffffull)));
+        }
+    }
+    // lexicographic (d2, ord) argmin: d2 >= 0, so its bit pattern orders like the value
+    const u64 bits = (u64)__double_as_longlong(best);
+    const u32 hi = (u32)(bits >> 32), lo = (u32)bits;
+    const u32 mhi = __reduce_min_sync(gm, hi);
+    const u32 mlo = __reduce_min_sync(gm, hi == mhi ? lo : 0xffffffffu);
+    const bool cand = (hi == mhi) && (lo == mlo);
+    const u32 mord = __reduce_min_sync(gm, cand ? (u32)ord : 0x7fffffffu);
+    const bool found = mord != 0x7fffffffu;
+    const int owner = found ? (int)((mord % MAXP) & 15u) : 0;          // slot s of a voxel is scanned by lane s & 15
+    tx = __shfl_sync(gm, bx, owner, 16);
+    ty = __shfl_sync(gm, by, owner, 16);
+    tz = __shfl_sync(gm, bz, owner, 16);
+    bd2 = __longlong_as_double((long long)(((u64)mhi << 32) | (u64)mlo));
+    bord = (int)mord;
+    int cons = (found && gl == owner) ? 1 : 0;
+    if (t2 != nullptr) {
+#pragma unroll
+        for (int j = 0; j < ICP_KX; ++j) {
+            const double r = cons == 0 ? best : (cons == 1 ? sec : INFINITY);
+            const int rord = cons == 0 ? ord : sord;
+            const u64 rbits = (u64)__double_as_longlong(r);
+            const u32 rhi = (u32)(rbits >> 32), rlo = (u32)rbits;
+            const u32 mrhi = __reduce_min_sync(gm, rhi);
+            const u32 mrlo = __reduce_min_sync(gm, rhi == mrhi ? rlo : 0xffffffffu);
+            const bool has = found && mrhi < 0x7ff00000u;
+            const int ownj = __ffs((__ballot_sync(gm, rhi == mrhi && rlo == mrlo) >> gs) & 0xffffu) - 1;
+            int oj = __shfl_sync(gm, rord, ownj, 16);
+            if (!has) oj = -1;
+            ord2[j] = oj;
+            t2[3 * j] = t2[3 * j + 1] = t2[3 * j + 2] = 0.0;
+            if (has) {      // its coordinates: one more (cache-hot) read of the voxel it sits in
+                if (gl == ownj) ++cons;
+                const int vj = oj / MAXP;
+                const VoxelBlock* Bj = L.blocks + HW_ID(vj);
+                const int sj = oj % MAXP;
+                t2[3 * j] = __ldg(&Bj->x[sj]); t2[3 * j + 1] = __ldg(&Bj->y[sj]); t2[3 * j + 2] = __ldg(&Bj->z[sj]);
+            }
+        }
+    }
+    // lower bound of the squared distance to every candidate that was not handed out
+    double other = cons == 0 ? best : (cons == 1 ? sec : thr);
+    if ((remaining >> gl) & 1u) other = fmin(other, lb[0]);
+    if ((remaining >> (gl + 16)) & 1u) other = fmin(other, lb[1]);
+    const u32 ohi = __reduce_min_sync(gm, (u32)((u64)__double_as_longlong(other) >> 32));
+    const double d2_other = __longlong_as_double((long long)((u64)ohi << 32));     // low word zero: rounds down
+    others = found ? sqrt(d2_other) * (1.0 - 1e-12) : -1.0;
+#undef HW_MASK27
+#undef HW_ID
     return found;
 }
 
@@ -1431,10 +1728,14 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
             }
             __syncthreads();
             ICP_TICK(0);
-            // ---- 2. full search of the listed points, one warp each
+            // ---- 2. full search of the listed points: one HALF-warp each (two queries per warp at a time)
             const int nmiss = s_nmiss;
             if (threadIdx.x == 0) s_searches += nmiss;
+#ifndef PTK_ICP_FULLWARP_SEARCH
+            for (int i = 2 * warp + (lane >> 4); i < nmiss; i += 2 * ICP_WARPS) {
+#else
             for (int i = warp; i < nmiss; i += ICP_WARPS) {
+#endif
                 const int mq = s_miss[i];
                 const int msp = k0 * 32 + mq;
                 const int mp = (b + (k0 + (mq >> 5)) * nblk) * 32 + (mq & 31);
@@ -1446,8 +1747,13 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 u64 qkey;
                 double t2[3 * ICP_KX];
                 int ord2[ICP_KX];
+#ifndef PTK_ICP_FULLWARP_SEARCH
+                const bool found = halfwarp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey, t2, ord2);
+                if ((lane & 15) == 0) {
+#else
                 const bool found = warp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey, t2, ord2);
                 if (lane == 0) {
+#endif
                     C_TX(msp, mp) = tx; C_TY(msp, mp) = ty; C_TZ(msp, mp) = tz;
 #pragma unroll
                     for (int j = 0; j < ICP_KX; ++j) {

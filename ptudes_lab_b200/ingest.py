@@ -300,15 +300,70 @@ def _bag_records(buf, pos: int, end: int):
         pos = d0 + dl
 
 
+class BagReader:
+    """Messages of ROS1 bag file(s) (format 2.0) - the part of `rosbags.highlevel.AnyReader` bag.py uses.
+    Chunks with `none` or `bz2` compression; messages come chunk by chunk, in time order within a chunk (a
+    recorder writes its chunks in arrival order).  `connections`: {id: (topic, msgtype, md5sum)} seen so far."""
+
+    def __init__(self, paths):
+        self.paths = [Path(p) for p in paths] if isinstance(paths, (list, tuple)) else [Path(paths)]
+        self.connections: Dict[Tuple[int, int], Tuple[str, str, str]] = {}
+
+    def _scan(self, fi, path, buf, pos, end, want):
+        msgs = []
+        for h, d in _bag_records(buf, pos, end):
+            op = h["op"][0]
+            if op == 0x07:                                  # connection
+                cid = struct.unpack("<I", h["conn"])[0]
+                ch = _bag_fields(bytes(d))
+                topic = h.get("topic", ch.get("topic", b"")).decode()
+                self.connections[(fi, cid)] = (topic, ch.get("type", b"").decode(), ch.get("md5sum", b"").decode())
+            elif op == 0x02:                                # message data
+                cid = struct.unpack("<I", h["conn"])[0]
+                sec, nsec = struct.unpack("<II", h["time"])
+                msgs.append((sec * 10**9 + nsec, cid, d))
+            elif op == 0x05:                                # chunk
+                comp = h["compression"].decode()
+                if comp == "none":
+                    inner = d
+                elif comp == "bz2":
+                    inner = memoryview(bz2.decompress(bytes(d)))
+                else:
+                    raise ValueError(f"{path}: chunk compression '{comp}' is not supported (none, bz2)")
+                yield from self._scan(fi, path, inner, 0, len(inner), want)
+        msgs.sort(key=lambda m: m[0])
+        for t, cid, d in msgs:
+            conn = self.connections.get((fi, cid), ("", "", ""))
+            if want(conn):
+                yield conn, t, d
+
+    def messages(self, want):
+        """(connection, timestamp ns, serialized message) of every message whose connection passes `want`."""
+        for fi, path in enumerate(self.paths):
+            data = memoryview(np.memmap(path, dtype=np.uint8, mode="r"))
+            if bytes(data[:13]) != b"#ROSBAG V2.0\n":
+                raise ValueError(f"{path}: not a ROS bag (format 2.0)")
+            yield from self._scan(fi, path, data, 13, len(data), want)
+
+    def scan_connections(self):
+        """Read every connection record (a pass over the file: bag.py looks at `connections` before iterating)."""
+        for _ in self.messages(lambda c: False):
+            pass
+        return list(self.connections.values())
+
+
+def _packetmsg_buf(d) -> bytes:
+    n = struct.unpack_from("<I", d, 0)[0]                   # ouster_ros/PacketMsg: uint8[] buf
+    return bytes(d[4:4 + n])
+
+
 class OusterRawBagSource:
     """`OusterRawBagSource(data_path, info)` (bag.py:21-97): Ouster raw packets out of ROS1 bag(s): the
     `ouster_ros/PacketMsg` messages (md5 4f7b...b5e3, `uint8[] buf`) of the topics ending in `lidar_packets` /
-    `imu_packets`.  Own reader of the bag format 2.0 (rosbags is absent): chunks with `none` or `bz2`
-    compression, messages yielded chunk by chunk in time order within a chunk (a recorder writes its chunks in
-    arrival order)."""
+    `imu_packets` (or the two named topics).  Own reader of the bag format (rosbags is absent)."""
 
     def __init__(self, data_path, info, *, rate: float = 0.0, lidar_topic: str = "", imu_topic: str = ""):
-        self._paths = [Path(p) for p in data_path] if isinstance(data_path, (list, tuple)) else [Path(data_path)]
+        self._reader = BagReader(data_path)
         self._metadata = info
         self._rate = rate
         self._lidar_topic, self._imu_topic = lidar_topic, imu_topic
@@ -327,58 +382,22 @@ class OusterRawBagSource:
             return "imu"
         return None
 
-    def _messages(self, path: Path):
-        data = memoryview(np.memmap(path, dtype=np.uint8, mode="r"))
-        if bytes(data[:13]) != b"#ROSBAG V2.0\n":
-            raise ValueError(f"{path}: not a ROS bag (format 2.0)")
-        conns: Dict[int, Tuple[str, str]] = {}
-
-        def scan(buf, pos, end):
-            msgs = []
-            for h, d in _bag_records(buf, pos, end):
-                op = h["op"][0]
-                if op == 0x07:                                  # connection
-                    cid = struct.unpack("<I", h["conn"])[0]
-                    ch = _bag_fields(bytes(d))
-                    topic = h.get("topic", ch.get("topic", b"")).decode()
-                    conns[cid] = (topic, ch.get("md5sum", b"").decode())
-                    if self._wanted(topic) and topic not in self._topics:
-                        self._topics.append(topic)
-                elif op == 0x02:                                # message data
-                    cid = struct.unpack("<I", h["conn"])[0]
-                    sec, nsec = struct.unpack("<II", h["time"])
-                    msgs.append((sec * 10**9 + nsec, cid, d))
-                elif op == 0x05:                                # chunk
-                    comp = h["compression"].decode()
-                    if comp == "none":
-                        inner = d
-                    elif comp == "bz2":
-                        inner = memoryview(bz2.decompress(bytes(d)))
-                    else:
-                        raise ValueError(f"{path}: chunk compression '{comp}' is not supported (none, bz2)")
-                    yield from scan(inner, 0, len(inner))
-            msgs.sort(key=lambda m: m[0])
-            for t, cid, d in msgs:
-                topic, md5 = conns.get(cid, ("", ""))
-                kind = self._wanted(topic)
-                if kind and md5 == OUSTER_PACKETMSG_MD5:
-                    n = struct.unpack_from("<I", d, 0)[0]       # PacketMsg: uint8[] buf
-                    yield kind, t / 10**9, bytes(d[4:4 + n])
-
-        yield from scan(data, 13, len(data))
-
     def __iter__(self) -> Iterator[Union[LidarPacket, ImuPacket]]:
         import time
         real_start, bag_start = time.monotonic(), None
-        for path in self._paths:
-            for kind, ts, buf in self._messages(path):
-                if self._rate:
-                    bag_start = ts if bag_start is None else bag_start
-                    time.sleep(max(0.0, (ts - bag_start) / self._rate - (time.monotonic() - real_start)))
-                if kind == "lidar":
-                    yield LidarPacket(buf, self._metadata, ts)
-                else:
-                    yield ImuPacket(buf, self._metadata, ts)
+        for (topic, _, md5), t, d in self._reader.messages(lambda c: self._wanted(c[0]) is not None):
+            if topic not in self._topics:
+                self._topics.append(topic)
+            ts = t / 10**9
+            if self._rate:
+                bag_start = ts if bag_start is None else bag_start
+                time.sleep(max(0.0, (ts - bag_start) / self._rate - (time.monotonic() - real_start)))
+            if md5 != OUSTER_PACKETMSG_MD5:
+                continue
+            if self._wanted(topic) == "lidar":
+                yield LidarPacket(_packetmsg_buf(d), self._metadata, ts)
+            else:
+                yield ImuPacket(_packetmsg_buf(d), self._metadata, ts)
 
     @property
     def topics(self) -> List[str]:
@@ -390,6 +409,33 @@ class OusterRawBagSource:
 
     def close(self) -> None:
         pass
+
+
+class IMUBagSource:
+    """`IMUBagSource(data_path, imu_topic)` (bag.py:99-150): IMU samples of ROS bags, from `sensor_msgs/Imu`
+    messages (header stamp, angular_velocity, linear_acceleration) or Ouster `imu_packets`."""
+
+    def __init__(self, data_path, imu_topic: Optional[str] = None):
+        self._reader = BagReader(data_path)
+        conns = [c for c in self._reader.scan_connections()
+                 if c[1] == "sensor_msgs/Imu" or (c[1] == "ouster_ros/PacketMsg" and c[0].endswith("imu_packets"))]
+        assert len(conns), "Expect any topic with msgtype: sensor_msgs/msg/Imu or Ouster imu_packets types but found None"
+        if imu_topic is not None:
+            self._conns = [c for c in conns if c[0] == imu_topic]
+            assert len(self._conns), f"Expect a topic with msgtype: sensor_msgs/msg/Imu and '{imu_topic}' name but found None"
+        else:
+            self._conns = [conns[0]]
+
+    def __iter__(self) -> Iterator[IMU]:
+        for (topic, typ, _), t, d in self._reader.messages(lambda c: c in self._conns):
+            if typ == "sensor_msgs/Imu":
+                # std_msgs/Header: seq u32, stamp (sec u32, nsec u32), frame_id string; then orientation (4 f64) +
+                # covariance (9), angular_velocity (3) + covariance (9), linear_acceleration (3) + covariance (9)
+                _, sec, nsec, n = struct.unpack_from("<IIII", d, 0)
+                v = struct.unpack_from("<37d", d, 16 + n)
+                yield IMU(np.array(v[25:28]), np.array(v[13:16]), sec + nsec * 1e-9)
+            else:
+                yield imu_from_packet(ImuPacket(_packetmsg_buf(d), None, t * 1e-9))
 
 
 def read_packet_source(file_path: str, meta=None):

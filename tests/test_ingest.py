@@ -195,6 +195,25 @@ def test_bag_source_yields_the_packet_messages(tmp_path, compression):
     assert len(list(d)) == len(out)
 
 
+def test_imu_bag_source(tmp_path):
+    """bag.py:99-150: sensor_msgs/Imu topics, or Ouster imu_packets when that is what the bag has."""
+    msgs = []
+    for i in range(7):
+        t = 50.0 + 0.01 * i
+        msgs.append((t, "/alphasense/imu", io.imu_msg(i, t, "imu_link", (0.1 * i, -0.2, 0.3), (0.0, 9.8, 0.01 * i))))
+        msgs.append((t + 0.001, "/os/imu_packets", io.imu_packet(int(t * 1e9), 0, 0, (0, 0, 1), (90.0, 0, 0))))
+    path = tmp_path / "imu.bag"
+    io.write_bag(path, msgs, per_chunk=4, imu_topics=("/alphasense/imu",))
+    out = list(ingest.IMUBagSource(path, imu_topic="/alphasense/imu"))
+    assert len(out) == 7
+    assert np.allclose(out[3].avel, (0.3, -0.2, 0.3)) and np.allclose(out[3].lacc, (0.0, 9.8, 0.03)) and abs(out[3].ts - 50.03) < 1e-6
+    pk = list(ingest.IMUBagSource(path, imu_topic="/os/imu_packets"))
+    assert len(pk) == 7 and np.allclose(pk[0].avel, (np.pi / 2, 0, 0)) and np.allclose(pk[0].lacc, (0, 0, ingest.GRAV))
+    assert len(list(ingest.IMUBagSource(path))) == 7              # the first IMU connection of the bag
+    with pytest.raises(AssertionError):
+        ingest.IMUBagSource(path, imu_topic="/nope")
+
+
 # ---- GPU ------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("prof", PROFILES)
