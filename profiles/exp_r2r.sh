@@ -1,0 +1,16 @@
+#!/bin/bash
+# round-2 experiment batch R: triangle-per-lane LDLT (default) against the column-per-lane form (_cols); vectorised decode
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > $O/r2r_tests.log 2>&1; echo "tests rc=$?"; tail -3 $O/r2r_tests.log
+run() { # suffix lanes contexts tag
+  PTK_LIB_SUFFIX=$1 timeout 300 python bench.py --lanes $2 --contexts $3 --no-side-runs --no-cpu-baseline --no-e2e \
+     > $O/r2r_v$1_l$2c$3$4.json 2> $O/r2r_v$1_l$2c$3$4.err; echo "v$1 l$2 c$3 $4 rc=$?"
+}
+run "" 48 1
+run _cols 48 1
+run "" 64 8
+run _cols 64 8
+run "" 64 8 b
+run _cols 64 8 b
+timeout 600 python bench.py > $O/r2r_bench.json 2> $O/r2r_bench.err; echo "bench rc=$?"

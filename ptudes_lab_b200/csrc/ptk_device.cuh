@@ -888,164 +888,6 @@ __device__ __forceinline__ bool warp_nearest(const MapView& L, double sx, double
     return found;
 }
 
-// The same search by HALF a warp (16 lanes): the two halves of a warp carry two independent queries, so a block's
-// missed points are searched 2 x ICP_WARPS at a time - the search phase of an ICP iteration is usually one round
-// instead of two.  A lane probes voxels gl and gl + 16 of the 27 and scans slots gl and gl + 16 (< 20) of a visited
-// voxel; every collective names only the half's lanes, so the halves may diverge freely.  Pruning rule, winner
-// (lexicographic (d2, order id) minimum, tie rule B.6), runner-ups and the `others` bound are those of warp_nearest.
-__device__ __forceinline__ bool halfwarp_nearest(const MapView& L, double sx, double sy, double sz, int lane, double max_d2,
-                                                 double& bd2, int& bord, double& tx, double& ty, double& tz, double& others,
-                                                 u64* qkey, double* t2, int* ord2) {
-    const int gl = lane & 15, gs = lane & 16;
-    const u32 gm = gs ? 0xffff0000u : 0x0000ffffu;
-    const double v = L.voxel;
-    int kx, ky, kz;
-    voxel_key(sx, sy, sz, v, L.voxel_inv, kx, ky, kz);
-    const bool inr = key_in_range(kx, ky, kz);
-    if (qkey) *qkey = inr ? pack_key(kx, ky, kz) : KEY_EMPTY;
-    u32 id[2] = {NONE, NONE};
-    double lb[2] = {INFINITY, INFINITY};
-    {
-        u64 key[2];
-        u32 slot[2];
-        ulonglong2 raw[2];
-        bool have[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int c = gl + 16 * h;
-            have[h] = inr && c < 27;
-            const int di = c / 9 - 1, dj = (c / 3) % 3 - 1, dk = c % 3 - 1;
-            const int nx = kx + di, ny = ky + dj, nz = kz + dk;
-            key[h] = pack_key(nx, ny, nz);
-            slot[h] = hash_map_key(key[h]) & L.mask;
-            if (have[h]) {
-                raw[h] = __ldg(reinterpret_cast<const ulonglong2*>(L.slots + slot[h]));
-                // voxel n covers [n v, (n+1) v) for n > 0, (-v, v) for n == 0 and ((n-1) v, n v] for n < 0
-                double lo, hi, ax, ay, az;
-                lo = (double)(nx > 0 ? nx : nx - 1) * v; hi = (double)(nx < 0 ? nx : nx + 1) * v;
-                ax = fmax(fmax(lo - sx, sx - hi) - 1e-7, 0.0);
-                lo = (double)(ny > 0 ? ny : ny - 1) * v; hi = (double)(ny < 0 ? ny : ny + 1) * v;
-                ay = fmax(fmax(lo - sy, sy - hi) - 1e-7, 0.0);
-                lo = (double)(nz > 0 ? nz : nz - 1) * v; hi = (double)(nz < 0 ? nz : nz + 1) * v;
-                az = fmax(fmax(lo - sz, sz - hi) - 1e-7, 0.0);
-                lb[h] = ((ax * ax + ay * ay) + az * az) * (1.0 - 1e-9);
-            }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (!have[h]) continue;
-            while (true) {
-                if (raw[h].x == key[h]) { id[h] = (u32)raw[h].y; break; }
-                if (raw[h].x == KEY_EMPTY) break;
-                slot[h] = (slot[h] + 1) & L.mask;
-                raw[h] = __ldg(reinterpret_cast<const ulonglong2*>(L.slots + slot[h]));
-            }
-            if (id[h] == NONE) lb[h] = INFINITY;
-        }
-    }
-    // 27-bit masks over the voxels as the whole half sees them: voxel c sits in lane c & 15, element c >> 4
-#define HW_MASK27(p0, p1) ((((__ballot_sync(gm, (p0)) >> gs) & 0xffffu)) | (((__ballot_sync(gm, (p1)) >> gs) & 0x7ffu) << 16))
-#define HW_ID(c) __shfl_sync(gm, ((c) >> 4) ? id[1] : id[0], (c) & 15, 16)
-    double best = INFINITY, sec = INFINITY, thr = INFINITY, bx = 0, by = 0, bz = 0;
-    int ord = 0x7fffffff, sord = 0x7fffffff;
-    double bound = max_d2;
-    u32 remaining = HW_MASK27(id[0] != NONE, id[1] != NONE);
-    bool first = true;
-    while (true) {
-        u32 mask = HW_MASK27(lb[0] <= bound, lb[1] <= bound) & remaining;
-        if (!mask) break;
-        int v0, v1, v2, v3;
-        if (first) {
-            // the query's own voxel (box distance 0) and the three nearest other boxes, fetched together
-            first = false;
-            const u32 k0b = ((u32)((u64)__double_as_longlong(lb[0]) >> 32) & ~31u) | (u32)gl;
-            const u32 k1b = ((u32)((u64)__double_as_longlong(lb[1]) >> 32) & ~31u) | (u32)(gl + 16);
-            u32 m = mask;
-#define HW_PICK(mm) __reduce_min_sync(gm, min(((mm) >> gl) & 1u ? k0b : 0xffffffffu, ((mm) >> (gl + 16)) & 1u ? k1b : 0xffffffffu))
-            v0 = (int)(HW_PICK(m) & 31u); m &= ~(1u << v0);
-            v1 = v2 = v3 = v0;
-            if (m) { v1 = (int)(HW_PICK(m) & 31u); m &= ~(1u << v1); }
-            if (m) { v2 = (int)(HW_PICK(m) & 31u); m &= ~(1u << v2); }
-            if (m) { v3 = (int)(HW_PICK(m) & 31u); }
-#undef HW_PICK
-        } else {
-            v0 = __ffs(mask) - 1; mask &= mask - 1;
-            v1 = v0; v2 = v0; v3 = v0;
-            if (mask) { v1 = __ffs(mask) - 1; mask &= mask - 1; }
-            if (mask) { v2 = __ffs(mask) - 1; mask &= mask - 1; }
-            if (mask) { v3 = __ffs(mask) - 1; }
-        }
-        remaining &= ~((1u << v0) | (1u << v1) | (1u << v2) | (1u << v3));
-        const VoxelBlock* B0 = L.blocks + HW_ID(v0);
-        const VoxelBlock* B1 = L.blocks + HW_ID(v1);
-        const VoxelBlock* B2 = L.blocks + HW_ID(v2);
-        const VoxelBlock* B3 = L.blocks + HW_ID(v3);
-        nn_visit(B0, v0, gl, gl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
-        if (v1 != v0) nn_visit(B1, v1, gl, gl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
-        if (v2 != v0) nn_visit(B2, v2, gl, gl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
-        if (v3 != v0) nn_visit(B3, v3, gl, gl, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
-        if (gl < MAXP - 16) {
-            nn_visit(B0, v0, gl + 16, gl + 16, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
-            if (v1 != v0) nn_visit(B1, v1, gl + 16, gl + 16, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
-            if (v2 != v0) nn_visit(B2, v2, gl + 16, gl + 16, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
-            if (v3 != v0) nn_visit(B3, v3, gl + 16, gl + 16, sx, sy, sz, best, sec, thr, ord, sord, bx, by, bz);
-        }
-        {   // an upper bound of the half-wide minimum of the non-negative bests with one redux
-            const u32 mhi = __reduce_min_sync(gm, (u32)((u64)__double_as_longlong(best) >> 32));
-            bound = fmin(bound, __longlong_as_double((long long)(((u64)mhi << 32) | 0xffffffffull)));
-        }
-    }
-    // lexicographic (d2, ord) argmin: d2 >= 0, so its bit pattern orders like the value
-    const u64 bits = (u64)__double_as_longlong(best);
-    const u32 hi = (u32)(bits >> 32), lo = (u32)bits;
-    const u32 mhi = __reduce_min_sync(gm, hi);
-    const u32 mlo = __reduce_min_sync(gm, hi == mhi ? lo : 0xffffffffu);
-    const bool cand = (hi == mhi) && (lo == mlo);
-    const u32 mord = __reduce_min_sync(gm, cand ? (u32)ord : 0x7fffffffu);
-    const bool found = mord != 0x7fffffffu;
-    const int owner = found ? (int)((mord % MAXP) & 15u) : 0;          // slot s of a voxel is scanned by lane s & 15
-    tx = __shfl_sync(gm, bx, owner, 16);
-    ty = __shfl_sync(gm, by, owner, 16);
-    tz = __shfl_sync(gm, bz, owner, 16);
-    bd2 = __longlong_as_double((long long)(((u64)mhi << 32) | (u64)mlo));
-    bord = (int)mord;
-    int cons = (found && gl == owner) ? 1 : 0;
-    if (t2 != nullptr) {
-#pragma unroll
-        for (int j = 0; j < ICP_KX; ++j) {
-            const double r = cons == 0 ? best : (cons == 1 ? sec : INFINITY);
-            const int rord = cons == 0 ? ord : sord;
-            const u64 rbits = (u64)__double_as_longlong(r);
-            const u32 rhi = (u32)(rbits >> 32), rlo = (u32)rbits;
-            const u32 mrhi = __reduce_min_sync(gm, rhi);
-            const u32 mrlo = __reduce_min_sync(gm, rhi == mrhi ? rlo : 0xffffffffu);
-            const bool has = found && mrhi < 0x7ff00000u;
-            const int ownj = __ffs((__ballot_sync(gm, rhi == mrhi && rlo == mrlo) >> gs) & 0xffffu) - 1;
-            int oj = __shfl_sync(gm, rord, ownj, 16);
-            if (!has) oj = -1;
-            ord2[j] = oj;
-            t2[3 * j] = t2[3 * j + 1] = t2[3 * j + 2] = 0.0;
-            if (has) {      // its coordinates: one more (cache-hot) read of the voxel it sits in
-                if (gl == ownj) ++cons;
-                const int vj = oj / MAXP;
-                const VoxelBlock* Bj = L.blocks + HW_ID(vj);
-                const int sj = oj % MAXP;
-                t2[3 * j] = __ldg(&Bj->x[sj]); t2[3 * j + 1] = __ldg(&Bj->y[sj]); t2[3 * j + 2] = __ldg(&Bj->z[sj]);
-            }
-        }
-    }
-    // lower bound of the squared distance to every candidate that was not handed out
-    double other = cons == 0 ? best : (cons == 1 ? sec : thr);
-    if ((remaining >> gl) & 1u) other = fmin(other, lb[0]);
-    if ((remaining >> (gl + 16)) & 1u) other = fmin(other, lb[1]);
-    const u32 ohi = __reduce_min_sync(gm, (u32)((u64)__double_as_longlong(other) >> 32));
-    const double d2_other = __longlong_as_double((long long)((u64)ohi << 32));     // low word zero: rounds down
-    others = found ? sqrt(d2_other) * (1.0 - 1e-12) : -1.0;
-#undef HW_MASK27
-#undef HW_ID
-    return found;
-}
-
 // ---- TMA pieces (1-D bulk copy global -> shared, completion counted on an mbarrier) -----------------------------
 __device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* mbar, u32 count) {
@@ -1338,92 +1180,90 @@ __constant__ signed char kJtJMap[36] = {
     0, -4, 3, 5, 6, 7,
     4, 0, -2, 6, 8, 9,
     -3, 2, 0, 7, 9, 10};
-// LDL^T with diagonal pivoting of the 6x6 normal equations, oracle/canon.py ldlt_solve6 operation
-// for operation (explicit row/column swaps, same divisions, same order of subtractions), but laid
-// out for latency: lane j (< 6) keeps column j of the symmetric matrix in registers, values travel
-// by shuffles, the independent divisions / trailing updates of a step run on separate lanes, and
-// nothing touches shared memory until the result.  Both copies of every off-diagonal entry are
-// updated with the operand roles of the canonical (row >= column) form, so they stay bit-equal.
+// LDL^T with diagonal pivoting of the 6x6 normal equations, oracle/canon.py ldlt_solve6 operation for operation
+// (same pivot choice, same divisions, same (a[j][k] * d) then multiply-subtract, same subtraction order in the two
+// substitutions), laid out for latency: ONE ENTRY of the lower triangle per lane (lane t = i (i + 1) / 2 + j holds
+// a[i][j], i >= j; the canonical algorithm never reads the upper triangle again once a column is eliminated).  A
+// pivot step is four dependent shuffle stages - diagonal fetch, the symmetric permutation as ONE indexed shuffle,
+// pivot broadcast, the two L factors of an entry.  (A column-per-lane form with divergent updates took 7.6 k cycles
+// per solve; this one about 6.4 k, most of it the seven dependent double-precision divisions.)
 // Writes x to dx_out[6] (shared memory) and returns whether the solve is finite; warp-uniform.
-__device__ __forceinline__ bool ldlt_solve6_warp(const double* red, int lane, double* dx_out) {
+__device__ __forceinline__ int tri_idx(int i, int j) { return (i * (i + 1)) / 2 + j; }
+__device__ __forceinline__ bool ldlt_solve6_tri(const double* red, int lane, double* dx_out) {
     const u32 FULL = 0xffffffffu;
-    const int j = lane < 6 ? lane : 5;          // lanes >= 6 shadow lane 5
-    double c[6], b[6];
-    int perm[6];
+    // (mi, mj) of this lane; lanes >= 21 shadow lane 20
+    int mi = 0, mj = 0;
+    {
+        const int t = lane < 21 ? lane : 20;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const int m = kJtJMap[i * 6 + j];
-        c[i] = m > 0 ? red[m - 1] : (m < 0 ? -red[-m - 1] : 0.0);
-        b[i] = -red[10 + i];
-        perm[i] = i;
+        for (int i = 1; i < 6; ++i) if (t >= (i * (i + 1)) / 2) mi = i;
+        mj = t - (mi * (mi + 1)) / 2;
     }
-    bool ok = true;
+    double a;
+    {
+        const int m = kJtJMap[mi * 6 + mj];
+        a = m > 0 ? red[m - 1] : (m < 0 ? -red[-m - 1] : 0.0);
+    }
+    int perm[6] = {0, 1, 2, 3, 4, 5};
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        double dj = c[0];
-#pragma unroll
-        for (int i = 1; i < 6; ++i) if (j == i) dj = c[i];
-        const double adj = fabs(dj);
         int p = k;
-        double best = __shfl_sync(FULL, adj, k);
+        double best = fabs(__shfl_sync(FULL, a, tri_idx(k, k)));
 #pragma unroll
         for (int i = k + 1; i < 6; ++i) {
-            const double v = __shfl_sync(FULL, adj, i);
+            const double v = fabs(__shfl_sync(FULL, a, tri_idx(i, i)));
             if (v > best) { best = v; p = i; }
         }
-        if (p != k) {
-            const double tc = c[k], tb = b[k];
-            const int tp = perm[k];
+        if (p != k) {                                   // warp-uniform
+            int si = mi == k ? p : (mi == p ? k : mi);
+            int sj = mj == k ? p : (mj == p ? k : mj);
+            if (si < sj) { const int t = si; si = sj; sj = t; }
+            a = __shfl_sync(FULL, a, tri_idx(si, sj));
+            const int tk = perm[k];
 #pragma unroll
             for (int r = k + 1; r < 6; ++r)
-                if (r == p) { c[k] = c[r]; c[r] = tc; b[k] = b[r]; b[r] = tb; perm[k] = perm[r]; perm[r] = tp; }
-            const int src = (j == k) ? p : ((j == p) ? k : j);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) c[i] = __shfl_sync(FULL, c[i], src);
+                if (r == p) { perm[k] = perm[r]; perm[r] = tk; }
         }
-        const double d = __shfl_sync(FULL, c[k], k);
-        if (d == 0.0 || d != d) { ok = false; break; }
-        const double l = c[k] / d;                  // lane i > k: a[k][i] == a[i][k]  ->  L(i,k)
-        if (j > k) c[k] = l;
-        double li[6];
-#pragma unroll
-        for (int i = k + 1; i < 6; ++i) li[i] = __shfl_sync(FULL, l, i);
-        if (j == k) {
-#pragma unroll
-            for (int i = k + 1; i < 6; ++i) c[i] = li[i];
-        } else if (j > k) {
-            const double ljd = l * d;
-#pragma unroll
-            for (int i = k + 1; i < 6; ++i) {
-                if (i >= j) c[i] = c[i] - li[i] * ljd;          // a[i][j] -= a[i][k] * (a[j][k] * d)
-                else c[i] = c[i] - l * (li[i] * d);             // mirror a[j][i] -= a[j][k] * (a[i][k] * d)
-            }
+        const double d = __shfl_sync(FULL, a, tri_idx(k, k));
+        if (d == 0.0 || d != d) return false;
+        if (mj == k && mi > k) a = a / d;                            // L(i, k)
+        if (k < 5) {
+            const double li = __shfl_sync(FULL, a, tri_idx(mi, k));  // (read by the trailing entries only)
+            const double lj = __shfl_sync(FULL, a, tri_idx(mj, k));
+            if (mj > k) a = a - li * (lj * d);                       // a[i][j] -= a[i][k] * (a[j][k] * d), i >= j > k
         }
     }
-    if (!ok) return false;
-    double y = b[0], dj = c[0];
-    int pj = perm[0];
+    // rows live in lanes 0..5 from here on: y = P b, L z = y, w = z / D, L^T v = w
+    const int r = lane < 6 ? lane : 5;
+    int pr = perm[0];
 #pragma unroll
-    for (int i = 1; i < 6; ++i) if (j == i) { y = b[i]; dj = c[i]; pj = perm[i]; }
+    for (int i = 1; i < 6; ++i) if (r == i) pr = perm[i];
+    double y = -red[10 + pr];
+    double lrow[5], lcol[5];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {                   // L z = P b (column sweep = the same subtraction order per row)
+    for (int q = 0; q < 5; ++q) {
+        lrow[q] = __shfl_sync(FULL, a, r > q ? tri_idx(r, q) : 0);              // L(r, q), q < r
+        lcol[q] = __shfl_sync(FULL, a, q + 1 > r ? tri_idx(q + 1, r) : 0);      // L(q + 1, r), q + 1 > r
+    }
+    const double dr = __shfl_sync(FULL, a, tri_idx(r, r));
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {                   // column sweep = the canonical subtraction order of every row
         const double yq = __shfl_sync(FULL, y, q);
-        if (j > q) y = y - c[q] * yq;
+        if (r > q) y = y - lrow[q] * yq;
     }
-    y = y / dj;
+    y = y / dr;
+    double yv[6];
 #pragma unroll
-    for (int i = 4; i >= 0; --i) {                  // L^T v = w, rows 4..0, subtractions in ascending column order
-        double yv[6];
+    for (int i = 4; i >= 0; --i) {                  // rows 4..0; a row subtracts its terms in ascending column order
+        yv[i + 1] = __shfl_sync(FULL, y, i + 1);    // final since the previous round
+        if (r == i) {
 #pragma unroll
-        for (int q = i + 1; q < 6; ++q) yv[q] = __shfl_sync(FULL, y, q);
-        if (j == i) {
-#pragma unroll
-            for (int q = i + 1; q < 6; ++q) y = y - c[q] * yv[q];
+            for (int q = i + 1; q < 6; ++q) y = y - lcol[q - 1] * yv[q];
         }
     }
     const bool fin = fabs(y) <= 1.7976931348623157e308;
-    ok = (__ballot_sync(FULL, fin || lane >= 6) == FULL);
-    if (lane < 6) dx_out[pj] = y;
+    const bool ok = (__ballot_sync(FULL, fin || lane >= 6) == FULL);
+    if (lane < 6) dx_out[pr] = y;
     __syncwarp();
     return ok;
 }
@@ -1435,7 +1275,7 @@ struct SolveSmem {
 // Warp 0 of every block: expand the 17 sums into the 6x6 system, solve it (ldlt_solve6_warp), update
 // T_icp, decide termination (kiss-icp RegisterFrame loop body after BuildLinearSystem).
 __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, StepOut& O, const double* red, SolveSmem* S,
-                                            Rigid* sE, SE3q* sT, int* s_done, int it, bool writer, int lane) {
+                                            Rigid* sE, SE3q* sT, int* s_done, int it, bool writer, int lane, double eps, int max_iters) {
 #ifdef PTK_SOLVE_CLOCKS
     __shared__ long long s_sc[6];
     long long tl_ = clock64();
@@ -1450,7 +1290,8 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
     if (n_corr == 0) {
         status = 1; done = 1;            // B.5
     } else {
-        ok = ldlt_solve6_warp(red, lane, S->dx);
+        SOLVE_TICK(0);
+        ok = ldlt_solve6_tri(red, lane, S->dx);
         SOLVE_TICK(1);
         SOLVE_TICK(2);
         if (!ok) { status = 2; done = 1; }
@@ -1466,9 +1307,9 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
             *sT = se3q_mul(Eq, *sT);
             SOLVE_TICK(4);
             nrm = sqrt(((((dx[0] * dx[0] + dx[1] * dx[1]) + dx[2] * dx[2]) + dx[3] * dx[3]) + dx[4] * dx[4]) + dx[5] * dx[5]);
-            if (nrm < L.eps) done = 1;
+            if (nrm < eps) done = 1;
         }
-        if (it + 1 >= L.max_iters) done = 1;
+        if (it + 1 >= max_iters) done = 1;
         *sE = Enew;
         *s_done = done;
         if (done && writer) {
@@ -1476,6 +1317,12 @@ __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, Ste
             O.iterations = it + 1; O.n_corr = n_corr; O.status = status; O.dx_norm = nrm;
         }
         SOLVE_TICK(5);
+#ifdef PTK_SOLVE_CLOCKS
+        if (done && writer) {     // this build reports the solve's own phases instead of the iteration's
+#pragma unroll
+            for (int k = 0; k < 6; ++k) O.icp_cyc[k] = s_sc[k];
+        }
+#endif
     }
 #undef SOLVE_TICK
 }
@@ -1613,6 +1460,11 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
         return;
     }
     const int n_groups = (n_src + 31) >> 5;
+    // lane constants the loop would otherwise re-read from global memory after every barrier
+    const double lane_eps = L.eps;
+    const int lane_max_iters = L.max_iters, lane_trace_iters = L.trace_iters, lane_ng_cap = L.ng_cap, lane_cap_points = L.cap_points;
+    double* const lane_part_a = L.part_a;
+    double* const lane_part_b = L.part_b;
     // groups of this block: b, b + nblk, b + 2 nblk, ... (interleaved: the source is in beam order, and how far a
     // point moves per iteration - hence how often its cache entry misses - varies with the beam; dealing the
     // groups round-robin gives every block the same mix, so the blocks reach the barrier together)
@@ -1648,7 +1500,7 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
 #define ICP_TICK(slot) do { if (clk) { const long long t_ = clock64(); s_cyc[slot] += t_ - tlast; tlast = t_; } } while (0)
 
     for (int it = 0;; ++it) {
-        double* part = (it & 1) ? L.part_b : L.part_a;
+        double* part = (it & 1) ? lane_part_b : lane_part_a;
         for (int k0 = 0; k0 < n_local; k0 += ICP_CHUNK) {
             const int gc = min(ICP_CHUNK, n_local - k0);   // local groups k0 .. k0 + gc, one per warp
             const int q = threadIdx.x;                     // point of this thread within the chunk
@@ -1689,7 +1541,7 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                     const double others = C_SLACK(sp, p);
                     if (others > 0.0) {
                         const double mx = sx - C_PX(sp, p), my = sy - C_PY(sp, p), mz = sz - C_PZ(sp, p);
-                        const double moved = sqrt((mx * mx + my * my) + mz * mz);
+                        const double moved2 = (mx * mx + my * my) + mz * mz;
                         double ex = C_TX(sp, p) - sx, ey = C_TY(sp, p) - sy, ez = C_TZ(sp, p) - sz;
                         double da2 = (ex * ex + ey * ey) + ez * ez;              // as the search computes it
 #pragma unroll
@@ -1707,7 +1559,12 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                                 da2 = db2;
                             }
                         }
-                        if (sqrt(da2) + moved + 1e-9 < others) {
+                        // |p - w| + |p - p0| + 1e-9 < others, without the two square roots (the fp64 pipe is what this
+                        // pass waits for): with o = others - 1e-9, a + m < o  <=>  o^2 - a^2 - m^2 > 0 and
+                        // 4 a^2 m^2 < (o^2 - a^2 - m^2)^2; the factor keeps the test on the safe side of rounding
+                        const double o1 = others - 1e-9;
+                        const double rhs = (o1 * o1 - da2) - moved2;
+                        if (o1 > 0.0 && rhs > 0.0 && 4.0 * (da2 * moved2) < (rhs * rhs) * (1.0 - 1e-12)) {
                             int kx, ky, kz;
                             voxel_key(sx, sy, sz, voxel, voxel_inv, kx, ky, kz);
                             miss = !(key_in_range(kx, ky, kz) && pack_key(kx, ky, kz) == C_KEY(sp, p));
@@ -1728,14 +1585,12 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
             }
             __syncthreads();
             ICP_TICK(0);
-            // ---- 2. full search of the listed points: one HALF-warp each (two queries per warp at a time)
+            // ---- 2. full search of the listed points, one warp each (a HALF-warp per point - two queries per warp at
+            // a time - measured slower: 1.24 against 1.02 ms per 48-lane launch; a search is bound by the length of
+            // its own instruction chain, which the narrower form makes longer)
             const int nmiss = s_nmiss;
             if (threadIdx.x == 0) s_searches += nmiss;
-#ifndef PTK_ICP_FULLWARP_SEARCH
-            for (int i = 2 * warp + (lane >> 4); i < nmiss; i += 2 * ICP_WARPS) {
-#else
             for (int i = warp; i < nmiss; i += ICP_WARPS) {
-#endif
                 const int mq = s_miss[i];
                 const int msp = k0 * 32 + mq;
                 const int mp = (b + (k0 + (mq >> 5)) * nblk) * 32 + (mq & 31);
@@ -1747,13 +1602,8 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 u64 qkey;
                 double t2[3 * ICP_KX];
                 int ord2[ICP_KX];
-#ifndef PTK_ICP_FULLWARP_SEARCH
-                const bool found = halfwarp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey, t2, ord2);
-                if ((lane & 15) == 0) {
-#else
                 const bool found = warp_nearest(s_map, qx, qy, qz, lane, max_d2, d2, ord, tx, ty, tz, others, &qkey, t2, ord2);
                 if (lane == 0) {
-#endif
                     C_TX(msp, mp) = tx; C_TY(msp, mp) = ty; C_TZ(msp, mp) = tz;
 #pragma unroll
                     for (int j = 0; j < ICP_KX; ++j) {
@@ -1830,10 +1680,14 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                         const double tx = wtx, ty = wty, tz = wtz;
                         const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
                         const double d2 = (dx * dx + dy * dy) + dz * dz;
-                        acc = sqrt(d2) < max_corr;
+                        // sqrt(d2) < max_corr: away from the threshold the squares decide (as in range_pass)
+                        const double mc2 = max_corr * max_corr;
+                        if (d2 < mc2 * (1.0 - 1e-12)) acc = true;
+                        else if (d2 > mc2 * (1.0 + 1e-12)) acc = false;
+                        else acc = sqrt(d2) < max_corr;
                         if (acc) lin_terms(sx, sy, sz, tx, ty, tz, kern, c);
                     }
-                    if (it < L.trace_iters) L.trace[(size_t)it * L.cap_points + p] = acc ? ord : -1;
+                    if (it < lane_trace_iters) L.trace[(size_t)it * lane_cap_points + p] = acc ? ord : -1;
                 }
                 if (!acc) {
 #pragma unroll
@@ -1841,8 +1695,8 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
                 }
                 const double mine = warp_reduce16(c, lane);
                 const u32 nacc = __popc(__ballot_sync(0xffffffffu, acc));   // a sum of 1.0s is exact in any order
-                if (lane < 16) part[(size_t)(__brev((u32)lane) >> 28) * L.ng_cap + grp] = mine;
-                else if (lane == 16) part[(size_t)16 * L.ng_cap + grp] = (double)nacc;
+                if (lane < 16) part[(size_t)(__brev((u32)lane) >> 28) * lane_ng_cap + grp] = mine;
+                else if (lane == 16) part[(size_t)16 * lane_ng_cap + grp] = (double)nacc;
             }
         }
         // ---- one barrier over the lane's blocks (icp_arrive was zeroed by the previous kernel)
@@ -1860,12 +1714,12 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
         // 16 sums, one warp each, with the canonical tree; the 17th (correspondence count) is a sum of
         // small integers - exact in any order - so all warps share it instead of one warp doing two trees
         for (int v = warp; v < 16; v += ICP_WARPS) {
-            const double x = warp_tree_sum(part + (size_t)v * L.ng_cap, n_groups, lane);
+            const double x = warp_tree_sum(part + (size_t)v * lane_ng_cap, n_groups, lane);
             if (lane == 0) red[v] = x;
         }
         {
             int cnt = 0;
-            for (int g = threadIdx.x; g < n_groups; g += ICP_THREADS) cnt += (int)__ldcg(part + (size_t)16 * L.ng_cap + g);
+            for (int g = threadIdx.x; g < n_groups; g += ICP_THREADS) cnt += (int)__ldcg(part + (size_t)16 * lane_ng_cap + g);
             cnt = __reduce_add_sync(0xffffffffu, cnt);
             if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
         }
@@ -1874,7 +1728,7 @@ __global__ void __launch_bounds__(ICP_THREADS, PTK_ICP_MINBLOCKS) k_icp(LaneDev*
         if (warp == 0) {
             if (lane == 0) { red[16] = (double)s_cnt; s_cnt = 0; }
             __syncwarp();
-            icp_solve_step(L, P, O, red, &sS, &sE, &sT, &s_done, it, b == 0, lane);
+            icp_solve_step(L, P, O, red, &sS, &sE, &sT, &s_done, it, b == 0, lane, lane_eps, lane_max_iters);
         }
         __syncthreads();
         ICP_TICK(5);
@@ -2207,7 +2061,7 @@ __global__ void __launch_bounds__(NSUM * 32) k_shard_solve(LaneDev* lanes, int l
     }
     if (threadIdx.x == 0) sT = it == 0 ? se3q_identity() : L.icp_Tq;
     __syncthreads();
-    if (warp == 0) icp_solve_step(L, P, O, red, &sS, &sE, &sT, &s_done, it, true, lane);
+    if (warp == 0) icp_solve_step(L, P, O, red, &sS, &sE, &sT, &s_done, it, true, lane, L.eps, L.max_iters);
     __syncthreads();
     if (threadIdx.x == 0) { L.icp_E = sE; L.icp_Tq = sT; L.icp_done = s_done; }
 }

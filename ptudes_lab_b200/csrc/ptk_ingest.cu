@@ -57,106 +57,173 @@ __host__ __device__ inline void col_header(const DevFormat& F, const unsigned ch
 // ---- TMA (1-D bulk copy global -> shared, completion on an mbarrier) ---------------------------------
 __device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// One block per packet slot: blockIdx.x = slot within the frame, blockIdx.y = frame.
+// Persistent blocks walk the packet slots (slot index = frame * packets_per_frame + position) with TWO shared-memory
+// buffers: while a packet is being decoded the next one is already on its way (one TMA bulk copy each, completion on
+// the buffer's mbarrier), so every SM keeps several packet loads in flight all the time.
+__device__ __forceinline__ void tma_packet(unsigned char* dst, const unsigned char* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(saddr(dst)), "l"(src), "r"(bytes), "r"(saddr(bar)) : "memory");
+}
+
 __global__ void __launch_bounds__(256) k_decode_packets(const unsigned char* __restrict__ packets, DevFormat F, ptk_scan_fields out,
-                                                        unsigned int* frame_done, int use_tma) {
-    extern __shared__ __align__(16) unsigned char s_pkt[];
+                                                        unsigned int* frame_done, int n_slots, int use_tma, int vec_ok) {
+    extern __shared__ __align__(16) unsigned char s_buf[];
     __shared__ int s_mid[64];
-    __shared__ unsigned long long s_bar;
+    __shared__ unsigned long long s_bar[2];
     __shared__ int s_last;
-    const int f = blockIdx.y;
-    const unsigned char* g = packets + ((size_t)f * F.ppf + blockIdx.x) * (size_t)F.pkt_size;
-    if (use_tma) {
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(&s_bar)) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(&s_bar)), "r"((uint32_t)F.pkt_size) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(saddr(s_pkt)), "l"(g), "r"((uint32_t)F.pkt_size), "r"(saddr(&s_bar)) : "memory");
-        }
-        __syncthreads();            // the barrier is initialised before anybody polls it
-        uint32_t ok;
-        do {
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(ok) : "r"(saddr(&s_bar)) : "memory");
-        } while (!ok);
-    } else {
-        for (int i = threadIdx.x; i < F.pkt_size; i += blockDim.x) s_pkt[i] = g[i];
-        __syncthreads();
-    }
-    const size_t img = (size_t)f * F.H * F.W, hdr = (size_t)f * F.W;
-    if ((int)threadIdx.x < F.cpp) {
-        uint64_t ts; int mid; uint32_t st;
-        col_header(F, s_pkt, threadIdx.x, ts, mid, st);
-        const bool valid = (st & 1u) && mid < F.W;
-        s_mid[threadIdx.x] = valid ? mid : -1;
-        if (valid) {
-            out.timestamp[hdr + mid] = ts;
-            out.status[hdr + mid] = st;
-            out.measurement_id[hdr + mid] = (unsigned short)mid;
-        }
-    }
-    __syncthreads();
-    // consecutive threads = consecutive columns of one row: 4*cpp contiguous bytes of the image per row
-    const int n = F.H * F.cpp;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int c = i % F.cpp, p = i / F.cpp;
-        const int mid = s_mid[c];
-        if (mid < 0) continue;
-        const unsigned char* ch = s_pkt + F.pkt_hdr + (size_t)c * F.col_size + F.col_hdr + (size_t)p * F.ch_size;
-        const size_t o = img + (size_t)p * F.W + mid;
-        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(ch);
-        if (F.profile == PTK_PROFILE_LEGACY) {
-            out.range[o] = w0 & 0x000fffffu;
-            if (out.reflectivity) out.reflectivity[o] = rd16(ch + 4);
-            if (out.signal) out.signal[o] = rd16(ch + 6);
-            if (out.near_ir) out.near_ir[o] = rd16(ch + 8);
-        } else if (F.profile == PTK_PROFILE_RNG19_RFL8_SIG16_NIR16) {
-            out.range[o] = w0 & 0x0007ffffu;
-            if (out.reflectivity) out.reflectivity[o] = ch[4];
-            if (out.signal) out.signal[o] = rd16(ch + 6);
-            if (out.near_ir) out.near_ir[o] = rd16(ch + 8);
-        } else if (F.profile == PTK_PROFILE_RNG15_RFL8_NIR8) {
-            out.range[o] = (w0 & 0x7fffu) << 3;
-            if (out.reflectivity) out.reflectivity[o] = ch[2];
-            if (out.near_ir) out.near_ir[o] = (unsigned short)((unsigned)ch[3] << 4);
-        } else {    // RNG19_RFL8_SIG16_NIR16_DUAL
-            out.range[o] = w0 & 0x0007ffffu;
-            if (out.reflectivity) out.reflectivity[o] = ch[3];
-            if (out.range2) out.range2[o] = rd32(ch + 4) & 0x0007ffffu;
-            if (out.signal) out.signal[o] = rd16(ch + 8);
-            if (out.near_ir) out.near_ir[o] = rd16(ch + 12);
-        }
-    }
-    // ScanBatcher's zero fill: the last block of a frame clears the columns nobody wrote (status still 0)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&frame_done[f], 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // (columns checked 256 at a time; the usual frame has none missing and this is one pass of W/256 loads)
     __shared__ int s_nmiss;
     __shared__ unsigned short s_misscol[256];
-    for (int w0 = 0; w0 < F.W; w0 += blockDim.x) {
-        if (threadIdx.x == 0) s_nmiss = 0;
-        __syncthreads();
-        const int w = w0 + threadIdx.x;
-        if (w < F.W && !(__ldcg(out.status + hdr + w) & 1u)) {
-            s_misscol[atomicAdd(&s_nmiss, 1)] = (unsigned short)w;
-            out.timestamp[hdr + w] = 0; out.status[hdr + w] = 0; out.measurement_id[hdr + w] = 0;
+    const uint32_t stride = ((uint32_t)F.pkt_size + 15u) & ~15u;
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(&s_bar[0])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(&s_bar[1])) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if ((int)blockIdx.x < n_slots) tma_packet(s_buf, packets + (size_t)blockIdx.x * F.pkt_size, (uint32_t)F.pkt_size, &s_bar[0]);
+        }
+        __syncthreads();            // the barriers are initialised before anybody polls them
+    }
+    int it = 0;
+    for (int idx = blockIdx.x; idx < n_slots; idx += gridDim.x, ++it) {
+        const int cur = it & 1;
+        unsigned char* s_pkt = s_buf + (size_t)cur * stride;
+        const int f = idx / F.ppf;
+        if (use_tma) {
+            // the other buffer was released by the barrier that ended the previous iteration
+            const int nxt = idx + gridDim.x;
+            if (threadIdx.x == 0 && nxt < n_slots)
+                tma_packet(s_buf + (size_t)(cur ^ 1) * stride, packets + (size_t)nxt * F.pkt_size, (uint32_t)F.pkt_size, &s_bar[cur ^ 1]);
+            const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+            uint32_t ok;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(ok) : "r"(saddr(&s_bar[cur])), "r"(parity) : "memory");
+            } while (!ok);
+        } else {
+            const unsigned char* g = packets + (size_t)idx * F.pkt_size;
+            for (int i = threadIdx.x; i < F.pkt_size; i += blockDim.x) s_pkt[i] = g[i];
+            __syncthreads();
+        }
+        const size_t img = (size_t)f * F.H * F.W, hdr = (size_t)f * F.W;
+        if ((int)threadIdx.x < F.cpp) {
+            uint64_t ts; int mid; uint32_t st;
+            col_header(F, s_pkt, threadIdx.x, ts, mid, st);
+            const bool valid = (st & 1u) && mid < F.W;
+            s_mid[threadIdx.x] = valid ? mid : -1;
+            if (valid) {
+                out.timestamp[hdr + mid] = ts;
+                out.status[hdr + mid] = st;
+                out.measurement_id[hdr + mid] = (unsigned short)mid;
+            }
         }
         __syncthreads();
-        const int nm = s_nmiss;
-        for (int i = threadIdx.x; i < nm * F.H; i += blockDim.x) {
-            const size_t o = img + (size_t)(i / nm) * F.W + s_misscol[i % nm];
-            out.range[o] = 0;
-            if (out.range2) out.range2[o] = 0;
-            if (out.reflectivity) out.reflectivity[o] = 0;
-            if (out.signal) out.signal[o] = 0;
-            if (out.near_ir) out.near_ir[o] = 0;
+        // channel data -> images.  Fast path (every Ouster format: 16 columns per packet, measurement ids of a packet
+        // consecutive and aligned): a thread takes one row of FOUR columns and writes its four pixels with one 16 B
+        // (u32 fields) / 8 B (u16 fields) store; four threads cover the 64 B a packet contributes to an image row.
+        bool quads = (F.cpp % 4 == 0) && vec_ok;
+        if (quads) {
+            for (int c = 0; c < F.cpp; c += 4) {
+                const int m0 = s_mid[c];
+                quads = quads && m0 >= 0 && (m0 & 3) == 0 && s_mid[c + 1] == m0 + 1 && s_mid[c + 2] == m0 + 2 && s_mid[c + 3] == m0 + 3;
+            }
         }
+        if (quads) {
+            const int groups = F.cpp >> 2;
+            const int n = F.H * groups;
+            uint32_t rmask = 0x0007ffffu, rsh = 0;
+            if (F.profile == PTK_PROFILE_LEGACY) rmask = 0x000fffffu;
+            else if (F.profile == PTK_PROFILE_RNG15_RFL8_NIR8) { rmask = 0x7fffu; rsh = 3; }
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int g = i % groups, p = i / groups;
+                const int c0 = g << 2;
+                const unsigned char* ch = s_pkt + F.pkt_hdr + (size_t)c0 * F.col_size + F.col_hdr + (size_t)p * F.ch_size;
+                const size_t o = img + (size_t)p * F.W + s_mid[c0];
+                uint32_t w0[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w0[j] = *reinterpret_cast<const uint32_t*>(ch + (size_t)j * F.col_size);
+                *reinterpret_cast<uint4*>(out.range + o) = make_uint4((w0[0] & rmask) << rsh, (w0[1] & rmask) << rsh, (w0[2] & rmask) << rsh,
+                                                                      (w0[3] & rmask) << rsh);
+                if (out.reflectivity || out.signal || out.near_ir || out.range2) {
+                    unsigned short refl[4], sig[4] = {0, 0, 0, 0}, nir[4];
+                    uint32_t r2[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned char* cj = ch + (size_t)j * F.col_size;
+                        if (F.profile == PTK_PROFILE_LEGACY) { refl[j] = rd16(cj + 4); sig[j] = rd16(cj + 6); nir[j] = rd16(cj + 8); }
+                        else if (F.profile == PTK_PROFILE_RNG19_RFL8_SIG16_NIR16) { refl[j] = cj[4]; sig[j] = rd16(cj + 6); nir[j] = rd16(cj + 8); }
+                        else if (F.profile == PTK_PROFILE_RNG15_RFL8_NIR8) { refl[j] = cj[2]; nir[j] = (unsigned short)((unsigned)cj[3] << 4); }
+                        else { refl[j] = cj[3]; r2[j] = rd32(cj + 4) & 0x0007ffffu; sig[j] = rd16(cj + 8); nir[j] = rd16(cj + 12); }
+                    }
+                    auto pack = [](const unsigned short* v) { return make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16)); };
+                    if (out.reflectivity) *reinterpret_cast<uint2*>(out.reflectivity + o) = pack(refl);
+                    if (out.signal && F.profile != PTK_PROFILE_RNG15_RFL8_NIR8) *reinterpret_cast<uint2*>(out.signal + o) = pack(sig);
+                    if (out.near_ir) *reinterpret_cast<uint2*>(out.near_ir + o) = pack(nir);
+                    if (out.range2 && F.profile == PTK_PROFILE_RNG19_RFL8_SIG16_NIR16_DUAL) *reinterpret_cast<uint4*>(out.range2 + o) = make_uint4(r2[0], r2[1], r2[2], r2[3]);
+                }
+            }
+        } else {
+            // general path: consecutive threads = consecutive columns of one row
+            const int n = F.H * F.cpp;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int c = i % F.cpp, p = i / F.cpp;
+                const int mid = s_mid[c];
+                if (mid < 0) continue;
+                const unsigned char* ch = s_pkt + F.pkt_hdr + (size_t)c * F.col_size + F.col_hdr + (size_t)p * F.ch_size;
+                const size_t o = img + (size_t)p * F.W + mid;
+                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(ch);
+                if (F.profile == PTK_PROFILE_LEGACY) {
+                    out.range[o] = w0 & 0x000fffffu;
+                    if (out.reflectivity) out.reflectivity[o] = rd16(ch + 4);
+                    if (out.signal) out.signal[o] = rd16(ch + 6);
+                    if (out.near_ir) out.near_ir[o] = rd16(ch + 8);
+                } else if (F.profile == PTK_PROFILE_RNG19_RFL8_SIG16_NIR16) {
+                    out.range[o] = w0 & 0x0007ffffu;
+                    if (out.reflectivity) out.reflectivity[o] = ch[4];
+                    if (out.signal) out.signal[o] = rd16(ch + 6);
+                    if (out.near_ir) out.near_ir[o] = rd16(ch + 8);
+                } else if (F.profile == PTK_PROFILE_RNG15_RFL8_NIR8) {
+                    out.range[o] = (w0 & 0x7fffu) << 3;
+                    if (out.reflectivity) out.reflectivity[o] = ch[2];
+                    if (out.near_ir) out.near_ir[o] = (unsigned short)((unsigned)ch[3] << 4);
+                } else {    // RNG19_RFL8_SIG16_NIR16_DUAL
+                    out.range[o] = w0 & 0x0007ffffu;
+                    if (out.reflectivity) out.reflectivity[o] = ch[3];
+                    if (out.range2) out.range2[o] = rd32(ch + 4) & 0x0007ffffu;
+                    if (out.signal) out.signal[o] = rd16(ch + 8);
+                    if (out.near_ir) out.near_ir[o] = rd16(ch + 12);
+                }
+            }
+        }
+        // ScanBatcher's zero fill: whoever finishes the LAST packet slot of a frame clears the columns nobody wrote
+        // (status still 0).  The barrier also releases this iteration's buffer and s_mid.
+        __threadfence();
         __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(&frame_done[f], 1u) == (unsigned)F.ppf - 1u);
+        __syncthreads();
+        if (!s_last) continue;              // block-uniform
+        __threadfence();
+        // (columns checked 256 at a time; the usual frame has none missing and this is one pass of W/256 loads)
+        for (int w0 = 0; w0 < F.W; w0 += blockDim.x) {
+            if (threadIdx.x == 0) s_nmiss = 0;
+            __syncthreads();
+            const int w = w0 + threadIdx.x;
+            if (w < F.W && !(__ldcg(out.status + hdr + w) & 1u)) {
+                s_misscol[atomicAdd(&s_nmiss, 1)] = (unsigned short)w;
+                out.timestamp[hdr + w] = 0; out.status[hdr + w] = 0; out.measurement_id[hdr + w] = 0;
+            }
+            __syncthreads();
+            const int nm = s_nmiss;
+            for (int i = threadIdx.x; i < nm * F.H; i += blockDim.x) {
+                const size_t o = img + (size_t)(i / nm) * F.W + s_misscol[i % nm];
+                out.range[o] = 0;
+                if (out.range2) out.range2[o] = 0;
+                if (out.reflectivity) out.reflectivity[o] = 0;
+                if (out.signal) out.signal[o] = 0;
+                if (out.near_ir) out.near_ir[o] = 0;
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -185,9 +252,20 @@ int decode_device(const ptk_packet_format& pf, const unsigned char* d_packets, i
     // a column counts as written when bit 0 of its status is set: start from "nothing written"
     ICK(cudaMemsetAsync(out.status, 0, sizeof(unsigned int) * (size_t)n_frames * F.W, st));
     const int use_tma = (F.pkt_size % 16 == 0) && (((uintptr_t)d_packets) % 16 == 0);
-    const size_t smem = (size_t)F.pkt_size + 16;
+    const size_t smem = 2 * (((size_t)F.pkt_size + 15) & ~(size_t)15);
     if (smem > 48 * 1024) ICK(cudaFuncSetAttribute(k_decode_packets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_decode_packets<<<dim3(F.ppf, n_frames), 256, smem, st>>>(d_packets, F, out, d_done, use_tma);
+    // vector stores need the images 16 B / 8 B aligned and rows a multiple of four columns
+    auto al = [](const void* q, uintptr_t a) { return q == nullptr || ((uintptr_t)q % a) == 0; };
+    const int vec_ok = (F.W % 4 == 0) && al(out.range, 16) && al(out.range2, 16) && al(out.reflectivity, 8) && al(out.signal, 8) &&
+                       al(out.near_ir, 8);
+    // persistent grid: as many blocks as fit at once (a multiple of the SM count), never more than there are packets
+    int dev = 0, sms = 0, per_sm = 0;
+    ICK(cudaGetDevice(&dev));
+    ICK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ICK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_packets, 256, smem));
+    const int n_slots = n_frames * F.ppf;
+    const int grid = std::max(1, std::min(n_slots, sms * std::max(per_sm, 1)));
+    k_decode_packets<<<grid, 256, smem, st>>>(d_packets, F, out, d_done, n_slots, use_tma, vec_ok);
     ICK(cudaGetLastError());
     ICK(cudaFreeAsync(d_done, st));
     return PTK_OK;
