@@ -10,11 +10,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <deque>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -197,9 +199,11 @@ __global__ void __launch_bounds__(256) k_decode_packets(const unsigned char* __r
         }
         // ScanBatcher's zero fill: whoever finishes the LAST packet slot of a frame clears the columns nobody wrote
         // (status still 0).  The barrier also releases this iteration's buffer and s_mid.
-        __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(&frame_done[f], 1u) == (unsigned)F.ppf - 1u);
+        if (threadIdx.x == 0) {             // release: the barrier ordered the block's stores before this fence
+            __threadfence();
+            s_last = (atomicAdd(&frame_done[f], 1u) == (unsigned)F.ppf - 1u);
+        }
         __syncthreads();
         if (!s_last) continue;              // block-uniform
         __threadfence();
@@ -253,18 +257,32 @@ int decode_device(const ptk_packet_format& pf, const unsigned char* d_packets, i
     ICK(cudaMemsetAsync(out.status, 0, sizeof(unsigned int) * (size_t)n_frames * F.W, st));
     const int use_tma = (F.pkt_size % 16 == 0) && (((uintptr_t)d_packets) % 16 == 0);
     const size_t smem = 2 * (((size_t)F.pkt_size + 15) & ~(size_t)15);
-    if (smem > 48 * 1024) ICK(cudaFuncSetAttribute(k_decode_packets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (raised once per device and size: the attribute call is not free, and this runs once per decoded frame)
+    static std::mutex attr_mu;
+    static size_t attr_set[64] = {0};
+    int dev = 0;
+    ICK(cudaGetDevice(&dev));
+    if (smem > 48 * 1024) {
+        std::lock_guard<std::mutex> lk(attr_mu);
+        if (attr_set[dev & 63] < smem) {
+            ICK(cudaFuncSetAttribute(k_decode_packets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[dev & 63] = smem;
+        }
+    }
     // vector stores need the images 16 B / 8 B aligned and rows a multiple of four columns
     auto al = [](const void* q, uintptr_t a) { return q == nullptr || ((uintptr_t)q % a) == 0; };
     const int vec_ok = (F.W % 4 == 0) && al(out.range, 16) && al(out.range2, 16) && al(out.reflectivity, 8) && al(out.signal, 8) &&
                        al(out.near_ir, 8);
     // persistent grid: as many blocks as fit at once (a multiple of the SM count), never more than there are packets
-    int dev = 0, sms = 0, per_sm = 0;
-    ICK(cudaGetDevice(&dev));
+    int sms = 0, per_sm = 0;
     ICK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     ICK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_packets, 256, smem));
     const int n_slots = n_frames * F.ppf;
-    const int grid = std::max(1, std::min(n_slots, sms * std::max(per_sm, 1)));
+    int grid = std::max(1, std::min(n_slots, sms * std::max(per_sm, 1)));
+    if (const char* e = getenv("PTK_DECODE_BLOCKS_PER_SM")) {       // tuning: 0 = one block per packet slot
+        const int v = atoi(e);
+        grid = v <= 0 ? std::max(1, n_slots) : std::max(1, std::min(n_slots, sms * v));
+    }
     k_decode_packets<<<grid, 256, smem, st>>>(d_packets, F, out, d_done, n_slots, use_tma, vec_ok);
     ICK(cudaGetLastError());
     ICK(cudaFreeAsync(d_done, st));

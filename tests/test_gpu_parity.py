@@ -481,6 +481,38 @@ def test_100_scan_trajectory_equals_the_cpu_port():
     ref.close()
 
 
+def test_os2_long_run_with_prune_equals_the_cpu_port():
+    """config 3 as the survey meant it: OS2-128 2048x10, max_range 200 m (voxel 2 m), a platform that travels 240 m
+    (30 m/s, 80 scans) so that the local map grows large and the 200 m prune erases voxels scan after scan.  Poses,
+    iteration counts and the map's size equal the C port of the oracle at every scan."""
+    import torch
+    from oracle import port
+    from ptudes_lab_b200 import odometry, synth
+    seq = synth.SynthSequence(synth.OS2_128_2048, synth.street_scene(), synth.StreetTrajectory(0, speed=30.0, x0=-150.0), 0)
+    gen = synth.TorchScanGenerator(seq, torch.device("cuda", 0))
+    cfg = odometry.load_config(None, deskew=True, max_range=200.0)
+    o = odometry.Odometry(cfg, max_points=262144, map_capacity=65536)
+    o.set_sensor(seq.dirs)
+    ref = port.PortKissICP(_max_range=200.0, threads=8)
+    vox = []
+    try:
+        for k in range(80):
+            rng, _, _ = gen.range_image(k)
+            pose, st = o.register_scan(rng)
+            xyz, ts = synth.project_scan(rng.cpu().numpy().astype(np.uint32), seq.dirs)
+            ref.register_points(xyz, ts, 0.1 * (k + 1))
+            assert np.array_equal(pose, ref.pose), k
+            assert st["iterations"] == ref.last_stats["iterations"], k
+            assert (st["n_voxels"], st["map_points"]) == (ref.last_counts["n_vox"], ref.last_counts["map_points"]), k
+            vox.append(st["n_voxels"])
+        # every scan adds voxels ahead; the map can only shrink between two scans if the prune erased more than that
+        assert any(b < a for a, b in zip(vox, vox[1:])), vox
+        assert np.linalg.norm(pose[:3, 3]) > 200.0
+    finally:
+        o.close()
+        ref.close()
+
+
 def test_wide_batch_uses_one_block_per_lane_and_the_global_cache(tiny_seq):
     """300 lanes > the co-resident block budget: the ICP launch is split into chunks with ONE block per
     lane, whose 34 groups (> 1024 points) no longer fit the shared-memory cache, so the global-memory
