@@ -347,13 +347,16 @@ def side_ingest(local, frames=384, reps=20):
     for _ in range(3):
         ingest.decode_frames(pf, d_packets, frames, device=local, out=out)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        ingest.decode_frames(pf, d_packets, frames, device=local, out=out)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    blocks = []
+    for _ in range(5):                      # like the peak it is compared with (MEASURED_PEAKS.json: best of 10): best block
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ingest.decode_frames(pf, d_packets, frames, device=local, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        blocks.append(e0.elapsed_time(e1) / reps)
+    ms = min(blocks)
     algo = frames * (pf.packets_per_frame * pf.lidar_packet_size + H * W * 4 + W * (8 + 4 + 2))
     peak, peak_src = measured_peaks()
     # (b) packet by packet through the batcher
@@ -379,6 +382,8 @@ def side_ingest(local, frames=384, reps=20):
     dt = time.perf_counter() - t0
     lib.ptk_batcher_destroy(h)
     return {"value": frames / (ms * 1e-3), "unit": "scans/s", "frames_per_launch": frames, "ms_per_launch": ms,
+            "timing": f"CUDA events around {reps} launches, best of 5 such blocks (ms per launch of each block: "
+                      f"{[round(b, 4) for b in blocks]})",
             "roofline": {"bound": "hbm", "kernel": "k_decode_packets", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": algo / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo},
