@@ -706,6 +706,15 @@ def run_ptk(args):
         "step_hbm_frac": (total_algo / (ms_dev * 1e-3) / 1e9) / peak,
         "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items() if v[1] > 0},
     }
+    if G > 1:
+        # the G contexts' launches of the kernel overlap in time: a launch's duration is the time it SHARES the GPU
+        # with G - 1 others, so the per-launch figure above is a lower bound.  What the kernel moves as a whole:
+        # all its algorithmic bytes of the timed region over the region's duration (it is running somewhere on the
+        # GPU for most of it).
+        agg = algo[dom] / (ms_dev * 1e-3) / 1e9
+        out["roofline"]["concurrent_launches"] = G
+        out["roofline"]["achieved_all_launches"] = agg
+        out["roofline"]["frac_all_launches"] = agg / peak
     last = stats_acc[-1][0]
     out["counters"] = {k: last[k] for k in ("n_in", "n_range", "n_ds", "n_src", "n_voxels", "map_points",
                                              "iterations", "n_corr")}

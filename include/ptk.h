@@ -184,6 +184,14 @@ int ptk_get_prediction_model(const ptk_ctx* ctx, int lane, double* out16);
  * only known inside the step because ComputeThreshold mutates state; this returns the last
  * sigma used). */
 double ptk_last_sigma(const ptk_ctx* ctx, int lane);
+/* The three state changes of the step for callers that run it PIECEWISE, i.e. keep the body of
+ * KissICPWrapper._kiss_register_frame (kiss.py:83-131) and only swap the kiss-icp objects:
+ * KissICP.get_adaptive_threshold() (kiss.py:99: initial threshold until has_moved(), then
+ * AdaptiveThreshold.compute_threshold(), which accumulates the last model deviation - a call with side effects, as
+ * upstream), adaptive_threshold.update_model_deviation(T) (kiss.py:128) and poses.append(pose) (kiss.py:130). */
+int ptk_get_adaptive_threshold(ptk_ctx* ctx, int lane, double* sigma);
+int ptk_update_model_deviation(ptk_ctx* ctx, int lane, const double* T16);
+int ptk_append_pose(ptk_ctx* ctx, int lane, const double* T16);
 
 /* ---- pieces, one per kiss-icp binding the wrapper or tests reach --------------------
  * kiss_icp_pybind._deskew_scan(frame, timestamps, start_pose, finish_pose) (kiss.py:76-78,90) */

@@ -75,6 +75,9 @@ SYMBOLS = {
     "ptk_get_pose": (C.c_int, [_P, C.c_int, C.c_int, _D]),
     "ptk_get_prediction_model": (C.c_int, [_P, C.c_int, _D]),
     "ptk_last_sigma": (C.c_double, [_P, C.c_int]),
+    "ptk_get_adaptive_threshold": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "ptk_update_model_deviation": (C.c_int, [_P, C.c_int, _D]),
+    "ptk_append_pose": (C.c_int, [_P, C.c_int, _D]),
     "ptk_deskew_scan": (C.c_int, [_P, _D, _D, C.c_int, _D, _D, _D, _P]),
     "ptk_preprocess": (C.c_int, [_P, _D, C.c_int, C.c_double, C.c_double, _D, C.POINTER(C.c_int), _P]),
     "ptk_voxel_down_sample": (C.c_int, [_P, _D, C.c_int, C.c_double, _D, _I, C.POINTER(C.c_int), _P]),

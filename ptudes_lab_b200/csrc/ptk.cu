@@ -893,6 +893,28 @@ extern "C" double ptk_last_sigma(const ptk_ctx* ctx, int lane) {
     return ctx->lanes[lane].last_sigma;
 }
 
+extern "C" int ptk_get_adaptive_threshold(ptk_ctx* ctx, int lane, double* sigma) {
+    if (!ctx || lane < 0 || lane >= ctx->B || !sigma) return PTK_E_ARG;
+    LaneHost& LH = ctx->lanes[lane];
+    *sigma = has_moved(ctx->cfg, LH) ? compute_threshold(ctx->cfg, LH.thr) : ctx->cfg.initial_threshold;
+    LH.last_sigma = *sigma;
+    return PTK_OK;
+}
+
+extern "C" int ptk_update_model_deviation(ptk_ctx* ctx, int lane, const double* T16) {
+    if (!ctx || lane < 0 || lane >= ctx->B || !T16) return PTK_E_ARG;
+    rigid_from_mat16(T16, ctx->lanes[lane].thr.deviation);
+    return PTK_OK;
+}
+
+extern "C" int ptk_append_pose(ptk_ctx* ctx, int lane, const double* T16) {
+    if (!ctx || lane < 0 || lane >= ctx->B || !T16) return PTK_E_ARG;
+    Rigid T;
+    rigid_from_mat16(T16, T);
+    ctx->lanes[lane].poses.push_back(T);
+    return PTK_OK;
+}
+
 // ---- stand-alone pieces (scratch lane = index B) -------------------------------------
 static int scratch_params(ptk_ctx* ctx, StepParams& P, cudaStream_t st, bool k2, bool k3) {
     int S = ctx->B;

@@ -33,15 +33,48 @@ class _Compensator:
         return self._odo.deskew_scan(frame, timestamps, poses[-2], poses[-1])
 
 
+class _AdaptiveThreshold:
+    """kiss_icp AdaptiveThreshold face (kiss.py:128): the state itself lives in the library."""
+
+    def __init__(self, odo):
+        self._odo = odo
+
+    def update_model_deviation(self, model_deviation):
+        self._odo.update_model_deviation(model_deviation)
+
+
+class _PoseList(list):
+    """`KissICP.poses`: a list whose `append` (kiss.py:130) also reaches the library's pose list, which the
+    prediction model, the deskew twist and has_moved() are computed from.  The fused step appends on the
+    library side itself and records the pose here with `_record`."""
+
+    def __init__(self, odo):
+        super().__init__()
+        self._odo = odo
+
+    def append(self, pose):
+        self._odo.append_pose(pose)
+        super().append(pose)
+
+    def _record(self, pose):
+        super().append(pose)
+
+
 class _Kiss:
-    """The members of kiss_icp.kiss_icp.KissICP that ptudes reads through `wrapper._kiss`."""
+    """The members of kiss_icp.kiss_icp.KissICP that ptudes reads through `wrapper._kiss` - enough of them that the
+    reference's own `_kiss_register_frame` body (kiss.py:83-131) runs over this object unchanged, piece by piece
+    (`tests/test_gpu_parity.py::test_reference_body_runs_piecewise`); the wrapper below uses the fused step."""
 
     def __init__(self, config, **odo_kw):
         self.config = config
         self._odo = _odo.Odometry(config, **odo_kw)
-        self.poses: List[PoseH] = []
+        self.poses: List[PoseH] = _PoseList(self._odo)
         self.compensator = _Compensator(self._odo)
         self.local_map = _odo.VoxelHashMap(self._odo, 0)
+        self.adaptive_threshold = _AdaptiveThreshold(self._odo)
+
+    def get_adaptive_threshold(self):
+        return self._odo.get_adaptive_threshold()
 
     def get_prediction_model(self):
         # same arithmetic as the library uses for its own constant-velocity guess
@@ -136,7 +169,7 @@ class KissICPWrapper:
         self._err_dt.append(st["err_dt"])           # kiss.py:122-124
         self._err_drot.append(st["err_drot"])
         self._sigmas.append(st["sigma"])
-        self._kiss.poses.append(new_pose)           # kiss.py:130
+        self._kiss.poses._record(new_pose)          # kiss.py:130 (the library appended its own copy in the step)
         self._last_stats = st
 
     @property

@@ -263,6 +263,20 @@ class Odometry:
         self._check(self._lib.ptk_get_prediction_model(self._h, lane, addr(out)))
         return out
 
+    def get_adaptive_threshold(self, lane=0):
+        """KissICP.get_adaptive_threshold() (kiss.py:99); like upstream it accumulates the last model deviation."""
+        v = C.c_double()
+        self._check(self._lib.ptk_get_adaptive_threshold(self._h, lane, C.byref(v)))
+        return v.value
+
+    def update_model_deviation(self, T, lane=0):
+        """adaptive_threshold.update_model_deviation(T) (kiss.py:128)."""
+        self._check(self._lib.ptk_update_model_deviation(self._h, lane, addr(_mat16(T))))
+
+    def append_pose(self, T, lane=0):
+        """KissICP.poses.append(T) (kiss.py:130) for the library's own pose list (prediction model, has_moved)."""
+        self._check(self._lib.ptk_append_pose(self._h, lane, addr(_mat16(T))))
+
     def last_sigma(self, lane=0):
         return self._lib.ptk_last_sigma(self._h, lane)
 

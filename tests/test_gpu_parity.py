@@ -324,6 +324,40 @@ def test_wrapper_drop_in(tiny_seq):
     assert np.array_equal(f, rf) and np.array_equal(s, rs)
 
 
+def test_reference_body_runs_piecewise(tiny_seq):
+    """The reference's own `_kiss_register_frame` (kiss.py:83-131) calls kiss-icp piece by piece: compensator.deskew_scan,
+    preprocess, voxelize, get_adaptive_threshold, get_prediction_model, registration.register_frame,
+    adaptive_threshold.update_model_deviation, local_map.update, poses.append.  The same sequence over this
+    package's kiss-icp-shaped objects (`kiss._Kiss`, `odometry.register_frame`) gives the fused step's poses; the
+    guess and the model deviation are NumPy products here as in the reference, hence a tolerance instead of `==`."""
+    from ptudes_lab_b200 import odometry
+    from ptudes_lab_b200.kiss import _Kiss
+    cfg = odometry.load_config(None, deskew=True, max_range=100.0)
+    cfg.data.min_range = 5.0
+    k = _Kiss(cfg, device=0, max_points=16384, map_capacity=16384)
+    ref = ko.OracleKissICPWrapper()
+    try:
+        for s in range(6):
+            xyz, ts, tsec, _ = tiny_seq.points(s)
+            ref.register_points(xyz, ts, tsec)
+            frame = k.compensator.deskew_scan(xyz, k.poses, ts)                      # kiss.py:90
+            frame = k.preprocess(frame)                                              # :93
+            source, frame_ds = k.voxelize(frame)                                     # :96
+            sigma = k.get_adaptive_threshold()                                       # :99
+            guess = (k.poses[-1] if k.poses else np.eye(4)) @ k.get_prediction_model()   # :102-105
+            pose = odometry.register_frame(points=source, voxel_map=k.local_map, initial_guess=guess,
+                                           max_correspondance_distance=3 * sigma, kernel=sigma / 3)   # :108-114
+            k.adaptive_threshold.update_model_deviation(np.linalg.inv(guess) @ pose)     # :128
+            k.local_map.update(frame_ds, pose)                                       # :129
+            k.poses.append(pose)                                                     # :130
+            assert abs(sigma - ref._sigmas[-1]) < 1e-9, s
+            assert np.allclose(pose, ref.pose, rtol=0, atol=1e-8), s
+            assert len(source) == ref.last_counts["n_src"] and len(frame_ds) == ref.last_counts["n_ds"]
+        assert k._odo.num_poses() == 6 and len(k.poses) == 6
+    finally:
+        k._odo.close()
+
+
 def test_register_scan_range_image_path(tiny_seq):
     """ptk_register_scan (projection + mask + column timestamps on the device, kiss.py:59-61)
     against the oracle fed with the host-projected cloud, and against the xyz entry point."""
