@@ -94,10 +94,6 @@ struct ptk_ctx {
     double* d_col_ts = nullptr;
     std::vector<void*> sensor_allocs;
     cudaStream_t copy_stream = nullptr;      // H2D prefetch of the next scans (ptk_prefetch_scan_batch)
-    // PTK_ICP_PRIORITY=1: the ICP kernels of a step go to a HIGH-PRIORITY side stream (joined by events), so that when
-    // several contexts share the GPU a lane's ICP blocks are placed ahead of other contexts' pending streaming blocks
-    cudaStream_t icp_stream = nullptr;
-    cudaEvent_t icp_ev0 = nullptr, icp_ev1 = nullptr;
     cudaEvent_t pf_event = nullptr;
     std::vector<const unsigned int*> pf_pending;   // host images to copy during the next step
     int num_sms = 148;
@@ -331,18 +327,6 @@ extern "C" int ptk_ctx_create(ptk_ctx** out, int device, const ptk_config* cfg_i
         }
         cudaGetLastError();
     }
-    if (const char* pr = getenv("PTK_ICP_PRIORITY")) {
-        if (atoi(pr) > 0) {
-            int least = 0, greatest = 0;
-            cudaDeviceGetStreamPriorityRange(&least, &greatest);
-            if (cudaStreamCreateWithPriority(&ctx->icp_stream, cudaStreamNonBlocking, greatest) != cudaSuccess ||
-                cudaEventCreateWithFlags(&ctx->icp_ev0, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&ctx->icp_ev1, cudaEventDisableTiming) != cudaSuccess) {
-                ctx->err = "PTK_ICP_PRIORITY: cannot create the priority stream";
-                return bail(PTK_E_CUDA);
-            }
-        }
-    }
     ctx->lanes.resize(ctx->B + 1);
     for (int l = 0; l <= ctx->B; ++l) {
         int rc = lane_alloc(ctx, ctx->lanes[l], l == ctx->B);
@@ -385,9 +369,6 @@ extern "C" int ptk_ctx_destroy(ptk_ctx* ctx) {
     if (ctx->pf_event) cudaEventDestroy(ctx->pf_event);
     if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->icp_stream) cudaStreamDestroy(ctx->icp_stream);
-    if (ctx->icp_ev0) cudaEventDestroy(ctx->icp_ev0);
-    if (ctx->icp_ev1) cudaEventDestroy(ctx->icp_ev1);
     if (ctx->h_params) cudaFreeHost(ctx->h_params);
     if (ctx->h_outs) cudaFreeHost(ctx->h_outs);
     delete ctx;
@@ -708,17 +689,8 @@ static int run_step(ptk_ctx* ctx, int l0, int cnt, const double* const* xyz, con
         if (!LH.have_last || LH.last_out.n_src <= 0) { groups_hint = 0; break; }
         groups_hint = std::max(groups_hint, (int)(((long long)LH.last_out.n_src * 5 / 4 + 31) / 32) + 1);
     }
-    if (ctx->icp_stream) {
-        CK(cudaEventRecord(ctx->icp_ev0, st));
-        CK(cudaStreamWaitEvent(ctx->icp_stream, ctx->icp_ev0, 0));
-        rc = launch_icp(ctx, l0, cnt, groups_hint, ctx->icp_stream);
-        if (rc) return rc;
-        CK(cudaEventRecord(ctx->icp_ev1, ctx->icp_stream));
-        CK(cudaStreamWaitEvent(st, ctx->icp_ev1, 0));
-    } else {
-        rc = launch_icp(ctx, l0, cnt, groups_hint, st);
-        if (rc) return rc;
-    }
+    rc = launch_icp(ctx, l0, cnt, groups_hint, st);
+    if (rc) return rc;
     return step_finish(ctx, l0, cnt, nmax, out_poses, stats, st);
 }
 

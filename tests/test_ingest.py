@@ -336,3 +336,58 @@ def test_synthetic_packet_encoder_equals_the_oracle_encoder(prof):
     a = ingest.encode_scan_packets(pf, 77, f["RANGE"], ts, signal=f["SIGNAL"])
     b = io.encode_frame(F, 77, {"RANGE": f["RANGE"], "SIGNAL": f["SIGNAL"]}, ts)
     assert [bytes(x) for x in a] == b
+
+
+def test_host_batcher_random_streams():
+    """Property test: random packet streams (lost, repeated, locally reordered packets, stragglers of the previous
+    frame, frame-id wrap-around) grouped by ptk_batcher_* decode to what the oracle's ScanBatcher rules give."""
+    from hypothesis import given, settings, strategies as st_
+
+    F = io.Format(io.RNG19, 2, 16, 64)
+    pf = ingest.PacketFormat(io.RNG19, F.H, F.cpp, F.W)
+    lib = _ffi.load()
+
+    @settings(max_examples=30, deadline=None)
+    @given(st_.integers(0, 2**32 - 1))
+    def run(seed):
+        rng = np.random.default_rng(seed)
+        first = int(rng.integers(65530, 65536))
+        frames, _ = _stream(F, 5, seed=seed % 1000, first_id=first)
+        s = []
+        for k, fr in enumerate(frames):
+            fr = [p for p in fr if rng.random() > 0.15]                       # lost
+            fr += [fr[i] for i in rng.integers(0, max(len(fr), 1), size=int(rng.integers(0, 2))) if fr]   # repeated
+            if len(fr) > 1 and rng.random() < 0.5:                            # locally reordered
+                i = int(rng.integers(0, len(fr) - 1))
+                fr[i], fr[i + 1] = fr[i + 1], fr[i]
+            if k and fr and rng.random() < 0.5:                               # a straggler of the previous frame
+                fr.insert(1, frames[k - 1][int(rng.integers(0, F.ppf))])
+            s += fr
+        want = io.batch_stream(F, s)
+        h = C.c_void_p()
+        assert lib.ptk_batcher_create(C.byref(h), -1, C.byref(pf.c), 3) == 0
+        got, ready = [], C.c_int()
+
+        def drain():
+            p, fid = C.c_void_p(), C.c_int()
+            assert lib.ptk_batcher_peek(h, C.byref(p), C.byref(fid), None) == 0
+            raw = C.string_at(p.value, F.ppf * F.size)
+            got.append((fid.value, [raw[i * F.size:(i + 1) * F.size] for i in range(F.ppf)]))
+            assert lib.ptk_batcher_pop(h) == 0
+
+        for pkt in s:
+            assert lib.ptk_batcher_push(h, np.frombuffer(pkt, dtype=np.uint8).ctypes.data, C.byref(ready)) == 0
+            while ready.value:
+                drain()
+                ready.value -= 1
+        assert lib.ptk_batcher_flush(h, C.byref(ready)) == 0
+        if ready.value:
+            drain()
+        lib.ptk_batcher_destroy(h)
+        assert [g[0] for g in got] == [w[0] for w in want]
+        for (_, slots), (_, pkts) in zip(got, want):
+            ref, dec = io.decode_frame(F, pkts), io.decode_frame(F, slots)
+            for k in ("RANGE", "timestamp", "status", "measurement_id"):
+                assert np.array_equal(ref[k], dec[k]), k
+
+    run()
