@@ -101,7 +101,7 @@ struct ptk_ctx {
     int icp_max_blocks_per_lane = 1 << 20;   // PTK_ICP_MAX_BLOCKS_PER_LANE: fewer blocks = cheaper barrier, slower searches
     int icp_cluster = 0;              // blocks per lane of the cluster launch of wide batches (0: not available)
     int icp_cluster_min_lanes = 56;   // batch width from which the cluster launch is used
-    bool blocking_sync = false;       // wait for a step on a blocking-sync event (the thread sleeps) instead of spinning:
+    bool blocking_sync = false;       // wait for a step without monopolising a core (yielding poll or blocking-sync event):
     cudaEvent_t sync_event = nullptr; // set by ptk_fleet_replay, whose worker threads may outnumber the host cores
     // hash-sharded mode with in-kernel exchange: this rank's buffer and every rank's buffer as mapped here
     void* xch_local = nullptr;
@@ -709,9 +709,20 @@ static int step_finish(ptk_ctx* ctx, int l0, int cnt, int nmax, double* out_pose
         if (prc) return prc;
     }
     if (ctx->blocking_sync) {
-        if (!ctx->sync_event) CK(cudaEventCreateWithFlags(&ctx->sync_event, cudaEventBlockingSync | cudaEventDisableTiming));
+        // More worker threads than host cores.  PTK_FLEET_WAIT=yield (default): poll the event and give the core away
+        // between polls - a thread with launches to make gets it at once, nobody sleeps through its step's end;
+        // PTK_FLEET_WAIT=block: sleep on a blocking-sync event (no CPU while waiting, a wake-up latency per step).
+        static const bool yield_wait = !(getenv("PTK_FLEET_WAIT") && !strcmp(getenv("PTK_FLEET_WAIT"), "block"));
+        if (!ctx->sync_event)
+            CK(cudaEventCreateWithFlags(&ctx->sync_event, (yield_wait ? 0 : cudaEventBlockingSync) | cudaEventDisableTiming));
         CK(cudaEventRecord(ctx->sync_event, st));
-        CK(cudaEventSynchronize(ctx->sync_event));
+        if (yield_wait) {
+            cudaError_t q;
+            while ((q = cudaEventQuery(ctx->sync_event)) == cudaErrorNotReady) sched_yield();
+            CK(q);
+        } else {
+            CK(cudaEventSynchronize(ctx->sync_event));
+        }
     } else {
         CK(cudaStreamSynchronize(st));
     }
