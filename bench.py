@@ -158,12 +158,17 @@ class ClockSampler:
 
 
 def source_sha():
-    """sha256 (16 hex digits) of the kernel sources: ties a committed ncu capture to the code that produced it."""
+    """sha256 (16 hex digits) of the kernel sources with comments and white space removed: ties a committed ncu
+    capture to the CODE that produced it (editing a comment does not orphan a capture, editing a kernel does)."""
     import hashlib
+    import re
     h = hashlib.sha256()
     for f in ("ptk_device.cuh", "ptk_canon.cuh"):
-        with open(os.path.join(ROOT, "ptudes_lab_b200", "csrc", f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(ROOT, "ptudes_lab_b200", "csrc", f), "r") as fh:
+            src = fh.read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        h.update(re.sub(r"\s+", "", src).encode())
     return h.hexdigest()[:16]
 
 

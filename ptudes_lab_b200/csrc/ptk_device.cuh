@@ -1272,7 +1272,7 @@ struct SolveSmem {
     double dx[6];
 };
 
-// Warp 0 of every block: expand the 17 sums into the 6x6 system, solve it (ldlt_solve6_warp), update
+// Warp 0 of every block: expand the 17 sums into the 6x6 system, solve it (ldlt_solve6_tri), update
 // T_icp, decide termination (kiss-icp RegisterFrame loop body after BuildLinearSystem).
 __device__ __noinline__ void icp_solve_step(LaneDev& L, const StepParams& P, StepOut& O, const double* red, SolveSmem* S,
                                             Rigid* sE, SE3q* sT, int* s_done, int it, bool writer, int lane, double eps, int max_iters) {

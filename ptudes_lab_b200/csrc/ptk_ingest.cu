@@ -450,19 +450,17 @@ extern "C" int ptk_batcher_push(ptk_batcher* b, const unsigned char* packet, int
         int rc = batcher_open(b, fid);
         if (rc) return rc;
     }
-    // the slot of a packet is given by its first column (sensors send whole, aligned column groups)
+    // the slot of a packet follows from the measurement id of any VALID column (sensors send whole, aligned column
+    // groups; a column without the valid bit may carry a blank header); a packet without a valid column has nothing
+    // to contribute
     DevFormat F = dev_format(b->pf);
-    uint64_t ts; int mid; uint32_t st;
-    col_header(F, packet, 0, ts, mid, st);
-    if (mid % F.cpp != 0 || mid / F.cpp >= F.ppf) {
-        // first column invalid (its header may be blank): place by any valid column
-        bool placed = false;
-        for (int c = 1; c < F.cpp && !placed; ++c) {
-            col_header(F, packet, c, ts, mid, st);
-            if ((st & 1u) && mid >= c && (mid - c) % F.cpp == 0 && (mid - c) / F.cpp < F.ppf) { mid -= c; placed = true; }
-        }
-        if (!placed) { ++b->dropped; if (frames_ready) *frames_ready = (int)b->closed.size(); return PTK_OK; }
+    int mid = -1;
+    for (int c = 0; c < F.cpp; ++c) {
+        uint64_t ts; int m; uint32_t st;
+        col_header(F, packet, c, ts, m, st);
+        if ((st & 1u) && m >= c && (m - c) % F.cpp == 0 && (m - c) / F.cpp < F.ppf) { mid = m - c; break; }
     }
+    if (mid < 0) { ++b->dropped; if (frames_ready) *frames_ready = (int)b->closed.size(); return PTK_OK; }
     const int slot = mid / F.cpp;
     memcpy(b->h_ring + (size_t)b->cur.ring * b->frame_bytes + (size_t)slot * F.pkt_size, packet, F.pkt_size);
     if (!b->cur.present[slot]) { b->cur.present[slot] = 1; ++b->cur.n_packets; }

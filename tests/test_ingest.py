@@ -118,6 +118,35 @@ def test_host_batcher_groups_frames_like_the_oracle(prof):
             assert np.array_equal(ref[k], dec[k]), k
 
 
+def test_packet_with_a_blank_first_column_goes_to_its_own_slot():
+    """A column without the valid bit may carry a blank header (measurement id 0): the packet's position in the frame
+    follows from its valid columns, not from that header."""
+    F = io.Format(io.RNG19, 4, 16, 64)
+    f, ts = _fields(F, 5, full=False)
+    valid = np.ones(F.W, bool)
+    valid[32] = False
+    pk = io.encode_frame(F, 3, f, ts, valid=valid)
+    blank = bytearray(pk[2])
+    blank[F.pkt_hdr:F.pkt_hdr + F.col_hdr] = bytes(F.col_hdr)         # first column of packet 2: header all zero
+    pk[2] = bytes(blank)
+    pf = ingest.PacketFormat(io.RNG19, F.H, F.cpp, F.W)
+    lib = _ffi.load()
+    h = C.c_void_p()
+    assert lib.ptk_batcher_create(C.byref(h), -1, C.byref(pf.c), 2) == 0
+    ready = C.c_int()
+    for p in pk + [bytes(F.size)[:2] + (3).to_bytes(2, "little") + bytes(F.size - 4)]:      # + a packet without any valid column
+        assert lib.ptk_batcher_push(h, np.frombuffer(p, dtype=np.uint8).ctypes.data, C.byref(ready)) == 0
+    assert lib.ptk_batcher_flush(h, C.byref(ready)) == 0 and ready.value == 1
+    ptr, n = C.c_void_p(), C.c_int()
+    assert lib.ptk_batcher_peek(h, C.byref(ptr), None, C.byref(n)) == 0 and n.value == F.ppf
+    raw = C.string_at(ptr.value, F.ppf * F.size)
+    slots = [raw[i * F.size:(i + 1) * F.size] for i in range(F.ppf)]
+    assert slots == pk
+    want, got = io.decode_frame(F, pk), io.decode_frame(F, slots)
+    assert np.array_equal(want["RANGE"], got["RANGE"]) and want["status"][32] == 0 and want["RANGE"][:, 32].sum() == 0
+    lib.ptk_batcher_destroy(h)
+
+
 def _ffi_code(name):
     return {v: k for k, v in _ffi.ERRORS.items()}[name]
 
