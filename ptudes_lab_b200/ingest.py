@@ -438,6 +438,21 @@ class IMUBagSource:
                 yield imu_from_packet(ImuPacket(_packetmsg_buf(d), None, t * 1e-9))
 
 
+def read_metadata_json(meta_path: str):
+    """`read_metadata_json` (utils.py:157-168): SensorInfo from a sensor metadata file, with the reference's backfill
+    of `lidar_mode` for the Newer College 2020 metadata."""
+    import json
+    from .ouster_compat import SensorInfo
+    with open(meta_path) as f:
+        js = json.load(f)
+    if "beam_altitude_angles" in js and "beam_azimuth_angles" in js and "lidar_mode" not in js:
+        print(f"WARNING: lidar_mode is not present in legacy metadata '{meta_path}' so using lidar_mode: 1024x10")
+        js["lidar_mode"] = "1024x10"
+    if hasattr(SensorInfo, "from_json"):
+        return SensorInfo.from_json(json.dumps(js))
+    return SensorInfo(json.dumps(js))           # the real ouster-sdk class
+
+
 def read_packet_source(file_path: str, meta=None):
     """`read_packet_source` (utils.py:171-187): pcap file, bag file, or a directory of bags."""
     file = Path(file_path)

@@ -420,3 +420,43 @@ def test_host_batcher_random_streams():
                 assert np.array_equal(ref[k], dec[k]), k
 
     run()
+
+
+def test_sensor_info_from_json_and_xyz_lut_known_answers(tmp_path):
+    """utils.py:157-168 + `client.XYZLut` without ouster-sdk: metadata JSON (legacy and firmware >= 2.5 layout) ->
+    SensorInfo -> lookup tables by the documented range-to-XYZ formula.  Known answers: a level beam without azimuth
+    offset looks along +x at measurement id 0 and along -y a quarter turn later (the encoder runs clockwise); the beam
+    origin offset n enters as (r - n) * direction + n * (cos enc, sin enc, 0); the default lidar-to-sensor transform
+    turns the frame by 180 degrees about z and lifts it 36.18 mm."""
+    import json
+    from ptudes_lab_b200.ouster_compat import HAVE_OUSTER, XYZLut
+    if HAVE_OUSTER:
+        pytest.skip("the real ouster-sdk classes are in use")
+    legacy = {"beam_altitude_angles": [10.0, 0.0, -10.0, -20.0], "beam_azimuth_angles": [0.0, 0.0, 3.0, -3.0],
+              "lidar_origin_to_beam_origin_mm": 15.8, "lidar_to_sensor_transform": [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1],
+              "data_format": {"pixels_per_column": 4, "columns_per_packet": 16, "columns_per_frame": 64,
+                              "udp_profile_lidar": "RNG19_RFL8_SIG16_NIR16"}}
+    p = tmp_path / "meta.json"
+    p.write_text(json.dumps(legacy))
+    info = ingest.read_metadata_json(str(p))                    # no lidar_mode: backfilled like the reference does
+    assert info.mode == "1024x10" and (info.format.columns_per_frame, info.format.pixels_per_column) == (64, 4)
+    assert ingest.PacketFormat.from_info(info).profile == io.RNG19
+    lut = XYZLut(info)
+    r = np.zeros((4, 64), np.uint32)
+    r[1, 0] = r[1, 16] = 10000
+    r[0, 32] = 5000
+    xyz = lut(r)
+    assert np.allclose(xyz[1, 0], (10.0, 0.0, 0.0), atol=1e-12) and np.allclose(xyz[1, 16], (0.0, -10.0, 0.0), atol=1e-12)
+    n, c, s_ = 0.0158, np.cos(np.radians(10.0)), np.sin(np.radians(10.0))
+    assert np.allclose(xyz[0, 32], (-(5.0 - n) * c - n, 0.0, (5.0 - n) * s_), atol=1e-12)
+    assert np.all(xyz[2] == 0) and lut.range_unit == 1.0
+    # firmware >= 2.5 layout, default lidar-to-sensor transform
+    new = {"beam_intrinsics": {"beam_altitude_angles": legacy["beam_altitude_angles"], "beam_azimuth_angles": legacy["beam_azimuth_angles"],
+                               "beam_to_lidar_transform": [1, 0, 0, 15.8, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]},
+           "lidar_data_format": legacy["data_format"], "config_params": {"lidar_mode": "64x10", "udp_port_lidar": 7510},
+           "sensor_info": {"prod_line": "OS-1-4"}}
+    from ptudes_lab_b200.ouster_compat import SensorInfo
+    info2 = SensorInfo.from_json(json.dumps(new))
+    assert info2.mode == "64x10" and info2.udp_port_lidar == 7510 and info2.lidar_origin_to_beam_origin_mm == 15.8
+    xyz2 = XYZLut(info2)(r)
+    assert np.allclose(xyz2[1, 0], (-10.0, 0.0, 0.03618), atol=1e-12) and np.allclose(xyz2[1, 16], (0.0, 10.0, 0.03618), atol=1e-12)
