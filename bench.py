@@ -809,7 +809,9 @@ def cpu_baseline_leg(args, host_scans, dirs, min_r, max_r, T):
     cores = os.cpu_count() or 1
     val, n_steps, secs, poses = cpu_port_fleet(host_scans, dirs, min_r, max_r, args.warmup, args.cpu_seconds, cores)
     L = len(host_scans)
+    up = probe_upstream()
     return ({"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+             "upstream_kiss_icp": up if up else "not importable on this box (nor under baseline/_ref): the port stands in",
              "sample": f"NumPy projection of the RANGE image (kiss.py:59-61) + oracle/kiss_port.c (C restatement of the "
                        f"kiss-icp 0.2.x step, gcc {cpu_port_fleet.flags} + OpenMP): {L} of the lanes' sequences run "
                        f"concurrently, one per host thread, scans {args.warmup}..{args.warmup + n_steps - 1} timed "
@@ -817,6 +819,22 @@ def cpu_baseline_leg(args, host_scans, dirs, min_r, max_r, T):
 
 
 # --------------------------------------------------------------------------------------
+def probe_upstream():
+    """SURVEY 8c run-time probe: version of the REAL kiss-icp if this box has it (environment or baseline/_ref)."""
+    for extra in (None, os.path.join(ROOT, "baseline", "_ref")):
+        if extra is not None:
+            if not os.path.isdir(extra):
+                continue
+            if extra not in sys.path:
+                sys.path.insert(0, extra)
+        try:
+            import kiss_icp
+            return "kiss-icp " + str(getattr(kiss_icp, "__version__", "?"))
+        except Exception:
+            continue
+    return None
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path on the box's host cores.
     kiss-icp 0.2.x is not installable here and /root/reference holds no compilable source for the
