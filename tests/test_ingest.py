@@ -460,3 +460,38 @@ def test_sensor_info_from_json_and_xyz_lut_known_answers(tmp_path):
     assert info2.mode == "64x10" and info2.udp_port_lidar == 7510 and info2.lidar_origin_to_beam_origin_mm == 15.8
     xyz2 = XYZLut(info2)(r)
     assert np.allclose(xyz2[1, 0], (-10.0, 0.0, 0.03618), atol=1e-12) and np.allclose(xyz2[1, 16], (0.0, 10.0, 0.03618), atol=1e-12)
+
+
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ingest_tiny.npz"))
+
+
+@pytest.mark.parametrize("prof", PROFILES)
+def test_oracle_decodes_the_golden_packets(prof):
+    """tests/golden/ingest_tiny.npz (make_ingest_golden.py): committed packet bytes -> committed fields."""
+    g = _golden()
+    F = io.Format(prof, 4, 16, 32)
+    pk = [bytes(p) for p in g[f"p{prof}_packets"]]
+    assert len(pk) == F.ppf and len(pk[0]) == F.size and io.frame_id(F, pk[1]) == 65535
+    d = io.decode_frame(F, pk)
+    for k, v in d.items():
+        assert np.array_equal(v, g[f"p{prof}_{k}"]), k
+    assert d["status"][19] == 0 and not d["RANGE"][:, 19].any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prof", PROFILES)
+def test_device_decodes_the_golden_packets(prof):
+    import torch
+    g = _golden()
+    pf = ingest.PacketFormat(prof, 4, 16, 32)
+    names = ("RANGE", "RANGE2", "REFLECTIVITY", "SIGNAL", "NEAR_IR")
+    out = ingest.decode_frames(pf, np.ascontiguousarray(g[f"p{prof}_packets"]).reshape(-1), 1, fields=names)
+    torch.cuda.synchronize()
+    for n in names:
+        if (n == "RANGE2" and prof != io.DUAL) or (n == "SIGNAL" and prof == io.RNG15):
+            continue
+        assert np.array_equal(out[n][0].cpu().numpy().astype(np.uint32), g[f"p{prof}_{n}"].astype(np.uint32)), n
+    assert np.array_equal(out["timestamp"][0].cpu().numpy().view(np.uint64), g[f"p{prof}_timestamp"])
+    assert np.array_equal(out["status"][0].cpu().numpy().view(np.uint32), g[f"p{prof}_status"])
