@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # PTK_LIB_SUFFIX / PTK_NVCC_EXTRA: build and load a tuning variant next to the default library
-# (e.g. PTK_LIB_SUFFIX=_mb3 PTK_NVCC_EXTRA="-DPTK_IQ_MINBLOCKS=3")
+# (e.g. PTK_LIB_SUFFIX=_kx3 PTK_NVCC_EXTRA="-DPTK_ICP_KX=3"; the experiment batches profiles/exp_r2*.sh use it)
 LIB = os.path.join(CSRC, "libptk%s.so" % os.environ.get("PTK_LIB_SUFFIX", ""))
 SOURCES = [os.path.join(CSRC, "ptk.cu"), os.path.join(CSRC, "ptk_ingest.cu"), os.path.join(CSRC, "ptk_ekf.cpp")]
 HEADERS = [os.path.join(CSRC, "ptk_device.cuh"), os.path.join(CSRC, "ptk_canon.cuh"),
