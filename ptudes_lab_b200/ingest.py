@@ -476,45 +476,37 @@ class OusterLidarData:
         self._scan_idx = 0
 
     def withScanIdx(self, *, start_scan: int = 0, end_scan: Optional[int] = None):
-        """Make an iterator with (scanIdx, scan/imu)"""
-        w = self._source.metadata.format.columns_per_frame
-        h = self._source.metadata.format.pixels_per_column
-
-        ls_write = None
-        pf = PacketFormat.from_info(self._source.metadata)
-        batch = ScanBatcher(w, pf, device=self._device)
-
-        scan_idx = 0
-
-        it = iter(self._source)
-        while True:
-            try:
-                packet = next(it)
-            except StopIteration:
-                if ls_write is not None:
-                    if batch.flush(ls_write):
-                        yield scan_idx, ls_write
-                    scan_idx += 1
-                batch.close()
-                return
-
-            if isinstance(packet, LidarPacket):
-                ls_write = ls_write or DeviceLidarScan(h, w, self._fields, self._device)
-                if batch(packet, ls_write):
-                    # finished frame (the packet that closed it already sits in the next frame's slots)
+        """(scan index, DeviceLidarScan | IMU) in packet order, with the reference's semantics (data.py:31-77): IMU
+        samples carry the index of the scan being assembled; a scan is handed out when the first packet of the next
+        frame arrives (or the stream ends while one is being assembled); scans before `start_scan` are batched and
+        counted but not handed out; iteration stops once a scan past `end_scan` has been closed."""
+        info = self._source.metadata
+        w, h = info.format.columns_per_frame, info.format.pixels_per_column
+        batcher = ScanBatcher(w, PacketFormat.from_info(info), device=self._device)
+        scan_idx, scan = 0, None
+        try:
+            for packet in self._source:
+                if isinstance(packet, ImuPacket):
                     if scan_idx >= start_scan:
-                        yield scan_idx, ls_write
-                    scan_idx += 1
-
-                    if end_scan is not None and scan_idx > end_scan:
-                        break
-
-                    ls_write = None
-
-            elif isinstance(packet, ImuPacket):
+                        yield scan_idx, imu_from_packet(packet)
+                    continue
+                if not isinstance(packet, LidarPacket):
+                    continue
+                if scan is None:
+                    scan = DeviceLidarScan(h, w, self._fields, self._device)
+                if not batcher(packet, scan):
+                    continue
+                # the frame is complete (the packet that closed it already sits in the next frame's slots)
                 if scan_idx >= start_scan:
-                    yield scan_idx, imu_from_packet(packet)
-        batch.close()
+                    yield scan_idx, scan
+                scan_idx += 1
+                scan = None
+                if end_scan is not None and scan_idx > end_scan:
+                    return
+            if scan is not None and batcher.flush(scan):
+                yield scan_idx, scan
+        finally:
+            batcher.close()
 
     def __iter__(self):
         """Make an iterator just data"""
