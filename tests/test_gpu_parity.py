@@ -720,11 +720,20 @@ def test_fleet_replay_over_several_contexts(tiny_seq):
             h[...] = tiny_seq.scan(k).range_mm
             host.append(h)
         dev = [torch.as_tensor(tiny_seq.scan(k).range_mm.astype(np.int32), device="cuda:0") for k in range(n)]
-        for images in (host, dev):
+        # third pass: the workers outnumber the host cores (affinity narrowed to one core), so they wait for their
+        # steps with the yielding poll instead of a spinning synchronize - as 8 ranks x 8 contexts do on a 32-core box
+        import os
+        cores = os.sched_getaffinity(0)
+        for images, narrow in ((host, False), (dev, False), (host, True)):
             for o in odos:
                 o.reset()
             ranges = [[[images[k]] * b for k in range(n)] for b in batches]
-            poses, stats = odometry.fleet_replay(odos, ranges, [s.cuda_stream for s in streams], want_stats=True)
+            if narrow:
+                os.sched_setaffinity(0, {min(cores)})
+            try:
+                poses, stats = odometry.fleet_replay(odos, ranges, [s.cuda_stream for s in streams], want_stats=True)
+            finally:
+                os.sched_setaffinity(0, cores)
             for g, b in enumerate(batches):
                 assert poses[g].shape == (n, b, 4, 4)
                 for k in range(n):
