@@ -143,22 +143,32 @@ def imu_packet(sys_ts, accel_ts, gyro_ts, accel_g, gyro_dps):
 
 
 # ---- writers (test inputs) ---------------------------------------------------------------------------
-def write_pcap(path, datagrams, mtu=1500, nanos=False, vlan=False):
-    """datagrams: list of (ts seconds, dst port, payload).  Ethernet + IPv4 + UDP; payloads larger than the MTU
-    are sent as IP fragments (what a sensor's 24 kB lidar packets look like on the wire)."""
+def write_pcap(path, datagrams, mtu=1500, nanos=False, vlan=False, linktype=1, shuffle_fragments=False):
+    """datagrams: list of (ts seconds, dst port, payload).  IPv4 + UDP under an Ethernet (linktype 1, optionally
+    VLAN-tagged), Linux cooked (113) or raw-IP (101) link layer; payloads larger than the MTU are sent as IP fragments
+    (what a sensor's 24 kB lidar packets look like on the wire), optionally with the fragments of a datagram out of
+    order."""
     with open(path, "wb") as f:
-        f.write(struct.pack("<IHHiIII", 0xA1B23C4D if nanos else 0xA1B2C3D4, 2, 4, 0, 0, 65535, 1))
+        f.write(struct.pack("<IHHiIII", 0xA1B23C4D if nanos else 0xA1B2C3D4, 2, 4, 0, 0, 65535, linktype))
         ident = 1
         for ts, port, payload in datagrams:
             udp = struct.pack(">HHHH", 40000, port, 8 + len(payload), 0) + payload
             step = (mtu - 20) // 8 * 8
-            for off in range(0, len(udp), step):
+            offs = list(range(0, len(udp), step))
+            if shuffle_fragments and len(offs) > 2:
+                offs = [offs[-1]] + offs[1:-1] + [offs[0]]
+            for off in offs:
                 part = udp[off:off + step]
                 more = off + step < len(udp)
                 ip = struct.pack(">BBHHHBBH4s4s", 0x45, 0, 20 + len(part), ident, (0x2000 if more else 0) | (off // 8), 64, 17, 0,
                                  bytes([192, 168, 1, 10]), bytes([192, 168, 1, 2]))
-                eth = b"\x02" * 6 + b"\x04" * 6 + (b"\x81\x00\x00\x05" if vlan else b"") + b"\x08\x00"
-                rec = eth + ip + part
+                if linktype == 1:
+                    link = b"\x02" * 6 + b"\x04" * 6 + (b"\x81\x00\x00\x05" if vlan else b"") + b"\x08\x00"
+                elif linktype == 113:
+                    link = struct.pack(">HHH8sH", 0, 1, 6, b"\x02" * 6 + b"\x00\x00", 0x0800)
+                else:
+                    link = b""
+                rec = link + ip + part
                 sec = int(ts)
                 frac = int(round((ts - sec) * (1e9 if nanos else 1e6)))
                 f.write(struct.pack("<IIII", sec, frac, len(rec), len(rec)) + rec)

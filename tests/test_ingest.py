@@ -199,6 +199,28 @@ def test_pcap_reader_reassembles_fragmented_datagrams(tmp_path, nanos, vlan):
     assert m.ts == 123456789 / 10**9 and np.allclose(m.lacc, ingest.GRAV * ip.accel) and np.allclose(m.avel, np.pi * ip.angular_vel / 180)
 
 
+@pytest.mark.parametrize("linktype", [113, 101])
+def test_pcap_reader_other_link_layers_and_fragment_order(tmp_path, linktype):
+    """Linux cooked and raw-IP captures; fragments of a datagram arriving last-first."""
+    F = io.Format(io.RNG15, 64, 16, 64)                            # 4352-byte packets: three fragments each
+    f, ts = _fields(F, 8, full=False)
+    pk = io.encode_frame(F, 1, f, ts)
+    assert F.size > 2 * 1480
+    path = tmp_path / "b.pcap"
+    io.write_pcap(path, [(1.0 + i, 7502, p) for i, p in enumerate(pk)], linktype=linktype, shuffle_fragments=True)
+
+    class Meta:
+        class format:
+            pixels_per_column, columns_per_frame, columns_per_packet, udp_profile_lidar = F.H, F.W, F.cpp, io.RNG15
+
+    out = list(ingest.PcapSource(str(path), Meta))
+    assert [p.buf for p in out] == pk and [round(p.capture_timestamp) for p in out] == [1, 2, 3, 4]
+    bad = tmp_path / "c.pcap"
+    bad.write_bytes(b"\x0a\x0d\x0d\x0a" + bytes(40))           # a pcapng section header
+    with pytest.raises(_ffi.PtkError):
+        ingest.PcapSource(str(bad), Meta)
+
+
 @pytest.mark.parametrize("compression", ["none", "bz2"])
 def test_bag_source_yields_the_packet_messages(tmp_path, compression):
     F = io.Format(io.RNG19, 8, 16, 64)
