@@ -337,7 +337,7 @@ int ptk_batcher_decode(ptk_batcher* b, const ptk_scan_fields* out, int* frame_id
 int ptk_batcher_peek(ptk_batcher* b, const unsigned char** packets, int* frame_id, int* n_packets);
 int ptk_batcher_pop(ptk_batcher* b);
 
-/* pcap.Pcap(file, meta) as far as data.py needs it: UDP payloads of a classic pcap file in capture order
+/* pcap.Pcap(file, meta) as far as data.py needs it: UDP payloads of a pcap or pcapng file in capture order
  * (Ethernet / VLAN / Linux cooked / raw IP link types, IPv4 with reassembly of fragmented datagrams -
  * a 128-beam lidar packet is 17 Ethernet frames). */
 typedef struct ptk_pcap ptk_pcap;

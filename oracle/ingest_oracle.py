@@ -175,6 +175,32 @@ def write_pcap(path, datagrams, mtu=1500, nanos=False, vlan=False, linktype=1, s
             ident = (ident + 1) & 0xFFFF
 
 
+def pcap_to_pcapng(src, dst, tsresol=9, big_endian=False):
+    """Rewrite a classic little-endian pcap as a pcapng file (section header, one interface description with an
+    if_tsresol option, enhanced packet blocks) - the format Wireshark writes by default."""
+    e = ">" if big_endian else "<"
+    raw = open(src, "rb").read()
+    magic, _, _, _, _, _, linktype = struct.unpack_from("<IHHiIII", raw, 0)
+    nanos = magic == 0xA1B23C4D
+
+    def block(btype, body):
+        pad = (-len(body)) % 4
+        total = 12 + len(body) + pad
+        return struct.pack(e + "II", btype, total) + body + b"\x00" * pad + struct.pack(e + "I", total)
+
+    out = block(0x0A0D0D0A, struct.pack(e + "IHHq", 0x1A2B3C4D, 1, 0, -1))
+    opt = struct.pack(e + "HHB3x", 9, 1, tsresol) + struct.pack(e + "HH", 0, 0)
+    out += block(1, struct.pack(e + "HHI", linktype, 0, 65535) + opt)
+    pos = 24
+    while pos + 16 <= len(raw):
+        sec, frac, incl, orig = struct.unpack_from("<IIII", raw, pos)
+        data = raw[pos + 16:pos + 16 + incl]
+        pos += 16 + incl
+        ticks = (sec * 10**9 + frac * (1 if nanos else 1000)) * 10**tsresol // 10**9
+        out += block(6, struct.pack(e + "IIIII", 0, ticks >> 32, ticks & 0xFFFFFFFF, incl, orig) + data)
+    open(dst, "wb").write(out)
+
+
 def _bag_header(**kv):
     b = b""
     for k, v in kv.items():

@@ -524,6 +524,10 @@ struct ptk_pcap {
     std::map<Key, Frag> frags;
     long long seq = 0;
     std::vector<unsigned char> rec;
+    // pcapng: one entry per interface description block of the current section
+    bool ng = false;
+    struct Iface { uint32_t linktype; double tick; };
+    std::vector<Iface> ifaces;
 };
 
 static uint32_t sw32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24); }
@@ -541,10 +545,13 @@ extern "C" int ptk_pcap_open(ptk_pcap** out, const char* path) {
     else if (magic == 0xd4c3b2a1u) p->swap = true;
     else if (magic == 0xa1b23c4du) p->nanos = true;
     else if (magic == 0x4d3cb2a1u) { p->swap = true; p->nanos = true; }
-    else { fclose(f); delete p; g_ingest_err = "pcap: not a classic pcap file (pcapng is not supported)"; return PTK_E_ARG; }
-    uint32_t lt;
-    memcpy(&lt, h + 20, 4);
-    p->linktype = p->swap ? sw32(lt) : lt;
+    else if (magic == 0x0a0d0d0au) { p->ng = true; fseek(f, 0, SEEK_SET); }      // pcapng: blocks, parsed as they come
+    else { fclose(f); delete p; g_ingest_err = "pcap: neither a pcap nor a pcapng file"; return PTK_E_ARG; }
+    if (!p->ng) {
+        uint32_t lt;
+        memcpy(&lt, h + 20, 4);
+        p->linktype = p->swap ? sw32(lt) : lt;
+    }
     p->f = f;
     *out = p;
     return PTK_OK;
@@ -560,30 +567,86 @@ extern "C" int ptk_pcap_close(ptk_pcap* p) {
 extern "C" int ptk_pcap_next(ptk_pcap* p, unsigned char* buf, int cap, int* len, int* dst_port, double* ts) {
     if (!p || !buf || !len) return PTK_E_ARG;
     while (true) {
-        unsigned char rh[16];
-        if (fread(rh, 1, 16, p->f) != 16) return 0;
-        uint32_t sec, frac, incl;
-        memcpy(&sec, rh, 4); memcpy(&frac, rh + 4, 4); memcpy(&incl, rh + 8, 4);
-        if (p->swap) { sec = sw32(sec); frac = sw32(frac); incl = sw32(incl); }
-        if (incl > (1u << 26)) { g_ingest_err = "pcap: corrupt record"; return PTK_E_ARG; }
-        p->rec.resize(incl);
-        if (incl && fread(p->rec.data(), 1, incl, p->f) != incl) return 0;
-        const double t = (double)sec + (double)frac * (p->nanos ? 1e-9 : 1e-6);
+        uint32_t incl = 0, linktype = p->linktype;
+        double t = 0.0;
+        if (!p->ng) {
+            unsigned char rh[16];
+            if (fread(rh, 1, 16, p->f) != 16) return 0;
+            uint32_t sec, frac;
+            memcpy(&sec, rh, 4); memcpy(&frac, rh + 4, 4); memcpy(&incl, rh + 8, 4);
+            if (p->swap) { sec = sw32(sec); frac = sw32(frac); incl = sw32(incl); }
+            if (incl > (1u << 26)) { g_ingest_err = "pcap: corrupt record"; return PTK_E_ARG; }
+            p->rec.resize(incl);
+            if (incl && fread(p->rec.data(), 1, incl, p->f) != incl) return 0;
+            t = (double)sec + (double)frac * (p->nanos ? 1e-9 : 1e-6);
+        } else {
+            // pcapng block: type, total length, body, total length again
+            unsigned char bh[8];
+            if (fread(bh, 1, 8, p->f) != 8) return 0;
+            uint32_t type, total;
+            memcpy(&type, bh, 4); memcpy(&total, bh + 4, 4);
+            if (type == 0x0a0d0d0au) {                  // section header: its byte-order magic decides the endianness
+                unsigned char bo[4];
+                if (fread(bo, 1, 4, p->f) != 4) return 0;
+                uint32_t m;
+                memcpy(&m, bo, 4);
+                p->swap = (m == 0x4d3c2b1au);
+                if (p->swap) total = sw32(total);
+                if (total < 16 || total > (1u << 26)) { g_ingest_err = "pcapng: corrupt section header"; return PTK_E_ARG; }
+                fseek(p->f, (long)total - 12, SEEK_CUR);
+                p->ifaces.clear();
+                continue;
+            }
+            if (p->swap) { type = sw32(type); total = sw32(total); }
+            if (total < 12 || total > (1u << 26)) { g_ingest_err = "pcapng: corrupt block"; return PTK_E_ARG; }
+            std::vector<unsigned char>& body = p->rec;
+            body.resize(total - 8);
+            if (fread(body.data(), 1, total - 8, p->f) != total - 8) return 0;
+            auto u16 = [&](size_t o) { uint16_t v; memcpy(&v, body.data() + o, 2); return p->swap ? (uint16_t)((v >> 8) | (v << 8)) : v; };
+            auto u32 = [&](size_t o) { uint32_t v; memcpy(&v, body.data() + o, 4); return p->swap ? sw32(v) : v; };
+            if (type == 1) {                            // interface description: link type + timestamp resolution option
+                ptk_pcap::Iface I{u16(0), 1e-6};
+                size_t o = 8;
+                while (o + 4 <= body.size() - 4) {
+                    const uint16_t code = u16(o), olen = u16(o + 2);
+                    if (code == 0) break;
+                    if (code == 9 && olen >= 1) {       // if_tsresol
+                        const unsigned char r = body[o + 4];
+                        I.tick = (r & 0x80) ? 1.0 / (double)(1ull << (r & 0x7f)) : 1.0;
+                        if (!(r & 0x80)) for (int k = 0; k < r; ++k) I.tick /= 10.0;
+                    }
+                    o += 4 + ((olen + 3u) & ~3u);
+                }
+                p->ifaces.push_back(I);
+                continue;
+            }
+            if (type != 6) continue;                    // only enhanced packet blocks carry what we want
+            if (body.size() < 24) continue;
+            const uint32_t ifid = u32(0);
+            if (ifid >= p->ifaces.size()) continue;
+            const uint64_t ticks = ((uint64_t)u32(4) << 32) | u32(8);
+            incl = u32(12);
+            if ((size_t)incl + 20 > body.size()) continue;
+            t = (double)ticks * p->ifaces[ifid].tick;
+            linktype = p->ifaces[ifid].linktype;
+            memmove(body.data(), body.data() + 20, incl);
+            body.resize(incl);
+        }
         const unsigned char* d = p->rec.data();
         int n = (int)incl, off = 0;
         // link layer -> start of the IP header
-        if (p->linktype == 1) {                       // Ethernet (+ VLAN tags)
+        if (linktype == 1) {                       // Ethernet (+ VLAN tags)
             if (n < 14) continue;
             int et = (d[12] << 8) | d[13];
             off = 14;
             while ((et == 0x8100 || et == 0x88a8) && n >= off + 4) { et = (d[off + 2] << 8) | d[off + 3]; off += 4; }
             if (et != 0x0800) continue;
-        } else if (p->linktype == 113) {              // Linux cooked capture
+        } else if (linktype == 113) {              // Linux cooked capture
             if (n < 16 || ((d[14] << 8) | d[15]) != 0x0800) continue;
             off = 16;
-        } else if (p->linktype == 0) {                // BSD loopback: 4-byte family
+        } else if (linktype == 0) {                // BSD loopback: 4-byte family
             off = 4;
-        } else if (p->linktype == 101 || p->linktype == 228 || p->linktype == 12) {   // raw IP
+        } else if (linktype == 101 || linktype == 228 || linktype == 12) {   // raw IP
             off = 0;
         } else { g_ingest_err = "pcap: unsupported link type"; return PTK_E_ARG; }
         if (n < off + 20 || (d[off] >> 4) != 4) continue;

@@ -240,7 +240,8 @@ def decode_frames(pf: PacketFormat, packets, n_frames: int, device: int = 0, fie
 # ---- packet sources ------------------------------------------------------------------------------------
 class PcapSource:
     """`pcap.Pcap(file_path, meta)` (utils.py:179): lidar and IMU packets of a pcap file in capture order.
-    Native reader (`ptk_pcap_*`): Ethernet / VLAN / cooked / raw-IP link types, IPv4 reassembly."""
+    Native reader (`ptk_pcap_*`): classic pcap and pcapng, Ethernet / VLAN / cooked / raw-IP link types, IPv4
+    reassembly."""
 
     def __init__(self, file_path: str, metadata, lidar_port: Optional[int] = None, imu_port: Optional[int] = None):
         self._path = str(file_path)

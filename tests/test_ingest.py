@@ -215,8 +215,14 @@ def test_pcap_reader_other_link_layers_and_fragment_order(tmp_path, linktype):
 
     out = list(ingest.PcapSource(str(path), Meta))
     assert [p.buf for p in out] == pk and [round(p.capture_timestamp) for p in out] == [1, 2, 3, 4]
+    # the same capture as pcapng (what Wireshark writes), little and big endian, micro- and nanosecond ticks
+    for be, res in ((False, 6), (True, 9)):
+        ng = tmp_path / f"ng{int(be)}.pcap"
+        io.pcap_to_pcapng(path, ng, tsresol=res, big_endian=be)
+        out = list(ingest.PcapSource(str(ng), Meta))
+        assert [p.buf for p in out] == pk and [round(p.capture_timestamp) for p in out] == [1, 2, 3, 4]
     bad = tmp_path / "c.pcap"
-    bad.write_bytes(b"\x0a\x0d\x0d\x0a" + bytes(40))           # a pcapng section header
+    bad.write_bytes(b"not a capture file" + bytes(40))
     with pytest.raises(_ffi.PtkError):
         ingest.PcapSource(str(bad), Meta)
 
