@@ -345,6 +345,11 @@ int ptk_pcap_open(ptk_pcap** out, const char* path);
 int ptk_pcap_close(ptk_pcap* p);
 /* next UDP datagram: payload copied to buf (at most cap bytes), returns 1, 0 at the end of the file */
 int ptk_pcap_next(ptk_pcap* p, unsigned char* buf, int cap, int* len, int* dst_port, double* ts);
+/* LZ4 frame decompression (magic 0x184D2204; dependent or independent blocks, stored blocks, checksums skipped):
+ * what `rosbag record --lz4` chunks are compressed with.  Returns 0 and the size written, PTK_E_CAPACITY if `cap`
+ * is too small, PTK_E_ARG for a malformed frame. */
+int ptk_lz4_frame_decompress(const unsigned char* src, unsigned long long n, unsigned char* dst, unsigned long long cap,
+                             unsigned long long* out_len);
 /* text of the last failure of an ingest call on this thread */
 const char* ptk_ingest_last_error(void);
 

@@ -201,6 +201,61 @@ def pcap_to_pcapng(src, dst, tsresol=9, big_endian=False):
     open(dst, "wb").write(out)
 
 
+def lz4_block_compress(data: bytes) -> bytes:
+    """A plain greedy LZ4 block compressor (hash of 4-byte windows; the format's end-of-block rules: the last five
+    bytes are literals, no match starts in the last twelve).  Test input for the native decoder."""
+    n, out, anchor, i, table = len(data), bytearray(), 0, 0, {}
+
+    def emit(lit: bytes, mlen: int, offset: int):
+        ll = len(lit)
+        token = (min(ll, 15) << 4) | (min(mlen - 4, 15) if mlen else 0)
+        out.append(token)
+        if ll >= 15:
+            r = ll - 15
+            while r >= 255:
+                out.append(255); r -= 255
+            out.append(r)
+        out.extend(lit)
+        if mlen:
+            out.extend(struct.pack("<H", offset))
+            if mlen - 4 >= 15:
+                r = mlen - 4 - 15
+                while r >= 255:
+                    out.append(255); r -= 255
+                out.append(r)
+
+    while i + 12 < n:
+        key = data[i:i + 4]
+        j = table.get(key)
+        table[key] = i
+        if j is not None and i - j <= 65535:
+            m = 4
+            while i + m < n - 5 and data[j + m] == data[i + m]:
+                m += 1
+            emit(data[anchor:i], m, i - j)
+            i += m
+            anchor = i
+        else:
+            i += 1
+    emit(data[anchor:], 0, 0)
+    return bytes(out)
+
+
+def lz4_frame(data: bytes, block=65536, stored_every=0) -> bytes:
+    """LZ4 frame with independent blocks (FLG 0x60, BD 0x40 = 64 KB blocks); every `stored_every`-th block is written
+    uncompressed (high bit of the block size).  The header checksum byte is not computed (our decoder skips it)."""
+    out = bytearray(struct.pack("<IBBB", 0x184D2204, 0x60, 0x40, 0))
+    for k, o in enumerate(range(0, len(data), block)):
+        raw = data[o:o + block]
+        comp = lz4_block_compress(raw)
+        if (stored_every and k % stored_every == stored_every - 1) or len(comp) >= len(raw):
+            out += struct.pack("<I", len(raw) | 0x80000000) + raw
+        else:
+            out += struct.pack("<I", len(comp)) + comp
+    out += struct.pack("<I", 0)
+    return bytes(out)
+
+
 def _bag_header(**kv):
     b = b""
     for k, v in kv.items():
@@ -250,5 +305,5 @@ def write_bag(path, messages, compression="none", per_chunk=50, imu_topics=()):
                 nsec = int(round((ts - sec) * 1e9))
                 body += _bag_record(_bag_header(op=b"\x02", conn=struct.pack("<I", cid[topic]), time=struct.pack("<II", sec, nsec)),
                                     payload if topic in imu_topics else struct.pack("<I", len(payload)) + payload)
-            data = bz2.compress(body) if compression == "bz2" else body
+            data = bz2.compress(body) if compression == "bz2" else (lz4_frame(body, stored_every=3) if compression == "lz4" else body)
             f.write(_bag_record(_bag_header(op=b"\x05", compression=compression.encode(), size=struct.pack("<I", len(body))), data))

@@ -129,6 +129,7 @@ SYMBOLS = {
     "ptk_pcap_open": (C.c_int, [C.POINTER(_P), C.c_char_p]),
     "ptk_pcap_close": (C.c_int, [_P]),
     "ptk_pcap_next": (C.c_int, [_P, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "ptk_lz4_frame_decompress": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
     "ptk_ingest_last_error": (C.c_char_p, []),
     "ptk_host_alloc": (C.c_int, [C.POINTER(_P), C.c_ulonglong]),
     "ptk_host_free": (C.c_int, [_P]),

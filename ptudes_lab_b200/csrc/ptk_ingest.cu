@@ -704,4 +704,57 @@ extern "C" int ptk_pcap_next(ptk_pcap* p, unsigned char* buf, int cap, int* len,
     }
 }
 
+// ---- LZ4 frame format (lz4 Frame Format Description 1.6; block format: token / literals / offset / match) -------
+extern "C" int ptk_lz4_frame_decompress(const unsigned char* src, unsigned long long n, unsigned char* dst, unsigned long long cap,
+                                        unsigned long long* out_len) {
+    if (!src || !dst || !out_len) return PTK_E_ARG;
+    auto bad = [](const char* m) { g_ingest_err = std::string("lz4: ") + m; return PTK_E_ARG; };
+    size_t ip = 0, op = 0;
+    if (n < 7 || rd32(src) != 0x184D2204u) return bad("not an LZ4 frame");
+    const unsigned flg = src[4];
+    if ((flg >> 6) != 1) return bad("unsupported frame version");
+    const bool block_checksum = flg & 0x10, content_size = flg & 0x08, content_checksum = flg & 0x04, dict_id = flg & 0x01;
+    ip = 6 + (content_size ? 8 : 0) + (dict_id ? 4 : 0) + 1;          // magic, FLG, BD, [size], [dict], header checksum
+    if (ip > n) return bad("truncated header");
+    while (true) {
+        if (ip + 4 > n) return bad("truncated frame");
+        const uint32_t bs = rd32(src + ip);
+        ip += 4;
+        if (bs == 0) break;                                            // end mark
+        const size_t len = bs & 0x7fffffffu;
+        if (ip + len > n) return bad("truncated block");
+        if (bs & 0x80000000u) {                                        // stored block
+            if (op + len > cap) { g_ingest_err = "lz4: output buffer too small"; return PTK_E_CAPACITY; }
+            memcpy(dst + op, src + ip, len);
+            op += len;
+        } else {
+            size_t b = ip;
+            const size_t bend = ip + len;
+            while (b < bend) {
+                const unsigned token = src[b++];
+                size_t lit = token >> 4;
+                if (lit == 15) { unsigned c; do { if (b >= bend) return bad("bad literal length"); c = src[b++]; lit += c; } while (c == 255); }
+                if (b + lit > bend) return bad("literals run past the block");
+                if (op + lit > cap) { g_ingest_err = "lz4: output buffer too small"; return PTK_E_CAPACITY; }
+                memcpy(dst + op, src + b, lit);
+                op += lit; b += lit;
+                if (b >= bend) break;                                  // the last sequence has no match
+                if (b + 2 > bend) return bad("truncated offset");
+                const size_t offset = src[b] | (src[b + 1] << 8);
+                b += 2;
+                size_t ml = (token & 15) + 4;
+                if ((token & 15) == 15) { unsigned c; do { if (b >= bend) return bad("bad match length"); c = src[b++]; ml += c; } while (c == 255); }
+                if (offset == 0 || offset > op) return bad("match offset out of range");
+                if (op + ml > cap) { g_ingest_err = "lz4: output buffer too small"; return PTK_E_CAPACITY; }
+                for (size_t k = 0; k < ml; ++k) dst[op + k] = dst[op + k - offset];     // overlapping copies are the point
+                op += ml;
+            }
+        }
+        ip += len + (block_checksum ? 4 : 0);
+    }
+    (void)content_checksum;
+    *out_len = op;
+    return PTK_OK;
+}
+
 extern "C" const char* ptk_ingest_last_error(void) { return g_ingest_err.c_str(); }

@@ -301,9 +301,20 @@ def _bag_records(buf, pos: int, end: int):
         pos = d0 + dl
 
 
+def lz4_frame_decompress(data, size: int) -> bytes:
+    """An LZ4 frame (what `rosbag record --lz4` compresses chunks with) -> `size` bytes; native (`ptk_lz4_frame_decompress`)."""
+    src = np.frombuffer(data, dtype=np.uint8)
+    dst = np.empty(max(int(size), 1), dtype=np.uint8)
+    n = C.c_ulonglong()
+    _check(_ffi.load().ptk_lz4_frame_decompress(src.ctypes.data, src.size, dst.ctypes.data, dst.size, C.byref(n)))
+    if n.value != size:
+        raise ValueError(f"lz4 chunk: {n.value} bytes after decompression, the chunk header says {size}")
+    return dst[:n.value].tobytes()
+
+
 class BagReader:
     """Messages of ROS1 bag file(s) (format 2.0) - the part of `rosbags.highlevel.AnyReader` bag.py uses.
-    Chunks with `none` or `bz2` compression; messages come chunk by chunk, in time order within a chunk (a
+    Chunks with `none`, `bz2` or `lz4` compression; messages come chunk by chunk, in time order within a chunk (a
     recorder writes its chunks in arrival order).  `connections`: {id: (topic, msgtype, md5sum)} seen so far."""
 
     def __init__(self, paths):
@@ -329,8 +340,10 @@ class BagReader:
                     inner = d
                 elif comp == "bz2":
                     inner = memoryview(bz2.decompress(bytes(d)))
+                elif comp == "lz4":
+                    inner = memoryview(lz4_frame_decompress(d, struct.unpack("<I", h["size"])[0]))
                 else:
-                    raise ValueError(f"{path}: chunk compression '{comp}' is not supported (none, bz2)")
+                    raise ValueError(f"{path}: chunk compression '{comp}' is not supported (none, bz2, lz4)")
                 yield from self._scan(fi, path, inner, 0, len(inner), want)
         msgs.sort(key=lambda m: m[0])
         for t, cid, d in msgs:

@@ -227,7 +227,33 @@ def test_pcap_reader_other_link_layers_and_fragment_order(tmp_path, linktype):
         ingest.PcapSource(str(bad), Meta)
 
 
-@pytest.mark.parametrize("compression", ["none", "bz2"])
+def test_lz4_frame_decoder():
+    """ptk_lz4_frame_decompress against a plain LZ4 compressor (oracle): random, repetitive and empty inputs, stored
+    blocks, long literal / match runs, a hand-made frame with DEPENDENT blocks, malformed frames."""
+    rng = np.random.default_rng(5)
+    cases = [b"", b"a", b"abcdefgh" * 5000, bytes(rng.integers(0, 256, 70000, dtype=np.uint8)),
+             bytes(rng.integers(0, 4, 200000, dtype=np.uint8)), b"x" * 100000 + bytes(range(256)) * 40]
+    for data in cases:
+        for stored in (0, 2):
+            fr = io.lz4_frame(data, stored_every=stored)
+            assert ingest.lz4_frame_decompress(fr, len(data)) == data
+    assert len(io.lz4_frame(b"abcdefgh" * 5000)) < 400                      # it does compress
+    # dependent blocks (FLG 0x40): the second block is one match reaching 10 bytes back into the first + 5 literals
+    first = b"0123456789"
+    blk1 = bytes([len(first) << 4]) + first
+    blk2 = bytes([(0 << 4) | (8 - 4)]) + (10).to_bytes(2, "little") + bytes([5 << 4]) + b"ABCDE"
+    fr = (0x184D2204).to_bytes(4, "little") + bytes([0x40, 0x40, 0]) + len(blk1).to_bytes(4, "little") + blk1 + \
+        len(blk2).to_bytes(4, "little") + blk2 + bytes(4)
+    assert ingest.lz4_frame_decompress(fr, 23) == b"0123456789" + b"01234567" + b"ABCDE"
+    with pytest.raises(_ffi.PtkError):
+        ingest.lz4_frame_decompress(b"\x00" * 16, 4)                          # not a frame
+    with pytest.raises(_ffi.PtkError):
+        ingest.lz4_frame_decompress(io.lz4_frame(b"abcdefgh" * 100)[:-9], 800)  # truncated
+    with pytest.raises(ValueError):
+        ingest.lz4_frame_decompress(io.lz4_frame(b"abcdefgh" * 100), 900)      # size mismatch with the chunk header
+
+
+@pytest.mark.parametrize("compression", ["none", "bz2", "lz4"])
 def test_bag_source_yields_the_packet_messages(tmp_path, compression):
     F = io.Format(io.RNG19, 8, 16, 64)
     f, ts = _fields(F, 4, full=False)
