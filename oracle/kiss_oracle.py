@@ -97,11 +97,19 @@ def preprocess(frame, max_range, min_range):
     return frame[range_mask(frame, max_range, min_range)]
 
 
-def upstream_voxel_hash(keys):
+# Second multiplier of upstream's VoxelHash.  SURVEY A.5 gives the classic spatial-hash prime 19349663 (Teschner et
+# al.); kiss-icp's own VoxelHashMap.hpp is remembered by some as carrying 19349669 instead (a long-standing typo of
+# that prime).  Neither can be checked here.  It only matters to the order="robin_map" EMULATION (which bucket a voxel
+# lands in); the measured size of the ordering effect is the same with either (profiles/r2_order_delta*.json).
+UPSTREAM_HASH_Y = 19349663
+
+
+def upstream_voxel_hash(keys, hash_y=None):
     """kiss-icp VoxelHash (A.5): ((1 << 20) - 1) & (x*73856093 ^ y*19349663 ^ z*83492791) on the int32
     lanes reinterpreted as uint32.  Known answers: (1,2,3) -> 363078, (-1,0,0) -> 592803."""
+    hy = UPSTREAM_HASH_Y if hash_y is None else hash_y
     k = np.asarray(keys).reshape(-1, 3).astype(np.int64) & 0xFFFFFFFF
-    h = ((k[:, 0] * 73856093) & 0xFFFFFFFF) ^ ((k[:, 1] * 19349663) & 0xFFFFFFFF) ^ ((k[:, 2] * 83492791) & 0xFFFFFFFF)
+    h = ((k[:, 0] * 73856093) & 0xFFFFFFFF) ^ ((k[:, 1] * hy) & 0xFFFFFFFF) ^ ((k[:, 2] * 83492791) & 0xFFFFFFFF)
     return (h & ((1 << 20) - 1)).astype(np.int64)
 
 

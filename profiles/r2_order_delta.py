@@ -7,7 +7,7 @@ produces: hash of SURVEY A.5, power-of-two buckets, reserve(frame.size()), robin
 erase-while-iterating skip).  The first-grid selection SETS are identical by construction; what differs
 is the order, hence which point is "first" in the second grid and in every map voxel (kiss.py:96,129).
 
-  python profiles/r2_order_delta.py [config] [scans]   ->  profiles/r2_order_delta.json
+  python profiles/r2_order_delta.py [config] [scans] [hash multiplier y]   ->  profiles/r2_order_delta[_hashyN].json
 
 TEST INFRASTRUCTURE (imports oracle/).  The emulation is still a restatement from memory of the public
 upstream sources, not a run of kiss-icp: the numbers say how sensitive the odometry is to the order, and
@@ -30,6 +30,8 @@ from ptudes_lab_b200.ins.data import calc_ate        # noqa: E402
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "os0_quad"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+    if len(sys.argv) > 3:       # the other candidate for upstream's second hash multiplier (see oracle/kiss_oracle.py)
+        ko.UPSTREAM_HASH_Y = int(sys.argv[3])
     seq = synth.make_sequence(name, 0)
     a = ko.OracleKissICPWrapper(order="index")
     b = ko.OracleKissICPWrapper(order="robin_map")
@@ -72,7 +74,9 @@ def main():
         "prune_skips_total": int(sum(r["prune_skips"] for r in rows)),
         "per_scan": rows,
     }
-    with open(os.path.join(ROOT, "profiles", "r2_order_delta.json"), "w") as f:
+    out["upstream_hash_y"] = ko.UPSTREAM_HASH_Y
+    suffix = "" if ko.UPSTREAM_HASH_Y == 19349663 else f"_hashy{ko.UPSTREAM_HASH_Y}"
+    with open(os.path.join(ROOT, "profiles", f"r2_order_delta{suffix}.json"), "w") as f:
         json.dump(out, f, indent=1)
     print({k: v for k, v in out.items() if k != "per_scan"})
 
